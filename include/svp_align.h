@@ -1,0 +1,148 @@
+/*
+ * svp_align.h — C-ABI of the B200 pairwise-alignment hot path (libsvp_align.so).
+ *
+ * The reference (bihealth/svirlpool) has no FFI for this path: every alignment is a
+ * subprocess call to minimap2 through
+ *     util.align_reads_with_minimap()          src/svirlpool/util/util.py:162-238
+ * issued at
+ *     AVA  (read-vs-read, one container)       src/svirlpool/localassembly/consensus.py:1378-1386
+ *     reads -> consensus                       src/svirlpool/localassembly/consensus.py:851-857
+ *     consensus -> reference                   src/svirlpool/localassembly/consensus_align.py:1977-1987
+ * and its SAM output is consumed by
+ *     consensus_lib.parse_directed_signals_from_ava()      consensus_lib.py:279-345
+ *     alignments_to_rafs.parse_SVsignals_from_alignment()  alignments_to_rafs.py:174-258
+ * The entry points below are what a ctypes/cffi binding added at that seam would call
+ * (see INTEGRATION.md). Plain pointers and sizes only; no torch types; never throws.
+ *
+ * The same declarations are implemented twice:
+ *   svp_*   — CUDA (sm_100a) implementation, svirlpool_b200/csrc/  -> libsvp_align.so
+ *   svpo_*  — CPU oracle (test infrastructure only), oracle/svp_oracle.c -> liboracle
+ * The alignment semantics both must satisfy bit-for-bit are in DESIGN.md §3 (ALIGN_SPEC).
+ */
+#ifndef SVP_ALIGN_H
+#define SVP_ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVP_ABI_VERSION 1
+
+/* return codes */
+#define SVP_OK               0
+#define SVP_ERR_ARG         -1   /* invalid argument (see svp_last_error) */
+#define SVP_ERR_CUDA        -2   /* CUDA runtime failure */
+#define SVP_ERR_NOMEM       -3   /* device or host allocation failed */
+#define SVP_ERR_UNSUPPORTED -4   /* scoring/limits outside what the kernels implement */
+#define SVP_ERR_NODEVICE    -5   /* no CUDA device: there is NO CPU fallback */
+
+/* per-pair status bits (svp_result.status) */
+#define SVP_ST_OK            0u
+#define SVP_ST_NOHIT         1u  /* best local score == 0: no alignment ("unmapped") */
+#define SVP_ST_CIGAR_OVF     2u  /* CIGAR longer than the pair's slot; counts/coords still valid */
+#define SVP_ST_SCORE_OVF     4u  /* score range exceeded the kernel's lane type (must not happen) */
+#define SVP_ST_BAD_PAIR      8u  /* pair descriptor invalid (index, band) */
+
+/* CIGAR op codes: BAM encoding, word = len << 4 | op */
+#define SVP_CIGAR_M 0u
+#define SVP_CIGAR_I 1u
+#define SVP_CIGAR_D 2u
+
+/* Scoring profile. Two presets are provided by svp_scoring_preset():
+ *   "map-ont"/"ava-ont": minimap2 defaults A=2 B=4 O=4,24 E=2,1 (verified on the 20 frozen
+ *       reference alignments)
+ *   "last": single-piece affine with a 4x4 matrix and separate ins/del costs, as trained by
+ *       last-train into a lamassemble .mat (consensus.py:777). */
+typedef struct svp_scoring {
+    int32_t matrix[16];   /* substitution score s[q*4+t], q,t in 0..3 (A,C,G,T) */
+    int32_t del_open1, del_ext1;   /* deletion (target-only, CIGAR D) piece 1: cost(k) = open + k*ext */
+    int32_t ins_open1, ins_ext1;   /* insertion (query-only, CIGAR I) piece 1 */
+    int32_t del_open2, del_ext2;   /* piece 2 (long gaps); open2 < 0 disables the second piece */
+    int32_t ins_open2, ins_ext2;
+    int32_t min_signal_size;       /* indel runs >= this enter sv_dist (consensus.py:1441-1445: 12) */
+    int32_t zdrop;                 /* Z-trim threshold (minimap2 -z, default 400); 0 disables */
+    int32_t zdrop_ext;             /* per-diagonal allowance of the Z-trim test (minimap2: the long-gap extension e2) */
+    int32_t reserved;
+} svp_scoring;
+
+/* One alignment problem: query sequence index, target sequence index (into the batch's
+ * sequence table), strand, and the diagonal band d = t_pos - q_pos in [band_lo, band_lo+band_w).
+ * band_w must be a positive multiple of 32. */
+typedef struct svp_pair {
+    uint32_t q;          /* query sequence index */
+    uint32_t t;          /* target sequence index */
+    int32_t  band_lo;    /* lowest diagonal of the band */
+    uint32_t band_w;     /* number of diagonals (multiple of 32) */
+    uint32_t flags;      /* bit0: align the reverse complement of the query */
+    uint32_t cigar_off;  /* first word of this pair's slot in the cigar buffer */
+    uint32_t cigar_cap;  /* slot size in words */
+    uint32_t reserved;
+} svp_pair;
+#define SVP_PAIR_REVCOMP 1u
+
+typedef struct svp_result {
+    int32_t  score;
+    uint32_t status;
+    int32_t  q_beg, q_end;   /* aligned interval on the ORIENTED query (after revcomp), 0-based half-open */
+    int32_t  t_beg, t_end;   /* aligned interval on the target */
+    uint32_t n_match, n_mismatch;
+    uint32_t n_ins_ops, n_ins_bp;
+    uint32_t n_del_ops, n_del_bp;
+    uint32_t cigar_off;      /* first word of the CIGAR (inside the pair's slot) */
+    uint32_t cigar_len;      /* number of words */
+    double   sv_dist;        /* sum over indel runs >= min_signal_size of (1-exp(-(s/30)^1.5))*s
+                                (consensus_lib.py:24-37, 353-396 with unit weights) */
+    uint64_t cells;          /* DP cells of the spec (band ∩ matrix) for this pair */
+} svp_result;
+
+typedef struct svp_handle svp_handle;
+
+int         svp_abi_version(void);
+int         svp_device_count(void);
+int         svp_scoring_preset(const char* name, svp_scoring* out);
+/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default
+ * 1/2 of free memory); the library processes a batch in waves that fit the arena. */
+int         svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out);
+void        svp_destroy(svp_handle* h);
+const char* svp_last_error(const svp_handle* h);
+
+/* Align n_pairs pairs. Sequences are 2-bit packed (A=0,C=1,G=2,T=3; base k of a sequence lives
+ * in bits 2*(k%4).. of byte seq_off[s] + k/4); seq_off[] entries must be multiples of 16.
+ * All buffers are HOST memory; results and CIGAR words are written to caller-allocated arrays.
+ * Blocking; one call at a time per handle. */
+int svp_align_batch(svp_handle* h,
+                    const uint8_t* packed_seqs, size_t packed_bytes,
+                    const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                    const svp_pair* pairs, uint32_t n_pairs,
+                    svp_result* results,
+                    uint32_t* cigar_buf, size_t cigar_words);
+
+/* Device-resident variant: every pointer is a DEVICE pointer (e.g. torch tensor data_ptr()).
+ * Used by bench.py for the HBM-resident `value` measurement. stream: cudaStream_t or NULL. */
+int svp_align_batch_device(svp_handle* h,
+                           const uint8_t* d_packed_seqs, size_t packed_bytes,
+                           const uint64_t* d_seq_off, const uint32_t* d_seq_len, uint32_t n_seqs,
+                           const svp_pair* d_pairs, const svp_pair* h_pairs, uint32_t n_pairs,
+                           svp_result* d_results,
+                           uint32_t* d_cigar_buf, size_t cigar_words,
+                           void* stream);
+
+/* Timing / accounting of the last svp_align_batch*() call on this handle (CUDA events on the
+ * stream the kernels ran on). */
+typedef struct svp_stats {
+    double   fwd_ms;        /* sum over waves of the forward DP kernel(s) */
+    double   tb_ms;         /* sum over waves of the traceback kernel */
+    double   total_ms;      /* first launch -> last kernel end */
+    uint64_t cells;         /* spec cells aligned */
+    uint64_t tb_bytes;      /* traceback bytes written to HBM */
+    uint32_t fwd_launches, tb_launches, waves, reserved;
+} svp_stats;
+int svp_get_stats(const svp_handle* h, svp_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVP_ALIGN_H */

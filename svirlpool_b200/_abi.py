@@ -1,0 +1,78 @@
+"""numpy/ctypes views of the structs in include/svp_align.h (one definition, used by the CUDA
+binding and — in tests only — by the oracle binding)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+
+SVP_OK, SVP_ERR_ARG, SVP_ERR_CUDA, SVP_ERR_NOMEM, SVP_ERR_UNSUPPORTED, SVP_ERR_NODEVICE = 0, -1, -2, -3, -4, -5
+ST_OK, ST_NOHIT, ST_CIGAR_OVF, ST_SCORE_OVF, ST_BAD_PAIR = 0, 1, 2, 4, 8
+PAIR_REVCOMP = 1
+
+SCORING_DTYPE = np.dtype([
+    ("matrix", "<i4", (16,)),
+    ("del_open1", "<i4"), ("del_ext1", "<i4"), ("ins_open1", "<i4"), ("ins_ext1", "<i4"),
+    ("del_open2", "<i4"), ("del_ext2", "<i4"), ("ins_open2", "<i4"), ("ins_ext2", "<i4"),
+    ("min_signal_size", "<i4"), ("zdrop", "<i4"), ("zdrop_ext", "<i4"), ("reserved", "<i4"),
+])
+PAIR_DTYPE = np.dtype([
+    ("q", "<u4"), ("t", "<u4"), ("band_lo", "<i4"), ("band_w", "<u4"),
+    ("flags", "<u4"), ("cigar_off", "<u4"), ("cigar_cap", "<u4"), ("reserved", "<u4"),
+])
+RESULT_DTYPE = np.dtype([
+    ("score", "<i4"), ("status", "<u4"), ("q_beg", "<i4"), ("q_end", "<i4"), ("t_beg", "<i4"), ("t_end", "<i4"),
+    ("n_match", "<u4"), ("n_mismatch", "<u4"), ("n_ins_ops", "<u4"), ("n_ins_bp", "<u4"),
+    ("n_del_ops", "<u4"), ("n_del_bp", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"),
+    ("sv_dist", "<f8"), ("cells", "<u8"),
+])
+STATS_DTYPE = np.dtype([
+    ("fwd_ms", "<f8"), ("tb_ms", "<f8"), ("total_ms", "<f8"), ("cells", "<u8"), ("tb_bytes", "<u8"),
+    ("fwd_launches", "<u4"), ("tb_launches", "<u4"), ("waves", "<u4"), ("reserved", "<u4"),
+])
+assert SCORING_DTYPE.itemsize == 112 and PAIR_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 72
+assert STATS_DTYPE.itemsize == 56
+
+# every symbol include/svp_align.h declares (checked by tests/test_abi.py against the built library)
+EXPORTS = ("svp_abi_version", "svp_device_count", "svp_scoring_preset", "svp_create", "svp_destroy",
+           "svp_last_error", "svp_align_batch", "svp_align_batch_device", "svp_get_stats")
+
+
+def ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def pack_2bit(seqs: list[str | bytes]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """2-bit pack sequences (A=0 C=1 G=2 T=3, base k in bits 2*(k%4) of byte k//4), each sequence
+    starting on a 16-byte boundary. Returns (packed uint8, seq_off uint64, seq_len uint32).
+    Letters outside ACGT (N, IUPAC) are packed as A: the 2-bit alphabet has no fifth symbol
+    (DESIGN.md §3.1)."""
+    lut = np.zeros(256, dtype=np.uint8)
+    for ch, code in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("a", 0), ("c", 1), ("g", 2), ("t", 3)):
+        lut[ord(ch)] = code
+    n = len(seqs)
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint32, count=n)
+    nbytes = ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
+    off = np.zeros(n, dtype=np.uint64)
+    if n > 1:
+        off[1:] = np.cumsum(nbytes[:-1])
+    total = int(nbytes.sum()) + 16
+    packed = np.zeros(total, dtype=np.uint8)
+    for k, s in enumerate(seqs):
+        raw = np.frombuffer(s.encode() if isinstance(s, str) else bytes(s), dtype=np.uint8)
+        codes = lut[raw]
+        pad = (-len(codes)) % 4
+        if pad:
+            codes = np.concatenate((codes, np.zeros(pad, dtype=np.uint8)))
+        quad = codes.reshape(-1, 4)
+        packed[int(off[k]):int(off[k]) + len(quad)] = quad[:, 0] | (quad[:, 1] << 2) | (quad[:, 2] << 4) | (quad[:, 3] << 6)
+    return packed, off, lens
+
+
+def cigartuples(cigar_buf: np.ndarray, result) -> list[tuple[int, int]]:
+    """(op, len) list of one svp_result's CIGAR."""
+    o, n = int(result["cigar_off"]), int(result["cigar_len"])
+    w = cigar_buf[o:o + n]
+    return list(zip((w & 15).tolist(), (w >> 4).tolist()))

@@ -1,0 +1,250 @@
+"""Host drivers of the alignment hot path: build pair batches, choose bands, turn svp_result rows
+into alignment records.
+
+What the reference does with `minimap2 | samtools sort` subprocesses and SAM parsing
+    AVA, one container            consensus.py:1362-1400   (-x ava-ont --sam-hit-only -U 25,35 -H)
+    reads -> consensus            consensus.py:851-857     (-x map-ont -Y --sam-hit-only --secondary=no)
+    consensus -> reference        consensus_align.py:1977-1987
+is done here with one `engine.align_batch()` call per batch of pairs. `engine` is
+svirlpool_b200.aligner.Aligner (CUDA, the only product engine); tests inject the CPU oracle through
+the same interface to check parity.
+
+Alignment semantics: DESIGN.md §3 (banded local affine alignment, two-piece gaps). What is NOT
+reproduced from minimap2: seeding/chaining heuristics, MAPQ, the choice of primary vs
+supplementary among equal-scoring hits.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._abi import PAIR_DTYPE, PAIR_REVCOMP, ST_CIGAR_OVF, ST_NOHIT, cigartuples, pack_2bit
+from .datatypes import CIGAR_H, CIGAR_S, AlignedRecord
+
+MIN_DP_SCORE = 80          # minimap2 -s default: hits below this peak DP score are not reported
+
+
+def round_up(x: int, g: int) -> int:
+    return (x + g - 1) // g * g
+
+
+def full_band(m: int, n: int, granule: int = 32) -> tuple[int, int]:
+    """Band covering the whole m x n matrix: diagonals -(m-1) .. n-1."""
+    lo = -(m - 1)
+    return lo, round_up(m + n - 1, granule)
+
+
+def offset_band(m: int, n: int, d_start: int = 0, d_end: int | None = None, slack: int = 300,
+                granule: int = 32) -> tuple[int, int]:
+    """Band around the line from diagonal d_start (where the two sequences begin to overlap) to
+    d_end (default n - m: both ends co-terminal), widened by slack on both sides and rounded up to
+    the granule; never wider than the full matrix."""
+    if d_end is None:
+        d_end = n - m
+    lo = min(d_start, d_end) - slack
+    hi = max(d_start, d_end) + slack
+    w = round_up(hi - lo + 1, granule)
+    flo, fw = full_band(m, n, granule)
+    if w >= fw:
+        return flo, fw
+    return lo, w
+
+
+def cigar_cap_for(m: int, n: int) -> int:
+    """CIGAR slot size (words) for a pair: generous for 10-15 % error reads; an overflow is
+    reported per pair (SVP_ST_CIGAR_OVF) and retried by the caller with the worst case m + n."""
+    return min(m + n, (m + n) // 3 + 64)
+
+
+@dataclass
+class PairBatch:
+    """Sequences + pair descriptors in the layout of svp_align_batch()."""
+
+    names: list[str]
+    seqs: list[str]
+    packed: np.ndarray
+    seq_off: np.ndarray
+    seq_len: np.ndarray
+    pairs: np.ndarray
+    cigar_words: int
+
+    @staticmethod
+    def build(names: list[str], seqs: list[str], pair_specs: list[tuple[int, int, int, int, int]],
+              cap_fn=cigar_cap_for) -> "PairBatch":
+        """pair_specs: (q_index, t_index, band_lo, band_w, flags)."""
+        packed, off, lens = pack_2bit(seqs)
+        pairs = np.zeros(len(pair_specs), dtype=PAIR_DTYPE)
+        pos = 0
+        for k, (q, t, lo, w, fl) in enumerate(pair_specs):
+            cap = cap_fn(int(lens[q]), int(lens[t]))
+            pairs[k] = (q, t, lo, w, fl, pos, cap, 0)
+            pos += cap
+        return PairBatch(names, seqs, packed, off, lens, pairs, max(pos, 1))
+
+
+def run_batch(engine, batch: PairBatch) -> tuple[np.ndarray, np.ndarray]:
+    """Align a batch; pairs whose CIGAR slot overflowed are re-run once with worst-case slots."""
+    res, cig = engine.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    ovf = np.nonzero(res["status"] & ST_CIGAR_OVF)[0]
+    if len(ovf):
+        specs = [(int(p["q"]), int(p["t"]), int(p["band_lo"]), int(p["band_w"]), int(p["flags"])) for p in batch.pairs[ovf]]
+        retry = PairBatch.build(batch.names, batch.seqs, specs, cap_fn=lambda m, n: m + n)
+        res2, cig2 = engine.align_batch(retry.packed, retry.seq_off, retry.seq_len, retry.pairs, retry.cigar_words)
+        base = len(cig)
+        cig = np.concatenate((cig, cig2))
+        res2 = res2.copy()
+        res2["cigar_off"] += base
+        res[ovf] = res2
+    return res, cig
+
+
+def record_from_result(res, cig: np.ndarray, query_name: str, target_name: str, query_len: int, revcomp: bool,
+                       supplementary: bool = False, query_sequence: str | None = None,
+                       query_offset: int = 0, query_total: int | None = None) -> AlignedRecord | None:
+    """One svp_result -> AlignedRecord (None when the pair has no hit). CIGAR = clip + ops + clip in
+    the orientation of the target, SAM style: soft clips (S), or hard clips (H) for supplementary
+    records. query_offset/query_total place a sub-sequence alignment back on the full read
+    (ORIGINAL orientation)."""
+    if int(res["status"]) & ST_NOHIT or int(res["cigar_len"]) == 0:
+        return None
+    total = query_len if query_total is None else query_total
+    qb, qe = int(res["q_beg"]), int(res["q_end"])           # oriented sub-sequence coordinates
+    if revcomp:
+        lead = (total - query_offset - query_len) + qb      # what precedes the hit in the rc'd full read
+    else:
+        lead = query_offset + qb
+    trail = total - lead - (qe - qb)
+    clip = CIGAR_H if supplementary else CIGAR_S
+    ct = cigartuples(cig, res)
+    if lead:
+        ct.insert(0, (clip, lead))
+    if trail:
+        ct.append((clip, trail))
+    flag = (16 if revcomp else 0) | (2048 if supplementary else 0)
+    nm = int(res["n_mismatch"]) + int(res["n_ins_bp"]) + int(res["n_del_bp"])
+    return AlignedRecord(query_name=query_name, reference_name=target_name, reference_start=int(res["t_beg"]),
+                         cigartuples=ct, flag=flag, mapping_quality=60, query_sequence=query_sequence,
+                         tags={"NM": nm, "AS": int(res["score"])})
+
+
+# ---------------------------------------------------------------------------------------------
+# all-vs-all inside one container
+# ---------------------------------------------------------------------------------------------
+
+def ava_pair_specs(names: list[str], lens, strands: dict[str, str] | None, offsets: dict[str, int] | None,
+                   slack: int, granule: int, full: bool) -> tuple[list[tuple[int, int, int, int, int]], list[tuple[int, int, bool]]]:
+    """Pair list of one container: every unordered pair once, query = the lexicographically smaller
+    name (minimap2 -X keeps query < target). Unknown strands -> both orientations are aligned."""
+    order = sorted(range(len(names)), key=lambda k: names[k])
+    specs, meta = [], []
+    for a in range(len(order)):
+        for b in range(a + 1, len(order)):
+            q, t = order[a], order[b]
+            m, n = int(lens[q]), int(lens[t])
+            if strands is None:
+                orientations = (False, True)
+            else:
+                orientations = (strands[names[q]] != strands[names[t]],)
+            for rc in orientations:
+                if full:
+                    lo, w = full_band(m, n, granule)
+                else:
+                    d0 = 0
+                    if offsets is not None and not rc:
+                        d0 = offsets[names[q]] - offsets[names[t]]
+                    lo, w = offset_band(m, n, d_start=d0, d_end=(n - m) if offsets is None or rc else None,
+                                        slack=slack, granule=granule)
+                specs.append((q, t, lo, w, PAIR_REVCOMP if rc else 0))
+                meta.append((q, t, rc))
+    return specs, meta
+
+
+def ava_align(engine, reads: dict[str, str], strands: dict[str, str] | None = None,
+              offsets: dict[str, int] | None = None, slack: int = 300, granule: int = 32, full: bool = False,
+              min_score: int = MIN_DP_SCORE) -> list[AlignedRecord]:
+    """All-vs-all alignment of the reads of one container -> alignment records (the in-memory
+    equivalent of the AVA BAM of consensus.py:1378-1400), sorted by (target, position)."""
+    names = list(reads)
+    seqs = [reads[k] for k in names]
+    lens = [len(s) for s in seqs]
+    specs, meta = ava_pair_specs(names, lens, strands, offsets, slack, granule, full)
+    if not specs:
+        return []
+    batch = PairBatch.build(names, seqs, specs)
+    res, cig = run_batch(engine, batch)
+    return ava_records(names, lens, meta, res, cig, min_score)
+
+
+def ava_records(names, lens, meta, res, cig, min_score: int = MIN_DP_SCORE) -> list[AlignedRecord]:
+    best: dict[tuple[int, int], int] = {}
+    for k, (q, t, rc) in enumerate(meta):
+        if int(res[k]["status"]) & ST_NOHIT or int(res[k]["score"]) < min_score:
+            continue
+        cur = best.get((q, t))
+        if cur is None or int(res[k]["score"]) > int(res[cur]["score"]):   # equal scores: forward (listed first) wins
+            best[(q, t)] = k
+    out = []
+    for (q, t), k in best.items():
+        rec = record_from_result(res[k], cig, names[q], names[t], int(lens[q]), meta[k][2])
+        if rec is not None:
+            out.append(rec)
+    order = {n: k for k, n in enumerate(sorted(names))}
+    out.sort(key=lambda r: (order[r.reference_name], r.reference_start, r.query_name))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# one query vs one target with supplementary hits (reads -> consensus, consensus -> window)
+# ---------------------------------------------------------------------------------------------
+
+def map_queries(engine, queries: dict[str, str], target_name: str, target: str, min_score: int = MIN_DP_SCORE,
+                min_flank: int = 40, max_rounds: int = 8, granule: int = 32) -> list[AlignedRecord]:
+    """Map each query to the target like `minimap2 -x map-ont --secondary=no`: the best local hit
+    over both strands, then — iteratively — the best hit of every unaligned query flank of at least
+    min_flank bases, kept when its score reaches min_score. The highest-scoring hit of a query is
+    its primary record (soft clips), the others are supplementary (hard clips). Records are returned
+    sorted by target position."""
+    n = len(target)
+    # task: (query name, sub-sequence start, sub-sequence end) in ORIGINAL read coordinates
+    tasks = [(name, 0, len(seq)) for name, seq in queries.items() if len(seq) > 0]
+    hits: dict[str, list[tuple[int, bool, int, int, object, np.ndarray]]] = {name: [] for name in queries}
+    for _ in range(max_rounds):
+        if not tasks:
+            break
+        names, seqs, specs = [target_name], [target], []
+        for name, a, b in tasks:
+            names.append(f"{name}:{a}-{b}")
+            seqs.append(queries[name][a:b])
+            lo, w = full_band(b - a, n, granule)
+            specs.append((len(seqs) - 1, 0, lo, w, 0))
+            specs.append((len(seqs) - 1, 0, lo, w, PAIR_REVCOMP))
+        batch = PairBatch.build(names, seqs, specs)
+        res, cig = run_batch(engine, batch)
+        nxt = []
+        for k, (name, a, b) in enumerate(tasks):
+            fwd, rev = res[2 * k], res[2 * k + 1]
+            pick, rc = (fwd, False) if int(fwd["score"]) >= int(rev["score"]) else (rev, True)
+            if int(pick["status"]) & ST_NOHIT or int(pick["score"]) < min_score:
+                continue
+            hits[name].append((int(pick["score"]), rc, a, b, pick.copy(), cig))
+            qb, qe, sub = int(pick["q_beg"]), int(pick["q_end"]), b - a
+            if rc:                                    # oriented -> original coordinates inside the sub-sequence
+                qb, qe = sub - qe, sub - qb
+            if qb >= min_flank:
+                nxt.append((name, a, a + qb))
+            if sub - qe >= min_flank:
+                nxt.append((name, a + qe, b))
+        tasks = nxt
+    out = []
+    for name, hs in hits.items():
+        if not hs:
+            continue
+        primary = max(range(len(hs)), key=lambda k: (hs[k][0], -k))
+        for k, (score, rc, a, b, r, cig) in enumerate(hs):
+            rec = record_from_result(r, cig, name, target_name, b - a, rc, supplementary=(k != primary),
+                                     query_offset=a, query_total=len(queries[name]))
+            if rec is not None:
+                out.append(rec)
+    out.sort(key=lambda r: (r.reference_start, r.query_name))
+    return out

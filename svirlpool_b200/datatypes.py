@@ -1,0 +1,147 @@
+"""Host-side data types of the hot path.
+
+Mirrors the parts of svirlpool.util.datatypes the path touches:
+  SVsignal            /root/reference/src/svirlpool/util/datatypes.py:25-72
+  SV type codes       datatypes.py:10-22  (0 INS, 1 DEL, 3 BNDL, 4 BNDR)
+plus AlignedRecord, a pysam.AlignedSegment stand-in carrying exactly the attributes the
+reference's consumers read (seam S1): query_name, reference_name,
+reference_start/end, cigartuples, is_reverse, is_unmapped, query_alignment_start/end/length,
+reference_length, is_secondary, is_supplementary, flag.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from functools import total_ordering
+
+INS, DEL, BNDL, BNDR = 0, 1, 3, 4
+SV_TYPE_DICT = {0: "INS", 1: "DEL", 2: "DEL", 3: "BND", 4: "BND", 5: "INV", 6: "DUP"}
+
+# SAM/BAM CIGAR op codes
+CIGAR_M, CIGAR_I, CIGAR_D, CIGAR_N, CIGAR_S, CIGAR_H, CIGAR_P, CIGAR_EQ, CIGAR_X = range(9)
+CIGAR_CHARS = "MIDNSHP=X"
+
+
+@total_ordering
+@dataclass(eq=False)
+class SVsignal:
+    """One SV signal read off a CIGAR (datatypes.py:25-72): ordered by (ref_start, ref_end);
+    equality and hash over all six fields."""
+
+    ref_start: int
+    ref_end: int
+    read_start: int
+    read_end: int
+    size: int
+    sv_type: int
+
+    def _key(self):
+        return (self.ref_start, self.ref_end, self.read_start, self.read_end, self.size, self.sv_type)
+
+    def __eq__(self, other):
+        return isinstance(other, SVsignal) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __lt__(self, other):
+        return (self.ref_start, self.ref_end) < (other.ref_start, other.ref_end)
+
+    def unstructure(self) -> dict:
+        return {"ref_start": self.ref_start, "ref_end": self.ref_end, "read_start": self.read_start,
+                "read_end": self.read_end, "size": self.size, "sv_type": self.sv_type}
+
+    def _get_description(self, chr: str) -> str:
+        return (f"region={chr}:{self.ref_start}-{self.ref_end}, type={SV_TYPE_DICT.get(self.sv_type, 'UNK')}, "
+                f"size={self.size}, read_span={self.read_start}-{self.read_end}")
+
+
+@dataclass
+class AlignedRecord:
+    """Duck-typed pysam.AlignedSegment: what `svp_align_batch` results become on the host."""
+
+    query_name: str
+    reference_name: str | None
+    reference_start: int
+    cigartuples: list[tuple[int, int]] | None
+    flag: int = 0
+    mapping_quality: int = 60
+    query_sequence: str | None = None
+    tags: dict = field(default_factory=dict)
+
+    # --- flag views -------------------------------------------------------------------------
+    @property
+    def is_reverse(self) -> bool:
+        return bool(self.flag & 16)
+
+    @property
+    def is_forward(self) -> bool:
+        return not self.is_reverse
+
+    @property
+    def is_unmapped(self) -> bool:
+        return bool(self.flag & 4)
+
+    @property
+    def is_secondary(self) -> bool:
+        return bool(self.flag & 256)
+
+    @property
+    def is_supplementary(self) -> bool:
+        return bool(self.flag & 2048)
+
+    # --- coordinates (pysam semantics) ---------------------------------------------------------
+    def _sum(self, ops) -> int:
+        return sum(n for op, n in (self.cigartuples or ()) if op in ops)
+
+    @property
+    def reference_length(self) -> int:
+        return self._sum((CIGAR_M, CIGAR_D, CIGAR_N, CIGAR_EQ, CIGAR_X))
+
+    @property
+    def reference_end(self) -> int | None:
+        if self.cigartuples is None:
+            return None
+        return self.reference_start + self.reference_length
+
+    @property
+    def query_alignment_start(self) -> int:
+        """Offset of the first aligned base in the stored SEQ: soft clips count, hard clips do not."""
+        ct = self.cigartuples or ()
+        start = 0
+        for op, n in ct:
+            if op == CIGAR_H:
+                continue
+            if op == CIGAR_S:
+                start += n
+                continue
+            break
+        return start
+
+    @property
+    def query_alignment_length(self) -> int:
+        return self._sum((CIGAR_M, CIGAR_I, CIGAR_EQ, CIGAR_X))
+
+    @property
+    def query_alignment_end(self) -> int:
+        return self.query_alignment_start + self.query_alignment_length
+
+    @property
+    def query_length(self) -> int:
+        return self._sum((CIGAR_M, CIGAR_I, CIGAR_S, CIGAR_EQ, CIGAR_X))
+
+    @property
+    def cigarstring(self) -> str | None:
+        if self.cigartuples is None:
+            return None
+        return "".join(f"{n}{CIGAR_CHARS[op]}" for op, n in self.cigartuples)
+
+
+def cigar_from_string(s: str) -> list[tuple[int, int]]:
+    out, num = [], 0
+    for ch in s:
+        if ch.isdigit():
+            num = num * 10 + ord(ch) - 48
+        else:
+            out.append((CIGAR_CHARS.index(ch), num))
+            num = 0
+    return out
