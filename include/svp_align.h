@@ -120,15 +120,16 @@ int svp_align_batch(svp_handle* h,
                     svp_result* results,
                     uint32_t* cigar_buf, size_t cigar_words);
 
-/* Device-resident variant: every pointer is a DEVICE pointer (e.g. torch tensor data_ptr()).
- * Used by bench.py for the HBM-resident `value` measurement. stream: cudaStream_t or NULL. */
+/* Device-resident variant: the bulk data — packed sequences in, results and CIGAR words out — are
+ * DEVICE pointers on the handle's device (e.g. torch tensor data_ptr()); the launch plan (sequence
+ * table and pair descriptors) stays in HOST memory. Every sequence must be readable up to the next
+ * 16-byte boundary. Used by bench.py for the HBM-resident `value` measurement. Blocking. */
 int svp_align_batch_device(svp_handle* h,
                            const uint8_t* d_packed_seqs, size_t packed_bytes,
-                           const uint64_t* d_seq_off, const uint32_t* d_seq_len, uint32_t n_seqs,
-                           const svp_pair* d_pairs, const svp_pair* h_pairs, uint32_t n_pairs,
+                           const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                           const svp_pair* pairs, uint32_t n_pairs,
                            svp_result* d_results,
-                           uint32_t* d_cigar_buf, size_t cigar_words,
-                           void* stream);
+                           uint32_t* d_cigar_buf, size_t cigar_words);
 
 /* Timing / accounting of the last svp_align_batch*() call on this handle (CUDA events on the
  * stream the kernels ran on). */

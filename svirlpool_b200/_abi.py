@@ -71,6 +71,23 @@ def pack_2bit(seqs: list[str | bytes]) -> tuple[np.ndarray, np.ndarray, np.ndarr
     return packed, off, lens
 
 
+def pack_codes(seqs: list[np.ndarray]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """pack_2bit() for sequences already given as base-code arrays (uint8, values 0..3)."""
+    n = len(seqs)
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint32, count=n)
+    nbytes = ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
+    off = np.zeros(n, dtype=np.uint64)
+    if n > 1:
+        off[1:] = np.cumsum(nbytes[:-1])
+    packed = np.zeros(int(nbytes.sum()) + 16, dtype=np.uint8)
+    for k, codes in enumerate(seqs):
+        pad = (-len(codes)) % 4
+        c = np.concatenate((codes, np.zeros(pad, dtype=np.uint8))) if pad else codes
+        quad = c.reshape(-1, 4)
+        packed[int(off[k]):int(off[k]) + len(quad)] = quad[:, 0] | (quad[:, 1] << 2) | (quad[:, 2] << 4) | (quad[:, 3] << 6)
+    return packed, off, lens
+
+
 def cigartuples(cigar_buf: np.ndarray, result) -> list[tuple[int, int]]:
     """(op, len) list of one svp_result's CIGAR."""
     o, n = int(result["cigar_off"]), int(result["cigar_len"])

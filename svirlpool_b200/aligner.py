@@ -1,0 +1,127 @@
+"""ctypes binding of libsvp_align.so (include/svp_align.h) — the only compute engine of this package.
+
+There is no CPU fallback: a missing library, a missing GPU or an unsupported scoring profile raises
+(AlignerError / SVP_ERR_* codes), it never silently degrades. The error mapping mirrors what the
+reference's seam raises (util.align_reads_with_minimap, util/util.py:162-238): alignment failures
+surface as a subprocess.CalledProcessError subclass, which the reference's callers already catch
+(consensus.py:1387-1396).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi
+from ._abi import PAIR_DTYPE, RESULT_DTYPE, SCORING_DTYPE, STATS_DTYPE, SVP_OK, ptr
+
+LIB_PATH = Path(__file__).resolve().parent / "libsvp_align.so"
+
+
+class AlignerError(subprocess.CalledProcessError):
+    """Raised for every non-zero return code of the C-ABI."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(code, "libsvp_align", output=message)
+        self.message = message
+
+    def __str__(self) -> str:
+        return f"libsvp_align error {self.returncode}: {self.message}"
+
+
+def load_library(path: Path | None = None) -> C.CDLL:
+    path = Path(path) if path else LIB_PATH
+    if not path.exists():
+        raise FileNotFoundError(
+            f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C svirlpool_b200/csrc). svirlpool_b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    lib.svp_abi_version.restype = C.c_int
+    lib.svp_device_count.restype = C.c_int
+    lib.svp_scoring_preset.restype = C.c_int
+    lib.svp_create.restype = C.c_int
+    lib.svp_create.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.svp_destroy.restype = None
+    lib.svp_destroy.argtypes = [C.c_void_p]
+    lib.svp_last_error.restype = C.c_char_p
+    lib.svp_last_error.argtypes = [C.c_void_p]
+    lib.svp_get_stats.restype = C.c_int
+    lib.svp_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+    batch_args = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                  C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.svp_align_batch.restype = C.c_int
+    lib.svp_align_batch.argtypes = batch_args
+    lib.svp_align_batch_device.restype = C.c_int
+    lib.svp_align_batch_device.argtypes = batch_args
+    if lib.svp_abi_version() != _abi.ABI_VERSION:
+        raise RuntimeError(f"ABI mismatch: library {lib.svp_abi_version()}, python {_abi.ABI_VERSION}")
+    return lib
+
+
+def scoring_preset(name: str, lib: C.CDLL | None = None) -> np.ndarray:
+    lib = lib or load_library()
+    s = np.zeros(1, dtype=SCORING_DTYPE)
+    if lib.svp_scoring_preset(name.encode(), ptr(s)) != SVP_OK:
+        raise ValueError(f"unknown scoring preset {name!r}")
+    return s
+
+
+class Aligner:
+    """One handle = one GPU + one scoring profile. Not thread-safe; one call at a time."""
+
+    def __init__(self, device: int = 0, preset: str = "map-ont", scoring: np.ndarray | None = None,
+                 tb_bytes: int = 0, lib_path: Path | None = None):
+        self._h = None
+        self.lib = load_library(lib_path)
+        self.scoring = scoring if scoring is not None else scoring_preset(preset, self.lib)
+        self.device = device
+        handle = C.c_void_p()
+        rc = self.lib.svp_create(int(device), ptr(self.scoring), int(tb_bytes), C.byref(handle))
+        if rc != SVP_OK:
+            raise AlignerError(rc, (self.lib.svp_last_error(None) or b"").decode())
+        self._h = handle
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.svp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != SVP_OK:
+            raise AlignerError(rc, (self.lib.svp_last_error(self._h) or b"").decode())
+
+    def align_batch(self, packed: np.ndarray, seq_off: np.ndarray, seq_len: np.ndarray, pairs: np.ndarray,
+                    cigar_words: int) -> tuple[np.ndarray, np.ndarray]:
+        """Host buffers in, host buffers out (svp_align_batch): H2D, kernels, D2H inside the call."""
+        assert pairs.dtype == PAIR_DTYPE and packed.dtype == np.uint8
+        res = np.zeros(len(pairs), dtype=RESULT_DTYPE)
+        cig = np.zeros(max(int(cigar_words), 1), dtype=np.uint32)
+        self._check(self.lib.svp_align_batch(self._h, ptr(packed), packed.nbytes, ptr(seq_off), ptr(seq_len), len(seq_len),
+                                             ptr(pairs), len(pairs), ptr(res), ptr(cig), len(cig)))
+        return res, cig
+
+    def align_batch_device(self, d_packed_ptr: int, packed_bytes: int, seq_off: np.ndarray, seq_len: np.ndarray,
+                           pairs: np.ndarray, d_results_ptr: int, d_cigar_ptr: int, cigar_words: int) -> None:
+        """Sequences/results/CIGARs resident on the device (raw pointers, e.g. torch data_ptr())."""
+        self._check(self.lib.svp_align_batch_device(self._h, C.c_void_p(d_packed_ptr), packed_bytes, ptr(seq_off), ptr(seq_len),
+                                                    len(seq_len), ptr(pairs), len(pairs), C.c_void_p(d_results_ptr),
+                                                    C.c_void_p(d_cigar_ptr), int(cigar_words)))
+
+    def stats(self) -> dict:
+        s = np.zeros(1, dtype=STATS_DTYPE)
+        self._check(self.lib.svp_get_stats(self._h, ptr(s)))
+        return {k: s[0][k].item() for k in STATS_DTYPE.names}

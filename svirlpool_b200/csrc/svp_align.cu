@@ -1,0 +1,374 @@
+// svp_align.cu — C-ABI of the alignment hot path (include/svp_align.h) on top of the sm_100a
+// kernels in svp_kernels.cuh. Host side: validate, plan pairs into waves that fit the traceback
+// arena, group a wave's pairs by CTA width, launch forward + traceback kernels, time them with
+// CUDA events on the launching stream. No CPU fallback: without a CUDA device every entry point
+// that computes returns SVP_ERR_NODEVICE.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "svp_kernels.cuh"
+
+using namespace svp;
+
+namespace {
+
+// Two instantiations of the kernels: KP = 4 packed registers per state array per thread (16 diagonals
+// per thread, 512 per warp) for bands up to 16 warps x 512 = 8192 diagonals, KP = 8 (1024 per warp)
+// for wider bands up to 16384.
+constexpr int MAX_WARPS = 16;
+constexpr int S16_SCORE_LIMIT = 32000;
+static inline int kp_of(const Task& t) { return (t.flags & TASK_KP8) ? 8 : 4; }
+static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * (2 * kp_of(t)) * (uint64_t)(t.band_w / 2); }
+static inline uint64_t best_entries_of(const Task& t) { return (uint64_t)(t.band_w / (4 * kp_of(t))) * 2; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct svp_handle {
+    int device = 0;
+    svp_scoring scoring{};
+    Consts cs{};
+    cudaStream_t stream = nullptr;
+    uint8_t* arena = nullptr; size_t arena_bytes = 0;
+    DevBuf d_tasks, d_order, d_bests, d_seqs, d_results, d_cigar;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    svp_stats stats{};
+    std::string err;
+    int max_smem_optin = 0;
+};
+
+static thread_local std::string g_err;
+
+static int fail(svp_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_err = msg;
+    return code;
+}
+#define CUDA_TRY(h, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(h, e_ == cudaErrorMemoryAllocation ? SVP_ERR_NOMEM : SVP_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" int svp_abi_version(void) { return SVP_ABI_VERSION; }
+
+extern "C" int svp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int svp_scoring_preset(const char* name, svp_scoring* s) {
+    if (!name || !s) return SVP_ERR_ARG;
+    memset(s, 0, sizeof(*s));
+    s->min_signal_size = 12;
+    const std::string nm(name);
+    if (nm == "map-ont" || nm == "ava-ont") {          // minimap2 defaults -A2 -B4 -O4,24 -E2,1 -z400
+        for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) s->matrix[a * 4 + b] = (a == b) ? 2 : -4;
+        s->del_open1 = s->ins_open1 = 4;  s->del_ext1 = s->ins_ext1 = 2;
+        s->del_open2 = s->ins_open2 = 24; s->del_ext2 = s->ins_ext2 = 1;
+        s->zdrop = 400; s->zdrop_ext = 1;
+        return SVP_OK;
+    }
+    if (nm == "last") {                                // shape of a last-train .mat; stand-in numbers
+        static const int m[16] = { 5, -8, -4, -9,   -8, 6, -9, -4,   -4, -9, 6, -8,   -9, -4, -8, 5 };
+        memcpy(s->matrix, m, sizeof(m));
+        s->del_open1 = 10; s->del_ext1 = 3; s->ins_open1 = 12; s->ins_ext1 = 2;
+        s->del_open2 = s->ins_open2 = -1;
+        s->zdrop = 400; s->zdrop_ext = 2;
+        return SVP_OK;
+    }
+    return SVP_ERR_ARG;
+}
+
+// Scoring the round-1 kernels implement: one match score and one mismatch score (the matrix must be
+// {A on the diagonal, -B elsewhere}), insertion costs == deletion costs, one or two gap pieces, and
+// steps small enough that neighbouring H differ by < 128 (low-byte traceback).
+static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
+    const int A = s.matrix[0], B = -s.matrix[1];
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b)
+        if (s.matrix[a * 4 + b] != (a == b ? A : -B)) { why = "substitution matrix is not match/mismatch (full 4x4 matrices: not implemented in the CUDA kernels yet)"; return SVP_ERR_UNSUPPORTED; }
+    if (A <= 0 || B <= 0) { why = "match must be > 0 and mismatch < 0"; return SVP_ERR_ARG; }
+    if (s.del_open1 != s.ins_open1 || s.del_ext1 != s.ins_ext1 || s.del_open2 != s.ins_open2 || (s.del_open2 >= 0 && s.del_ext2 != s.ins_ext2)) {
+        why = "insertion and deletion costs differ (not implemented in the CUDA kernels yet)"; return SVP_ERR_UNSUPPORTED; }
+    if (s.del_open1 < 0 || s.del_ext1 <= 0 || (s.del_open2 >= 0 && s.del_ext2 <= 0)) { why = "gap costs must be open >= 0, ext > 0"; return SVP_ERR_ARG; }
+    const int two = s.del_open2 >= 0;
+    const int g1 = two ? std::min(s.del_open1 + s.del_ext1, s.del_open2 + s.del_ext2) : s.del_open1 + s.del_ext1;   // cheapest 1-base gap
+    if (4 * (A + B + g1) > 127) { why = "scores too large for the low-byte traceback (4*(match+mismatch+gap1) must be <= 127)"; return SVP_ERR_UNSUPPORTED; }
+    auto pk16 = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
+    c.mat = pk16(A); c.mis = pk16(-B);
+    c.ne1 = pk16(-s.del_ext1); c.noe1 = pk16(-(s.del_open1 + s.del_ext1));
+    c.ne2 = two ? pk16(-s.del_ext2) : 0; c.noe2 = two ? pk16(-(s.del_open2 + s.del_ext2)) : NEGV;
+    c.two_piece = two;
+    c.s_match = A; c.s_mismatch = -B; c.open1 = s.del_open1; c.ext1 = s.del_ext1; c.open2 = two ? s.del_open2 : 0; c.ext2 = two ? s.del_ext2 : 0;
+    c.min_signal = s.min_signal_size; c.zdrop = s.zdrop; c.zdrop_ext = s.zdrop_ext;
+    return SVP_OK;
+}
+
+extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out) {
+    if (!scoring || !out) return fail(nullptr, SVP_ERR_ARG, "null argument");
+    *out = nullptr;
+    int ndev = svp_device_count();
+    if (ndev <= 0) return fail(nullptr, SVP_ERR_NODEVICE, "no CUDA device visible; svirlpool_b200 has no CPU fallback");
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) return fail(nullptr, SVP_ERR_ARG, "device index out of range");
+    Consts cs{};
+    std::string why;
+    int rc = make_consts(*scoring, cs, why);
+    if (rc != SVP_OK) return fail(nullptr, rc, why);
+    svp_handle* h = new svp_handle();
+    h->device = device; h->scoring = *scoring; h->cs = cs;
+    auto bail = [&](int code, const std::string& m) { g_err = m; svp_destroy(h); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    for (cudaEvent_t* e : { &h->ev_a, &h->ev_b, &h->ev_c, &h->ev_t0, &h->ev_t1 })
+        if (cudaEventCreate(e) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaEventCreate failed");
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaFuncSetAttribute(svp_fwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(svp_fwd_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    cudaFuncSetAttribute(svp_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
+    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 2, (size_t)64 << 30);
+    want = (want + 255) & ~(size_t)255;
+    if (cudaMalloc((void**)&h->arena, want) != cudaSuccess) { cudaGetLastError(); return bail(SVP_ERR_NOMEM, "cannot allocate the traceback arena"); }
+    h->arena_bytes = want;
+    *out = h;
+    return SVP_OK;
+}
+
+extern "C" void svp_destroy(svp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->arena) cudaFree(h->arena);
+    for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar }) b->release();
+    for (cudaEvent_t e : { h->ev_a, h->ev_b, h->ev_c, h->ev_t0, h->ev_t1 }) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* svp_last_error(const svp_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+extern "C" int svp_get_stats(const svp_handle* h, svp_stats* out) {
+    if (!h || !out) return SVP_ERR_ARG;
+    *out = h->stats;
+    return SVP_OK;
+}
+
+// #{(i, j) : 1<=i<=m, 1<=j<=n, j - i <= x}
+static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
+    // row i contributes clamp(i + x, 0, n)
+    int64_t total = 0;
+    const int64_t i0 = std::max<int64_t>(1, 1 - x);            // first row with i + x >= 1
+    const int64_t i1 = std::min<int64_t>(m, n - x - 1);        // last row with i + x <= n - 1
+    if (i1 >= i0) total += (i1 - i0 + 1) * (i0 + i1) / 2 + x * (i1 - i0 + 1);
+    const int64_t i2 = std::max<int64_t>(1, n - x);            // first row with i + x >= n
+    if (i2 <= m) total += n * (m - i2 + 1);
+    return total;
+}
+
+struct Plan {
+    std::vector<Task> tasks;                     // all pairs, input order
+    std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
+};
+
+static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                      size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
+    memset(&t, 0, sizeof(t));
+    t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
+    bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && p.band_w <= (uint32_t)(MAX_WARPS * 1024) &&
+              (size_t)p.cigar_off + p.cigar_cap <= cigar_words;
+    if (ok) {
+        for (uint32_t s : { p.q, p.t }) {
+            const uint64_t bytes = ((uint64_t)seq_len[s] + 3) / 4;
+            const uint64_t end = need_padding ? ((seq_off[s] + bytes + 15) & ~(uint64_t)15) : seq_off[s] + bytes;
+            if ((seq_off[s] & 15u) || end > packed_bytes || seq_len[s] == 0 || seq_len[s] > (1u << 28)) ok = false;
+        }
+    }
+    if (!ok) { t.flags |= TASK_INVALID; return; }
+    t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
+    t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
+    t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
+    if (p.band_w > (uint32_t)(MAX_WARPS * 512)) t.flags |= TASK_KP8;
+    const int steps_per_iter = 2 * kp_of(t);
+    const int64_t m = t.m, n = t.n, lo = p.band_lo, hi = lo + (int64_t)p.band_w - 1;
+    if (lo > n - 1 || hi < -(m - 1)) { t.flags |= TASK_INVALID; return; }     // band misses the matrix
+    t.cells = (uint64_t)(cells_below(m, n, hi) - cells_below(m, n, lo - 1));
+    // first / last anti-diagonal holding a real in-band cell
+    int64_t rmin;
+    if (lo <= 0 && hi >= 0) rmin = 2; else rmin = 2 + std::min(std::llabs(lo), std::llabs(hi));
+    const int64_t dpeak = std::min(std::max<int64_t>(n - m, lo), hi);        // diagonal whose last cell is furthest
+    const int64_t rmax = (dpeak <= n - m) ? 2 * m + dpeak : 2 * n - dpeak;
+    int64_t rb = rmin;
+    if (((rb - lo) & 1) != 0) rb -= 1;                                       // step 0 must be an A-step
+    const int64_t steps = rmax - rb + 1;
+    t.r_begin = (int32_t)rb;
+    t.n_iter = (int32_t)((steps + steps_per_iter - 1) / steps_per_iter);
+}
+
+static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar) {
+    const Consts& cs = h->cs;
+    cudaStream_t st = h->stream;
+    h->stats = svp_stats{};
+    const size_t n = tasks.size();
+    if (n == 0) return SVP_OK;
+    // score range of the s16 lanes
+    for (Task& t : tasks)
+        if (!(t.flags & TASK_INVALID) && (int64_t)std::min(t.m, t.n) * cs.s_match > S16_SCORE_LIMIT) t.flags |= TASK_INVALID | TASK_TOO_LONG;
+
+    // waves: consecutive tasks whose traceback rows fit the arena
+    std::vector<std::pair<size_t, size_t>> waves;
+    {
+        size_t first = 0; uint64_t used = 0, best_used = 0;
+        for (size_t k = 0; k < n; ++k) {
+            Task& t = tasks[k];
+            uint64_t need = 0, nbest = 0;
+            if (!(t.flags & TASK_INVALID)) {
+                need = (tb_bytes_of(t) + 255) & ~(uint64_t)255;
+                nbest = best_entries_of(t);
+                if (need > h->arena_bytes) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds the arena; create the handle with a larger max_tb_bytes");
+            }
+            if (used + need > h->arena_bytes) { waves.emplace_back(first, k); first = k; used = 0; best_used = 0; }
+            t.tb_off = used; t.best_off = best_used;
+            used += need; best_used += nbest;
+        }
+        waves.emplace_back(first, n);
+    }
+    CUDA_TRY(h, h->d_tasks.reserve(n * sizeof(Task)));
+    CUDA_TRY(h, h->d_order.reserve(n * sizeof(uint32_t)));
+    uint64_t max_best = 0;
+    for (auto& w : waves) { uint64_t b = 0; for (size_t k = w.first; k < w.second; ++k) if (!(tasks[k].flags & TASK_INVALID)) b += best_entries_of(tasks[k]); max_best = std::max(max_best, b); }
+    CUDA_TRY(h, h->d_bests.reserve(std::max<uint64_t>(max_best, 1) * sizeof(uint2)));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, st));
+
+    // per wave: order lists grouped by CTA width (warps)
+    std::vector<uint32_t> order(n);
+    struct Group { int nwarp; int kp; size_t first, count; size_t smem; };
+    std::vector<std::vector<Group>> wave_groups(waves.size());
+    size_t pos = 0;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        std::map<int, std::vector<uint32_t>> by_w;
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k) {
+            const Task& t = tasks[k];
+            if (t.flags & TASK_INVALID) continue;
+            const int per_warp = 128 * kp_of(t);
+            const int nw = (t.band_w + per_warp - 1) / per_warp;
+            by_w[nw + (kp_of(t) == 8 ? 1000 : 0)].push_back((uint32_t)k);
+        }
+        for (auto& kv : by_w) {
+            // longest pairs first inside a group: the tail of the launch is short pairs
+            std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
+            size_t smem = 0;
+            const int nwarp = kv.first % 1000, kp = kv.first >= 1000 ? 8 : 4;
+            for (uint32_t k : kv.second) {
+                const Task& t = tasks[k];
+                const size_t qpad = ((((size_t)t.m + 15) >> 4) + 3) & ~(size_t)3, tpad = ((((size_t)t.n + 15) >> 4) + 3) & ~(size_t)3;
+                smem = std::max(smem, (qpad + tpad) * 4 + (size_t)2 * nwarp * sizeof(uint4));
+            }
+            if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
+            wave_groups[wv].push_back({ nwarp, kp, pos, kv.second.size(), smem });
+            std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
+            pos += kv.second.size();
+        }
+    }
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(h->d_order.p, order.data(), pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+
+    const Task* d_tasks = (const Task*)h->d_tasks.p;
+    const uint32_t* d_order = (const uint32_t*)h->d_order.p;
+    uint2* d_bests = (uint2*)h->d_bests.p;
+    CUDA_TRY(h, cudaEventRecord(h->ev_t0, st));
+    std::vector<float> fwd_ms_v, tb_ms_v;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_a, st));
+        for (const Group& gq : wave_groups[wv]) {
+            if (gq.kp == 8)
+                svp_fwd_kernel<8, true><<<(unsigned)gq.count, gq.nwarp * 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
+            else if (gq.nwarp == 1)
+                svp_fwd_kernel<4, false><<<(unsigned)gq.count, 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
+            else
+                svp_fwd_kernel<4, true><<<(unsigned)gq.count, gq.nwarp * 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
+            h->stats.fwd_launches++;
+        }
+        CUDA_TRY(h, cudaEventRecord(h->ev_b, st));
+        const int nt = (int)(waves[wv].second - waves[wv].first);
+        if (nt > 0) {
+            const int warps_per_block = 4;
+            bool any8 = false, any4 = false;
+            for (size_t k = waves[wv].first; k < waves[wv].second; ++k) { if (tasks[k].flags & TASK_KP8) any8 = true; else any4 = true; }
+            if (any4) {
+                svp_tb_kernel<4><<<(nt + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+                    d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+                h->stats.tb_launches++;
+            }
+            if (any8) {
+                svp_tb_kernel<8><<<(nt + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+                    d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+                h->stats.tb_launches++;
+            }
+        }
+        CUDA_TRY(h, cudaEventRecord(h->ev_c, st));
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_c));
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, h->ev_a, h->ev_b);
+        cudaEventElapsedTime(&b, h->ev_b, h->ev_c);
+        h->stats.fwd_ms += a; h->stats.tb_ms += b;
+        h->stats.waves++;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_t1, st));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_t1));
+    float tot = 0; cudaEventElapsedTime(&tot, h->ev_t0, h->ev_t1);
+    h->stats.total_ms = tot;
+    for (const Task& t : tasks) if (!(t.flags & TASK_INVALID)) { h->stats.cells += t.cells; h->stats.tb_bytes += tb_bytes_of(t); }
+    CUDA_TRY(h, cudaGetLastError());
+    return SVP_OK;
+}
+
+extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seqs, size_t packed_bytes,
+                                      const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                                      const svp_pair* pairs, uint32_t n_pairs, svp_result* d_results,
+                                      uint32_t* d_cigar_buf, size_t cigar_words) {
+    if (!h) return SVP_ERR_ARG;
+    if (!d_packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !d_results || (!d_cigar_buf && cigar_words))
+        return fail(h, SVP_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<Task> tasks(n_pairs);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
+    return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
+}
+
+extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes,
+                               const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                               const svp_pair* pairs, uint32_t n_pairs, svp_result* results,
+                               uint32_t* cigar_buf, size_t cigar_words) {
+    if (!h) return SVP_ERR_ARG;
+    if (!packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !results || (!cigar_buf && cigar_words))
+        return fail(h, SVP_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t padded = ((packed_bytes + 15) & ~(size_t)15) + 64;
+    CUDA_TRY(h, h->d_seqs.reserve(padded));
+    CUDA_TRY(h, h->d_results.reserve(std::max<size_t>(n_pairs, 1) * sizeof(svp_result)));
+    CUDA_TRY(h, h->d_cigar.reserve(std::max<size_t>(cigar_words, 1) * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMemsetAsync((uint8_t*)h->d_seqs.p + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
+    std::vector<Task> tasks(n_pairs);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
+    int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
+    if (rc != SVP_OK) return rc;
+    if (n_pairs) CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));
+    if (cigar_words) CUDA_TRY(h, cudaMemcpyAsync(cigar_buf, h->d_cigar.p, cigar_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SVP_OK;
+}
