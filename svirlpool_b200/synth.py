@@ -120,6 +120,19 @@ def region_config2(region_id: int, n_reads: int = 30, mean_len: int = 8000, sd_l
     return Region(region_id, names, reads, strands, offsets, hap_of, sv_size=sv, meta={"sv_pos": pos, "length": length})
 
 
+def region_config2_shape(region_id: int, mean_len: int = 8000, sd_len: int = 800) -> tuple[int, int]:
+    """(template length, signed SV size) of region_config2(region_id) without generating its reads —
+    the same first draws of the same generator; used by the scheduler to cost regions cheaply."""
+    rng = np.random.Generator(np.random.PCG64(10_000 + region_id))
+    length = int(np.clip(rng.normal(mean_len, sd_len), mean_len // 2, mean_len + mean_len // 2))
+    rng.integers(0, 4, length)
+    size = int(round(np.exp(rng.uniform(np.log(50), np.log(2000)))))
+    pos = int(rng.uniform(0.2, 0.8) * length)
+    if rng.random() < 0.5:
+        return length, size
+    return length, -min(size, length - pos - 100)
+
+
 def region_pairs(region: Region, slack: int = 300, granule: int = 512) -> list[tuple[int, int, int, int, int]]:
     """AVA pair specs (q, t, band_lo, band_w, flags) of one region with local read indices: every
     unordered pair once, query = lexicographically smaller name, strand from the known read
