@@ -16,10 +16,17 @@ using namespace svp;
 
 namespace {
 
-// Two instantiations of the kernels: KP = 4 packed registers per state array per thread (16 diagonals
-// per thread, 512 per warp) for bands up to 16 warps x 512 = 8192 diagonals, KP = 8 (1024 per warp)
-// for wider bands up to 16384.
+// Two widths of the kernels: KP = 4 packed registers per state array per thread (16 diagonals per
+// thread, 512 per warp) and KP = 8 (32 per thread, 1024 per warp); a pair runs on whichever needs
+// fewer issue slots for its band (choose_kp), on 1..16 warps.
 constexpr int MAX_WARPS = 16;
+// measured/estimated warp-instructions per step of the inner loop (SASS count), used only to choose KP
+static inline int step_cost(int kp, int nwarp) { return kp == 8 ? (nwarp > 1 ? 132 : 122) : (nwarp > 1 ? 80 : 72); }
+static inline int choose_kp(uint32_t band_w) {
+    const int w4 = (int)((band_w + 511) / 512), w8 = (int)((band_w + 1023) / 1024);
+    if (w4 > MAX_WARPS) return 8;
+    return (w8 * step_cost(8, w8) < w4 * step_cost(4, w4)) ? 8 : 4;
+}
 constexpr int S16_SCORE_LIMIT = 32000;
 static inline int kp_of(const Task& t) { return (t.flags & TASK_KP8) ? 8 : 4; }
 static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * (2 * kp_of(t)) * (uint64_t)(t.band_w / 2); }
@@ -136,9 +143,11 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     for (cudaEvent_t* e : { &h->ev_a, &h->ev_b, &h->ev_c, &h->ev_t0, &h->ev_t1 })
         if (cudaEventCreate(e) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaEventCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    cudaFuncSetAttribute(svp_fwd_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-    cudaFuncSetAttribute(svp_fwd_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-    cudaFuncSetAttribute(svp_fwd_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+    for (const void* fn : { (const void*)svp_fwd_kernel<4, false, true>, (const void*)svp_fwd_kernel<4, true, true>,
+                            (const void*)svp_fwd_kernel<8, false, true>, (const void*)svp_fwd_kernel<8, true, true>,
+                            (const void*)svp_fwd_kernel<4, false, false>, (const void*)svp_fwd_kernel<4, true, false>,
+                            (const void*)svp_fwd_kernel<8, false, false>, (const void*)svp_fwd_kernel<8, true, false> })
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
     size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 2, (size_t)64 << 30);
@@ -180,6 +189,21 @@ static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
     return total;
 }
 
+template <int KPV, bool MULTI, bool TWO>
+static void launch_one(unsigned grid, int nwarp, size_t smem, cudaStream_t st, const Task* tasks, const uint32_t* order,
+                       const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
+    svp_fwd_kernel<KPV, MULTI, TWO><<<grid, nwarp * 32, smem, st>>>(tasks, order, seqs, arena, bests, cs);
+}
+
+static void launch_fwd(int kp, int nwarp, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
+                       const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
+    const bool multi = nwarp > 1;
+#define SVP_CASE(K, M, T) if (kp == K && multi == M && two == T) return launch_one<K, M, T>(grid, nwarp, smem, st, tasks, order, seqs, arena, bests, cs)
+    SVP_CASE(4, false, true); SVP_CASE(4, true, true); SVP_CASE(8, false, true); SVP_CASE(8, true, true);
+    SVP_CASE(4, false, false); SVP_CASE(4, true, false); SVP_CASE(8, false, false); SVP_CASE(8, true, false);
+#undef SVP_CASE
+}
+
 struct Plan {
     std::vector<Task> tasks;                     // all pairs, input order
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
@@ -202,7 +226,7 @@ static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off
     t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
-    if (p.band_w > (uint32_t)(MAX_WARPS * 512)) t.flags |= TASK_KP8;
+    if (choose_kp(p.band_w) == 8) t.flags |= TASK_KP8;
     const int steps_per_iter = 2 * kp_of(t);
     const int64_t m = t.m, n = t.n, lo = p.band_lo, hi = lo + (int64_t)p.band_w - 1;
     if (lo > n - 1 || hi < -(m - 1)) { t.flags |= TASK_INVALID; return; }     // band misses the matrix
@@ -275,8 +299,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int nwarp = kv.first % 1000, kp = kv.first >= 1000 ? 8 : 4;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
-                const size_t qpad = ((((size_t)t.m + 15) >> 4) + 3) & ~(size_t)3, tpad = ((((size_t)t.n + 15) >> 4) + 3) & ~(size_t)3;
-                smem = std::max(smem, (qpad + tpad) * 4 + (size_t)2 * nwarp * sizeof(uint4));
+                smem = std::max(smem, (size_t)seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
             }
             if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
             wave_groups[wv].push_back({ nwarp, kp, pos, kv.second.size(), smem });
@@ -294,12 +317,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     for (size_t wv = 0; wv < waves.size(); ++wv) {
         CUDA_TRY(h, cudaEventRecord(h->ev_a, st));
         for (const Group& gq : wave_groups[wv]) {
-            if (gq.kp == 8)
-                svp_fwd_kernel<8, true><<<(unsigned)gq.count, gq.nwarp * 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
-            else if (gq.nwarp == 1)
-                svp_fwd_kernel<4, false><<<(unsigned)gq.count, 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
-            else
-                svp_fwd_kernel<4, true><<<(unsigned)gq.count, gq.nwarp * 32, gq.smem, st>>>(d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
+            launch_fwd(gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, st, d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }
         CUDA_TRY(h, cudaEventRecord(h->ev_b, st));

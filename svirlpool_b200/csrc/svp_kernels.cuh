@@ -64,82 +64,126 @@ __device__ __forceinline__ uint32_t heq_mask(uint32_t a, uint32_t b) {
     return __heq2_mask(ha, hb);
 }
 
-// fp16 code of base `pos` (1-based) of a 2-bit packed sequence in shared memory; NaN outside [1, len]
-__device__ __forceinline__ uint32_t base_code(const uint32_t* s, int pos, int len) {
-    const unsigned p = (unsigned)(pos - 1);
-    uint32_t code = QNAN16;
-    if (p < (unsigned)len) {
-        const uint32_t w = s[p >> 4];
-        code = 0x3C00u | (((w >> ((p & 15u) * 2u)) & 3u) << 8);
-    }
-    return code;
-}
-
 // ---------------------------------------------------------------------------------------------
 // forward DP
 // ---------------------------------------------------------------------------------------------
-template <int KP, bool MULTI>
+__device__ __forceinline__ uint32_t pin(uint32_t v) {      // keep a constant in a register (no LDC re-loads in the loop)
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
+// base p (0-based) at byte SEQ_PAD + p, with 0x7E (NaN) in the bytes before and after; positions are
+// clamped into [SEQ_PAD-1, SEQ_PAD+len] so every out-of-range position reads a NaN: virtual cells
+// never match and no range test is needed in the loop.
+constexpr int SEQ_PAD = 16;
+__host__ __device__ __forceinline__ int seq_image_bytes(int len) { return (SEQ_PAD + len + 1 + 15) & ~15; }
+
+// 16 bases of one 2-bit packed word -> 16 code bytes (four 32-bit words)
+__device__ __forceinline__ uint4 expand16(uint32_t w) {
+    uint32_t o[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = (w >> (8 * k)) & 0xFFu;
+        o[k] = ((x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u) + 0x3C3C3C3Cu;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int KP, bool MULTI, bool TWO>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(16) uint8_t smem8[];
     const Task tk = tasks[order[blockIdx.x]];
     const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
-    const int qwords = (tk.m + 15) >> 4, twords = (tk.n + 15) >> 4;
-    const int qpad = (qwords + 3) & ~3, tpad = (twords + 3) & ~3;
-    uint32_t* qs = smem;
-    uint32_t* ts = smem + qpad;
-    uint4* mbox = reinterpret_cast<uint4*>(smem + qpad + tpad);      // [2][nwarp] mailboxes (MULTI)
+    const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
+    uint8_t* qimg = smem8;
+    uint8_t* timg = smem8 + qbytes;
+    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + SEQ_PAD - 1;   // + clamped 1-based position
+    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + SEQ_PAD - 1;
+    // mailboxes (MULTI): A[w] = lane 0 of warp w after an A-step, A[nwarp] = constants;
+    //                    B[w+1] = lane 31 of warp w after a B-step, B[0] = constants
+    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(smem8 + qbytes + tbytes);
+    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
 
-    // ---- stage the two sequences in shared memory (2-bit packed) -------------------------------
+    const uint32_t c_ne1 = pin(cs.ne1), c_noe1 = pin(cs.noe1), c_ne2 = pin(cs.ne2), c_noe2 = pin(cs.noe2);
+    const uint32_t c_mat = pin(cs.mat), c_mis = pin(cs.mis), c_neg = pin(NEGV);
+
+    // ---- stage both sequences as code bytes ------------------------------------------------------
     {
-        const uint4* tsrc = reinterpret_cast<const uint4*>(seqs + tk.t_off);
-        for (int k = g; k < (tpad >> 2); k += blockDim.x)
-            __pipeline_memcpy_async(reinterpret_cast<uint4*>(ts) + k, tsrc + k, 16);
+        const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
+        for (int w = g; w < (tk.n + 15) >> 4; w += blockDim.x)
+            *reinterpret_cast<uint4*>(timg + SEQ_PAD + 16 * w) = expand16(__ldg(tsrc + w));
+        const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
         if (!(tk.flags & SVP_PAIR_REVCOMP)) {
-            const uint4* qsrc = reinterpret_cast<const uint4*>(seqs + tk.q_off);
-            for (int k = g; k < (qpad >> 2); k += blockDim.x)
-                __pipeline_memcpy_async(reinterpret_cast<uint4*>(qs) + k, qsrc + k, 16);
+            for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x)
+                *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(__ldg(qsrc + w));
         } else {
-            // reverse complement while staging: oriented base p = 3 - original base (m-1-p)
-            const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
-            for (int w = g; w < qpad; w += blockDim.x) {
-                uint32_t out = 0;
+            // oriented base p = complement of original base m-1-p
+            for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x) {
+                uint32_t packed = 0;
                 #pragma unroll
                 for (int b = 0; b < 16; ++b) {
                     const int p = w * 16 + b;
                     if (p < tk.m) {
                         const unsigned o = (unsigned)(tk.m - 1 - p);
-                        const uint32_t c = (__ldg(qsrc + (o >> 4)) >> ((o & 15u) * 2u)) & 3u;
-                        out |= (3u - c) << (2 * b);
+                        packed |= (3u - ((__ldg(qsrc + (o >> 4)) >> ((o & 15u) * 2u)) & 3u)) << (2 * b);
                     }
                 }
-                qs[w] = out;
+                *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(packed);
             }
         }
-        if (MULTI && g < 2 * nwarp) mbox[g] = make_uint4(cs.noe1, cs.noe2, NEGV, NEGV);
-        __pipeline_commit();
-        __pipeline_wait_prior(0);
+        __syncthreads();
+        // NaN pads (after the bulk stores: the last 16-byte group may cover the trailing pad)
+        for (int k = g; k < SEQ_PAD; k += blockDim.x) { qimg[k] = 0x7E; timg[k] = 0x7E; }
+        for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) qimg[k] = 0x7E;
+        for (int k = SEQ_PAD + tk.n + g; k < tbytes; k += blockDim.x) timg[k] = 0x7E;
+        if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * g, c_noe1, c_noe2, c_neg, c_neg); }
         __syncthreads();
     }
 
-    const bool active = g * 4 * KP < tk.band_w;
+    const int n_thr_active = tk.band_w / (4 * KP);
+    const bool active = g < n_thr_active;
+    const bool lo_edge = (lane == 0);                           // left neighbour: mailbox / constants
+    const bool hi_edge = (lane == 31) || (g == n_thr_active - 1);   // up neighbour: mailbox / constants
     const int D0 = tk.band_lo + g * 4 * KP;
-    int I0 = (tk.r_begin - D0) / 2;          // exact: r_begin - D0 is even
-    int J0 = (tk.r_begin + D0) / 2;
+    const int I0 = (tk.r_begin - D0) / 2;          // exact: r_begin - D0 is even
+    const int J0 = (tk.r_begin + D0) / 2;
+    const int qmax = tk.m + 1, tmax = tk.n + 1;
 
+    auto code_at = [&](uint32_t sbase, int pos, int lim) -> uint32_t {   // fp16 code (16 bit) of a 1-based position
+        return lds_u8(sbase + (uint32_t)__vimin_s32_relu(pos, lim)) << 8;
+    };
     // packed state, slot k in the low half, slot KP+k in the high half
     uint32_t HA[KP], HB[KP], P1[KP], P2[KP], E1[KP], E2[KP], F1[KP], F2[KP], Q[KP], T[KP];
     #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        HA[k] = 0; HB[k] = 0; P1[k] = cs.noe1; P2[k] = cs.noe2;
-        E1[k] = NEGV; E2[k] = NEGV; F1[k] = NEGV; F2[k] = NEGV;
-        Q[k] = base_code(qs, I0 - k, tk.m) | (base_code(qs, I0 - (KP + k), tk.m) << 16);
-        T[k] = base_code(ts, J0 + k, tk.n) | (base_code(ts, J0 + KP + k, tk.n) << 16);
+        HA[k] = 0; HB[k] = 0; P1[k] = c_noe1; P2[k] = c_noe2;
+        E1[k] = c_neg; E2[k] = c_neg; F1[k] = c_neg; F2[k] = c_neg;
+        Q[k] = code_at(s_q, I0 - k, qmax) | (code_at(s_q, I0 - (KP + k), qmax) << 16);
+        T[k] = code_at(s_t, J0 + k, tmax) | (code_at(s_t, J0 + KP + k, tmax) << 16);
     }
+    int qpos = I0 + 1, tpos = J0 + 2 * KP;                   // next bases to enter
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
-    const int pitch = tk.band_w >> 1;                       // bytes per traceback row (one step)
+    const int pitch = tk.band_w >> 1;                        // bytes per traceback row (one step)
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
+    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
+    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
@@ -148,106 +192,101 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
             // =============================== A-step ===========================================
             {
                 uint32_t sP1 = __shfl_up_sync(0xffffffffu, P1[KP - 1], 1);
-                uint32_t sP2 = __shfl_up_sync(0xffffffffu, P2[KP - 1], 1);
                 uint32_t sE1 = __shfl_up_sync(0xffffffffu, E1[KP - 1], 1);
-                uint32_t sE2 = __shfl_up_sync(0xffffffffu, E2[KP - 1], 1);
-                if (lane == 0) {
-                    if (MULTI && warp > 0) { const uint4 v = mbox[nwarp + warp - 1]; sP1 = v.x; sP2 = v.y; sE1 = v.z; sE2 = v.w; }
-                    else { sP1 = cs.noe1; sP2 = cs.noe2; sE1 = NEGV; sE2 = NEGV; }
-                }
-                if (active) {
-                    const uint32_t P1m = __byte_perm(sP1, P1[KP - 1], 0x5432), P2m = __byte_perm(sP2, P2[KP - 1], 0x5432);
-                    const uint32_t E1m = __byte_perm(sE1, E1[KP - 1], 0x5432), E2m = __byte_perm(sE2, E2[KP - 1], 0x5432);
-                    #pragma unroll
-                    for (int k = KP - 1; k >= 0; --k) {
-                        const uint32_t p1l = k ? P1[k - 1] : P1m, p2l = k ? P2[k - 1] : P2m;
-                        const uint32_t e1l = k ? E1[k - 1] : E1m, e2l = k ? E2[k - 1] : E2m;
-                        const uint32_t e1 = __viaddmax_s16x2(e1l, cs.ne1, p1l);
-                        const uint32_t f1 = __viaddmax_s16x2(F1[k], cs.ne1, P1[k]);
-                        const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u) % KP]);
-                        const uint32_t h = __vadd2(HA[k], (mk & cs.mat) | (~mk & cs.mis));
-                        uint32_t H;
-                        if (cs.two_piece) {
-                            const uint32_t e2 = __viaddmax_s16x2(e2l, cs.ne2, p2l);
-                            const uint32_t f2 = __viaddmax_s16x2(F2[k], cs.ne2, P2[k]);
-                            H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
-                            E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, cs.noe2);
-                        } else {
-                            H = __vimax3_s16x2_relu(h, e1, f1);
-                        }
-                        HA[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, cs.noe1);
-                    }
-                    #pragma unroll
-                    for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
-                    if (KP == 4) {
-                        __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420)));
+                uint32_t sP2 = 0, sE2 = 0;
+                if (TWO) { sP2 = __shfl_up_sync(0xffffffffu, P2[KP - 1], 1); sE2 = __shfl_up_sync(0xffffffffu, E2[KP - 1], 1); }
+                uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
+                if (MULTI) mb = lds_v4(s_loB);
+                sP1 = lo_edge ? mb.x : sP1; sE1 = lo_edge ? mb.z : sE1;
+                if (TWO) { sP2 = lo_edge ? mb.y : sP2; sE2 = lo_edge ? mb.w : sE2; }
+                const uint32_t P1m = __byte_perm(sP1, P1[KP - 1], 0x5432), E1m = __byte_perm(sE1, E1[KP - 1], 0x5432);
+                const uint32_t P2m = TWO ? __byte_perm(sP2, P2[KP - 1], 0x5432) : 0u, E2m = TWO ? __byte_perm(sE2, E2[KP - 1], 0x5432) : 0u;
+                #pragma unroll
+                for (int k = KP - 1; k >= 0; --k) {
+                    const uint32_t p1l = k ? P1[k ? k - 1 : 0] : P1m, e1l = k ? E1[k ? k - 1 : 0] : E1m;
+                    const uint32_t e1 = __viaddmax_s16x2(e1l, c_ne1, p1l);
+                    const uint32_t f1 = __viaddmax_s16x2(F1[k], c_ne1, P1[k]);
+                    const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u) % KP]);
+                    const uint32_t h = __vadd2(HA[k], (mk & c_mat) | (~mk & c_mis));
+                    uint32_t H;
+                    if (TWO) {
+                        const uint32_t p2l = k ? P2[k ? k - 1 : 0] : P2m, e2l = k ? E2[k ? k - 1 : 0] : E2m;
+                        const uint32_t e2 = __viaddmax_s16x2(e2l, c_ne2, p2l);
+                        const uint32_t f2 = __viaddmax_s16x2(F2[k], c_ne2, P2[k]);
+                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, c_noe2);
                     } else {
-                        __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420),
-                                                                         __byte_perm(HA[4 % KP], HA[5 % KP], 0x6420), __byte_perm(HA[6 % KP], HA[7 % KP], 0x6420)));
+                        H = __vimax3_s16x2_relu(h, e1, f1);
                     }
+                    HA[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
+                }
+                #pragma unroll
+                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
+                if (active) {
+                    if (KP == 4) __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420)));
+                    else __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420),
+                                                                          __byte_perm(HA[4 % KP], HA[5 % KP], 0x6420), __byte_perm(HA[6 % KP], HA[7 % KP], 0x6420)));
                 }
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) mbox[warp] = make_uint4(P1[0], P2[0], F1[0], F2[0]);
+                    if (lane == 0) sts_v4(s_myA, P1[0], P2[0], F1[0], F2[0]);
                     __syncthreads();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
-                const uint32_t nt = base_code(ts, J0 + 2 * KP, tk.n);
-                T[u % KP] = __byte_perm(T[u % KP], nt, 0x5432);
+                const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
+                T[u % KP] = __byte_perm(T[u % KP], nb, 0x4232);
+                ++tpos;
             }
             // =============================== B-step ===========================================
             {
                 uint32_t sP1 = __shfl_down_sync(0xffffffffu, P1[0], 1);
-                uint32_t sP2 = __shfl_down_sync(0xffffffffu, P2[0], 1);
                 uint32_t sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1);
-                uint32_t sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
-                if (lane == 31) {
-                    if (MULTI && warp < nwarp - 1) { const uint4 v = mbox[warp + 1]; sP1 = v.x; sP2 = v.y; sF1 = v.z; sF2 = v.w; }
-                    else { sP1 = cs.noe1; sP2 = cs.noe2; sF1 = NEGV; sF2 = NEGV; }
-                }
-                if (active) {
-                    const uint32_t P1p = __byte_perm(P1[0], sP1, 0x5432), P2p = __byte_perm(P2[0], sP2, 0x5432);
-                    const uint32_t F1p = __byte_perm(F1[0], sF1, 0x5432), F2p = __byte_perm(F2[0], sF2, 0x5432);
-                    #pragma unroll
-                    for (int k = 0; k < KP; ++k) {
-                        const uint32_t p1u = (k < KP - 1) ? P1[(k + 1) % KP] : P1p, p2u = (k < KP - 1) ? P2[(k + 1) % KP] : P2p;
-                        const uint32_t f1u = (k < KP - 1) ? F1[(k + 1) % KP] : F1p, f2u = (k < KP - 1) ? F2[(k + 1) % KP] : F2p;
-                        const uint32_t e1 = __viaddmax_s16x2(E1[k], cs.ne1, P1[k]);
-                        const uint32_t f1 = __viaddmax_s16x2(f1u, cs.ne1, p1u);
-                        const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u + 1) % KP]);
-                        const uint32_t h = __vadd2(HB[k], (mk & cs.mat) | (~mk & cs.mis));
-                        uint32_t H;
-                        if (cs.two_piece) {
-                            const uint32_t e2 = __viaddmax_s16x2(E2[k], cs.ne2, P2[k]);
-                            const uint32_t f2 = __viaddmax_s16x2(f2u, cs.ne2, p2u);
-                            H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
-                            E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, cs.noe2);
-                        } else {
-                            H = __vimax3_s16x2_relu(h, e1, f1);
-                        }
-                        HB[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, cs.noe1);
-                    }
-                    #pragma unroll
-                    for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
-                    if (KP == 4) {
-                        __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420)));
+                uint32_t sP2 = 0, sF2 = 0;
+                if (TWO) { sP2 = __shfl_down_sync(0xffffffffu, P2[0], 1); sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1); }
+                uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
+                if (MULTI) mb = lds_v4(s_upA);
+                sP1 = hi_edge ? mb.x : sP1; sF1 = hi_edge ? mb.z : sF1;
+                if (TWO) { sP2 = hi_edge ? mb.y : sP2; sF2 = hi_edge ? mb.w : sF2; }
+                const uint32_t P1p = __byte_perm(P1[0], sP1, 0x5432), F1p = __byte_perm(F1[0], sF1, 0x5432);
+                const uint32_t P2p = TWO ? __byte_perm(P2[0], sP2, 0x5432) : 0u, F2p = TWO ? __byte_perm(F2[0], sF2, 0x5432) : 0u;
+                #pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    const uint32_t p1u = (k < KP - 1) ? P1[(k + 1) % KP] : P1p, f1u = (k < KP - 1) ? F1[(k + 1) % KP] : F1p;
+                    const uint32_t e1 = __viaddmax_s16x2(E1[k], c_ne1, P1[k]);
+                    const uint32_t f1 = __viaddmax_s16x2(f1u, c_ne1, p1u);
+                    const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u + 1) % KP]);
+                    const uint32_t h = __vadd2(HB[k], (mk & c_mat) | (~mk & c_mis));
+                    uint32_t H;
+                    if (TWO) {
+                        const uint32_t p2u = (k < KP - 1) ? P2[(k + 1) % KP] : P2p, f2u = (k < KP - 1) ? F2[(k + 1) % KP] : F2p;
+                        const uint32_t e2 = __viaddmax_s16x2(E2[k], c_ne2, P2[k]);
+                        const uint32_t f2 = __viaddmax_s16x2(f2u, c_ne2, p2u);
+                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, c_noe2);
                     } else {
-                        __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420),
-                                                                         __byte_perm(HB[4 % KP], HB[5 % KP], 0x6420), __byte_perm(HB[6 % KP], HB[7 % KP], 0x6420)));
+                        H = __vimax3_s16x2_relu(h, e1, f1);
                     }
+                    HB[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
+                }
+                #pragma unroll
+                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
+                if (active) {
+                    if (KP == 4) __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420)));
+                    else __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420),
+                                                                          __byte_perm(HB[4 % KP], HB[5 % KP], 0x6420), __byte_perm(HB[6 % KP], HB[7 % KP], 0x6420)));
                 }
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) mbox[nwarp + warp] = make_uint4(P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
+                    if (lane == 31) sts_v4(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
                     __syncthreads();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
-                const uint32_t nq = base_code(qs, I0 + 1, tk.m);
-                Q[(KP - 1 - u) % KP] = __byte_perm(nq, Q[(KP - 1 - u) % KP], 0x5410);
+                const uint32_t nb = lds_u8(s_q + (uint32_t)__vimin_s32_relu(qpos, qmax));
+                Q[(KP - 1 - u) % KP] = __byte_perm(nb, Q[(KP - 1 - u) % KP], 0x5401);
+                ++qpos;
             }
-            ++I0; ++J0;
         }
-        // which iteration first reached the running maximum, per half (end-cell search, §4.3)
+        // which iteration first reached the running maximum, per half (end-cell search)
         const uint32_t diff = best ^ snap;
         if (diff & 0xFFFFu) blk_lo = (uint32_t)it;
         if (diff >> 16) blk_hi = (uint32_t)it;
