@@ -252,7 +252,7 @@ def main() -> None:
     # ---- end to end through the host-buffer API -----------------------------------------------------
     def step_host(k: int):
         b = batches[k % n_distinct]
-        return al.align_batch(b["h_packed_pinned"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+        return al.align_batch_nocopy(b["h_packed_pinned"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
 
     step_host(0)
     sync_all()

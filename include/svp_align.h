@@ -109,10 +109,17 @@ int         svp_create(int device, const svp_scoring* scoring, size_t max_tb_byt
 void        svp_destroy(svp_handle* h);
 const char* svp_last_error(const svp_handle* h);
 
+/* Page-locked host memory for the buffers handed to svp_align_batch() (optional; pageable memory
+ * works, pinned memory makes the H2D/D2H copies asynchronous and fast). NULL on failure. */
+void*       svp_pinned_alloc(size_t bytes);
+void        svp_pinned_free(void* p);
+
 /* Align n_pairs pairs. Sequences are 2-bit packed (A=0,C=1,G=2,T=3; base k of a sequence lives
  * in bits 2*(k%4).. of byte seq_off[s] + k/4); seq_off[] entries must be multiples of 16.
  * All buffers are HOST memory; results and CIGAR words are written to caller-allocated arrays.
- * Blocking; one call at a time per handle. */
+ * On return the CIGARs are packed densely from cigar_buf[0] in pair order and result.cigar_off
+ * points at each of them (the per-pair slots of svp_pair only size the device scratch; a pair whose
+ * CIGAR does not fit its slot gets SVP_ST_CIGAR_OVF). Blocking; one call at a time per handle. */
 int svp_align_batch(svp_handle* h,
                     const uint8_t* packed_seqs, size_t packed_bytes,
                     const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,

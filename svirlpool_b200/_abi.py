@@ -36,7 +36,7 @@ assert SCORING_DTYPE.itemsize == 112 and PAIR_DTYPE.itemsize == 32 and RESULT_DT
 assert STATS_DTYPE.itemsize == 56
 
 # every symbol include/svp_align.h declares (checked by tests/test_abi.py against the built library)
-EXPORTS = ("svp_abi_version", "svp_device_count", "svp_scoring_preset", "svp_create", "svp_destroy",
+EXPORTS = ("svp_abi_version", "svp_device_count", "svp_scoring_preset", "svp_create", "svp_destroy", "svp_pinned_alloc", "svp_pinned_free",
            "svp_last_error", "svp_align_batch", "svp_align_batch_device", "svp_get_stats")
 
 

@@ -47,6 +47,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_destroy.argtypes = [C.c_void_p]
     lib.svp_last_error.restype = C.c_char_p
     lib.svp_last_error.argtypes = [C.c_void_p]
+    lib.svp_pinned_alloc.restype = C.c_void_p
+    lib.svp_pinned_alloc.argtypes = [C.c_size_t]
+    lib.svp_pinned_free.restype = None
+    lib.svp_pinned_free.argtypes = [C.c_void_p]
     lib.svp_get_stats.restype = C.c_int
     lib.svp_get_stats.argtypes = [C.c_void_p, C.c_void_p]
     batch_args = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
@@ -68,6 +72,30 @@ def scoring_preset(name: str, lib: C.CDLL | None = None) -> np.ndarray:
     return s
 
 
+class PinnedBuffer:
+    """A page-locked host buffer (svp_pinned_alloc) viewed as a numpy array; grows on demand."""
+
+    def __init__(self, lib: C.CDLL, dtype):
+        self.lib, self.dtype, self.ptr, self.cap = lib, np.dtype(dtype), None, 0
+
+    def view(self, n: int) -> np.ndarray:
+        n = max(int(n), 1)
+        if n > self.cap:
+            self.release()
+            cap = n + n // 4
+            p = self.lib.svp_pinned_alloc(cap * self.dtype.itemsize)
+            if not p:
+                raise MemoryError("svp_pinned_alloc failed")
+            self.ptr, self.cap = p, cap
+        buf = (C.c_uint8 * (self.cap * self.dtype.itemsize)).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=self.dtype, count=n)
+
+    def release(self) -> None:
+        if self.ptr:
+            self.lib.svp_pinned_free(self.ptr)
+            self.ptr, self.cap = None, 0
+
+
 class Aligner:
     """One handle = one GPU + one scoring profile. Not thread-safe; one call at a time."""
 
@@ -82,9 +110,13 @@ class Aligner:
         if rc != SVP_OK:
             raise AlignerError(rc, (self.lib.svp_last_error(None) or b"").decode())
         self._h = handle
+        self._res_buf = PinnedBuffer(self.lib, RESULT_DTYPE)
+        self._cig_buf = PinnedBuffer(self.lib, np.uint32)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            self._res_buf.release()
+            self._cig_buf.release()
             self.lib.svp_destroy(self._h)
             self._h = None
 
@@ -106,13 +138,24 @@ class Aligner:
 
     def align_batch(self, packed: np.ndarray, seq_off: np.ndarray, seq_len: np.ndarray, pairs: np.ndarray,
                     cigar_words: int) -> tuple[np.ndarray, np.ndarray]:
-        """Host buffers in, host buffers out (svp_align_batch): H2D, kernels, D2H inside the call."""
+        """Host buffers in, host buffers out (svp_align_batch): H2D, kernels, D2H inside the call.
+        Returns (results, cigar words); the CIGARs are dense in pair order (results["cigar_off"]).
+        With copy=False the arrays are views of the handle's pinned buffers, valid until the next call."""
+        return self._align_batch(packed, seq_off, seq_len, pairs, cigar_words, copy=True)
+
+    def align_batch_nocopy(self, packed, seq_off, seq_len, pairs, cigar_words):
+        return self._align_batch(packed, seq_off, seq_len, pairs, cigar_words, copy=False)
+
+    def _align_batch(self, packed, seq_off, seq_len, pairs, cigar_words, copy: bool):
         assert pairs.dtype == PAIR_DTYPE and packed.dtype == np.uint8
-        res = np.zeros(len(pairs), dtype=RESULT_DTYPE)
-        cig = np.zeros(max(int(cigar_words), 1), dtype=np.uint32)
+        res = self._res_buf.view(len(pairs))
+        cig = self._cig_buf.view(cigar_words)
         self._check(self.lib.svp_align_batch(self._h, ptr(packed), packed.nbytes, ptr(seq_off), ptr(seq_len), len(seq_len),
                                              ptr(pairs), len(pairs), ptr(res), ptr(cig), len(cig)))
-        return res, cig
+        used = int(res["cigar_off"][-1]) + int(res["cigar_len"][-1]) if len(res) else 0
+        if copy:
+            return res.copy(), cig[:max(used, 1)].copy()
+        return res, cig[:max(used, 1)]
 
     def align_batch_device(self, d_packed_ptr: int, packed_bytes: int, seq_off: np.ndarray, seq_len: np.ndarray,
                            pairs: np.ndarray, d_results_ptr: int, d_cigar_ptr: int, cigar_words: int) -> None:

@@ -52,10 +52,12 @@ struct svp_handle {
     int device = 0;
     svp_scoring scoring{};
     Consts cs{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;              // forward kernels + copies
+    cudaStream_t stream_aux[2] = { nullptr, nullptr };   // extra forward streams: a wave's CTA-width groups run concurrently
+    cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
+    std::vector<cudaEvent_t> events;            // pool, grown on demand
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
-    DevBuf d_tasks, d_order, d_bests, d_seqs, d_results, d_cigar;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    DevBuf d_tasks, d_order, d_bests, d_seqs, d_results, d_cigar, d_dense, d_dense_off;
     svp_stats stats{};
     std::string err;
     int max_smem_optin = 0;
@@ -139,9 +141,12 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     h->device = device; h->scoring = *scoring; h->cs = cs;
     auto bail = [&](int code, const std::string& m) { g_err = m; svp_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaSetDevice failed");
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
-    for (cudaEvent_t* e : { &h->ev_a, &h->ev_b, &h->ev_c, &h->ev_t0, &h->ev_t1 })
-        if (cudaEventCreate(e) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaEventCreate failed");
+    for (cudaStream_t& sx : h->stream_aux)
+        if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (const void* fn : { (const void*)svp_fwd_kernel<4, false, true>, (const void*)svp_fwd_kernel<4, true, true>,
                             (const void*)svp_fwd_kernel<8, false, true>, (const void*)svp_fwd_kernel<8, true, true>,
@@ -150,7 +155,7 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
-    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 2, (size_t)64 << 30);
+    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 10 * 8, (size_t)128 << 30);
     want = (want + 255) & ~(size_t)255;
     if (cudaMalloc((void**)&h->arena, want) != cudaSuccess) { cudaGetLastError(); return bail(SVP_ERR_NOMEM, "cannot allocate the traceback arena"); }
     h->arena_bytes = want;
@@ -161,13 +166,21 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
 extern "C" void svp_destroy(svp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
     if (h->arena) cudaFree(h->arena);
-    for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar }) b->release();
-    for (cudaEvent_t e : { h->ev_a, h->ev_b, h->ev_c, h->ev_t0, h->ev_t1 }) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (cudaStream_t sx : { h->stream, h->stream_aux[0], h->stream_aux[1], h->stream_tb }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
+
+extern "C" void* svp_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void svp_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char* svp_last_error(const svp_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
@@ -202,6 +215,18 @@ static void launch_fwd(int kp, int nwarp, bool two, unsigned grid, size_t smem, 
     SVP_CASE(4, false, true); SVP_CASE(4, true, true); SVP_CASE(8, false, true); SVP_CASE(8, true, true);
     SVP_CASE(4, false, false); SVP_CASE(4, true, false); SVP_CASE(8, false, false); SVP_CASE(8, true, false);
 #undef SVP_CASE
+}
+
+// CIGAR compaction for the host-buffer entry point: one warp per pair copies its (right-aligned) slot
+// content to the dense position computed on the host, so only the used words cross PCIe.
+__global__ void svp_cigar_gather(const svp_result* __restrict__ res, const uint32_t* __restrict__ dense_off,
+                                 const uint32_t* __restrict__ slots, uint32_t* __restrict__ dense, int n) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const uint32_t len = res[k].cigar_len;
+    const uint32_t* src = slots + res[k].cigar_off;
+    uint32_t* dst = dense + dense_off[k];
+    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
 }
 
 struct Plan {
@@ -253,8 +278,11 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     for (Task& t : tasks)
         if (!(t.flags & TASK_INVALID) && (int64_t)std::min(t.m, t.n) * cs.s_match > S16_SCORE_LIMIT) t.flags |= TASK_INVALID | TASK_TOO_LONG;
 
-    // waves: consecutive tasks whose traceback rows fit the arena
+    // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
+    // the traceback of wave w overlaps the forward pass of wave w+1
+    const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
     std::vector<std::pair<size_t, size_t>> waves;
+    std::vector<uint64_t> wave_best;
     {
         size_t first = 0; uint64_t used = 0, best_used = 0;
         for (size_t k = 0; k < n; ++k) {
@@ -263,24 +291,26 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             if (!(t.flags & TASK_INVALID)) {
                 need = (tb_bytes_of(t) + 255) & ~(uint64_t)255;
                 nbest = best_entries_of(t);
-                if (need > h->arena_bytes) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds the arena; create the handle with a larger max_tb_bytes");
+                if (need > half) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds half the arena; create the handle with a larger max_tb_bytes");
             }
-            if (used + need > h->arena_bytes) { waves.emplace_back(first, k); first = k; used = 0; best_used = 0; }
-            t.tb_off = used; t.best_off = best_used;
+            if (used + need > half) { waves.emplace_back(first, k); wave_best.push_back(best_used); first = k; used = 0; best_used = 0; }
+            t.tb_off = (waves.size() & 1) * half + used; t.best_off = best_used;
             used += need; best_used += nbest;
         }
-        waves.emplace_back(first, n);
+        waves.emplace_back(first, n); wave_best.push_back(best_used);
     }
+    uint64_t max_best = 1;
+    for (uint64_t b : wave_best) max_best = std::max(max_best, b);
+    for (size_t wv = 1; wv < waves.size(); wv += 2)
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k) tasks[k].best_off += max_best;
     CUDA_TRY(h, h->d_tasks.reserve(n * sizeof(Task)));
     CUDA_TRY(h, h->d_order.reserve(n * sizeof(uint32_t)));
-    uint64_t max_best = 0;
-    for (auto& w : waves) { uint64_t b = 0; for (size_t k = w.first; k < w.second; ++k) if (!(tasks[k].flags & TASK_INVALID)) b += best_entries_of(tasks[k]); max_best = std::max(max_best, b); }
-    CUDA_TRY(h, h->d_bests.reserve(std::max<uint64_t>(max_best, 1) * sizeof(uint2)));
+    CUDA_TRY(h, h->d_bests.reserve(2 * max_best * sizeof(uint2)));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, st));
 
-    // per wave: order lists grouped by CTA width (warps)
+    // per wave: order lists grouped by kernel variant and CTA width (warps)
     std::vector<uint32_t> order(n);
-    struct Group { int nwarp; int kp; size_t first, count; size_t smem; };
+    struct Group { int nwarp; int kp; size_t first, count; size_t smem; uint64_t work; };
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
@@ -295,60 +325,71 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         for (auto& kv : by_w) {
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
-            size_t smem = 0;
+            size_t smem = 0; uint64_t work = 0;
             const int nwarp = kv.first % 1000, kp = kv.first >= 1000 ? 8 : 4;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
                 smem = std::max(smem, (size_t)seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
+                work += (uint64_t)t.n_iter * nwarp * kp;
             }
             if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
-            wave_groups[wv].push_back({ nwarp, kp, pos, kv.second.size(), smem });
+            wave_groups[wv].push_back({ nwarp, kp, pos, kv.second.size(), smem, work });
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();
         }
+        // biggest group first, so the small ones fill the machine behind it
+        std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
     }
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(h->d_order.p, order.data(), pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     const Task* d_tasks = (const Task*)h->d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)h->d_order.p;
     uint2* d_bests = (uint2*)h->d_bests.p;
-    CUDA_TRY(h, cudaEventRecord(h->ev_t0, st));
-    std::vector<float> fwd_ms_v, tb_ms_v;
+    // events: per wave [fwd start, fwd end, tb end, aux join 0, aux join 1]; plus two for the whole call
+    const size_t EV_PER_WAVE = 5, n_ev = waves.size() * EV_PER_WAVE + 2;
+    while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
+    auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
+    cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
+    cudaStream_t sF[3] = { st, h->stream_aux[0], h->stream_aux[1] }, sT = h->stream_tb;
+    CUDA_TRY(h, cudaEventRecord(ev_t0, st));
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        CUDA_TRY(h, cudaEventRecord(h->ev_a, st));
-        for (const Group& gq : wave_groups[wv]) {
-            launch_fwd(gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, st, d_tasks, d_order + gq.first, d_seqs, h->arena, d_bests, cs);
+        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(st, EV(wv - 2, 2), 0));       // this arena half is free again
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), st));
+        const std::vector<Group>& groups = wave_groups[wv];
+        const int n_streams = (int)std::min<size_t>(3, groups.size());
+        for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const Group& gq = groups[gi];
+            launch_fwd(gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
+                       h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }
-        CUDA_TRY(h, cudaEventRecord(h->ev_b, st));
+        for (int a = 1; a < n_streams; ++a) {
+            CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sF[a]));
+            CUDA_TRY(h, cudaStreamWaitEvent(st, EV(wv, 2 + a), 0));
+        }
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), st));
+        CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
         const int nt = (int)(waves[wv].second - waves[wv].first);
         if (nt > 0) {
-            const int warps_per_block = 4;
-            bool any8 = false, any4 = false;
-            for (size_t k = waves[wv].first; k < waves[wv].second; ++k) { if (tasks[k].flags & TASK_KP8) any8 = true; else any4 = true; }
-            if (any4) {
-                svp_tb_kernel<4><<<(nt + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-                    d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-                h->stats.tb_launches++;
-            }
-            if (any8) {
-                svp_tb_kernel<8><<<(nt + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-                    d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-                h->stats.tb_launches++;
-            }
+            const int tpb = 64;
+            svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+            h->stats.tb_launches++;
         }
-        CUDA_TRY(h, cudaEventRecord(h->ev_c, st));
-        CUDA_TRY(h, cudaEventSynchronize(h->ev_c));
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, h->ev_a, h->ev_b);
-        cudaEventElapsedTime(&b, h->ev_b, h->ev_c);
-        h->stats.fwd_ms += a; h->stats.tb_ms += b;
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));
         h->stats.waves++;
     }
-    CUDA_TRY(h, cudaEventRecord(h->ev_t1, st));
-    CUDA_TRY(h, cudaEventSynchronize(h->ev_t1));
-    float tot = 0; cudaEventElapsedTime(&tot, h->ev_t0, h->ev_t1);
+    CUDA_TRY(h, cudaStreamWaitEvent(st, EV(waves.size() - 1, 2), 0));
+    CUDA_TRY(h, cudaEventRecord(ev_t1, st));
+    CUDA_TRY(h, cudaEventSynchronize(ev_t1));
+    float tot = 0; cudaEventElapsedTime(&tot, ev_t0, ev_t1);
     h->stats.total_ms = tot;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, EV(wv, 0), EV(wv, 1));      // forward pass of the wave (may overlap the previous wave's traceback)
+        cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));      // its traceback (includes waiting for SM slots)
+        h->stats.fwd_ms += a; h->stats.tb_ms += b;
+    }
     for (const Task& t : tasks) if (!(t.flags & TASK_INVALID)) { h->stats.cells += t.cells; h->stats.tb_bytes += tb_bytes_of(t); }
     CUDA_TRY(h, cudaGetLastError());
     return SVP_OK;
@@ -385,8 +426,27 @@ extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t
     for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
     int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
     if (rc != SVP_OK) return rc;
-    if (n_pairs) CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));
-    if (cigar_words) CUDA_TRY(h, cudaMemcpyAsync(cigar_buf, h->d_cigar.p, cigar_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (n_pairs) {
+        CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        // dense CIGAR layout in pair order; only the used words are copied back
+        std::vector<uint32_t> dense_off(n_pairs);
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < n_pairs; ++k) { dense_off[k] = (uint32_t)total; total += results[k].cigar_len; }
+        if (total > cigar_words) return fail(h, SVP_ERR_ARG, "cigar_buf smaller than the CIGARs produced");
+        if (total) {
+            CUDA_TRY(h, h->d_dense.reserve(total * sizeof(uint32_t)));
+            CUDA_TRY(h, h->d_dense_off.reserve(n_pairs * sizeof(uint32_t)));
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_dense_off.p, dense_off.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            const int wpb = 8;
+            svp_cigar_gather<<<(n_pairs + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>((const svp_result*)h->d_results.p, (const uint32_t*)h->d_dense_off.p,
+                                                                                  (const uint32_t*)h->d_cigar.p, (uint32_t*)h->d_dense.p, (int)n_pairs);
+            CUDA_TRY(h, cudaMemcpyAsync(cigar_buf, h->d_dense.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (uint32_t k = 0; k < n_pairs; ++k) results[k].cigar_off = dense_off[k];
+        h->stats.reserved = 1;
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SVP_OK;
 }

@@ -15,8 +15,9 @@
 //   of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
 //
 // Traceback    svp_tb_kernel<KP>
-//   One warp per pair. Rebuilds exact H values along the path from the stored low bytes
-//   (neighbouring H differ by less than 128), 32 cells per round trip to HBM.
+//   One thread per pair. Rebuilds exact H values along the path from the stored low bytes
+//   (neighbouring H differ by less than 128); latency-bound, overlapped with the
+//   next wave's forward pass on a second stream.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -301,33 +302,48 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 // ---------------------------------------------------------------------------------------------
 // traceback
 // ---------------------------------------------------------------------------------------------
-template <int KP>
+// Byte layout of the traceback rows (written by svp_fwd_kernel<KP>): row = step s = (i + j) - r_begin,
+// pitch = band_w / 2 bytes; inside a row thread g owns bytes [g*2KP, (g+1)*2KP); the byte of its slot
+// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (4 or 8).
 struct TbView {
     const uint8_t* base;      // arena + tb_off
     const uint32_t* seqs32;   // packed sequences (global)
-    int band_lo, band_w, r_begin, pitch, m, n;
+    int band_lo, band_w, r_begin, pitch, m, n, kp_log2;
     uint64_t q_word, t_word;  // word offsets of the packed sequences
     bool rc;
 
-    // low byte of H(i, j); 0 for virtual cells (i < 1 or j < 1) — callers check the band
-    __device__ __forceinline__ uint32_t lb(int i, int j) const {
-        if (i < 1 || j < 1) return 0;
-        const int x = (j - i) - band_lo, s = (i + j) - r_begin;
-        if (s < 0) return 0;
-        const int gthr = x / (4 * KP), y = x % (4 * KP), c = y >> 1, k = c % KP, half = c / KP;
-        return base[(size_t)s * pitch + gthr * (2 * KP) + (k >> 1) * 4 + (k & 1) * 2 + half];
+    // offset of diagonal x (band-relative) inside a row
+    __device__ __forceinline__ int col(int x) const {
+        const int y = x & ((4 << kp_log2) - 1), c = y >> 1;
+        const int k = c & ((1 << kp_log2) - 1), half = c >> kp_log2;
+        return ((x >> (2 + kp_log2)) << (1 + kp_log2)) + (k >> 1) * 4 + (k & 1) * 2 + half;
     }
-    __device__ __forceinline__ int qbase(int i) const {       // oriented query base, 1-based
-        unsigned p = (unsigned)(i - 1);
-        if (rc) { p = (unsigned)(m - i); }
-        const uint32_t w = __ldg(seqs32 + q_word + (p >> 4));
-        const int c = (w >> ((p & 15u) * 2u)) & 3;
-        return rc ? 3 - c : c;
+    // address of the stored byte of cell (i, j) (callers make sure the cell is real and inside the band)
+    __device__ __forceinline__ const uint8_t* addr(int i, int j) const {
+        return base + (ptrdiff_t)((i + j) - r_begin) * pitch + col((j - i) - band_lo);
     }
-    __device__ __forceinline__ int tbase(int j) const {
-        const unsigned p = (unsigned)(j - 1);
-        return (__ldg(seqs32 + t_word + (p >> 4)) >> ((p & 15u) * 2u)) & 3;
+    // bases at 1-based positions p, p+1, ..., base t in bits 2t (positions beyond len: unspecified)
+    __device__ __forceinline__ uint32_t window_asc(uint64_t word0, int len, int p) const {
+        const int p0 = max(p - 1, 0);
+        const int last = (len - 1) >> 4;
+        const uint32_t w0 = __ldg(seqs32 + word0 + min(p0 >> 4, last));
+        const uint32_t w1 = __ldg(seqs32 + word0 + min((p0 >> 4) + 1, last));
+        return __funnelshift_r(w0, w1, (p0 & 15) * 2);
     }
+    // bases at 1-based positions p, p-1, ..., p-n+1: base of cell k (position p-k) in bits 2k; n <= 16
+    __device__ __forceinline__ uint32_t window_desc(uint64_t word0, int len, int p, int n) const {
+        const int start = max(p - n + 1, 1);
+        const uint32_t asc = window_asc(word0, len, start);
+        uint32_t r = __brev(asc);                                   // group t -> bits 30-2t, bits swapped inside
+        r = ((r & 0x55555555u) << 1) | ((r >> 1) & 0x55555555u);    // undo the swap inside each 2-bit group
+        return r >> (30 - 2 * (p - start));
+    }
+    // bases of cells 0..n-1 of a diagonal run that starts at oriented query position i (cell k = i - k)
+    __device__ __forceinline__ uint32_t qwindow(int i, int n) const {
+        if (!rc) return window_desc(q_word, m, i, n);
+        return ~window_asc(q_word, m, m + 1 - i);                   // oriented P = complement of original m+1-P
+    }
+    __device__ __forceinline__ uint32_t twindow(int j, int n) const { return window_desc(t_word, this->n, j, n); }
 };
 
 __device__ __forceinline__ int gap_cost2(int o1, int e1, int o2, int e2, int two, int k) {
@@ -338,221 +354,215 @@ __device__ __forceinline__ int gap_cost2(int o1, int e1, int o2, int e2, int two
 
 __device__ __forceinline__ int sext8(uint32_t x) { return (int)(int8_t)(x & 0xFFu); }
 
-template <int KP>
-__global__ void __launch_bounds__(128)
+// One THREAD per pair, 32 independent walks per warp. A walk is a chain of dependent byte loads, so what
+// matters is the number of memory round trips and keeping the 32 lanes on ONE instruction stream:
+//   * a round = every lane issues all its loads (the diagonal/left/up predecessor bytes of the next S
+//     cells along its current diagonal, or — while it searches a gap longer than one — the next NSCAN
+//     cells of its row and column), then the loaded cells are processed by straight-line predicated
+//     code without data-dependent branches;
+//   * the Z-trim start (lowest H of the walk, §3.5) is only tracked as a position; the rare walk that is
+//     actually cut is replayed up to that position (same deterministic path) to rebuild CIGAR and counts.
+__global__ void __launch_bounds__(64)
 svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ tb,
               const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= n_tasks) return;
-    const Task tk = tasks[wid];
-    if (((tk.flags & TASK_KP8) != 0) != (KP == 8)) return;     // the other instantiation handles this pair
-    if (tk.flags & TASK_INVALID) {
-        if (lane == 0) {
-            svp_result bad;
-            memset(&bad, 0, sizeof(bad));
-            bad.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_SCORE_OVF : SVP_ST_BAD_PAIR;
-            bad.cigar_off = tk.cigar_off;
-            results[tk.pair_index] = bad;
-        }
-        return;
-    }
-    TbView<KP> v;
-    v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
-    v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
-    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
-    const int d_hi = tk.band_lo + tk.band_w - 1;
-
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_tasks) return;
+    const Task tk = tasks[tid];
     svp_result res;
     res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
     res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
     res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
+    if (tk.flags & TASK_INVALID) {
+        res.cells = 0;
+        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_SCORE_OVF : SVP_ST_BAD_PAIR;
+        results[tk.pair_index] = res;
+        return;
+    }
+    const int KP = (tk.flags & TASK_KP8) ? 8 : 4;
+    TbView v;
+    v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
+    v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
+    v.kp_log2 = (KP == 8) ? 3 : 2;
+    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    const int d_hi = tk.band_lo + tk.band_w - 1;
 
     // ---- 1. end cell: maximum over the per-thread-half records, earliest iteration ------------
     const int n_ent = (tk.band_w / (4 * KP)) * 2;
     int M = 0; uint32_t blk = 0xFFFFFFFFu;
-    for (int e = lane; e < n_ent; e += 32) {
-        const uint2 b = bests[tk.best_off + e];
+    for (int e = 0; e < n_ent; ++e) {
+        const uint2 b = __ldg(bests + tk.best_off + e);
         const int val = (int)(int16_t)b.x;
         if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
     }
-    #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const int M2 = __shfl_xor_sync(0xffffffffu, M, o);
-        const uint32_t b2 = __shfl_xor_sync(0xffffffffu, blk, o);
-        if (M2 > M || (M2 == M && b2 < blk)) { M = M2; blk = b2; }
-    }
     if (M <= 0) {
         res.status = SVP_ST_NOHIT;
-        if (lane == 0) results[tk.pair_index] = res;
+        results[tk.pair_index] = res;
         return;
     }
     if (M >= 32767 - cs.s_match) res.status |= SVP_ST_SCORE_OVF;
-    // all (thread, half) regions that reached M in iteration blk: rebuild the 2KP x 2KP block
+    // every (thread, half) block that reached M in iteration blk: rebuild its 2KP x 2KP cells from the low bytes
     int end_s = 0x7FFFFFFF, end_x = -1;
-    for (int e0 = 0; e0 < n_ent; e0 += 32) {
-        const int e = e0 + lane;
-        bool hit = false;
-        if (e < n_ent) { const uint2 b = bests[tk.best_off + e]; hit = ((int)(int16_t)b.x == M) && (b.y == blk); }
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask) {
-            const int src = __ffs(mask) - 1; mask &= mask - 1;
-            const int ee = e0 + src;
-            const int xbase = (ee >> 1) * 4 * KP + (ee & 1) * 2 * KP;     // first diagonal (band-relative) of the half
-            const int s0 = (int)blk * 2 * KP;
-            // cells idx = 0 .. 2*KP*KP-1: step s0 + idx/KP, diagonal xbase + 2*(idx%KP) + (step odd)
-            constexpr int NC = 2 * KP * KP;
-            int rel_prev_row0 = 0; uint32_t b_prev_row0 = 0;
-            int rel = 0; uint32_t bprev = 0;
-            int relmax = -(1 << 30);
-            int cand_s = 0x7FFFFFFF, cand_x = -1;
-            // sequential chain, executed uniformly by all lanes (bytes fetched 32 at a time)
-            for (int c0 = 0; c0 < NC; c0 += 32) {
-                const int idx = c0 + lane;
-                uint32_t mine = 0;
-                if (idx < NC) {
-                    const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
-                    // stored for every computed cell, virtual ones included: read the raw byte
-                    const int gthr = x / (4 * KP), y = x % (4 * KP), c = y >> 1, k = c % KP, half = c / KP;
-                    mine = v.base[(size_t)s * v.pitch + gthr * (2 * KP) + (k >> 1) * 4 + (k & 1) * 2 + half];
-                }
-                const int lim = min(32, NC - c0);
-                for (int l = 0; l < lim; ++l) {
-                    const uint32_t b = __shfl_sync(0xffffffffu, mine, l);
-                    const int id = c0 + l;
-                    if (id == 0) { rel = 0; }
-                    else if (id % KP == 0) { rel = rel_prev_row0 + sext8(b - b_prev_row0); }
-                    else { rel = rel + sext8(b - bprev); }
-                    if (id % KP == 0) { rel_prev_row0 = rel; b_prev_row0 = b; }
-                    bprev = b;
-                    const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
-                    if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
-                    else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
-                }
-            }
-            if (cand_s < end_s || (cand_s == end_s && cand_x > end_x)) { end_s = cand_s; end_x = cand_x; }
+    for (int e = 0; e < n_ent; ++e) {
+        const uint2 b = __ldg(bests + tk.best_off + e);
+        if ((int)(int16_t)b.x != M || b.y != blk) continue;
+        const int xbase = (e >> 1) * 4 * KP + (e & 1) * 2 * KP;      // first diagonal (band-relative) of the half
+        const int s0 = (int)blk * 2 * KP;
+        // cells id = 0 .. 2*KP*KP-1: step s0 + id/KP, diagonal xbase + 2*(id%KP) + (step odd); chained by neighbours
+        int rel = 0, rel_row0 = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
+        uint32_t bprev = 0, b_row0 = 0;
+        for (int id = 0; id < 2 * KP * KP; ++id) {
+            const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
+            const uint32_t bb = v.base[(size_t)s * v.pitch + v.col(x)];
+            if (id == 0) rel = 0;
+            else if (id % KP == 0) rel = rel_row0 + sext8(bb - b_row0);
+            else rel = rel + sext8(bb - bprev);
+            if (id % KP == 0) { rel_row0 = rel; b_row0 = bb; }
+            bprev = bb;
+            if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
+            else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
         }
+        if (cand_s < end_s || (cand_s == end_s && cand_x > end_x)) { end_s = cand_s; end_x = cand_x; }
     }
-    int i, j;
-    {
-        const int r = tk.r_begin + end_s, d = tk.band_lo + end_x;
-        i = (r - d) / 2; j = (r + d) / 2;
-    }
-    const int best_i = i, best_j = j;
+    const int best_i = ((tk.r_begin + end_s) - (tk.band_lo + end_x)) / 2;
+    const int best_j = ((tk.r_begin + end_s) + (tk.band_lo + end_x)) / 2;
 
     // ---- 2. walk back --------------------------------------------------------------------------
-    int H = M;
+    constexpr int S = 8, NSCAN = 6;
     uint32_t* slot = cigar + tk.cigar_off;
-    int wpos = (int)tk.cigar_cap;                    // runs are written right-aligned, backwards
-    uint32_t cur_op = 0, cur_len = 0; bool ovf = false;
-    uint32_t n_match = 0, n_mis = 0, n_io = 0, n_ib = 0, n_do = 0, n_db = 0;
-    // snapshot at the lowest H of the walk (Z-trim, §3.5)
-    int low = M + 1, low_i = i, low_j = j, low_wpos = wpos; uint32_t low_op = 0, low_len = 0; bool low_ovf = false;
-    uint32_t l_match = 0, l_mis = 0, l_io = 0, l_ib = 0, l_do = 0, l_db = 0;
+    const ptrdiff_t two_rows = 2 * (ptrdiff_t)v.pitch;
+    const int cost1 = gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, 1);
+    const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
 
-#define SVP_PUSH() do { if (cur_len) { if (wpos > 0) { --wpos; if (lane == 0) slot[wpos] = (cur_len << 4) | cur_op; } else ovf = true; } } while (0)
-#define SVP_EMIT(op, len) do { if (cur_len && cur_op == (op)) cur_len += (len); else { SVP_PUSH(); cur_op = (op); cur_len = (len); } } while (0)
-#define SVP_SNAP(hv) do { low = (hv); low_i = i; low_j = j; low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf; \
-        l_match = n_match; l_mis = n_mis; l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db; } while (0)
+    int i, j, H, wpos, low, low_i, low_j, mrun, scan_k, Hrow, Hcol;
+    uint32_t brow, bcol, n_match, n_mis, n_io, n_ib, n_do, n_db;
+    bool ovf, bad = false;
+    int stop_i = -1, stop_j = -1;            // replay target (cut walk): stop when the walk reaches this cell
+    bool cut = false; int cut_low = 0;
 
-    bool done = false;
-    while (!done) {
-        // ---- diagonal run: lane l looks at the cell (i-l, j-l) and its diagonal predecessor ----
-        const int ci = i - lane, cj = j - lane;
-        uint32_t bp = 0; int qc = 4, tc = 5;
-        if (ci >= 1 && cj >= 1) {
-            bp = v.lb(ci - 1, cj - 1);
-            qc = v.qbase(ci); tc = v.tbase(cj);
-        }
-        int l = 0;
-        bool gap = false;
-        for (; l < 32; ++l) {
-            // current cell (i, j) with exact H
-            if (H < low) SVP_SNAP(H);
-            if (H == 0 || i < 1 || j < 1) { done = true; break; }
-            if (cs.zdrop > 0) {
-                int dd = (j - i) - (low_j - low_i); dd = dd < 0 ? -dd : dd;
-                if (H - low > cs.zdrop + cs.zdrop_ext * dd) { done = true; break; }
+#define SVP_PUSH(op, len) do { if (wpos > 0) { --wpos; slot[wpos] = ((uint32_t)(len) << 4) | (op); } else ovf = true; } while (0)
+
+    for (int pass = 0; pass < 2; ++pass) {
+        i = best_i; j = best_j; H = M; wpos = (int)tk.cigar_cap; ovf = false;
+        low = M + 1; low_i = i; low_j = j; mrun = 0; scan_k = 0; Hrow = Hcol = 0; brow = bcol = 0;
+        n_match = n_mis = n_io = n_ib = n_do = n_db = 0;
+        bool done = false;
+        while (!done) {
+            const int d = j - i;
+            const bool in_scan = scan_k != 0;
+            // ---------------- loads of the round, all issued before any is used -----------------
+            const bool del_band = (d - 1 >= tk.band_lo), ins_band = (d + 1 <= d_hi);
+            const uint8_t* pd = v.addr(i - 1, j - 1);            // diagonal predecessor of cell 0 (stride: 2 rows per cell)
+            const uint8_t* pl = v.addr(i, j - 1);                // left neighbour of cell 0
+            const uint8_t* pu = v.addr(i - 1, j);                // up neighbour of cell 0
+            uint32_t bd[S], bl[S], bu[S];
+            #pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const bool in_q = (i - k - 1 >= 1), in_t = (j - k - 1 >= 1);
+                bd[k] = (!in_scan && in_q && in_t) ? (uint32_t)*(pd - k * two_rows) : 0u;
+                bl[k] = (!in_scan && i - k >= 1 && in_t && del_band) ? (uint32_t)*(pl - k * two_rows) : 0u;
+                bu[k] = (!in_scan && in_q && j - k >= 1 && ins_band) ? (uint32_t)*(pu - k * two_rows) : 0u;
             }
-            const uint32_t b = __shfl_sync(0xffffffffu, bp, l);
-            const int q1 = __shfl_sync(0xffffffffu, qc, l), t1 = __shfl_sync(0xffffffffu, tc, l);
-            const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(b - (uint32_t)H) : 0;
-            const int sc = (q1 == t1) ? cs.s_match : cs.s_mismatch;
-            if (H == Hd + sc) {
-                SVP_EMIT(SVP_CIGAR_M, 1u);
-                if (q1 == t1) ++n_match; else ++n_mis;
-                --i; --j; H = Hd;
-            } else { gap = true; break; }
-        }
-        if (done || !gap) continue;
-        // ---- gap: find the smallest k with H == H(i, j-k) - del(k), else H == H(i-k, j) - ins(k) ----
-        const int d = j - i;
-        int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
-        bool found = false;
-        for (int k0 = 0; !found; k0 += 32) {
-            const int k = k0 + lane + 1;
-            const bool del_ok_l = (j - k >= 1) && (d - k >= tk.band_lo);
-            const bool ins_ok_l = (i - k >= 1) && (d + k <= d_hi);
-            const uint32_t bd = del_ok_l ? v.lb(i, j - k) : 0;
-            const uint32_t bi = ins_ok_l ? v.lb(i - k, j) : 0;
-            bool any = false;
-            for (int l2 = 0; l2 < 32; ++l2) {
-                const int kk = k0 + l2 + 1;
-                const bool del_ok = (j - kk >= 1) && (d - kk >= tk.band_lo);
-                const bool ins_ok = (i - kk >= 1) && (d + kk <= d_hi);
-                if (!del_ok && !ins_ok) break;
-                any = true;
-                if (del_ok) {
-                    const uint32_t b = __shfl_sync(0xffffffffu, bd, l2);
-                    Hrow += sext8(b - brow); brow = b;
-                    if (H == Hrow - gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, kk)) {
-                        SVP_EMIT(SVP_CIGAR_D, (uint32_t)kk); ++n_do; n_db += kk; j -= kk; H = Hrow; found = true; break;
-                    }
-                }
-                if (ins_ok) {
-                    const uint32_t b = __shfl_sync(0xffffffffu, bi, l2);
-                    Hcol += sext8(b - bcol); bcol = b;
-                    if (H == Hcol - gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, kk)) {
-                        SVP_EMIT(SVP_CIGAR_I, (uint32_t)kk); ++n_io; n_ib += kk; i -= kk; H = Hcol; found = true; break;
+            uint32_t br[NSCAN], bc[NSCAN]; bool okr[NSCAN], okc[NSCAN];
+            #pragma unroll
+            for (int t = 0; t < NSCAN; ++t) {
+                const int k = scan_k + t;
+                okr[t] = in_scan && (j - k >= 1) && (d - k >= tk.band_lo);
+                okc[t] = in_scan && (i - k >= 1) && (d + k <= d_hi);
+                br[t] = okr[t] ? (uint32_t)*v.addr(i, j - k) : 0u;
+                bc[t] = okc[t] ? (uint32_t)*v.addr(i - k, j) : 0u;
+            }
+            const uint32_t diffwin = v.qwindow(i, S) ^ v.twindow(j, S);      // 2 bits per cell, 0 = same base
+            if (!in_scan && i - S - 1 >= 1 && j - S - 1 >= 1) {              // L2 prefetch for the next round
+                #pragma unroll
+                for (int k = S; k < 2 * S; k += 2) {
+                    const uint8_t* pk = pd - k * two_rows;
+                    if (pk - 2 * two_rows >= v.base) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk + v.pitch));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows + v.pitch));
                     }
                 }
             }
-            if (!found && !any) break;
-            if (!found) {
-                const int kk_next = k0 + 33;
-                if (!((j - kk_next >= 1) && (d - kk_next >= tk.band_lo)) && !((i - kk_next >= 1) && (d + kk_next <= d_hi))) break;
+            // ---------------- gap scan (lanes in the scan state) ------------------------------------
+            if (in_scan) {
+                bool found = false, dead = false;
+                #pragma unroll
+                for (int t = 0; t < NSCAN; ++t) {
+                    const int k = scan_k + t;
+                    const int cost = gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, k);
+                    if (!found && !dead) {
+                        if (!okr[t] && !okc[t]) dead = true;
+                        if (okr[t]) {
+                            Hrow += sext8(br[t] - brow); brow = br[t];
+                            if (H == Hrow - cost) { SVP_PUSH(SVP_CIGAR_D, k); ++n_do; n_db += k; j -= k; H = Hrow; found = true; }
+                        }
+                        if (!found && okc[t]) {
+                            Hcol += sext8(bc[t] - bcol); bcol = bc[t];
+                            if (H == Hcol - cost) { SVP_PUSH(SVP_CIGAR_I, k); ++n_io; n_ib += k; i -= k; H = Hcol; found = true; }
+                        }
+                    }
+                }
+                if (found) scan_k = 0;
+                else if (dead) { bad = true; done = true; }
+                else scan_k += NSCAN;
+                continue;
+            }
+            // ---------------- H state: up to S cells along the diagonal, predicated -----------------
+            bool alive = true, gap_here = false;
+            uint32_t gl = 0, gu = 0;
+            #pragma unroll
+            for (int k = 0; k < S; ++k) {
+                // stop conditions of the current cell
+                int dd = d - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+                const bool stop = alive && (H == 0 || i < 1 || j < 1 || (i == stop_i && j == stop_j) ||
+                                            (pass == 0 && H >= low && H - low > zdrop + cs.zdrop_ext * dd));
+                if (stop) { if (pass == 0 && H != 0 && i >= 1 && j >= 1) cut = true; done = true; alive = false; }
+                if (alive && H < low) { low = H; low_i = i; low_j = j; }
+                const bool same = ((diffwin >> (2 * k)) & 3u) == 0u;
+                const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(bd[k] - (uint32_t)H) : 0;
+                const bool isdiag = alive && (H == Hd + (same ? cs.s_match : cs.s_mismatch));
+                if (alive && !isdiag) { gap_here = true; gl = bl[k]; gu = bu[k]; alive = false; }
+                if (isdiag) { ++mrun; n_match += same ? 1u : 0u; n_mis += same ? 0u : 1u; --i; --j; H = Hd; }
+            }
+            if (done) continue;
+            if (gap_here) {
+                // the M run since the previous gap, then a gap of length 1 (deletion first) or the scan state
+                if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
+                const bool del_ok = (j - 1 >= 1) && del_band, ins_ok = (i - 1 >= 1) && ins_band;
+                const int Hl = H + sext8(gl - (uint32_t)H), Hu = H + sext8(gu - (uint32_t)H);
+                if (!del_ok && !ins_ok) { bad = true; done = true; }
+                else if (del_ok && H == Hl - cost1) { SVP_PUSH(SVP_CIGAR_D, 1); ++n_do; ++n_db; --j; H = Hl; }
+                else if (ins_ok && H == Hu - cost1) { SVP_PUSH(SVP_CIGAR_I, 1); ++n_io; ++n_ib; --i; H = Hu; }
+                else { scan_k = 2; Hrow = Hl; brow = gl; Hcol = Hu; bcol = gu; }
             }
         }
-        if (!found) { res.status |= SVP_ST_SCORE_OVF; done = true; }
+        if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
+        if (!cut || pass == 1) break;
+        stop_i = low_i; stop_j = low_j; cut_low = low;   // replay the (deterministic) walk up to the lowest point
     }
-    // rewind to the snapshot
-    i = low_i; j = low_j; wpos = low_wpos; cur_op = low_op; cur_len = low_len; ovf = low_ovf;
-    SVP_PUSH();
-    res.score = M - low;
-    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
-    res.n_match = l_match; res.n_mismatch = l_mis; res.n_ins_ops = l_io; res.n_ins_bp = l_ib; res.n_del_ops = l_do; res.n_del_bp = l_db;
 #undef SVP_PUSH
-#undef SVP_EMIT
-#undef SVP_SNAP
-    __syncwarp();
-    if (lane == 0) {
-        if (ovf) {
-            res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
-        } else {
-            res.cigar_len = tk.cigar_cap - (uint32_t)wpos;
-            res.cigar_off = tk.cigar_off + (uint32_t)wpos;
-            double dist = 0.0;
-            for (uint32_t a = (uint32_t)wpos; a < tk.cigar_cap; ++a) {
-                const uint32_t w = slot[a];
-                const uint32_t op = w & 15u, len = w >> 4;
-                if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
-                    const double s = (double)len;
-                    dist += (1.0 - exp(-pow(s / 30.0, 1.5))) * s;
-                }
+    if (bad) res.status |= SVP_ST_SCORE_OVF;
+    res.score = M - (cut ? cut_low : 0);
+    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
+    res.n_match = n_match; res.n_mismatch = n_mis; res.n_ins_ops = n_io; res.n_ins_bp = n_ib; res.n_del_ops = n_do; res.n_del_bp = n_db;
+    if (ovf) {
+        res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
+    } else {
+        res.cigar_len = tk.cigar_cap - (uint32_t)wpos;
+        res.cigar_off = tk.cigar_off + (uint32_t)wpos;
+        double dist = 0.0;
+        for (uint32_t a = (uint32_t)wpos; a < tk.cigar_cap; ++a) {
+            const uint32_t w = slot[a];
+            const uint32_t op = w & 15u, len = w >> 4;
+            if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
+                const double sz = (double)len;
+                dist += (1.0 - exp(-pow(sz / 30.0, 1.5))) * sz;
             }
-            res.sv_dist = dist;
         }
-        results[tk.pair_index] = res;
+        res.sv_dist = dist;
     }
+    results[tk.pair_index] = res;
 }
 
 }  // namespace svp

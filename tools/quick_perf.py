@@ -27,7 +27,7 @@ print(f"gen {time.time()-t0:.1f}s pairs={len(pairs)} mean band={pairs['band_w'].
 al = Aligner(0, tb_bytes=int(sys.argv[3]) << 30 if len(sys.argv) > 3 else 0)
 for rep in range(3):
     t0 = time.time()
-    res, cig = al.align_batch(packed, off, lens, pairs, pos)
+    res, cig = al.align_batch_nocopy(packed, off, lens, pairs, pos)
     dt = time.time() - t0
     st = al.stats()
     print(f"rep{rep}: wall {dt*1e3:.1f} ms  fwd {st['fwd_ms']:.1f} ms tb {st['tb_ms']:.1f} ms total {st['total_ms']:.1f} ms waves {st['waves']} "
