@@ -1,0 +1,75 @@
+"""The pieces of svirlpool.localassembly.consensus that consume alignments on the hot path, with the
+aligner calls replaced by the CUDA engine (/root/reference/src/svirlpool/localassembly/consensus.py):
+
+    parse_ReadAlignmentSignals_from_alignment   :2440-2464
+    pairwise_alignment_lengths                  :1276-1305
+    ava_similarity                              :1362-1467   (AVA alignment + consensus_lib pipeline of
+                                                              consensus_while_clustering, steps 1-4)
+    align_reads_to_consensus                    :851-857 / :2089-2096 (map-ont of reads vs consensus)
+
+Clustering, consensus assembly (lamassemble/racon) and padding stay with the reference's host code: they
+are outside the alignment path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import alignments_to_rafs, ava, consensus_lib
+from .datatypes import AlignedRecord, ReadAlignmentSignals
+
+
+def parse_ReadAlignmentSignals_from_alignment(samplename: str, alignment, min_signal_size: int, min_bnd_size: int
+                                              ) -> ReadAlignmentSignals:
+    """Signals of one alignment with read coordinates from get_start_end() (leading clip on forward, trailing
+    clip on reverse), sorted by reference position."""
+    ref_start, ref_end, read_start, read_end = alignments_to_rafs.get_start_end(alignment)
+    signals = alignments_to_rafs.parse_SVsignals_from_alignment(
+        alignment=alignment, ref_start=ref_start, ref_end=ref_end, read_start=read_start, read_end=read_end,
+        min_signal_size=min_signal_size, min_bnd_size=min_bnd_size)
+    return ReadAlignmentSignals(samplename=samplename, read_name=str(alignment.query_name),
+                                reference_name=str(alignment.reference_name),
+                                alignment_forward=bool(not alignment.is_reverse), SV_signals=sorted(signals))
+
+
+def pairwise_alignment_lengths(ava_alignments: list[AlignedRecord], read_names: list[str]) -> np.ndarray:
+    """Symmetric (n, n) matrix of query_alignment_length per read pair (0 without alignment); when a pair
+    has several alignments the last one in input order wins."""
+    index = {name: k for k, name in enumerate(read_names)}
+    out = np.zeros((len(read_names), len(read_names)), dtype=int)
+    for aln in ava_alignments:
+        if aln.is_unmapped or aln.query_name is None or aln.reference_name is None:
+            continue
+        a, b = index.get(aln.query_name), index.get(aln.reference_name)
+        if a is None or b is None:
+            continue
+        out[a, b] = out[b, a] = aln.query_alignment_length or 0
+    return out
+
+
+def ava_similarity(engine, reads: dict[str, str], strands: dict[str, str] | None = None, densities_weight: float = 0.0,
+                   min_signal_size: int = 12, min_bnd_size: int = 100, slack: int = 300, granule: int = 512
+                   ) -> tuple[np.ndarray, list[str], list[AlignedRecord]]:
+    """All-vs-all alignment of one container's reads on the GPU followed by the reference's similarity
+    pipeline (signals -> size densities -> importance densities -> directed signals -> similarity matrix),
+    i.e. steps 1-4 of consensus_while_clustering. Returns (similarity, read names, alignment records).
+    densities_weight defaults to 0.0 like the reference's CLI (consensus.py:3565-3572)."""
+    records = ava.ava_align(engine, reads, strands=strands, slack=slack, granule=granule)
+    names = list(reads)
+    lengths = {n: len(s) for n, s in reads.items()}
+    ava_signals = consensus_lib.parse_sv_signals_from_ava_alignments(records, min_signal_size, min_bnd_size)
+    size_dens = consensus_lib.sv_size_densities_from_ava_signals(ava_signals)
+    dens = consensus_lib.importance_densities_from_ava_signals(ava_signals=ava_signals, size_densities=size_dens)
+    directed = consensus_lib.parse_directed_signals_from_ava(records, min_signal_size, min_bnd_size)
+    sim, order = consensus_lib.pairwise_similarity_matrix(directed_signals=directed, densities=dens, read_lengths=lengths,
+                                                          all_read_names=names, densities_weight=densities_weight)
+    return sim, order, records
+
+
+def align_reads_to_consensus(engine, samplename: str, reads: dict[str, str], consensus_name: str, consensus_seq: str,
+                             min_signal_size: int = 8, min_bnd_size: int = 100
+                             ) -> tuple[list[AlignedRecord], list[ReadAlignmentSignals]]:
+    """Reads of a cluster vs their consensus (`-x map-ont --secondary=no`, consensus.py:851-857) and the
+    cut_read_alignment_signals derived from the records (min indel 8 / BND 100, :1616-1617)."""
+    records = ava.map_queries(engine, reads, consensus_name, consensus_seq)
+    signals = [parse_ReadAlignmentSignals_from_alignment(samplename, r, min_signal_size, min_bnd_size) for r in records]
+    return records, signals

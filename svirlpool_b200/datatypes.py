@@ -56,6 +56,21 @@ class SVsignal:
 
 
 @dataclass
+class ReadAlignmentSignals:
+    """SV signals of one read alignment (datatypes.py:195-203); SV_signals sorted by reference position."""
+
+    samplename: str
+    read_name: str
+    reference_name: str
+    alignment_forward: bool
+    SV_signals: list = field(default_factory=list)
+
+    def unstructure(self) -> dict:
+        return {"samplename": self.samplename, "read_name": self.read_name, "reference_name": self.reference_name,
+                "alignment_forward": self.alignment_forward, "SV_signals": [s.unstructure() for s in self.SV_signals]}
+
+
+@dataclass
 class AlignedRecord:
     """Duck-typed pysam.AlignedSegment: what `svp_align_batch` results become on the host."""
 

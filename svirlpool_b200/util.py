@@ -52,3 +52,45 @@ def read_fasta(path) -> dict[str, str]:
             elif name is not None:
                 seqs[name].append(line)
     return {k: "".join(v) for k, v in seqs.items()}
+
+
+def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", threads: int = 3, aln_args: str = "",
+                             logfile=None, timeout: float | None = None, engine=None) -> None:
+    """Drop-in for svirlpool.util.util.align_reads_with_minimap (util/util.py:162-238): FASTA path(s) in,
+    coordinate-sorted BAM out, computed by the CUDA aligner instead of `minimap2 | samtools sort`.
+
+    tech "ava-ont": all-vs-all of the reads (`reference` and `reads` are the same FASTA at the reference's
+    AVA call site, consensus.py:1378-1386); otherwise every read is mapped to every sequence of `reference`
+    (primary + supplementary records, `--secondary=no`). `threads`, `aln_args`, `logfile` and `timeout` are
+    accepted for signature compatibility (seeding options have no counterpart; the call is bounded by the
+    kernels, not by a child process). Failures raise aligner.AlignerError, a subprocess.CalledProcessError,
+    which the reference's callers already catch. `engine`: an Aligner to reuse; default one per call.
+    A `.bai` index is not written."""
+    from . import ava, sam
+    from .aligner import Aligner
+    paths = reads if isinstance(reads, list) else [reads]
+    queries: dict[str, str] = {}
+    for p in paths:
+        queries.update(read_fasta(p))
+    refs = read_fasta(reference)
+    own = engine is None
+    if own:
+        engine = Aligner(preset="ava-ont" if tech == "ava-ont" else "map-ont")
+    try:
+        if tech == "ava-ont":
+            records = ava.ava_align(engine, queries)
+            lengths = {n: len(s) for n, s in queries.items()}
+        else:
+            records = [r for name, seq in refs.items() for r in ava.map_queries(engine, queries, name, seq)]
+            lengths = {n: len(s) for n, s in refs.items()}
+        for r in records:
+            seq = queries[r.query_name]
+            r.query_sequence = reverse_complement(seq) if r.is_reverse else seq
+            if r.is_supplementary:                      # hard-clipped records carry only the aligned part
+                a = r.cigartuples[0][1] if r.cigartuples[0][0] == 5 else 0
+                r.query_sequence = r.query_sequence[a:a + r.query_alignment_length]
+        cmd = f"svirlpool_b200 -x {tech} {aln_args}".strip()
+        sam.write_bam(bamout, sam.sort_records(records, lengths), lengths, command=cmd)
+    finally:
+        if own:
+            engine.close()

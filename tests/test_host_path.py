@@ -1,0 +1,195 @@
+"""CIGAR consumers, batching, SAM/BAM seam, scheduler, synthetic data — everything on the host side
+of the path that needs no GPU. Expected values restate the reference's own tests where they exist."""
+import numpy as np
+import pytest
+
+from svirlpool_b200 import alignments_to_rafs, ava, consensus, consensus_lib, crs_to_batches, sam, scheduler, synth, util
+from svirlpool_b200.datatypes import AlignedRecord, SVsignal, cigar_from_string
+
+
+def rec(cigar, ref_start, flag=0, name="read-0", ref="ref", seq=None):
+    return AlignedRecord(query_name=name, reference_name=ref, reference_start=ref_start, cigartuples=cigar_from_string(cigar),
+                         flag=flag, query_sequence=seq)
+
+
+# ---- dummy inversion fixture: tests/test_alignments_to_rafs.py:46-155 ---------------------------
+INVERSION = [("2000M4000H", 0, 2048), ("2000H2000M2000H", 2000, 2064), ("4000S2000M", 4000, 0)]
+
+
+def test_get_start_end_inversion_records():
+    got = [alignments_to_rafs.get_start_end(rec(c, p, f)) for c, p, f in INVERSION]
+    assert got == [(0, 2000, 0, 2000), (2000, 4000, 2000, 4000), (4000, 6000, 4000, 6000)]
+
+
+def test_read_alignment_signals_inversion_records():
+    got = [consensus.parse_ReadAlignmentSignals_from_alignment("test", rec(c, p, f), 10, 1000) for c, p, f in INVERSION]
+    assert [g.alignment_forward for g in got] == [True, False, True]
+    assert got[0].SV_signals == [SVsignal(2000, 2000, 2000, 2000, 4000, 4)]
+    assert got[1].SV_signals == [SVsignal(2000, 2000, 4000, 4000, 2000, 3), SVsignal(4000, 4000, 2000, 2000, 2000, 4)]
+    assert got[2].SV_signals == [SVsignal(4000, 4000, 4000, 4000, 4000, 3)]
+    assert got[0].read_name == "read-0" and got[0].reference_name == "ref" and got[0].samplename == "test"
+
+
+def test_inversion_records_from_golden_through_oracle(golden, oracle):
+    """End to end on the CPU: oracle alignment of the fixture read -> same signals as the frozen records."""
+    case = next(c for c in golden["cases"] if c["name"] == "dummy_inversion")
+    recs = ava.map_queries(oracle, case["reads"], "ref", case["reference"])
+    sig = sorted((s.ref_start, s.read_start, s.size, s.sv_type) for r in recs
+                 for s in consensus.parse_ReadAlignmentSignals_from_alignment("t", r, 10, 1000).SV_signals)
+    assert sig == [(2000, 2000, 4000, 4), (2000, 4000, 2000, 3), (4000, 2000, 2000, 4), (4000, 4000, 4000, 3)]
+
+
+# ---- get_starts_ends / indels --------------------------------------------------------------------
+def test_starts_ends_forward_and_reverse():
+    t, x = np.array([4, 0, 1, 0, 2, 0, 5]), np.array([10, 50, 20, 30, 15, 40, 7])
+    rs, re_, fs, fe = util.get_starts_ends(t, x, reference_start=100, is_reverse=False)
+    assert rs.tolist() == [10, 10, 60, 80, 110, 110, 150] and re_.tolist() == [10, 60, 80, 110, 110, 150, 150]
+    assert fs.tolist() == [100, 100, 150, 150, 180, 195, 235] and fe.tolist() == [100, 150, 150, 180, 195, 235, 235]
+    rrs, rre, ffs, ffe = util.get_starts_ends(t, x, reference_start=100, is_reverse=True)
+    total = 10 + 50 + 20 + 30 + 40 + 7
+    assert rrs.tolist() == (total - re_).tolist() and rre.tolist() == (total - rs).tolist()
+    assert ffs.tolist() == fs.tolist() and ffe.tolist() == fe.tolist()
+
+
+def test_signals_order_thresholds_and_strand():
+    r = rec("150S100M20I100M5D100M30D50M12I10M120H", 1000)
+    sig = alignments_to_rafs.parse_SVsignals_from_alignment(r, r.reference_start, r.reference_end, r.query_alignment_start,
+                                                             r.query_alignment_end, min_signal_size=12, min_bnd_size=100)
+    assert [s.sv_type for s in sig] == [3, 4, 1, 0, 0]          # BNDL, BNDR, DELs, INSs
+    assert sig[0] == SVsignal(1000, 1000, 150, 150, 150, 3)
+    assert sig[1] == SVsignal(1395, 1395, 542, 542, 120, 4)
+    assert sig[2] == SVsignal(1305, 1335, 470, 470, 30, 1)
+    assert sig[3] == SVsignal(1100, 1100, 250, 270, 20, 0) and sig[4] == SVsignal(1385, 1385, 520, 532, 12, 0)
+    rev = rec("150S100M20I100M", 1000, flag=16)
+    s2 = alignments_to_rafs.parse_SVsignals_from_alignment(rev, 1000, 1200, rev.query_alignment_start, rev.query_alignment_end, 12, 100)
+    assert s2[0].sv_type == 3 and s2[0].read_start == rev.query_alignment_end       # swapped on reverse
+    assert s2[1] == SVsignal(1100, 1100, 100, 120, 20, 0)                            # mirrored into read orientation
+
+
+def test_directed_signals_use_aligned_span_as_ref_length():
+    recs = [rec("100S900M", 50, name="q", ref="t"), AlignedRecord("u", None, 0, None, flag=4)]
+    ds = consensus_lib.parse_directed_signals_from_ava(recs, 12, 100)
+    assert len(ds) == 1 and ds[0].ref_length == 900 and ds[0].query_name == "q" and ds[0].ref_name == "t"
+    pooled = consensus_lib.parse_sv_signals_from_ava_alignments(recs, 12, 100)
+    assert list(pooled) == ["t"] and pooled["t"][0].sv_type == 3
+
+
+# ---- crs_to_batches: tests/test_crs_to_batches.py ---------------------------------------------------
+def test_build_batches_rules(tmp_path):
+    b = crs_to_batches.build_batches({1: (["chr1"], 100, 200), 2: (["chr1"], 300, 400), 3: (["chr1"], 500, 600), 4: (["chr2"], 100, 200)}, 100, 10_000)
+    assert [x["crIDs"] for x in b] == [[1, 2, 3], [4]] and [x["chr"] for x in b] == ["chr1", "chr2"]
+    five = {k: (["chr1"], k * 100, k * 100 + 50) for k in range(1, 6)}
+    assert sorted(len(x["crIDs"]) for x in crs_to_batches.build_batches(five, 2, 10_000)) == [1, 2, 2]
+    span = crs_to_batches.build_batches({1: (["chr1"], 100, 200), 2: (["chr1"], 5000, 5100), 3: (["chr1"], 9000, 9100)}, 100, 5000)
+    assert sorted(tuple(x["crIDs"]) for x in span) == [(1, 2), (3,)]
+    wide = crs_to_batches.build_batches({1: (["chr1"], 100, 200), 2: (["chr1", "chr2"], 100, 200), 3: (["chr3"], 0, 100_000_000),
+                                         4: (["chr1"], 300, 400)}, 100, 1_000_000)
+    assert [x["crIDs"] for x in wide] == [[2], [3], [1, 4]] and wide[0]["chr"] == "chr1,chr2"
+    assert [x["batch_id"] for x in wide] == [0, 1, 2]
+    with pytest.raises(ValueError):
+        crs_to_batches.build_batches({}, 0, 10)
+    tsv, ids = tmp_path / "b.tsv", tmp_path / "ids.txt"
+    crs_to_batches.write_outputs(wide, tsv, ids)
+    assert tsv.read_text().splitlines()[0] == "batch_id\tchr\tstart\tend\tn_containers\tcrIDs"
+    for x in wide:
+        assert crs_to_batches._load_crIDs_from_batch_tsv(tsv, x["batch_id"]) == x["crIDs"]
+    assert ids.read_text().split() == ["0", "1", "2"]
+    with pytest.raises(ValueError):
+        crs_to_batches._load_crIDs_from_batch_tsv(tsv, 99)
+    with pytest.raises(FileNotFoundError):
+        crs_to_batches._load_crIDs_from_batch_tsv(tmp_path / "missing.tsv", 0)
+
+
+def test_container_db_roundtrip(tmp_path):
+    import json
+    import sqlite3
+    db = tmp_path / "containers.db"
+    conn = sqlite3.connect(db)
+    conn.execute("CREATE TABLE containers (crID INTEGER PRIMARY KEY, data TEXT)")
+    conn.execute("INSERT INTO containers VALUES (5, ?)", (json.dumps({"crs": [{"chr": "1", "referenceStart": 10, "referenceEnd": 90},
+                                                                            {"chr": "1", "referenceStart": 50, "referenceEnd": 400}]}),))
+    conn.execute("INSERT INTO containers VALUES (6, ?)", (json.dumps({"crs": []}),))
+    conn.commit(); conn.close()
+    out = crs_to_batches.crs_containers_to_batches(db, tmp_path / "t.tsv", tmp_path / "i.txt")
+    assert out == [{"batch_id": 0, "chr": "1", "start": 10, "end": 400, "crIDs": [5]}]
+
+
+# ---- SAM / BAM seam ---------------------------------------------------------------------------------
+def test_sam_and_bam_roundtrip(tmp_path):
+    recs = [rec("10S90M5D100M", 7, name="a", ref="t1", seq="ACGT" * 50), rec("200M", 0, flag=16, name="b", ref="t0", seq="T" * 200)]
+    recs[0].tags = {"NM": 5, "AS": 321}
+    refs = {"t0": 500, "t1": 900}
+    ordered = sam.sort_records(recs, refs)
+    assert [r.query_name for r in ordered] == ["b", "a"]
+    for writer, name in ((sam.write_sam, "x.sam"), (sam.write_bam, "x.bam")):
+        path = tmp_path / name
+        writer(path, ordered, refs)
+        back = list(sam.read_alignments(path))
+        assert [(r.query_name, r.reference_name, r.reference_start, r.cigarstring, r.flag, r.query_sequence) for r in back] == \
+               [(r.query_name, r.reference_name, r.reference_start, r.cigarstring, r.flag, r.query_sequence) for r in ordered]
+    parsed = consensus_lib.parse_directed_signals_from_ava(tmp_path / "x.bam", 5, 10)
+    assert [(d.query_name, d.ref_name, d.ref_length) for d in parsed] == [("b", "t0", 200), ("a", "t1", 195)]
+    assert parsed[1].signals[0].sv_type == 3 and parsed[1].signals[1] == SVsignal(97, 102, 100, 100, 5, 1)
+
+
+# ---- scheduler / synth ----------------------------------------------------------------------------------
+def test_band_cells_closed_form_matches_enumeration():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        m, n = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        lo, w = int(rng.integers(-45, 45)), int(rng.integers(1, 4)) * 32
+        brute = sum(1 for i in range(1, m + 1) for j in range(1, n + 1) if lo <= j - i < lo + w)
+        assert scheduler.band_cells(m, n, lo, w) == brute
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    rng = np.random.default_rng(3)
+    costs = (rng.pareto(1.3, 400) * 1000 + 10).astype(np.int64)
+    bins = scheduler.lpt_assign(costs, 8)
+    assert sorted(k for b in bins for k in b) == list(range(400))
+    assert bins == scheduler.lpt_assign(costs, 8)
+    naive = [list(range(k, 400, 8)) for k in range(8)]
+    assert scheduler.imbalance(costs, bins) <= scheduler.imbalance(costs, naive)
+    assert scheduler.imbalance(costs, bins) < 1.0 + max(costs) / (costs.sum() / 8)
+
+
+def test_synthetic_regions_are_reproducible_and_oriented():
+    a, b = synth.region_config2(7, n_reads=6, mean_len=1500, sd_len=100), synth.region_config2(7, n_reads=6, mean_len=1500, sd_len=100)
+    assert all(np.array_equal(x, y) for x, y in zip(a.reads, b.reads)) and a.strands == b.strands and a.sv_size == b.sv_size
+    assert (a.meta["length"], a.sv_size) == synth.region_config2_shape(7, mean_len=1500, sd_len=100)
+    specs = synth.region_pairs(a, granule=512)
+    assert len(specs) == 15 and all(w % 512 == 0 for *_, w, _ in specs)
+    order = sorted(range(6), key=lambda k: a.names[k])
+    assert all(a.names[q] < a.names[t] for q, t, *_ in specs) and specs[0][:2] == (order[0], order[1])
+    assert all((fl & 1) == (a.strands[q] != a.strands[t]) for q, t, _, _, fl in specs)
+    err = synth.noisy_copy(np.random.default_rng(1), np.random.default_rng(2).integers(0, 4, 20000).astype(np.uint8))
+    assert 0.97 < len(err) / 20000 < 1.03
+
+
+def test_ava_on_synthetic_region_with_oracle(oracle):
+    """Two haplotypes differing by one SV separate in the similarity matrix (CPU path: oracle engine)."""
+    reg = synth.region_config2(3, n_reads=8, mean_len=1800, sd_len=50)
+    reads = reg.read_strings()
+    sim, names, records = consensus.ava_similarity(oracle, reads, strands=dict(zip(reg.names, reg.strands)))
+    assert len(records) == 28 and names == reg.names
+    hap = np.array(reg.haplotypes)
+    same = sim[np.equal.outer(hap, hap) & ~np.eye(8, dtype=bool)]
+    diff = sim[~np.equal.outer(hap, hap)]
+    if abs(reg.sv_size) >= 50 and len(diff) and len(same):
+        assert same.mean() > diff.mean()
+    lens = consensus.pairwise_alignment_lengths(records, names)
+    assert lens.shape == (8, 8) and (lens == lens.T).all() and lens.max() > 1500
+
+
+def test_file_seam_align_reads_with_minimap(tmp_path, golden, oracle):
+    """S1 seam: FASTA in -> BAM out, consumed by the path-taking consensus_lib functions (oracle engine on CPU)."""
+    case = next(c for c in golden["cases"] if c["name"] == "simulated.with_deletion_reverse")
+    ref_fa, reads_fa, bam = tmp_path / "ref.fa", tmp_path / "reads.fa", tmp_path / "out.bam"
+    ref_fa.write_text(">ref\n" + case["reference"] + "\n")
+    reads_fa.write_text("".join(f">{n} desc\n{s}\n" for n, s in case["reads"].items()))
+    util.align_reads_with_minimap(reference=ref_fa, reads=reads_fa, bamout=bam, tech="map-ont", threads=1, engine=oracle)
+    back = list(sam.read_alignments(bam))
+    assert [(r.reference_start, r.is_reverse, r.cigarstring) for r in back] == [(0, True, "480M20D500M")]
+    assert back[0].query_sequence == util.reverse_complement(next(iter(case["reads"].values())))
+    ds = consensus_lib.parse_directed_signals_from_ava(bam, 12, 100)
+    assert ds[0].signals == [SVsignal(480, 500, 500, 500, 20, 1)]
