@@ -5,6 +5,7 @@
 // that computes returns SVP_ERR_NODEVICE.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -16,19 +17,28 @@ using namespace svp;
 
 namespace {
 
-// Two widths of the kernels: KP = 4 packed registers per state array per thread (16 diagonals per
-// thread, 512 per warp) and KP = 8 (32 per thread, 1024 per warp); a pair runs on whichever needs
-// fewer issue slots for its band (choose_kp), on 1..16 warps.
-constexpr int MAX_WARPS = 16;
-// measured/estimated warp-instructions per step of the inner loop (SASS count), used only to choose KP
-static inline int step_cost(int kp, int nwarp) { return kp == 8 ? (nwarp > 1 ? 132 : 122) : (nwarp > 1 ? 80 : 72); }
-static inline int choose_kp(uint32_t band_w) {
-    const int w4 = (int)((band_w + 511) / 512), w8 = (int)((band_w + 1023) / 1024);
-    if (w4 > MAX_WARPS) return 8;
-    return (w8 * step_cost(8, w8) < w4 * step_cost(4, w4)) ? 8 : 4;
-}
+// Kernel widths: KP packed registers per state array per thread = 4*KP diagonals per thread, 128*KP per
+// warp (KP = 4, 8, 12, 16 -> 512, 1024, 1536, 2048). A pair runs on the (KP, warps) combination that needs
+// the fewest issue slots for its band (choose_variant); single-warp CTAs need no barrier or mailbox.
 constexpr int S16_SCORE_LIMIT = 32000;
-static inline int kp_of(const Task& t) { return (t.flags & TASK_KP8) ? 8 : 4; }
+static inline int max_warps_of(int kp) { return kp <= 8 ? 16 : 8; }
+// warp-instructions per step of the inner loop (SASS counts), used only to rank variants
+static inline int step_cost(int kp, int nwarp) { return 22 + kp * 25 / 2 + (nwarp > 1 ? 10 : 0); }
+static int g_kp_mask = -1;          // tuning aid: env SVP_KP_MASK, bit (KP/4 - 1) allows that KP (default: all)
+static inline int choose_kp(uint32_t band_w) {
+    if (g_kp_mask < 0) { const char* e = getenv("SVP_KP_MASK"); g_kp_mask = e ? atoi(e) : 15; if (!(g_kp_mask & 15)) g_kp_mask = 15; }
+    int best_kp = 0; long best_cost = 0;
+    for (int kp : { 4, 8 }) {      // KP 12 / 16 single-warp variants were measured slower on B200 (150-250 registers per thread)
+        if (!(g_kp_mask & (1 << (kp / 4 - 1)))) continue;
+        if (band_w % (uint32_t)(4 * kp)) continue;
+        const int nw = (int)((band_w + 128 * kp - 1) / (128 * kp));
+        if (nw > max_warps_of(kp)) continue;
+        const long cost = (long)nw * step_cost(kp, nw);
+        if (!best_kp || cost < best_cost) { best_kp = kp; best_cost = cost; }
+    }
+    return best_kp;          // 0: band too wide for every variant
+}
+static inline int kp_of(const Task& t) { return (int)((t.flags & TASK_KP_MASK) >> TASK_KP_SHIFT); }
 static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * (2 * kp_of(t)) * (uint64_t)(t.band_w / 2); }
 static inline uint64_t best_entries_of(const Task& t) { return (uint64_t)(t.band_w / (4 * kp_of(t))) * 2; }
 
@@ -53,7 +63,8 @@ struct svp_handle {
     svp_scoring scoring{};
     Consts cs{};
     cudaStream_t stream = nullptr;              // forward kernels + copies
-    cudaStream_t stream_aux[2] = { nullptr, nullptr };   // extra forward streams: a wave's CTA-width groups run concurrently
+    cudaStream_t stream_aux[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
+                                                // wave run concurrently, and consecutive waves use different stream sets
     cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
     std::vector<cudaEvent_t> events;            // pool, grown on demand
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
@@ -148,11 +159,13 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    for (const void* fn : { (const void*)svp_fwd_kernel<4, false, true>, (const void*)svp_fwd_kernel<4, true, true>,
-                            (const void*)svp_fwd_kernel<8, false, true>, (const void*)svp_fwd_kernel<8, true, true>,
-                            (const void*)svp_fwd_kernel<4, false, false>, (const void*)svp_fwd_kernel<4, true, false>,
-                            (const void*)svp_fwd_kernel<8, false, false>, (const void*)svp_fwd_kernel<8, true, false> })
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+#define SVP_ATTR(K) \
+    cudaFuncSetAttribute(svp_fwd_kernel<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
+    cudaFuncSetAttribute(svp_fwd_kernel<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
+    cudaFuncSetAttribute(svp_fwd_kernel<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
+    cudaFuncSetAttribute(svp_fwd_kernel<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
+    SVP_ATTR(4); SVP_ATTR(8);
+#undef SVP_ATTR
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
     size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 10 * 8, (size_t)128 << 30);
@@ -170,7 +183,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     if (h->arena) cudaFree(h->arena);
     for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-    for (cudaStream_t sx : { h->stream, h->stream_aux[0], h->stream_aux[1], h->stream_tb }) if (sx) cudaStreamDestroy(sx);
+    for (cudaStream_t sx : { h->stream, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4], h->stream_tb }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
 
@@ -238,7 +251,7 @@ static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
-    bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && p.band_w <= (uint32_t)(MAX_WARPS * 1024) &&
+    bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && choose_kp(p.band_w) != 0 &&
               (size_t)p.cigar_off + p.cigar_cap <= cigar_words;
     if (ok) {
         for (uint32_t s : { p.q, p.t }) {
@@ -251,7 +264,7 @@ static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off
     t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
-    if (choose_kp(p.band_w) == 8) t.flags |= TASK_KP8;
+    t.flags |= (uint32_t)choose_kp(p.band_w) << TASK_KP_SHIFT;
     const int steps_per_iter = 2 * kp_of(t);
     const int64_t m = t.m, n = t.n, lo = p.band_lo, hi = lo + (int64_t)p.band_w - 1;
     if (lo > n - 1 || hi < -(m - 1)) { t.flags |= TASK_INVALID; return; }     // band misses the matrix
@@ -320,13 +333,13 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             if (t.flags & TASK_INVALID) continue;
             const int per_warp = 128 * kp_of(t);
             const int nw = (t.band_w + per_warp - 1) / per_warp;
-            by_w[nw + (kp_of(t) == 8 ? 1000 : 0)].push_back((uint32_t)k);
+            by_w[nw + 1000 * kp_of(t)].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
             size_t smem = 0; uint64_t work = 0;
-            const int nwarp = kv.first % 1000, kp = kv.first >= 1000 ? 8 : 4;
+            const int nwarp = kv.first % 1000, kp = kv.first / 1000;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
                 smem = std::max(smem, (size_t)seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
@@ -350,11 +363,15 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
     cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
-    cudaStream_t sF[3] = { st, h->stream_aux[0], h->stream_aux[1] }, sT = h->stream_tb;
+    // forward passes of consecutive waves stay in stream order (letting them overlap was measured slower: the
+    // earlier wave finishes later and so does its traceback); inside a wave the groups use three streams
+    cudaStream_t sets[2][3] = { { st, h->stream_aux[0], h->stream_aux[1] }, { st, h->stream_aux[0], h->stream_aux[1] } };
+    cudaStream_t sT = h->stream_tb;
     CUDA_TRY(h, cudaEventRecord(ev_t0, st));
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(st, EV(wv - 2, 2), 0));       // this arena half is free again
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), st));
+        cudaStream_t* sF = sets[wv & 1];
+        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(sF[0], EV(wv - 2, 2), 0));      // this arena half is free again
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sF[0]));
         const std::vector<Group>& groups = wave_groups[wv];
         const int n_streams = (int)std::min<size_t>(3, groups.size());
         for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
@@ -366,9 +383,9 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         }
         for (int a = 1; a < n_streams; ++a) {
             CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sF[a]));
-            CUDA_TRY(h, cudaStreamWaitEvent(st, EV(wv, 2 + a), 0));
+            CUDA_TRY(h, cudaStreamWaitEvent(sF[0], EV(wv, 2 + a), 0));
         }
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), st));
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sF[0]));
         CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
         const int nt = (int)(waves[wv].second - waves[wv].first);
         if (nt > 0) {

@@ -54,7 +54,8 @@ struct Consts {             // scoring in the packed form the kernels use
 
 constexpr uint32_t TASK_INVALID = 0x80000000u;   // Task.flags: descriptor rejected by the planner
 constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the score range exceeds s16
-constexpr uint32_t TASK_KP8 = 0x100u;            // pair runs on the KP=8 kernels (bands wider than 16 warps x 512)
+constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP of the kernel variant the pair runs on
+constexpr uint32_t TASK_KP_MASK = 0x1F00u;
 constexpr uint32_t NEGV = 0xC000C000u;   // s16x2 -16384: "minus infinity" for gap states
 constexpr uint32_t QNAN16 = 0x7E00u;     // fp16 NaN: sentinel base, never equal to anything
 
@@ -105,8 +106,25 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// low bytes of the 2*KP H values of one step -> this thread's 2*KP bytes of the traceback row
+template <int KP>
+__device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) {
+    uint32_t w[KP / 2];
+    #pragma unroll
+    for (int k = 0; k < KP / 2; ++k) w[k] = __byte_perm(Hs[2 * k], Hs[2 * k + 1], 0x6420);
+    if (KP % 8 == 0) {          // 16-byte aligned: g * 2KP is a multiple of 16
+        #pragma unroll
+        for (int k = 0; k < KP / 2; k += 4) __stcs(reinterpret_cast<uint4*>(p) + k / 4, make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]));
+    } else {                    // KP = 4, 12: 8-byte aligned
+        #pragma unroll
+        for (int k = 0; k < KP / 2; k += 2) __stcs(reinterpret_cast<uint2*>(p) + k / 2, make_uint2(w[k], w[k + 1]));
+    }
+}
+
+constexpr int fwd_max_threads(int kp, bool multi) { return !multi ? 32 : (kp <= 8 ? 512 : 256); }
+
 template <int KP, bool MULTI, bool TWO>
-__global__ void __launch_bounds__(MULTI ? 512 : 32)
+__global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
     extern __shared__ __align__(16) uint8_t smem8[];
@@ -223,11 +241,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 }
                 #pragma unroll
                 for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
-                if (active) {
-                    if (KP == 4) __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420)));
-                    else __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HA[0], HA[1], 0x6420), __byte_perm(HA[2], HA[3], 0x6420),
-                                                                          __byte_perm(HA[4 % KP], HA[5 % KP], 0x6420), __byte_perm(HA[6 % KP], HA[7 % KP], 0x6420)));
-                }
+                if (active) store_row<KP>(tbp, HA);
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 0) sts_v4(s_myA, P1[0], P2[0], F1[0], F2[0]);
@@ -271,11 +285,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 }
                 #pragma unroll
                 for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
-                if (active) {
-                    if (KP == 4) __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420)));
-                    else __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(__byte_perm(HB[0], HB[1], 0x6420), __byte_perm(HB[2], HB[3], 0x6420),
-                                                                          __byte_perm(HB[4 % KP], HB[5 % KP], 0x6420), __byte_perm(HB[6 % KP], HB[7 % KP], 0x6420)));
-                }
+                if (active) store_row<KP>(tbp, HB);
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 31) sts_v4(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
@@ -304,19 +314,21 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 // ---------------------------------------------------------------------------------------------
 // Byte layout of the traceback rows (written by svp_fwd_kernel<KP>): row = step s = (i + j) - r_begin,
 // pitch = band_w / 2 bytes; inside a row thread g owns bytes [g*2KP, (g+1)*2KP); the byte of its slot
-// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (4 or 8).
+// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (4, 8, 12 or 16).
 struct TbView {
     const uint8_t* base;      // arena + tb_off
     const uint32_t* seqs32;   // packed sequences (global)
-    int band_lo, band_w, r_begin, pitch, m, n, kp_log2;
+    int band_lo, band_w, r_begin, pitch, m, n, kp;
+    uint32_t magic;           // ceil(2^24 / (4*kp)): x / (4*kp) == (x * magic) >> 24 for x < 65536
     uint64_t q_word, t_word;  // word offsets of the packed sequences
     bool rc;
 
     // offset of diagonal x (band-relative) inside a row
     __device__ __forceinline__ int col(int x) const {
-        const int y = x & ((4 << kp_log2) - 1), c = y >> 1;
-        const int k = c & ((1 << kp_log2) - 1), half = c >> kp_log2;
-        return ((x >> (2 + kp_log2)) << (1 + kp_log2)) + (k >> 1) * 4 + (k & 1) * 2 + half;
+        const int g = (int)(((uint32_t)x * magic) >> 24);
+        const int c = (x - g * 4 * kp) >> 1;
+        const int half = c >= kp ? 1 : 0, k = c - half * kp;
+        return g * 2 * kp + (k >> 1) * 4 + (k & 1) * 2 + half;
     }
     // address of the stored byte of cell (i, j) (callers make sure the cell is real and inside the band)
     __device__ __forceinline__ const uint8_t* addr(int i, int j) const {
@@ -378,11 +390,11 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
         results[tk.pair_index] = res;
         return;
     }
-    const int KP = (tk.flags & TASK_KP8) ? 8 : 4;
+    const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
     TbView v;
     v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
     v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
-    v.kp_log2 = (KP == 8) ? 3 : 2;
+    v.kp = KP; v.magic = (1u << 24) / (uint32_t)(4 * KP) + 1u;
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
     const int d_hi = tk.band_lo + tk.band_w - 1;
 
