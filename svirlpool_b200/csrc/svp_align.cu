@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "svp_kernels.cuh"
+#include "svp_kernels_wide.cuh"
 
 using namespace svp;
 
@@ -39,7 +39,9 @@ static inline int choose_kp(uint32_t band_w) {
     return best_kp;          // 0: band too wide for every variant
 }
 static inline int kp_of(const Task& t) { return (int)((t.flags & TASK_KP_MASK) >> TASK_KP_SHIFT); }
-static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * (2 * kp_of(t)) * (uint64_t)(t.band_w / 2); }
+// steps per loop iteration of the kernel the pair runs on: 2*KP (s16 kernels), 16 (32-bit lane kernel, KP = 4 geometry)
+static inline int steps_per_iter_of(const Task& t) { return (t.flags & TASK_S32) ? 16 : 2 * kp_of(t); }
+static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * steps_per_iter_of(t) * (uint64_t)(t.band_w / 2); }
 static inline uint64_t best_entries_of(const Task& t) { return (uint64_t)(t.band_w / (4 * kp_of(t))) * 2; }
 
 struct DevBuf {
@@ -113,26 +115,45 @@ extern "C" int svp_scoring_preset(const char* name, svp_scoring* s) {
     return SVP_ERR_ARG;
 }
 
-// Scoring the round-1 kernels implement: one match score and one mismatch score (the matrix must be
-// {A on the diagonal, -B elsewhere}), insertion costs == deletion costs, one or two gap pieces, and
-// steps small enough that neighbouring H differ by < 128 (low-byte traceback).
+// Scoring the kernels implement. Fast path (svp_fwd_kernel): the matrix is {A on the diagonal, -B elsewhere} and
+// insertion costs == deletion costs. Everything else — a full 4x4 matrix (|entry| <= 127), separate insertion /
+// deletion costs — runs on the general kernels. Common limit: the traceback stores one byte per cell (H mod 256),
+// so H of cells one or two steps apart must differ by less than 128: 2 * (max entry + dearest 1-base gap) <= 127
+// (horizontally / vertically adjacent in-band cells differ by at most max entry + 1-base gap).
 static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
+    memset(&c, 0, sizeof(c));
+    int a_max = -(1 << 30);
+    for (int k = 0; k < 16; ++k) {
+        if (s.matrix[k] < -127 || s.matrix[k] > 127) { why = "substitution scores must fit a signed byte"; return SVP_ERR_ARG; }
+        a_max = std::max(a_max, s.matrix[k]);
+    }
+    if (a_max <= 0) { why = "the substitution matrix needs a positive entry"; return SVP_ERR_ARG; }
+    const bool two_d = s.del_open2 >= 0, two_i = s.ins_open2 >= 0;
+    if (s.del_open1 < 0 || s.del_ext1 <= 0 || s.ins_open1 < 0 || s.ins_ext1 <= 0 || (two_d && s.del_ext2 <= 0) || (two_i && s.ins_ext2 <= 0)) {
+        why = "gap costs must be open >= 0, ext > 0"; return SVP_ERR_ARG; }
+    // a kind with one piece repeats it as its second piece when the other kind has two
+    c.two_piece = (two_d || two_i) ? 1 : 0;
+    c.d_open1 = s.del_open1; c.d_ext1 = s.del_ext1; c.d_open2 = two_d ? s.del_open2 : s.del_open1; c.d_ext2 = two_d ? s.del_ext2 : s.del_ext1;
+    c.i_open1 = s.ins_open1; c.i_ext1 = s.ins_ext1; c.i_open2 = two_i ? s.ins_open2 : s.ins_open1; c.i_ext2 = two_i ? s.ins_ext2 : s.ins_ext1;
+    const int g1d = std::min(c.d_open1 + c.d_ext1, c.d_open2 + c.d_ext2), g1i = std::min(c.i_open1 + c.i_ext1, c.i_open2 + c.i_ext2);
+    if (2 * (a_max + std::max(g1d, g1i)) > 127) {
+        why = "scores too large for the one-byte traceback (2*(max matrix entry + dearest 1-base gap) must be <= 127)"; return SVP_ERR_UNSUPPORTED; }
+    if (std::max(std::max(c.d_open1 + c.d_ext1, c.d_open2 + c.d_ext2), std::max(c.i_open1 + c.i_ext1, c.i_open2 + c.i_ext2)) > 8000) {
+        why = "gap costs too large for 16-bit lanes"; return SVP_ERR_UNSUPPORTED; }
     const int A = s.matrix[0], B = -s.matrix[1];
-    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b)
-        if (s.matrix[a * 4 + b] != (a == b ? A : -B)) { why = "substitution matrix is not match/mismatch (full 4x4 matrices: not implemented in the CUDA kernels yet)"; return SVP_ERR_UNSUPPORTED; }
-    if (A <= 0 || B <= 0) { why = "match must be > 0 and mismatch < 0"; return SVP_ERR_ARG; }
-    if (s.del_open1 != s.ins_open1 || s.del_ext1 != s.ins_ext1 || s.del_open2 != s.ins_open2 || (s.del_open2 >= 0 && s.del_ext2 != s.ins_ext2)) {
-        why = "insertion and deletion costs differ (not implemented in the CUDA kernels yet)"; return SVP_ERR_UNSUPPORTED; }
-    if (s.del_open1 < 0 || s.del_ext1 <= 0 || (s.del_open2 >= 0 && s.del_ext2 <= 0)) { why = "gap costs must be open >= 0, ext > 0"; return SVP_ERR_ARG; }
-    const int two = s.del_open2 >= 0;
-    const int g1 = two ? std::min(s.del_open1 + s.del_ext1, s.del_open2 + s.del_ext2) : s.del_open1 + s.del_ext1;   // cheapest 1-base gap
-    if (4 * (A + B + g1) > 127) { why = "scores too large for the low-byte traceback (4*(match+mismatch+gap1) must be <= 127)"; return SVP_ERR_UNSUPPORTED; }
+    bool simple = A > 0 && B > 0 && s.del_open1 == s.ins_open1 && s.del_ext1 == s.ins_ext1 && two_d == two_i &&
+                  (!two_d || (s.del_open2 == s.ins_open2 && s.del_ext2 == s.ins_ext2));
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) if (s.matrix[a * 4 + b] != (a == b ? A : -B)) simple = false;
+    if (const char* e = getenv("SVP_FORCE_GENERAL")) if (atoi(e)) simple = false;     // test aid: run simple scoring on the general kernels
+    c.general = simple ? 0 : 1;
     auto pk16 = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
-    c.mat = pk16(A); c.mis = pk16(-B);
-    c.ne1 = pk16(-s.del_ext1); c.noe1 = pk16(-(s.del_open1 + s.del_ext1));
-    c.ne2 = two ? pk16(-s.del_ext2) : 0; c.noe2 = two ? pk16(-(s.del_open2 + s.del_ext2)) : NEGV;
-    c.two_piece = two;
-    c.s_match = A; c.s_mismatch = -B; c.open1 = s.del_open1; c.ext1 = s.del_ext1; c.open2 = two ? s.del_open2 : 0; c.ext2 = two ? s.del_ext2 : 0;
+    c.mat = pk16(A); c.mis = pk16(-B); c.s_match = A; c.s_mismatch = -B;
+    c.ne1 = pk16(-c.d_ext1); c.noe1 = pk16(-(c.d_open1 + c.d_ext1));
+    c.ne2 = c.two_piece ? pk16(-c.d_ext2) : 0; c.noe2 = c.two_piece ? pk16(-(c.d_open2 + c.d_ext2)) : NEGV;
+    c.d_ne1 = pk16(-c.d_ext1); c.d_noe1 = pk16(-(c.d_open1 + c.d_ext1)); c.d_ne2 = pk16(-c.d_ext2); c.d_noe2 = pk16(-(c.d_open2 + c.d_ext2));
+    c.i_ne1 = pk16(-c.i_ext1); c.i_noe1 = pk16(-(c.i_open1 + c.i_ext1)); c.i_ne2 = pk16(-c.i_ext2); c.i_noe2 = pk16(-(c.i_open2 + c.i_ext2));
+    for (int q = 0; q < 4; ++q) for (int t = 0; t < 4; ++t) c.tab[q] |= (uint32_t)(s.matrix[q * 4 + t] & 0xFF) << (8 * t);
+    c.a_max = a_max;
     c.min_signal = s.min_signal_size; c.zdrop = s.zdrop; c.zdrop_ext = s.zdrop_ext;
     return SVP_OK;
 }
@@ -159,13 +180,17 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-#define SVP_ATTR(K) \
-    cudaFuncSetAttribute(svp_fwd_kernel<K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
-    cudaFuncSetAttribute(svp_fwd_kernel<K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
-    cudaFuncSetAttribute(svp_fwd_kernel<K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); \
-    cudaFuncSetAttribute(svp_fwd_kernel<K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
+#define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
+#define SVP_ATTR(K) SVP_SMEM(svp_fwd_kernel<K, false, true>); SVP_SMEM(svp_fwd_kernel<K, true, true>); \
+                    SVP_SMEM(svp_fwd_kernel<K, false, false>); SVP_SMEM(svp_fwd_kernel<K, true, false>)
     SVP_ATTR(4); SVP_ATTR(8);
+    SVP_SMEM(svp_fwdg_kernel<false, true>); SVP_SMEM(svp_fwdg_kernel<true, true>); SVP_SMEM(svp_fwdg_kernel<false, false>); SVP_SMEM(svp_fwdg_kernel<true, false>);
+    SVP_SMEM(svp_fwd32_kernel<false, true, false>); SVP_SMEM(svp_fwd32_kernel<true, true, false>);
+    SVP_SMEM(svp_fwd32_kernel<false, false, false>); SVP_SMEM(svp_fwd32_kernel<true, false, false>);
+    SVP_SMEM(svp_fwd32_kernel<false, true, true>); SVP_SMEM(svp_fwd32_kernel<true, true, true>);
+    SVP_SMEM(svp_fwd32_kernel<false, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true>);
 #undef SVP_ATTR
+#undef SVP_SMEM
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
     size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 10 * 8, (size_t)128 << 30);
@@ -215,19 +240,26 @@ static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
     return total;
 }
 
-template <int KPV, bool MULTI, bool TWO>
-static void launch_one(unsigned grid, int nwarp, size_t smem, cudaStream_t st, const Task* tasks, const uint32_t* order,
-                       const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
-    svp_fwd_kernel<KPV, MULTI, TWO><<<grid, nwarp * 32, smem, st>>>(tasks, order, seqs, arena, bests, cs);
-}
+// kernel family of a pair
+enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3 };
 
-static void launch_fwd(int kp, int nwarp, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
+static void launch_fwd(int fam, int kp, int nwarp, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
                        const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
     const bool multi = nwarp > 1;
-#define SVP_CASE(K, M, T) if (kp == K && multi == M && two == T) return launch_one<K, M, T>(grid, nwarp, smem, st, tasks, order, seqs, arena, bests, cs)
-    SVP_CASE(4, false, true); SVP_CASE(4, true, true); SVP_CASE(8, false, true); SVP_CASE(8, true, true);
-    SVP_CASE(4, false, false); SVP_CASE(4, true, false); SVP_CASE(8, false, false); SVP_CASE(8, true, false);
+    const unsigned thr = (unsigned)nwarp * 32u;
+#define SVP_ARGS <<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs)
+#define SVP_CASE(K, M, T) if (fam == FAM_FAST && kp == K && multi == M && two == T) { svp_fwd_kernel<K, M, T> SVP_ARGS; return; }
+    SVP_CASE(4, false, true) SVP_CASE(4, true, true) SVP_CASE(8, false, true) SVP_CASE(8, true, true)
+    SVP_CASE(4, false, false) SVP_CASE(4, true, false) SVP_CASE(8, false, false) SVP_CASE(8, true, false)
 #undef SVP_CASE
+#define SVP_CASE(M, T) if (fam == FAM_GEN && multi == M && two == T) { svp_fwdg_kernel<M, T> SVP_ARGS; return; }
+    SVP_CASE(false, true) SVP_CASE(true, true) SVP_CASE(false, false) SVP_CASE(true, false)
+#undef SVP_CASE
+#define SVP_CASE(M, T, G) if (fam == (G ? FAM_S32_GEN : FAM_S32) && multi == M && two == T) { svp_fwd32_kernel<M, T, G> SVP_ARGS; return; }
+    SVP_CASE(false, true, false) SVP_CASE(true, true, false) SVP_CASE(false, false, false) SVP_CASE(true, false, false)
+    SVP_CASE(false, true, true) SVP_CASE(true, true, true) SVP_CASE(false, false, true) SVP_CASE(true, false, true)
+#undef SVP_CASE
+#undef SVP_ARGS
 }
 
 // CIGAR compaction for the host-buffer entry point: one warp per pair copies its (right-aligned) slot
@@ -247,12 +279,11 @@ struct Plan {
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
 };
 
-static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+static void plan_pair(const Consts& cs, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
-    bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && choose_kp(p.band_w) != 0 &&
-              (size_t)p.cigar_off + p.cigar_cap <= cigar_words;
+    bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && (size_t)p.cigar_off + p.cigar_cap <= cigar_words;
     if (ok) {
         for (uint32_t s : { p.q, p.t }) {
             const uint64_t bytes = ((uint64_t)seq_len[s] + 3) / 4;
@@ -264,8 +295,15 @@ static void plan_pair(const svp_pair& p, uint32_t index, const uint64_t* seq_off
     t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
-    t.flags |= (uint32_t)choose_kp(p.band_w) << TASK_KP_SHIFT;
-    const int steps_per_iter = 2 * kp_of(t);
+    // kernel variant: 32-bit lanes when the score can leave the s16 range; those and general scoring use the KP = 4 geometry
+    const bool wide = (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
+    int kp;
+    if (wide || cs.general) kp = (p.band_w <= 16u * 512u) ? 4 : 0;
+    else kp = choose_kp(p.band_w);
+    if (kp == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
+    if (wide) t.flags |= TASK_S32;
+    t.flags |= (uint32_t)kp << TASK_KP_SHIFT;
+    const int steps_per_iter = steps_per_iter_of(t);
     const int64_t m = t.m, n = t.n, lo = p.band_lo, hi = lo + (int64_t)p.band_w - 1;
     if (lo > n - 1 || hi < -(m - 1)) { t.flags |= TASK_INVALID; return; }     // band misses the matrix
     t.cells = (uint64_t)(cells_below(m, n, hi) - cells_below(m, n, lo - 1));
@@ -287,10 +325,6 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     h->stats = svp_stats{};
     const size_t n = tasks.size();
     if (n == 0) return SVP_OK;
-    // score range of the s16 lanes
-    for (Task& t : tasks)
-        if (!(t.flags & TASK_INVALID) && (int64_t)std::min(t.m, t.n) * cs.s_match > S16_SCORE_LIMIT) t.flags |= TASK_INVALID | TASK_TOO_LONG;
-
     // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
     // the traceback of wave w overlaps the forward pass of wave w+1
     const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
@@ -323,7 +357,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
 
     // per wave: order lists grouped by kernel variant and CTA width (warps)
     std::vector<uint32_t> order(n);
-    struct Group { int nwarp; int kp; size_t first, count; size_t smem; uint64_t work; };
+    struct Group { int fam; int nwarp; int kp; size_t first, count; size_t smem; uint64_t work; };
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
@@ -333,20 +367,23 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             if (t.flags & TASK_INVALID) continue;
             const int per_warp = 128 * kp_of(t);
             const int nw = (t.band_w + per_warp - 1) / per_warp;
-            by_w[nw + 1000 * kp_of(t)].push_back((uint32_t)k);
+            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
+            by_w[nw + 1000 * kp_of(t) + 100000 * fam].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
             size_t smem = 0; uint64_t work = 0;
-            const int nwarp = kv.first % 1000, kp = kv.first / 1000;
+            const int nwarp = kv.first % 1000, kp = (kv.first / 1000) % 100, fam = kv.first / 100000;
+            const int n_qimg = (fam == FAM_GEN || fam == FAM_S32_GEN) ? 2 : 1;            // general scoring stages two query images
+            const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
-                smem = std::max(smem, (size_t)seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
-                work += (uint64_t)t.n_iter * nwarp * kp;
+                smem = std::max(smem, (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
+                work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp));
             }
             if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
-            wave_groups[wv].push_back({ nwarp, kp, pos, kv.second.size(), smem, work });
+            wave_groups[wv].push_back({ fam, nwarp, kp, pos, kv.second.size(), smem, work });
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();
         }
@@ -377,7 +414,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const Group& gq = groups[gi];
-            launch_fwd(gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
+            launch_fwd(gq.fam, gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
                        h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }
@@ -421,7 +458,7 @@ extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seq
         return fail(h, SVP_ERR_ARG, "null argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
     return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
 }
 
@@ -440,7 +477,7 @@ extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t
     CUDA_TRY(h, cudaMemsetAsync((uint8_t*)h->d_seqs.p + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
     int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
     if (rc != SVP_OK) return rc;
     if (n_pairs) {

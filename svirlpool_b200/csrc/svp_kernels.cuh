@@ -42,18 +42,27 @@ struct Task {               // one pair, prepared on the host (svp_align.cu: pla
     uint32_t cigar_off, cigar_cap;
 };
 
-struct Consts {             // scoring in the packed form the kernels use
-    uint32_t mat, mis;      // s16x2: match score, mismatch score (negative)
+struct Consts {             // scoring in the forms the kernels use (svp_align.cu: make_consts)
+    // fast path (svp_fwd_kernel): one match and one mismatch score, insertion costs == deletion costs; s16x2
+    uint32_t mat, mis;      // match score, mismatch score (negative)
     uint32_t ne1, ne2;      // -ext1, -ext2
     uint32_t noe1, noe2;    // -(open1+ext1), -(open2+ext2)
-    int32_t  two_piece;
-    // scalar copies for the traceback
-    int32_t  s_match, s_mismatch, open1, ext1, open2, ext2;
+    // general path (svp_fwdg_kernel): full 4x4 matrix, separate deletion (E) / insertion (F) pieces; s16x2
+    uint32_t d_ne1, d_noe1, d_ne2, d_noe2;
+    uint32_t i_ne1, i_noe1, i_ne2, i_noe2;
+    uint32_t tab[4];        // substitution matrix as signed bytes: byte t of tab[q] = s(q, t)
+    int32_t  two_piece;     // both gap kinds carry two pieces (a one-piece kind repeats its piece)
+    int32_t  general;       // 0: fast path applies, 1: general path
+    // scalar copies (32-bit lane kernel, traceback)
+    int32_t  s_match, s_mismatch;
+    int32_t  d_open1, d_ext1, d_open2, d_ext2, i_open1, i_ext1, i_open2, i_ext2;
+    int32_t  a_max;         // largest matrix entry (score-range test)
     int32_t  min_signal, zdrop, zdrop_ext;
 };
 
 constexpr uint32_t TASK_INVALID = 0x80000000u;   // Task.flags: descriptor rejected by the planner
 constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the score range exceeds s16
+constexpr uint32_t TASK_S32 = 0x20000000u;       // pair runs on the 32-bit lane kernel (scores beyond the s16 range)
 constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP of the kernel variant the pair runs on
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;
 constexpr uint32_t NEGV = 0xC000C000u;   // s16x2 -16384: "minus infinity" for gap states
@@ -106,6 +115,42 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// Stage both sequences of a pair as code bytes in shared memory (query reverse-complemented on the fly when
+// the pair asks for it). The pads are NaN codes that differ between query (0x7E) and target (0x7D), so padded
+// positions compare unequal both as fp16 (s16x2 kernel) and as integers (s32 kernel). Ends with a barrier.
+__device__ __forceinline__ void stage_sequences(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qimg, uint8_t* timg,
+                                                int qbytes, int tbytes) {
+    const int g = threadIdx.x;
+    const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
+    for (int w = g; w < (tk.n + 15) >> 4; w += blockDim.x)
+        *reinterpret_cast<uint4*>(timg + SEQ_PAD + 16 * w) = expand16(__ldg(tsrc + w));
+    const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
+    if (!(tk.flags & SVP_PAIR_REVCOMP)) {
+        for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x)
+            *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(__ldg(qsrc + w));
+    } else {
+        // oriented base p = complement of original base m-1-p
+        for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x) {
+            uint32_t packed = 0;
+            #pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const int p = w * 16 + b;
+                if (p < tk.m) {
+                    const unsigned o = (unsigned)(tk.m - 1 - p);
+                    packed |= (3u - ((__ldg(qsrc + (o >> 4)) >> ((o & 15u) * 2u)) & 3u)) << (2 * b);
+                }
+            }
+            *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(packed);
+        }
+    }
+    __syncthreads();
+    // pads (after the bulk stores: the last 16-byte group may cover the trailing pad)
+    for (int k = g; k < SEQ_PAD; k += blockDim.x) { qimg[k] = 0x7E; timg[k] = 0x7D; }
+    for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) qimg[k] = 0x7E;
+    for (int k = SEQ_PAD + tk.n + g; k < tbytes; k += blockDim.x) timg[k] = 0x7D;
+    __syncthreads();
+}
+
 // low bytes of the 2*KP H values of one step -> this thread's 2*KP bytes of the traceback row
 template <int KP>
 __device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) {
@@ -143,38 +188,9 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const uint32_t c_ne1 = pin(cs.ne1), c_noe1 = pin(cs.noe1), c_ne2 = pin(cs.ne2), c_noe2 = pin(cs.noe2);
     const uint32_t c_mat = pin(cs.mat), c_mis = pin(cs.mis), c_neg = pin(NEGV);
 
-    // ---- stage both sequences as code bytes ------------------------------------------------------
-    {
-        const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
-        for (int w = g; w < (tk.n + 15) >> 4; w += blockDim.x)
-            *reinterpret_cast<uint4*>(timg + SEQ_PAD + 16 * w) = expand16(__ldg(tsrc + w));
-        const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
-        if (!(tk.flags & SVP_PAIR_REVCOMP)) {
-            for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x)
-                *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(__ldg(qsrc + w));
-        } else {
-            // oriented base p = complement of original base m-1-p
-            for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x) {
-                uint32_t packed = 0;
-                #pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    const int p = w * 16 + b;
-                    if (p < tk.m) {
-                        const unsigned o = (unsigned)(tk.m - 1 - p);
-                        packed |= (3u - ((__ldg(qsrc + (o >> 4)) >> ((o & 15u) * 2u)) & 3u)) << (2 * b);
-                    }
-                }
-                *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(packed);
-            }
-        }
-        __syncthreads();
-        // NaN pads (after the bulk stores: the last 16-byte group may cover the trailing pad)
-        for (int k = g; k < SEQ_PAD; k += blockDim.x) { qimg[k] = 0x7E; timg[k] = 0x7E; }
-        for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) qimg[k] = 0x7E;
-        for (int k = SEQ_PAD + tk.n + g; k < tbytes; k += blockDim.x) timg[k] = 0x7E;
-        if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * g, c_noe1, c_noe2, c_neg, c_neg); }
-        __syncthreads();
-    }
+    stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
+    if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * g, c_noe1, c_noe2, c_neg, c_neg); }
+    __syncthreads();
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -304,8 +320,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
         snap = best;
     }
     if (active) {
-        bests[tk.best_off + 2 * g]     = make_uint2(best & 0xFFFFu, blk_lo);
-        bests[tk.best_off + 2 * g + 1] = make_uint2(best >> 16, blk_hi);
+        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
+        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
     }
 }
 
@@ -403,7 +419,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
     int M = 0; uint32_t blk = 0xFFFFFFFFu;
     for (int e = 0; e < n_ent; ++e) {
         const uint2 b = __ldg(bests + tk.best_off + e);
-        const int val = (int)(int16_t)b.x;
+        const int val = (int)b.x;
         if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
     }
     if (M <= 0) {
@@ -411,12 +427,12 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
         results[tk.pair_index] = res;
         return;
     }
-    if (M >= 32767 - cs.s_match) res.status |= SVP_ST_SCORE_OVF;
+    if (!(tk.flags & TASK_S32) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
     // every (thread, half) block that reached M in iteration blk: rebuild its 2KP x 2KP cells from the low bytes
     int end_s = 0x7FFFFFFF, end_x = -1;
     for (int e = 0; e < n_ent; ++e) {
         const uint2 b = __ldg(bests + tk.best_off + e);
-        if ((int)(int16_t)b.x != M || b.y != blk) continue;
+        if ((int)b.x != M || b.y != blk) continue;
         const int xbase = (e >> 1) * 4 * KP + (e & 1) * 2 * KP;      // first diagonal (band-relative) of the half
         const int s0 = (int)blk * 2 * KP;
         // cells id = 0 .. 2*KP*KP-1: step s0 + id/KP, diagonal xbase + 2*(id%KP) + (step odd); chained by neighbours
@@ -442,7 +458,8 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
     constexpr int S = 8, NSCAN = 6;
     uint32_t* slot = cigar + tk.cigar_off;
     const ptrdiff_t two_rows = 2 * (ptrdiff_t)v.pitch;
-    const int cost1 = gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, 1);
+    const int cost1d = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1);
+    const int cost1i = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1);
     const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
 
     int i, j, H, wpos, low, low_i, low_j, mrun, scan_k, Hrow, Hcol;
@@ -483,7 +500,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
                 br[t] = okr[t] ? (uint32_t)*v.addr(i, j - k) : 0u;
                 bc[t] = okc[t] ? (uint32_t)*v.addr(i - k, j) : 0u;
             }
-            const uint32_t diffwin = v.qwindow(i, S) ^ v.twindow(j, S);      // 2 bits per cell, 0 = same base
+            const uint32_t qwin = v.qwindow(i, S), twin = v.twindow(j, S);   // 2 bits per cell along the diagonal
             if (!in_scan && i - S - 1 >= 1 && j - S - 1 >= 1) {              // L2 prefetch for the next round
                 #pragma unroll
                 for (int k = S; k < 2 * S; k += 2) {
@@ -502,16 +519,17 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
                 #pragma unroll
                 for (int t = 0; t < NSCAN; ++t) {
                     const int k = scan_k + t;
-                    const int cost = gap_cost2(cs.open1, cs.ext1, cs.open2, cs.ext2, cs.two_piece, k);
+                    const int costd = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, k);
+                    const int costi = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, k);
                     if (!found && !dead) {
                         if (!okr[t] && !okc[t]) dead = true;
                         if (okr[t]) {
                             Hrow += sext8(br[t] - brow); brow = br[t];
-                            if (H == Hrow - cost) { SVP_PUSH(SVP_CIGAR_D, k); ++n_do; n_db += k; j -= k; H = Hrow; found = true; }
+                            if (H == Hrow - costd) { SVP_PUSH(SVP_CIGAR_D, k); ++n_do; n_db += k; j -= k; H = Hrow; found = true; }
                         }
                         if (!found && okc[t]) {
                             Hcol += sext8(bc[t] - bcol); bcol = bc[t];
-                            if (H == Hcol - cost) { SVP_PUSH(SVP_CIGAR_I, k); ++n_io; n_ib += k; i -= k; H = Hcol; found = true; }
+                            if (H == Hcol - costi) { SVP_PUSH(SVP_CIGAR_I, k); ++n_io; n_ib += k; i -= k; H = Hcol; found = true; }
                         }
                     }
                 }
@@ -531,9 +549,11 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
                                             (pass == 0 && H >= low && H - low > zdrop + cs.zdrop_ext * dd));
                 if (stop) { if (pass == 0 && H != 0 && i >= 1 && j >= 1) cut = true; done = true; alive = false; }
                 if (alive && H < low) { low = H; low_i = i; low_j = j; }
-                const bool same = ((diffwin >> (2 * k)) & 3u) == 0u;
+                const uint32_t qc = (qwin >> (2 * k)) & 3u, tc = (twin >> (2 * k)) & 3u;
+                const bool same = qc == tc;
+                const int sub = (int)(int8_t)((cs.tab[qc] >> (8u * tc)) & 0xFFu);
                 const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(bd[k] - (uint32_t)H) : 0;
-                const bool isdiag = alive && (H == Hd + (same ? cs.s_match : cs.s_mismatch));
+                const bool isdiag = alive && (H == Hd + sub);
                 if (alive && !isdiag) { gap_here = true; gl = bl[k]; gu = bu[k]; alive = false; }
                 if (isdiag) { ++mrun; n_match += same ? 1u : 0u; n_mis += same ? 0u : 1u; --i; --j; H = Hd; }
             }
@@ -544,8 +564,8 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
                 const bool del_ok = (j - 1 >= 1) && del_band, ins_ok = (i - 1 >= 1) && ins_band;
                 const int Hl = H + sext8(gl - (uint32_t)H), Hu = H + sext8(gu - (uint32_t)H);
                 if (!del_ok && !ins_ok) { bad = true; done = true; }
-                else if (del_ok && H == Hl - cost1) { SVP_PUSH(SVP_CIGAR_D, 1); ++n_do; ++n_db; --j; H = Hl; }
-                else if (ins_ok && H == Hu - cost1) { SVP_PUSH(SVP_CIGAR_I, 1); ++n_io; ++n_ib; --i; H = Hu; }
+                else if (del_ok && H == Hl - cost1d) { SVP_PUSH(SVP_CIGAR_D, 1); ++n_do; ++n_db; --j; H = Hl; }
+                else if (ins_ok && H == Hu - cost1i) { SVP_PUSH(SVP_CIGAR_I, 1); ++n_io; ++n_ib; --i; H = Hu; }
                 else { scan_k = 2; Hrow = Hl; brow = gl; Hcol = Hu; bcol = gu; }
             }
         }

@@ -1,0 +1,416 @@
+// svp_kernels_wide.cuh — the forward-DP variants beside the fast path of svp_kernels.cuh. Same decomposition
+// (one CTA per pair, a thread owns consecutive diagonals, even ones = set A, odd ones = set B, one anti-diagonal
+// per step, neighbours by shuffle / mailbox) and the same traceback rows, so svp_tb_kernel serves all of them.
+//
+//   svp_fwdg_kernel<MULTI, TWO>       s16x2 lanes, KP = 4 geometry, GENERAL scoring: a full 4x4 substitution
+//                                     matrix (the shape of a last-train / lamassemble .mat, consensus.py:777) and
+//                                     separate insertion / deletion gap costs.
+//   svp_fwd32_kernel<MULTI, TWO, GEN> s32 lanes (one cell per register), KP = 4 geometry, for pairs whose score
+//                                     can leave the s16 range (match * min(m, n) > 32000: reads beyond ~16 kb);
+//                                     GEN selects general scoring.
+//
+// General scoring, substitution score of a cell = one byte out of the 16-byte matrix held in four registers
+// (tab[q] = row of query base q, byte t). PRMT picks one of 8 bytes per selector nibble, so two first-level PRMTs
+// look the 3-bit index (q & 1) * 4 + t up in rows {0,1} and rows {2,3}, and a third PRMT picks between the two by
+// (q >> 1) while replicating the sign into the upper byte of the 16-bit lane. The third selector depends on the
+// query base only and is kept per query register (Q2), updated when the query shifts. A selector nibble with bit 3
+// set makes PRMT return the sign (0x00 / 0xFF) of the byte instead: the pad code of positions outside a sequence,
+// so virtual cells score 0 or -1 — never positive, which is all the boundary logic needs.
+#pragma once
+#include "svp_kernels.cuh"
+
+namespace svp {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// 16 bases of one 2-bit packed word -> 16 raw codes (0..3), one per byte
+__device__ __forceinline__ uint4 expand16_codes(uint32_t w) {
+    uint32_t o[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = (w >> (8 * k)) & 0xFFu;
+        o[k] = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Shared-memory images for general scoring, one byte per base, base p at byte SEQ_PAD + p:
+//   qsel  = (q & 1) * 4            pad 0x08      first-level selector contribution of the query
+//   qsel2 = 0x80 | 0x44 * (q >> 1) pad 0x80      second-level selector byte of the low lane (the high lane adds 0x22)
+//   tsel  = t                      pad 0x08
+constexpr uint32_t GEN_PAD = 0x08u, GEN_PAD2 = 0x80u;
+__device__ __forceinline__ void stage_sequences_gen(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qsel, uint8_t* qsel2,
+                                                    uint8_t* tsel, int qbytes, int tbytes) {
+    const int g = threadIdx.x;
+    const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
+    for (int w = g; w < (tk.n + 15) >> 4; w += blockDim.x)
+        *reinterpret_cast<uint4*>(tsel + SEQ_PAD + 16 * w) = expand16_codes(__ldg(tsrc + w));
+    const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
+    for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x) {
+        uint32_t packed = 0;
+        if (!(tk.flags & SVP_PAIR_REVCOMP)) {
+            packed = __ldg(qsrc + w);
+        } else {
+            #pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                const int p = w * 16 + b;
+                if (p < tk.m) {
+                    const unsigned o = (unsigned)(tk.m - 1 - p);
+                    packed |= (3u - ((__ldg(qsrc + (o >> 4)) >> ((o & 15u) * 2u)) & 3u)) << (2 * b);
+                }
+            }
+        }
+        const uint4 c = expand16_codes(packed);
+        const uint32_t cc[4] = { c.x, c.y, c.z, c.w };
+        uint32_t s1[4], s2[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s1[k] = (cc[k] & 0x01010101u) << 2;
+            s2[k] = 0x80808080u | (((cc[k] >> 1) & 0x01010101u) * 0x44u);
+        }
+        *reinterpret_cast<uint4*>(qsel + SEQ_PAD + 16 * w) = make_uint4(s1[0], s1[1], s1[2], s1[3]);
+        *reinterpret_cast<uint4*>(qsel2 + SEQ_PAD + 16 * w) = make_uint4(s2[0], s2[1], s2[2], s2[3]);
+    }
+    __syncthreads();
+    for (int k = g; k < SEQ_PAD; k += blockDim.x) { qsel[k] = GEN_PAD; qsel2[k] = GEN_PAD2; tsel[k] = GEN_PAD; }
+    for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) { qsel[k] = GEN_PAD; qsel2[k] = GEN_PAD2; }
+    for (int k = SEQ_PAD + tk.n + g; k < tbytes; k += blockDim.x) tsel[k] = GEN_PAD;
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward DP, s16x2 lanes, general scoring (KP = 4 geometry)
+// ---------------------------------------------------------------------------------------------
+template <bool MULTI, bool TWO>
+__global__ void __launch_bounds__(MULTI ? 512 : 32)
+svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
+                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+    constexpr int KP = 4;
+    extern __shared__ __align__(16) uint8_t smem8[];
+    const Task tk = tasks[order[blockIdx.x]];
+    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
+    const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
+    uint8_t* qsel = smem8;
+    uint8_t* qsel2 = smem8 + qbytes;
+    uint8_t* tsel = smem8 + 2 * qbytes;
+    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qsel) + SEQ_PAD - 1;    // + clamped 1-based position
+    const uint32_t s_q2 = (uint32_t)__cvta_generic_to_shared(qsel2) + SEQ_PAD - 1;
+    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(tsel) + SEQ_PAD - 1;
+    // mailboxes (MULTI): A[w] = lane 0 of warp w after an A-step (H, -, F1, F2), A[nwarp] = constants;
+    //                    B[w+1] = lane 31 of warp w after a B-step (H, -, E1, E2), B[0] = constants
+    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(smem8 + 2 * qbytes + tbytes);
+    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
+
+    const uint32_t d_ne1 = pin(cs.d_ne1), d_noe1 = pin(cs.d_noe1), d_ne2 = pin(cs.d_ne2), d_noe2 = pin(cs.d_noe2);
+    const uint32_t i_ne1 = pin(cs.i_ne1), i_noe1 = pin(cs.i_noe1), i_ne2 = pin(cs.i_ne2), i_noe2 = pin(cs.i_noe2);
+    const uint32_t r0 = pin(cs.tab[0]), r1 = pin(cs.tab[1]), r2 = pin(cs.tab[2]), r3 = pin(cs.tab[3]);
+    const uint32_t c_neg = pin(NEGV);
+
+    stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
+    if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * g, 0u, 0u, c_neg, c_neg); }
+    __syncthreads();
+
+    const int n_thr_active = tk.band_w / (4 * KP);
+    const bool active = g < n_thr_active;
+    const bool lo_edge = (lane == 0);
+    const bool hi_edge = (lane == 31) || (g == n_thr_active - 1);
+    const int D0 = tk.band_lo + g * 4 * KP;
+    const int I0 = (tk.r_begin - D0) / 2;
+    const int J0 = (tk.r_begin + D0) / 2;
+    const int qmax = tk.m + 1, tmax = tk.n + 1;
+    auto at = [&](uint32_t sbase, int pos, int lim) -> uint32_t { return lds_u8(sbase + (uint32_t)__vimin_s32_relu(pos, lim)); };
+
+    // packed state: slot k in the low half, slot KP+k in the high half; selector registers: low lane in byte 0, high lane in byte 1
+    uint32_t HA[KP], HB[KP], E1[KP], E2[KP], F1[KP], F2[KP], Q[KP], Q2[KP], T[KP];
+    #pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        HA[k] = 0; HB[k] = 0; E1[k] = c_neg; E2[k] = c_neg; F1[k] = c_neg; F2[k] = c_neg;
+        Q[k] = at(s_q, I0 - k, qmax) | (at(s_q, I0 - (KP + k), qmax) << 8);
+        Q2[k] = at(s_q2, I0 - k, qmax) | ((at(s_q2, I0 - (KP + k), qmax) | 0x22u) << 8);
+        T[k] = at(s_t, J0 + k, tmax) | (at(s_t, J0 + KP + k, tmax) << 8);
+    }
+    int qpos = I0 + 1, tpos = J0 + 2 * KP;
+    uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
+    const int pitch = tk.band_w >> 1;
+    uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
+    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
+    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+
+    auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> uint32_t {
+        const uint32_t sel = q | t;
+        return prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);
+    };
+
+    #pragma unroll 1
+    for (int it = 0; it < tk.n_iter; ++it) {
+        #pragma unroll
+        for (int u = 0; u < KP; ++u) {
+            // =============================== A-step ===========================================
+            {
+                uint32_t sH = __shfl_up_sync(0xffffffffu, HB[KP - 1], 1);
+                uint32_t sE1 = __shfl_up_sync(0xffffffffu, E1[KP - 1], 1);
+                uint32_t sE2 = 0;
+                if (TWO) sE2 = __shfl_up_sync(0xffffffffu, E2[KP - 1], 1);
+                uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
+                if (MULTI) mb = lds_v4(s_loB);
+                sH = lo_edge ? mb.x : sH; sE1 = lo_edge ? mb.z : sE1;
+                if (TWO) sE2 = lo_edge ? mb.w : sE2;
+                const uint32_t Hm = __byte_perm(sH, HB[KP - 1], 0x5432), E1m = __byte_perm(sE1, E1[KP - 1], 0x5432);
+                const uint32_t E2m = TWO ? __byte_perm(sE2, E2[KP - 1], 0x5432) : 0u;
+                #pragma unroll
+                for (int k = KP - 1; k >= 0; --k) {
+                    const uint32_t hl = k ? HB[k ? k - 1 : 0] : Hm, e1l = k ? E1[k ? k - 1 : 0] : E1m;
+                    const uint32_t e1 = __viaddmax_s16x2(e1l, d_ne1, __vadd2(hl, d_noe1));
+                    const uint32_t f1 = __viaddmax_s16x2(F1[k], i_ne1, __vadd2(HB[k], i_noe1));
+                    const uint32_t h = __vadd2(HA[k], score(Q[(k - u + KP) % KP], Q2[(k - u + KP) % KP], T[(k + u) % KP]));
+                    uint32_t H;
+                    if (TWO) {
+                        const uint32_t e2l = k ? E2[k ? k - 1 : 0] : E2m;
+                        const uint32_t e2 = __viaddmax_s16x2(e2l, d_ne2, __vadd2(hl, d_noe2));
+                        const uint32_t f2 = __viaddmax_s16x2(F2[k], i_ne2, __vadd2(HB[k], i_noe2));
+                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        E2[k] = e2; F2[k] = f2;
+                    } else {
+                        H = __vimax3_s16x2_relu(h, e1, f1);
+                    }
+                    HA[k] = H; E1[k] = e1; F1[k] = f1;
+                }
+                #pragma unroll
+                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
+                if (active) store_row<KP>(tbp, HA);
+                tbp += pitch;
+                if (MULTI) {
+                    if (lane == 0) sts_v4(s_myA, HA[0], 0u, F1[0], F2[0]);
+                    __syncthreads();
+                }
+                // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
+                const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
+                T[u % KP] = __byte_perm(T[u % KP], nb, 0x5541);
+                ++tpos;
+            }
+            // =============================== B-step ===========================================
+            {
+                uint32_t sH = __shfl_down_sync(0xffffffffu, HA[0], 1);
+                uint32_t sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1);
+                uint32_t sF2 = 0;
+                if (TWO) sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
+                uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
+                if (MULTI) mb = lds_v4(s_upA);
+                sH = hi_edge ? mb.x : sH; sF1 = hi_edge ? mb.z : sF1;
+                if (TWO) sF2 = hi_edge ? mb.w : sF2;
+                const uint32_t Hp = __byte_perm(HA[0], sH, 0x5432), F1p = __byte_perm(F1[0], sF1, 0x5432);
+                const uint32_t F2p = TWO ? __byte_perm(F2[0], sF2, 0x5432) : 0u;
+                #pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    const uint32_t hu = (k < KP - 1) ? HA[(k + 1) % KP] : Hp, f1u = (k < KP - 1) ? F1[(k + 1) % KP] : F1p;
+                    const uint32_t e1 = __viaddmax_s16x2(E1[k], d_ne1, __vadd2(HA[k], d_noe1));
+                    const uint32_t f1 = __viaddmax_s16x2(f1u, i_ne1, __vadd2(hu, i_noe1));
+                    const uint32_t h = __vadd2(HB[k], score(Q[(k - u + KP) % KP], Q2[(k - u + KP) % KP], T[(k + u + 1) % KP]));
+                    uint32_t H;
+                    if (TWO) {
+                        const uint32_t f2u = (k < KP - 1) ? F2[(k + 1) % KP] : F2p;
+                        const uint32_t e2 = __viaddmax_s16x2(E2[k], d_ne2, __vadd2(HA[k], d_noe2));
+                        const uint32_t f2 = __viaddmax_s16x2(f2u, i_ne2, __vadd2(hu, i_noe2));
+                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        E2[k] = e2; F2[k] = f2;
+                    } else {
+                        H = __vimax3_s16x2_relu(h, e1, f1);
+                    }
+                    HB[k] = H; E1[k] = e1; F1[k] = f1;
+                }
+                #pragma unroll
+                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
+                if (active) store_row<KP>(tbp, HB);
+                tbp += pitch;
+                if (MULTI) {
+                    if (lane == 31) sts_v4(s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
+                    __syncthreads();
+                }
+                // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
+                const uint32_t off = (uint32_t)__vimin_s32_relu(qpos, qmax);
+                const uint32_t nb = lds_u8(s_q + off), nb2 = lds_u8(s_q2 + off);
+                Q[(KP - 1 - u) % KP] = __byte_perm(nb, Q[(KP - 1 - u) % KP], 0x1140);
+                Q2[(KP - 1 - u) % KP] = __byte_perm(nb2, Q2[(KP - 1 - u) % KP], 0x1140) | 0x2200u;
+                ++qpos;
+            }
+        }
+        const uint32_t diff = best ^ snap;
+        if (diff & 0xFFFFu) blk_lo = (uint32_t)it;
+        if (diff >> 16) blk_hi = (uint32_t)it;
+        snap = best;
+    }
+    if (active) {
+        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
+        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward DP, 32-bit lanes: one cell per register, K = 8 registers per state array per set; the thread owns
+// 2K = 16 diagonals = the geometry of the s16 kernels with KP = 4, and the row bytes are written in their byte
+// order. One loop iteration is 2K = 16 steps = two end-cell blocks of 2*KP = 8 steps.
+// ---------------------------------------------------------------------------------------------
+template <bool MULTI, bool TWO, bool GEN>
+__global__ void __launch_bounds__(MULTI ? 512 : 32)
+svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
+                 uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+    constexpr int K = 8, KPG = K / 2;
+    extern __shared__ __align__(16) uint8_t smem8[];
+    const Task tk = tasks[order[blockIdx.x]];
+    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
+    const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
+    uint8_t* qimg = smem8;                                   // GEN: qsel
+    uint8_t* qimg2 = smem8 + qbytes;                         // GEN only: qsel2
+    uint8_t* timg = smem8 + (GEN ? 2 : 1) * qbytes;
+    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + SEQ_PAD - 1;
+    const uint32_t s_q2 = (uint32_t)__cvta_generic_to_shared(qimg2) + SEQ_PAD - 1;
+    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + SEQ_PAD - 1;
+    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(timg + tbytes);
+    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
+    const int NEG = -(1 << 29);
+    const int d_ne1 = (int)pin((uint32_t)-cs.d_ext1), d_noe1 = (int)pin((uint32_t)-(cs.d_open1 + cs.d_ext1));
+    const int d_ne2 = (int)pin((uint32_t)-cs.d_ext2), d_noe2 = (int)pin((uint32_t)-(cs.d_open2 + cs.d_ext2));
+    const int i_ne1 = (int)pin((uint32_t)-cs.i_ext1), i_noe1 = (int)pin((uint32_t)-(cs.i_open1 + cs.i_ext1));
+    const int i_ne2 = (int)pin((uint32_t)-cs.i_ext2), i_noe2 = (int)pin((uint32_t)-(cs.i_open2 + cs.i_ext2));
+    const int c_mat = (int)pin((uint32_t)cs.s_match), c_mis = (int)pin((uint32_t)cs.s_mismatch), c_neg = (int)pin((uint32_t)NEG);
+    const uint32_t r0 = pin(cs.tab[0]), r1 = pin(cs.tab[1]), r2 = pin(cs.tab[2]), r3 = pin(cs.tab[3]);
+
+    if (GEN) stage_sequences_gen(tk, seqs, qimg, qimg2, timg, qbytes, tbytes);
+    else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
+    if (MULTI && g <= nwarp) {
+        sts_v4(s_mbA + 16u * g, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+        sts_v4(s_mbB + 16u * g, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+    }
+    __syncthreads();
+
+    const int n_thr_active = tk.band_w / (2 * K);
+    const bool active = g < n_thr_active;
+    const bool lo_edge = (lane == 0);
+    const bool hi_edge = (lane == 31) || (g == n_thr_active - 1);
+    const int D0 = tk.band_lo + g * 2 * K;
+    const int I0 = (tk.r_begin - D0) / 2, J0 = (tk.r_begin + D0) / 2;
+    const int qmax = tk.m + 1, tmax = tk.n + 1;
+
+    // second-level selector of a 32-bit lane from the qsel2 byte b (0x80 / 0xC4): nibbles (n0, 8|n0, 8|n0, 8|n0)
+    auto sel2_of = [](uint32_t b) -> uint32_t { return b | ((b >> 4) * 0x1100u); };
+    int HA[K], HB[K], E1[K], E2[K], F1[K], F2[K];
+    uint32_t Q[K], Q2[K], T[K];
+    #pragma unroll
+    for (int k = 0; k < K; ++k) {
+        HA[k] = 0; HB[k] = 0; E1[k] = c_neg; E2[k] = c_neg; F1[k] = c_neg; F2[k] = c_neg;
+        const uint32_t qo = (uint32_t)__vimin_s32_relu(I0 - k, qmax);
+        Q[k] = lds_u8(s_q + qo);
+        Q2[k] = GEN ? sel2_of(lds_u8(s_q2 + qo)) : 0u;
+        T[k] = lds_u8(s_t + (uint32_t)__vimin_s32_relu(J0 + k, tmax));
+    }
+    int qpos = I0 + 1, tpos = J0 + K;
+    int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
+    const int pitch = tk.band_w >> 1;
+    uint8_t* tbp = tb + tk.tb_off + (size_t)g * K;
+    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
+    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+
+    // bytes of slots c = 0..7 in the shared row order: word0 = slots [0,4,1,5], word1 = slots [2,6,3,7]
+    auto store8 = [&](const int (&Hs)[K]) {
+        const uint32_t a = __byte_perm((uint32_t)Hs[0], (uint32_t)Hs[4], 0x0040), b = __byte_perm((uint32_t)Hs[1], (uint32_t)Hs[5], 0x0040);
+        const uint32_t c = __byte_perm((uint32_t)Hs[2], (uint32_t)Hs[6], 0x0040), d = __byte_perm((uint32_t)Hs[3], (uint32_t)Hs[7], 0x0040);
+        __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(a, b, 0x5410), __byte_perm(c, d, 0x5410)));
+    };
+    auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> int {
+        if (GEN) {
+            const uint32_t sel = q | t;
+            return (int)prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);
+        }
+        return (q == t) ? c_mat : c_mis;
+    };
+    // one cell: (left H, left E) feed E, (up H, up F) feed F, hd = diagonal H + substitution score
+    auto cell = [&](int hd, int hl, int e1l, int e2l, int hu, int f1u, int f2u, int& e1, int& e2, int& f1, int& f2) -> int {
+        e1 = __viaddmax_s32(e1l, d_ne1, hl + d_noe1);
+        f1 = __viaddmax_s32(f1u, i_ne1, hu + i_noe1);
+        if (TWO) {
+            e2 = __viaddmax_s32(e2l, d_ne2, hl + d_noe2);
+            f2 = __viaddmax_s32(f2u, i_ne2, hu + i_noe2);
+            return __vimax3_s32_relu(__vimax3_s32(hd, e1, f1), e2, f2);
+        }
+        e2 = c_neg; f2 = c_neg;
+        return __vimax3_s32_relu(hd, e1, f1);
+    };
+
+    #pragma unroll 1
+    for (int it = 0; it < tk.n_iter; ++it) {
+        #pragma unroll
+        for (int u = 0; u < K; ++u) {
+            // =============================== A-step ===========================================
+            {
+                int sH = __shfl_up_sync(0xffffffffu, HB[K - 1], 1), sE1 = __shfl_up_sync(0xffffffffu, E1[K - 1], 1), sE2 = 0;
+                if (TWO) sE2 = __shfl_up_sync(0xffffffffu, E2[K - 1], 1);
+                uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+                if (MULTI) mb = lds_v4(s_loB);
+                sH = lo_edge ? (int)mb.x : sH; sE1 = lo_edge ? (int)mb.z : sE1;
+                if (TWO) sE2 = lo_edge ? (int)mb.w : sE2;
+                #pragma unroll
+                for (int k = K - 1; k >= 0; --k) {
+                    const int hl = k ? HB[k ? k - 1 : 0] : sH, e1l = k ? E1[k ? k - 1 : 0] : sE1, e2l = k ? E2[k ? k - 1 : 0] : sE2;
+                    const int hd = HA[k] + score(Q[(k - u + K) % K], Q2[(k - u + K) % K], T[(k + u) % K]);
+                    int e1, e2, f1, f2;
+                    HA[k] = cell(hd, hl, e1l, e2l, HB[k], F1[k], F2[k], e1, e2, f1, f2);
+                    E1[k] = e1; E2[k] = e2; F1[k] = f1; F2[k] = f2;
+                }
+                #pragma unroll
+                for (int k = 0; k < KPG; k += 2) { best_lo = __vimax3_s32(best_lo, HA[k], HA[k + 1]); best_hi = __vimax3_s32(best_hi, HA[KPG + k], HA[KPG + k + 1]); }
+                if (active) store8(HA);
+                tbp += pitch;
+                if (MULTI) {
+                    if (lane == 0) sts_v4(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
+                    __syncthreads();
+                }
+                T[u % K] = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));     // logical T[k] <- T[k+1]; new base in slot K-1
+                ++tpos;
+            }
+            // =============================== B-step ===========================================
+            {
+                int sH = __shfl_down_sync(0xffffffffu, HA[0], 1), sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1), sF2 = 0;
+                if (TWO) sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
+                uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+                if (MULTI) mb = lds_v4(s_upA);
+                sH = hi_edge ? (int)mb.x : sH; sF1 = hi_edge ? (int)mb.z : sF1;
+                if (TWO) sF2 = hi_edge ? (int)mb.w : sF2;
+                #pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int hu = (k < K - 1) ? HA[(k + 1) % K] : sH, f1u = (k < K - 1) ? F1[(k + 1) % K] : sF1, f2u = (k < K - 1) ? F2[(k + 1) % K] : sF2;
+                    const int hd = HB[k] + score(Q[(k - u + K) % K], Q2[(k - u + K) % K], T[(k + u + 1) % K]);
+                    int e1, e2, f1, f2;
+                    HB[k] = cell(hd, HA[k], E1[k], E2[k], hu, f1u, f2u, e1, e2, f1, f2);
+                    E1[k] = e1; E2[k] = e2; F1[k] = f1; F2[k] = f2;
+                }
+                #pragma unroll
+                for (int k = 0; k < KPG; k += 2) { best_lo = __vimax3_s32(best_lo, HB[k], HB[k + 1]); best_hi = __vimax3_s32(best_hi, HB[KPG + k], HB[KPG + k + 1]); }
+                if (active) store8(HB);
+                tbp += pitch;
+                if (MULTI) {
+                    if (lane == 31) sts_v4(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
+                    __syncthreads();
+                }
+                const uint32_t qo = (uint32_t)__vimin_s32_relu(qpos, qmax);                 // logical Q[k] <- Q[k-1]; new base in slot 0
+                Q[(K - 1 - u) % K] = lds_u8(s_q + qo);
+                if (GEN) Q2[(K - 1 - u) % K] = sel2_of(lds_u8(s_q2 + qo));
+                ++qpos;
+            }
+            if (u == KPG - 1 || u == K - 1) {          // end of an 8-step block: which block first reached the running maximum
+                const uint32_t blk = 2u * (uint32_t)it + (u == K - 1 ? 1u : 0u);
+                if (best_lo != snap_lo) { blk_lo = blk; snap_lo = best_lo; }
+                if (best_hi != snap_hi) { blk_hi = blk; snap_hi = best_hi; }
+            }
+        }
+    }
+    if (active) {
+        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
+        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
+    }
+}
+
+}  // namespace svp

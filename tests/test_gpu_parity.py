@@ -144,3 +144,121 @@ def test_multiple_waves_small_arena(oracle):
     with Aligner(device=0, tb_bytes=16 << 20) as small:
         run_both(small, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
         assert small.stats()["waves"] > 1
+
+
+# ---------------------------------------------------------------------------------------------
+# general scoring (full 4x4 matrix, separate insertion / deletion costs) and 32-bit lanes
+# ---------------------------------------------------------------------------------------------
+
+def noisy_batch(rng, n_pairs, length, band, granule=32, sv_every=3):
+    seqs, specs = [], []
+    for p in range(n_pairs):
+        tmpl = randseq(rng, length + int(rng.integers(-50, 50)))
+        a, b = mutate(rng, tmpl), mutate(rng, tmpl)
+        if p % sv_every == 0:
+            pos = len(b) // 2
+            sv = int(rng.integers(20, max(21, band // 3)))
+            b = b[:pos] + (randseq(rng, sv) if p % 2 else "") + b[pos + (0 if p % 2 else sv):]
+        rc = bool(rng.integers(2))
+        seqs += [revcomp(a) if rc else a, b]
+        lo, w = ava.offset_band(len(a), len(b), slack=max(8, band // 2 - 40), granule=granule)
+        specs.append((2 * p, 2 * p + 1, lo, w, PAIR_REVCOMP if rc else 0))
+    return [f"r{k}" for k in range(len(seqs))], seqs, specs
+
+
+def custom_scoring(matrix, d1, i1, d2=(-1, 0), i2=(-1, 0), zdrop=400, zdrop_ext=2):
+    from svirlpool_b200._abi import SCORING_DTYPE
+    s = np.zeros(1, dtype=SCORING_DTYPE)
+    s["matrix"][0] = np.asarray(matrix, dtype=np.int32).reshape(16)
+    s["del_open1"], s["del_ext1"] = d1
+    s["ins_open1"], s["ins_ext1"] = i1
+    s["del_open2"], s["del_ext2"] = d2
+    s["ins_open2"], s["ins_ext2"] = i2
+    s["min_signal_size"], s["zdrop"], s["zdrop_ext"] = 12, zdrop, zdrop_ext
+    return s
+
+
+LAST_LIKE = [[6, -18, -9, -19], [-18, 5, -20, -8], [-9, -20, 5, -18], [-19, -8, -18, 6]]
+SCORINGS = {
+    "last_preset": None,
+    "last_like_asym": custom_scoring(LAST_LIKE, (21, 9), (25, 7)),
+    "matrix_two_piece_asym": custom_scoring(LAST_LIKE, (8, 4), (10, 3), d2=(30, 2), i2=(36, 1), zdrop_ext=1),
+    "two_piece_del_only": custom_scoring([[3, -5, -4, -6], [-5, 3, -6, -4], [-4, -6, 3, -5], [-6, -4, -5, 3]], (5, 3), (6, 2), d2=(26, 1)),
+}
+
+
+@pytest.mark.parametrize("name", list(SCORINGS))
+@pytest.mark.parametrize("seed,length,band", [(31, 400, 64), (32, 2000, 512), (33, 3500, 1056)])
+def test_general_scoring(name, seed, length, band):
+    """4x4 matrices and asymmetric gap costs: svp_fwdg_kernel vs the oracle."""
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    scoring = SCORINGS[name]
+    kw = {"preset": "last"} if scoring is None else {"scoring": scoring}
+    rng = np.random.default_rng(seed)
+    names, seqs, specs = noisy_batch(rng, 10, length, band)
+    with Aligner(device=0, tb_bytes=2 << 30, **kw) as g:
+        run_both(g, OracleEngine(**kw), names, seqs, specs)
+
+
+def test_general_scoring_edge_cases():
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(41)
+    a = randseq(rng, 700)
+    seqs = [a, randseq(rng, 650), a[10:40], "ACGT" * 50, "A" * 300, "C" * 200]
+    names = ["a", "u", "tiny", "rep", "homoA", "homoC"]
+    specs = []
+    for q, t in [(1, 0), (2, 0), (0, 2), (3, 3), (4, 4), (3, 4), (0, 0), (5, 5), (4, 5)]:
+        lo, w = ava.full_band(len(seqs[q]), len(seqs[t]))
+        specs.append((q, t, lo, w, 0))
+        specs.append((q, t, lo, w, PAIR_REVCOMP))
+    specs += [(0, 0, -16, 32, 0), (0, 0, 100, 64, 0), (0, 0, -731, 64, 0), (0, 0, 668, 64, 0), (2, 0, 0, 32, 0)]
+    for scoring in (SCORINGS["last_like_asym"], SCORINGS["matrix_two_piece_asym"]):
+        with Aligner(device=0, tb_bytes=1 << 30, scoring=scoring) as g:
+            run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
+
+
+def test_forced_general_equals_fast_path(gpu, oracle, monkeypatch):
+    """map-ont scoring pushed through the general kernels (SVP_FORCE_GENERAL) gives the fast path's results."""
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(43)
+    names, seqs, specs = noisy_batch(rng, 12, 2500, 544)
+    batch = ava.PairBatch.build(names, seqs, specs)
+    fres, fcig = gpu.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    monkeypatch.setenv("SVP_FORCE_GENERAL", "1")
+    with Aligner(device=0, preset="map-ont", tb_bytes=1 << 30) as g:
+        gres, gcig = g.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    assert_same(batch, gres, gcig, fres, fcig)
+    ores, ocig = oracle.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    assert_same(batch, gres, gcig, ores, ocig)
+
+
+@pytest.mark.parametrize("seed,length,band", [(51, 17000, 512), (52, 21000, 1056), (53, 30000, 2048)])
+def test_long_reads_32bit_lanes(gpu, oracle, seed, length, band):
+    """Reads beyond the s16 score range (match * min(m, n) > 32000) run on svp_fwd32_kernel."""
+    rng = np.random.default_rng(seed)
+    names, seqs, specs = noisy_batch(rng, 4, length, band)
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert gres["score"].max() > 12000 and not (gres["status"] & 4).any()
+
+
+def test_long_reads_mixed_with_short(gpu, oracle):
+    """One batch holding s16 and s32 pairs (different kernel families in one wave)."""
+    rng = np.random.default_rng(54)
+    n1, s1, p1 = noisy_batch(rng, 6, 3000, 512)
+    n2, s2, p2 = noisy_batch(rng, 2, 18000, 512)
+    off = len(s1)
+    specs = p1 + [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in p2]
+    run_both(gpu, oracle, [f"r{k}" for k in range(off + len(s2))], s1 + s2, specs)
+
+
+def test_long_reads_general_scoring():
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    scoring = SCORINGS["last_like_asym"]
+    rng = np.random.default_rng(55)
+    names, seqs, specs = noisy_batch(rng, 3, 9000, 512)     # 6 * 9000 > 32000: 32-bit lanes + general scoring
+    with Aligner(device=0, tb_bytes=2 << 30, scoring=scoring) as g:
+        gres, _ = run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
+    assert gres["score"].max() > 4000
