@@ -52,6 +52,32 @@ def int_pipe_peak() -> dict:
     return best or {"gcups": 3056.0, "source": "profiles/intpipe_peaks_r01.json (hard-coded copy)"}
 
 
+def alu_pipe_peak(sm_mhz: float | None) -> dict:
+    """SURVEY.md §8(d) integer roofline: 14 int-ops per two-piece cell, 2 cells per s16x2 instruction, on the MEASURED
+    ALU-pipe issue rate (tools/pipe_mix_bench.cu -> profiles/pipe_mix_r01.json: warp-instructions/clk/SMSP of
+    VIADDMNMX.S16x2, 4 SMSPs x 148 SMs) at the SM clock sampled during the timed region."""
+    ipc, src = 0.5, "nominal 0.5 warp-instr/clk/SMSP"
+    f = ROOT / "profiles" / "pipe_mix_r01.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        for r in d["results"]:
+            if r["mix"] == "VIADDMNMX.S16x2":
+                ipc, src = float(r["ipc_per_smsp"]), "profiles/pipe_mix_r01.json"
+    mhz = sm_mhz or 1965.0
+    lane_ops = ipc * 32 * 4 * 148 * mhz * 1e6          # 16-bit-pair lane-ops per second on the ALU pipe
+    return {"gcups": lane_ops * 2 / 14 / 1e9, "ipc_per_smsp": ipc, "sm_mhz": mhz, "int_ops_per_cell": 14, "source": src}
+
+
+def traffic_ratio() -> dict | None:
+    """DRAM bytes / algorithmic bytes of the forward kernels from the latest ncu --set full capture in profiles/."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("ncu_fwd_r*.json")):
+        d = json.loads(f.read_text())
+        if "traffic_over_algorithmic" in d:
+            best = {"ratio": float(d["traffic_over_algorithmic"]), "source": f"profiles/{f.name}"}
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons of one GPU, sampled every 200 ms during the timed region."""
 
@@ -237,6 +263,7 @@ def main() -> None:
     sync_all()
     sampler = ClockSampler(local)
     t0 = time.perf_counter()
+    al.timer_mark(0)                                   # device stopwatch: CUDA events on the stream the kernels are launched on
     agg = {"fwd_ms": 0.0, "tb_ms": 0.0, "total_ms": 0.0, "cells": 0, "tb_bytes": 0, "fwd_launches": 0, "tb_launches": 0, "waves": 0}
     regions_done, seq_bytes = 0, 0
     for k in range(args.steps):
@@ -245,8 +272,10 @@ def main() -> None:
             agg[key] += st[key]
         regions_done += batches[(args.warmup + k) % n_distinct]["n_regions"]
         seq_bytes += batches[(args.warmup + k) % n_distinct]["seq_bytes"]
+    al.timer_mark(1)
     sync_all()
-    elapsed = time.perf_counter() - t0
+    wall_elapsed = time.perf_counter() - t0
+    elapsed = al.timer_elapsed_ms() / 1e3                # device time of the K steps, host gaps between calls included
     clocks = sampler.stop()
 
     # ---- end to end through the host-buffer API -----------------------------------------------------
@@ -257,6 +286,7 @@ def main() -> None:
     step_host(0)
     sync_all()
     t1 = time.perf_counter()
+    al.timer_mark(0)
     e2e_cells, h2d, d2h = 0, 0, 0
     for k in range(args.steps):
         b = batches[(args.warmup + k) % n_distinct]
@@ -264,8 +294,10 @@ def main() -> None:
         e2e_cells += int(res["cells"].sum())
         h2d += b["packed"].nbytes + len(b["pairs"]) * 88 + len(b["pairs"]) * 4
         d2h += res.nbytes + cig.nbytes
+    al.timer_mark(1)
     sync_all()
-    e2e_elapsed = time.perf_counter() - t1
+    e2e_wall = time.perf_counter() - t1
+    e2e_elapsed = max(al.timer_elapsed_ms() / 1e3, 1e-9)  # first H2D -> last D2H on the device, host planning in between included
 
     # ---- reduce over ranks: max time, summed work ---------------------------------------------------
     vec = torch.tensor([elapsed, e2e_elapsed, float(agg["cells"]), float(regions_done), float(e2e_cells), agg["fwd_ms"], agg["tb_ms"],
@@ -285,6 +317,9 @@ def main() -> None:
         algo_bytes = agg["tb_bytes"] + seq_bytes            # 1 B per spec-band cell row slot + packed reads
         achieved_gbs = algo_bytes / fwd_s / 1e9 if fwd_s > 0 else 0.0
         fwd_gcups = agg["cells"] / fwd_s / 1e9 if fwd_s > 0 else 0.0
+        tr = traffic_ratio()
+        ap_ = alu_pipe_peak(clocks.get("sm_mhz"))
+        n_fwd = max(int(agg["fwd_launches"]), 1)
         line = {
             "metric": METRIC, "value": cells / elapsed / 1e9, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
@@ -292,17 +327,26 @@ def main() -> None:
             "config": {"workload": "config2: 10k regions x 30 ONT-like reads x 8 kb, all-vs-all (435 pairs/region), map-ont scoring",
                        "regions_per_step_per_gpu": args.regions, "distinct_batches": n_distinct, "region_seeds": "10000+r",
                        "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE}", "sharding": "LPT by estimated cells, no collective",
-                       "l2": "inputs+traceback per step >> 126 MB L2 (traceback arena rewritten every step)"},
+                       "l2": "inputs+traceback per step >> 126 MB L2 (traceback arena rewritten every step)",
+                       "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it"},
+            "wall_ms_per_step": wall_elapsed / args.steps * 1e3,
             "e2e": {"value": e2e_cells_all / e2e_elapsed / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "regions_per_s": regions_all / e2e_elapsed},
+                    "d2h_bytes_per_step": d2h // args.steps, "regions_per_s": regions_all / e2e_elapsed,
+                    "wall_ms_per_step": e2e_wall / args.steps * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
-                         "traffic": None, "kernel": "svp_fwd_kernel", "peak_source": pk["source"],
-                         "launches": int(agg["fwd_launches"]), "avg_launch_ms": agg["fwd_ms"] / max(agg["fwd_launches"], 1),
+                         "traffic": (tr["ratio"] * algo_bytes / n_fwd) if tr else None,
+                         "traffic_note": (f"DRAM bytes per forward launch = algorithmic bytes per launch x {tr['ratio']:.4f} "
+                                          f"(dram__bytes_read+write / algorithmic, ncu --set full, {tr['source']})") if tr else None,
+                         "algorithmic_bytes_per_launch": algo_bytes / n_fwd,
+                         "kernel": "svp_fwd_kernel (all CTA-width groups of a wave; they run concurrently on 3 streams)", "peak_source": pk["source"],
+                         "launches": int(agg["fwd_launches"]), "avg_launch_ms": agg["fwd_ms"] / n_fwd,
                          "algorithmic_bytes_per_cell": 1.0,
                          "int_pipe": {"achieved_gcups": fwd_gcups, "peak_gcups": ip["gcups"], "frac": fwd_gcups / ip["gcups"],
-                                      "peak_source": ip["source"], "note": "the kernel is integer-ALU-bound, not HBM-bound (DESIGN.md §5)"}},
+                                      "peak_source": ip["source"],
+                                      "alu_pipe_14op": {"peak_gcups": ap_["gcups"], "frac": fwd_gcups / ap_["gcups"], **{k: ap_[k] for k in ("ipc_per_smsp", "sm_mhz", "int_ops_per_cell", "source")}},
+                                      "note": "the kernel is integer-ALU-bound, not HBM-bound (DESIGN.md §5); frac uses the stricter of the two denominators"}},
             "kernel_ms": {"fwd": agg["fwd_ms"], "traceback": agg["tb_ms"], "device_total": agg["total_ms"], "waves": agg["waves"]},
         }
         if not args.no_cpu_baseline and world == 1:

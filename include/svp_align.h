@@ -150,6 +150,13 @@ typedef struct svp_stats {
 } svp_stats;
 int svp_get_stats(const svp_handle* h, svp_stats* out);
 
+/* Device-side stopwatch for callers that time several calls as one region (bench.py): mark 0 and mark 1 are
+ * CUDA events recorded on the handle's main stream, which every kernel and copy of a call is ordered before
+ * when the call returns. svp_timer_elapsed_ms() waits for mark 1 and returns the device time between the marks
+ * (host gaps between calls included), or a negative SVP_ERR_* code. */
+int    svp_timer_mark(svp_handle* h, int which);
+double svp_timer_elapsed_ms(svp_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

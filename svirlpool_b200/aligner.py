@@ -53,6 +53,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_pinned_free.argtypes = [C.c_void_p]
     lib.svp_get_stats.restype = C.c_int
     lib.svp_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+    lib.svp_timer_mark.restype = C.c_int
+    lib.svp_timer_mark.argtypes = [C.c_void_p, C.c_int]
+    lib.svp_timer_elapsed_ms.restype = C.c_double
+    lib.svp_timer_elapsed_ms.argtypes = [C.c_void_p]
     batch_args = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                   C.c_void_p, C.c_void_p, C.c_size_t]
     lib.svp_align_batch.restype = C.c_int
@@ -163,6 +167,16 @@ class Aligner:
         self._check(self.lib.svp_align_batch_device(self._h, C.c_void_p(d_packed_ptr), packed_bytes, ptr(seq_off), ptr(seq_len),
                                                     len(seq_len), ptr(pairs), len(pairs), C.c_void_p(d_results_ptr),
                                                     C.c_void_p(d_cigar_ptr), int(cigar_words)))
+
+    def timer_mark(self, which: int) -> None:
+        """Record device stopwatch mark 0 / 1 on the handle's main stream (svp_timer_mark)."""
+        self._check(self.lib.svp_timer_mark(self._h, int(which)))
+
+    def timer_elapsed_ms(self) -> float:
+        ms = self.lib.svp_timer_elapsed_ms(self._h)
+        if ms < 0:
+            raise AlignerError(int(ms), "svp_timer_elapsed_ms failed")
+        return ms
 
     def stats(self) -> dict:
         s = np.zeros(1, dtype=STATS_DTYPE)

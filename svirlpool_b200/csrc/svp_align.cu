@@ -69,6 +69,7 @@ struct svp_handle {
                                                 // wave run concurrently, and consecutive waves use different stream sets
     cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
     std::vector<cudaEvent_t> events;            // pool, grown on demand
+    cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
     DevBuf d_tasks, d_order, d_bests, d_seqs, d_results, d_cigar, d_dense, d_dense_off;
     svp_stats stats{};
@@ -208,6 +209,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     if (h->arena) cudaFree(h->arena);
     for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : { h->stream, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4], h->stream_tb }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
@@ -226,6 +228,22 @@ extern "C" int svp_get_stats(const svp_handle* h, svp_stats* out) {
     if (!h || !out) return SVP_ERR_ARG;
     *out = h->stats;
     return SVP_OK;
+}
+
+extern "C" int svp_timer_mark(svp_handle* h, int which) {
+    if (!h || which < 0 || which > 1) return SVP_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->marks[which]) CUDA_TRY(h, cudaEventCreate(&h->marks[which]));
+    CUDA_TRY(h, cudaEventRecord(h->marks[which], h->stream));
+    return SVP_OK;
+}
+
+extern "C" double svp_timer_elapsed_ms(svp_handle* h) {
+    if (!h || !h->marks[0] || !h->marks[1]) return (double)SVP_ERR_ARG;
+    if (cudaEventSynchronize(h->marks[1]) != cudaSuccess) return (double)SVP_ERR_CUDA;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->marks[0], h->marks[1]) != cudaSuccess) return (double)SVP_ERR_CUDA;
+    return (double)ms;
 }
 
 // #{(i, j) : 1<=i<=m, 1<=j<=n, j - i <= x}
