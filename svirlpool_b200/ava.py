@@ -198,53 +198,90 @@ def ava_records(names, lens, meta, res, cig, min_score: int = MIN_DP_SCORE) -> l
 # one query vs one target with supplementary hits (reads -> consensus, consensus -> window)
 # ---------------------------------------------------------------------------------------------
 
-def map_queries(engine, queries: dict[str, str], target_name: str, target: str, min_score: int = MIN_DP_SCORE,
-                min_flank: int = 40, max_rounds: int = 8, granule: int = 32) -> list[AlignedRecord]:
-    """Map each query to the target like `minimap2 -x map-ont --secondary=no`: the best local hit
-    over both strands, then — iteratively — the best hit of every unaligned query flank of at least
-    min_flank bases, kept when its score reaches min_score. The highest-scoring hit of a query is
-    its primary record (soft clips), the others are supplementary (hard clips). Records are returned
-    sorted by target position."""
-    n = len(target)
-    # task: (query name, sub-sequence start, sub-sequence end) in ORIGINAL read coordinates
-    tasks = [(name, 0, len(seq)) for name, seq in queries.items() if len(seq) > 0]
-    hits: dict[str, list[tuple[int, bool, int, int, object, np.ndarray]]] = {name: [] for name in queries}
+@dataclass
+class MapJob:
+    """One query to be mapped to one target by map_jobs(). diag_fwd / diag_rev: expected diagonal (target position
+    minus position on the ORIENTED full query) of the forward / reverse-complement hit, or None when nothing is
+    known (full matrix). band_w: diagonals to cover around the expected one."""
+
+    name: str
+    seq: str
+    target: int = 0
+    diag_fwd: int | None = None
+    diag_rev: int | None = None
+    band_w: int = 0
+
+
+def _job_band(sub_len: int, n: int, diag: int | None, band_w: int, granule: int) -> tuple[int, int]:
+    flo, fw = full_band(sub_len, n, granule)
+    if diag is None or band_w <= 0:
+        return flo, fw
+    w = round_up(band_w, granule)
+    if w >= fw:
+        return flo, fw
+    return diag - w // 2, w
+
+
+def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[str], min_score: int = MIN_DP_SCORE,
+             min_flank: int = 40, max_rounds: int = 8, granule: int = 32) -> list[AlignedRecord]:
+    """Map every job's query to its target like `minimap2 -x map-ont --secondary=no`: the best local hit over both
+    strands, then — iteratively — the best hit of every unaligned query flank of at least min_flank bases, kept when
+    its score reaches min_score. The highest-scoring hit of a query is its primary record (soft clips), the others
+    are supplementary (hard clips). All jobs of a round share one svp_align_batch() call. Records come back sorted
+    by (target index, target position, query name)."""
+    # task: (job index, sub-sequence start, sub-sequence end) in ORIGINAL read coordinates
+    tasks = [(k, 0, len(j.seq)) for k, j in enumerate(jobs) if len(j.seq) > 0]
+    hits: dict[int, list] = {k: [] for k in range(len(jobs))}
     for _ in range(max_rounds):
         if not tasks:
             break
-        names, seqs, specs = [target_name], [target], []
-        for name, a, b in tasks:
-            names.append(f"{name}:{a}-{b}")
-            seqs.append(queries[name][a:b])
-            lo, w = full_band(b - a, n, granule)
-            specs.append((len(seqs) - 1, 0, lo, w, 0))
-            specs.append((len(seqs) - 1, 0, lo, w, PAIR_REVCOMP))
+        names, seqs, specs = list(target_names), list(targets), []
+        for k, a, b in tasks:
+            job = jobs[k]
+            full = len(job.seq)
+            names.append(f"{job.name}:{a}-{b}")
+            seqs.append(job.seq[a:b])
+            n = len(targets[job.target])
+            lo_f, w_f = _job_band(b - a, n, None if job.diag_fwd is None else job.diag_fwd + a, job.band_w, granule)
+            lo_r, w_r = _job_band(b - a, n, None if job.diag_rev is None else job.diag_rev + (full - b), job.band_w, granule)
+            specs.append((len(seqs) - 1, job.target, lo_f, w_f, 0))
+            specs.append((len(seqs) - 1, job.target, lo_r, w_r, PAIR_REVCOMP))
         batch = PairBatch.build(names, seqs, specs)
         res, cig = run_batch(engine, batch)
         nxt = []
-        for k, (name, a, b) in enumerate(tasks):
-            fwd, rev = res[2 * k], res[2 * k + 1]
-            pick, rc = (fwd, False) if int(fwd["score"]) >= int(rev["score"]) else (rev, True)
-            if int(pick["status"]) & ST_NOHIT or int(pick["score"]) < min_score:
+        for i, (k, a, b) in enumerate(tasks):
+            fwd, rev = res[2 * i], res[2 * i + 1]
+            fs = -1 if int(fwd["status"]) & ~ST_CIGAR_OVF else int(fwd["score"])
+            rs = -1 if int(rev["status"]) & ~ST_CIGAR_OVF else int(rev["score"])
+            pick, rc = (fwd, False) if fs >= rs else (rev, True)
+            if max(fs, rs) < min_score:
                 continue
-            hits[name].append((int(pick["score"]), rc, a, b, pick.copy(), cig))
+            hits[k].append((int(pick["score"]), rc, a, b, pick.copy(), cig))
             qb, qe, sub = int(pick["q_beg"]), int(pick["q_end"]), b - a
             if rc:                                    # oriented -> original coordinates inside the sub-sequence
                 qb, qe = sub - qe, sub - qb
             if qb >= min_flank:
-                nxt.append((name, a, a + qb))
+                nxt.append((k, a, a + qb))
             if sub - qe >= min_flank:
-                nxt.append((name, a + qe, b))
+                nxt.append((k, a + qe, b))
         tasks = nxt
     out = []
-    for name, hs in hits.items():
+    for k, hs in hits.items():
         if not hs:
             continue
-        primary = max(range(len(hs)), key=lambda k: (hs[k][0], -k))
-        for k, (score, rc, a, b, r, cig) in enumerate(hs):
-            rec = record_from_result(r, cig, name, target_name, b - a, rc, supplementary=(k != primary),
-                                     query_offset=a, query_total=len(queries[name]))
+        job = jobs[k]
+        primary = max(range(len(hs)), key=lambda i: (hs[i][0], -i))
+        for i, (score, rc, a, b, r, cig) in enumerate(hs):
+            rec = record_from_result(r, cig, job.name, target_names[job.target], b - a, rc, supplementary=(i != primary),
+                                     query_offset=a, query_total=len(job.seq))
             if rec is not None:
-                out.append(rec)
-    out.sort(key=lambda r: (r.reference_start, r.query_name))
-    return out
+                out.append((job.target, rec))
+    out.sort(key=lambda tr: (tr[0], tr[1].reference_start, tr[1].query_name))
+    return [r for _t, r in out]
+
+
+def map_queries(engine, queries: dict[str, str], target_name: str, target: str, min_score: int = MIN_DP_SCORE,
+                min_flank: int = 40, max_rounds: int = 8, granule: int = 32) -> list[AlignedRecord]:
+    """Every query vs ONE target over the full matrix (reads -> consensus, consensus.py:851-857); see map_jobs()."""
+    jobs = [MapJob(name=name, seq=seq) for name, seq in queries.items()]
+    return map_jobs(engine, jobs, [target_name], [target], min_score, min_flank, max_rounds, granule)

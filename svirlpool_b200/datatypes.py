@@ -160,3 +160,108 @@ def cigar_from_string(s: str) -> list[tuple[int, int]]:
             out.append((CIGAR_CHARS.index(ch), num))
             num = 0
     return out
+
+
+@dataclass(eq=False)
+class MergedSVSignal(SVsignal):
+    """SVsignal + chromosome, repeat ids and alt/ref sequences (datatypes.py:409-435); the unit
+    consensus_align_lib.parse_sv_signals_from_consensus returns."""
+
+    chr: str = ""
+    repeatIDs: list = field(default_factory=list)
+    original_alt_sequences: list = field(default_factory=list)
+    original_ref_sequences: list = field(default_factory=list)
+
+    def __hash__(self):
+        return hash(super().__hash__() + hash(self.chr))
+
+    def unstructure(self) -> dict:
+        d = super().unstructure()
+        d.update(chr=self.chr, repeatIDs=list(self.repeatIDs), original_alt_sequences=list(self.original_alt_sequences),
+                 original_ref_sequences=list(self.original_ref_sequences))
+        return d
+
+    def get_alt_sequence(self) -> str:
+        s = "".join(self.original_alt_sequences)
+        return s[: self.size] if self.sv_type == INS else s
+
+    def get_ref_sequence(self) -> str:
+        s = "".join(self.original_ref_sequences)
+        return s[: self.size] if self.sv_type == DEL else s
+
+
+@dataclass
+class SequenceObject:
+    """datatypes.py:323-341 (a read kept unused by a container)."""
+
+    name: str
+    id: str
+    sequence: str
+    description: str | None = None
+    qualities: list | None = None
+
+    def unstructure(self) -> dict:
+        return {"name": self.name, "id": self.id, "sequence": self.sequence, "description": self.description,
+                "qualities": self.qualities}
+
+
+@dataclass
+class Alignment:
+    """Serialisable alignment record (datatypes.py:344-402): the SAM fields as the dict pysam's
+    AlignedSegment.to_dict() produces (all values strings, 1-based ref_pos), plus coordinates and annotations.
+    One JSON object per line in the partitioned alignment files of consensus_align (consensus_align.py:661-735)."""
+
+    readname: str
+    reference_name: str
+    reference_ID: int
+    reference_start: int
+    reference_end: int
+    samdict: dict
+    headerdict: dict
+    annotations: dict | None = None
+    samplename: str | None = None
+
+    @classmethod
+    def from_record(cls, rec: "AlignedRecord", samplename: str | None = None, annotations: dict | None = None,
+                    reference_ID: int = 0, headerdict: dict | None = None) -> "Alignment":
+        tags = [f"{k}:{'i' if isinstance(v, int) else 'Z'}:{v}" for k, v in rec.tags.items()]
+        samdict = {"name": rec.query_name, "flag": str(rec.flag), "ref_name": rec.reference_name, "ref_pos": str(rec.reference_start + 1),
+                   "map_quality": str(rec.mapping_quality), "cigar": rec.cigarstring, "next_ref_name": "*", "next_ref_pos": "0",
+                   "length": "0", "seq": rec.query_sequence if rec.query_sequence is not None else "*", "qual": "*", "tags": tags}
+        return cls(readname=rec.query_name, reference_name=rec.reference_name, reference_ID=reference_ID,
+                   reference_start=rec.reference_start, reference_end=rec.reference_end, samdict=samdict,
+                   headerdict=headerdict or {}, annotations=annotations, samplename=samplename)
+
+    def to_record(self) -> "AlignedRecord":
+        sd = self.samdict
+        tags = {}
+        for t in sd.get("tags", []):
+            k, ty, v = t.split(":", 2)
+            tags[k] = int(v) if ty == "i" else v
+        seq = sd.get("seq")
+        return AlignedRecord(query_name=sd["name"], reference_name=sd["ref_name"], reference_start=int(sd["ref_pos"]) - 1,
+                             cigartuples=cigar_from_string(sd["cigar"]), flag=int(sd["flag"]),
+                             mapping_quality=int(sd.get("map_quality", 60)), query_sequence=None if seq in (None, "*") else seq, tags=tags)
+
+    to_pysam = to_record        # the reference's name for the same conversion (datatypes.py:376-378)
+
+    def is_reverse(self) -> bool:
+        return int(self.samdict["flag"]) & 0x10 != 0
+
+    def unstructure(self) -> dict:
+        return {"readname": self.readname, "reference_name": self.reference_name, "reference_ID": self.reference_ID,
+                "reference_start": self.reference_start, "reference_end": self.reference_end, "samdict": self.samdict,
+                "headerdict": self.headerdict, "annotations": self.annotations, "samplename": self.samplename}
+
+    @classmethod
+    def structure(cls, d: dict) -> "Alignment":
+        return cls(**{k: d.get(k) for k in ("readname", "reference_name", "reference_ID", "reference_start", "reference_end",
+                                            "samdict", "headerdict", "annotations", "samplename")})
+
+    def __eq__(self, value) -> bool:
+        return (self.samdict["ref_pos"] == value.samdict["ref_pos"] and self.samdict["ref_name"] == value.samdict["ref_name"]
+                and self.samdict["flag"] == value.samdict["flag"] and self.readname == value.readname
+                and self.samdict["cigar"] == value.samdict["cigar"])
+
+    def __hash__(self) -> int:
+        return hash((self.readname, self.reference_name, self.samplename, self.samdict["cigar"]))

@@ -94,3 +94,189 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
     finally:
         if own:
             engine.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference position <-> read position through a CIGAR (consensus_align consumer chain)
+# ---------------------------------------------------------------------------------------------
+import enum
+import logging
+
+log = logging.getLogger(__name__)
+
+_MATCH_OPS = (0, 7, 8)
+
+
+class Direction(enum.Enum):
+    """util/util.py:1329-1333."""
+    NONE = 0
+    LEFT = 1
+    RIGHT = 2
+    BOTH = 3
+
+
+def _cigar_arrays(alignment) -> tuple[np.ndarray, np.ndarray]:
+    ct = alignment.cigartuples
+    t = np.fromiter((op for op, _ in ct), dtype=np.int64, count=len(ct))
+    x = np.fromiter((n for _, n in ct), dtype=np.int64, count=len(ct))
+    return t, x
+
+
+def _walk_to_match(t: np.ndarray, block: int, step: int) -> int:
+    """Next block in direction `step` (+1 / -1) whose op is M/=/X; stops at the CIGAR's ends."""
+    if step > 0:
+        while t[block] not in _MATCH_OPS and block < len(t) - 1:
+            block += 1
+    else:
+        while t[block] not in _MATCH_OPS and block > 0:
+            block -= 1
+    return block
+
+
+def _swap_for_strand(direction: Direction, is_reverse: bool) -> Direction:
+    """Read RIGHT (increasing read coordinate) is reference LEFT for a reverse-strand alignment."""
+    if not is_reverse:
+        return direction
+    if direction == Direction.RIGHT:
+        return Direction.LEFT
+    if direction == Direction.LEFT:
+        return Direction.RIGHT
+    return direction
+
+
+def get_ref_pitx_on_read(alignment, position: int, direction: Direction, buffer_clipped_length: int = 0
+                         ) -> tuple[int, int, np.ndarray, np.ndarray]:
+    """Read position (ORIGINAL read orientation, hard clips counted) that corresponds to reference `position`,
+    the CIGAR block it falls into, and the op/length arrays — util/util.py:1365-1498, same conventions:
+    positions left/right of the aligned reference span snap to the clip boundary (optionally reaching
+    `buffer_clipped_length` into the clip); on an insertion or deletion block the position moves to the next
+    match block in `direction` (given in READ orientation)."""
+    is_reverse = alignment.is_reverse
+    ref_start, ref_end = alignment.reference_start, alignment.reference_end
+    t, x = _cigar_arrays(alignment)
+    aln_length = int(np.dot(x, _READLEN_OPS[t]))
+    left_clipped = int(x[0]) if t[0] in (4, 5) else 0
+    right_clipped = int(x[-1]) if t[-1] in (4, 5) else 0
+    if position < ref_start:
+        buffer = max(0, left_clipped - buffer_clipped_length)
+        return (aln_length - buffer, -1, t, x) if is_reverse else (buffer, 0, t, x)
+    if position >= ref_end:
+        last_ref_block = int(np.flatnonzero(_REF_OPS[t] == 1)[-1])
+        buffer = max(0, right_clipped - (buffer_clipped_length if position > ref_end else 0))
+        return (buffer, last_ref_block, t, x) if is_reverse else (aln_length - buffer, last_ref_block, t, x)
+    read_starts, read_ends, ref_starts, ref_ends = get_starts_ends(t, x, ref_start, is_reverse)
+    walk = _swap_for_strand(direction, is_reverse)
+    if direction == Direction.RIGHT:
+        block = int(np.flatnonzero((ref_starts <= position) & (position < ref_ends))[0])
+    elif direction == Direction.LEFT:
+        block = int(np.flatnonzero((ref_starts < position) & (position <= ref_ends))[0])
+    else:
+        block = int(np.flatnonzero((ref_starts <= position) & (position <= ref_ends))[0])
+    final_pos = -1
+    if t[block] in _MATCH_OPS:
+        final_pos = read_starts[block] + ((ref_ends[block] - position) if is_reverse else (position - ref_starts[block]))
+    if t[block] == 1:                      # on an insertion (only reachable with the closed-interval lookup)
+        if walk == Direction.RIGHT:
+            block = _walk_to_match(t, block, +1)
+            final_pos = read_starts[block]
+        else:
+            block = _walk_to_match(t, block, -1)
+            final_pos = read_ends[block]
+    if t[block] in (2, 3):                 # on a deletion / skipped region
+        if walk == Direction.LEFT:
+            block = _walk_to_match(t, block, -1)
+            final_pos = read_starts[block] if is_reverse else read_ends[block]
+        if walk == Direction.RIGHT:
+            block = _walk_to_match(t, block, +1)
+            final_pos = read_ends[block] if is_reverse else read_starts[block]
+        if direction in (Direction.NONE, Direction.BOTH):   # the nearer of the two flanking match blocks
+            bl, br = _walk_to_match(t, block, -1), _walk_to_match(t, block, +1)
+            if position - ref_ends[bl] < ref_starts[br] - position:
+                final_pos, block = (read_starts[bl] if is_reverse else read_ends[bl]), bl
+            else:
+                final_pos, block = (read_ends[br] if is_reverse else read_starts[br]), br
+    return int(final_pos), int(block), t, x
+
+
+def get_ref_position_on_read(alignment, position: int, direction: Direction, buffer_clipped_length: int = 0) -> int:
+    """util/util.py:1501-1510."""
+    return get_ref_pitx_on_read(alignment, position, direction, buffer_clipped_length)[0]
+
+
+def is_ref_position_on_aligned_read(alignment, position: int) -> bool:
+    """util/util.py:1513-1519."""
+    return alignment.reference_start <= position < alignment.reference_end
+
+
+def get_read_pitx_on_ref(alignment, position: int, direction: Direction) -> tuple[int, int, np.ndarray, np.ndarray]:
+    """Reference position that corresponds to read `position` (ORIGINAL read orientation) — util/util.py:1524-1648.
+    Positions in the clipped part before / after the aligned read span return the alignment's reference start / end
+    (swapped for reverse-strand alignments). Only LEFT and RIGHT are supported; anything else is treated as RIGHT
+    (with a warning), as the reference does."""
+    is_reverse = alignment.is_reverse
+    ref_start, ref_end = alignment.reference_start, alignment.reference_end
+    t, x = _cigar_arrays(alignment)
+    read_start = 0
+    if is_reverse:
+        if t[-1] in (4, 5):
+            read_start = int(x[-1])
+    elif t[0] in (4, 5):
+        read_start = int(x[0])
+    read_end = read_start + int(np.dot(x, _READ_OPS[t]))
+    read_blocks = np.flatnonzero(_READ_OPS[t] == 1)
+    if position <= read_start:
+        return (int(ref_end), int(read_blocks[-1]), t, x) if is_reverse else (int(ref_start), 0, t, x)
+    if position >= read_end:
+        return (int(ref_start), 0, t, x) if is_reverse else (int(ref_end), int(read_blocks[-1]), t, x)
+    read_starts, read_ends, ref_starts, ref_ends = get_starts_ends(t, x, ref_start, is_reverse)
+    if direction not in (Direction.RIGHT, Direction.LEFT):
+        log.warning("Other directions than LEFT or RIGHT are not supported. Using RIGHT as default.")
+        direction = Direction.RIGHT
+    walk = _swap_for_strand(direction, is_reverse)
+    if direction == Direction.RIGHT:
+        block = int(np.flatnonzero((read_starts <= position) & (position < read_ends))[0])
+    else:
+        block = int(np.flatnonzero((read_starts < position) & (position <= read_ends))[0])
+    final_pos = -1
+    if t[block] in _MATCH_OPS:
+        if is_reverse:
+            final_pos = ref_ends[block] - (position - read_starts[block])
+        else:
+            final_pos = ref_starts[block] + position - read_starts[block]
+    if t[block] == 2:
+        if walk == Direction.RIGHT:
+            block = _walk_to_match(t, block, +1)
+            final_pos = ref_starts[block]
+        else:
+            block = _walk_to_match(t, block, -1)
+            final_pos = ref_ends[block]
+    if t[block] == 1:
+        if walk == Direction.LEFT:
+            if block > 0:                  # (an insertion in the very first block keeps -1, as in the reference)
+                block = _walk_to_match(t, block, -1)
+                final_pos = ref_starts[block] if is_reverse else ref_ends[block]
+        elif walk == Direction.RIGHT:
+            block = _walk_to_match(t, block, +1)
+            final_pos = ref_ends[block] if is_reverse else ref_starts[block]
+    return int(final_pos), int(block), t, x
+
+
+def get_read_position_on_ref(alignment, position: int, direction: Direction) -> int:
+    """util/util.py:1651-1656."""
+    return get_read_pitx_on_ref(alignment, position, direction)[0]
+
+
+def get_interval_on_read_in_region(a, start: int, end: int, buffer_clipped_length: int = 0) -> tuple[int, int]:
+    """Read interval covering reference [start, end) — util/util.py:716-736."""
+    start, end = (end, start) if start > end else (start, end)
+    istart = get_ref_position_on_read(a, start, Direction.RIGHT, buffer_clipped_length)
+    iend = get_ref_position_on_read(a, end, Direction.RIGHT, buffer_clipped_length)
+    return (iend, istart) if a.is_reverse else (istart, iend)
+
+
+def get_interval_on_ref_in_region(a, start: int, end: int) -> tuple[int, int]:
+    """Reference interval covering read [start, end) — util/util.py:739-749."""
+    start, end = (end, start) if a.is_reverse else (start, end)
+    istart = get_read_position_on_ref(a, start, Direction.RIGHT)
+    iend = get_read_position_on_ref(a, end, Direction.LEFT)
+    return min(iend, istart), max(iend, istart)
