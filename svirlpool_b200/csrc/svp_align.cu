@@ -39,6 +39,15 @@ static inline int choose_kp(uint32_t band_w) {
     return best_kp;          // 0: band too wide for every variant
 }
 static inline int kp_of(const Task& t) { return (int)((t.flags & TASK_KP_MASK) >> TASK_KP_SHIFT); }
+static inline int cluster_of(const Task& t) { return std::max(1, (int)((t.flags & TASK_CL_MASK) >> TASK_CL_SHIFT)); }
+constexpr int MAX_CLUSTER = 8;                  // portable cluster size limit
+// CTAs (16 warps each) a band needs with `diag_per_warp` diagonals per warp, rounded up to a power of two; 0: too wide
+static inline int cluster_for(uint32_t band_w, int diag_per_warp) {
+    const int64_t per_cta = 16 * (int64_t)diag_per_warp;
+    int c = 1;
+    while ((int64_t)c * per_cta < (int64_t)band_w) c *= 2;
+    return c <= MAX_CLUSTER ? c : 0;
+}
 // steps per loop iteration of the kernel the pair runs on: 2*KP (s16 kernels), 16 (32-bit lane kernel, KP = 4 geometry)
 static inline int steps_per_iter_of(const Task& t) { return (t.flags & TASK_S32) ? 16 : 2 * kp_of(t); }
 static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * steps_per_iter_of(t) * (uint64_t)(t.band_w / 2); }
@@ -190,6 +199,10 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     SVP_SMEM(svp_fwd32_kernel<false, false, false>); SVP_SMEM(svp_fwd32_kernel<true, false, false>);
     SVP_SMEM(svp_fwd32_kernel<false, true, true>); SVP_SMEM(svp_fwd32_kernel<true, true, true>);
     SVP_SMEM(svp_fwd32_kernel<false, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true>);
+    SVP_SMEM(svp_fwd_kernel<8, true, true, true>); SVP_SMEM(svp_fwd_kernel<8, true, false, true>);
+    SVP_SMEM(svp_fwdg_kernel<true, true, true>); SVP_SMEM(svp_fwdg_kernel<true, false, true>);
+    SVP_SMEM(svp_fwd32_kernel<true, true, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, false, true>);
+    SVP_SMEM(svp_fwd32_kernel<true, true, true, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true, true>);
 #undef SVP_ATTR
 #undef SVP_SMEM
     size_t free_b = 0, total_b = 0;
@@ -261,10 +274,34 @@ static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
 // kernel family of a pair
 enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3 };
 
-static void launch_fwd(int fam, int kp, int nwarp, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
+template <typename Kern>
+static void launch_cluster(Kern kern, int cluster, unsigned n_pairs, unsigned thr, size_t smem, cudaStream_t st, const Task* tasks,
+                           const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_pairs * (unsigned)cluster, 1, 1);
+    cfg.blockDim = dim3(thr, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, tasks, order, seqs, arena, bests, cs);
+}
+
+static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
                        const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
     const bool multi = nwarp > 1;
     const unsigned thr = (unsigned)nwarp * 32u;
+    if (cluster > 1) {       // 16-warp CTAs, `cluster` of them per pair
+#define SVP_CL(COND, ...) if (COND) { launch_cluster(__VA_ARGS__, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
+        SVP_CL(fam == FAM_FAST && two, svp_fwd_kernel<8, true, true, true>) SVP_CL(fam == FAM_FAST && !two, svp_fwd_kernel<8, true, false, true>)
+        SVP_CL(fam == FAM_GEN && two, svp_fwdg_kernel<true, true, true>) SVP_CL(fam == FAM_GEN && !two, svp_fwdg_kernel<true, false, true>)
+        SVP_CL(fam == FAM_S32 && two, svp_fwd32_kernel<true, true, false, true>) SVP_CL(fam == FAM_S32 && !two, svp_fwd32_kernel<true, false, false, true>)
+        SVP_CL(fam == FAM_S32_GEN && two, svp_fwd32_kernel<true, true, true, true>) SVP_CL(fam == FAM_S32_GEN && !two, svp_fwd32_kernel<true, false, true, true>)
+#undef SVP_CL
+        return;
+    }
 #define SVP_ARGS <<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs)
 #define SVP_CASE(K, M, T) if (fam == FAM_FAST && kp == K && multi == M && two == T) { svp_fwd_kernel<K, M, T> SVP_ARGS; return; }
     SVP_CASE(4, false, true) SVP_CASE(4, true, true) SVP_CASE(8, false, true) SVP_CASE(8, true, true)
@@ -315,10 +352,15 @@ static void plan_pair(const Consts& cs, const svp_pair& p, uint32_t index, const
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
     // kernel variant: 32-bit lanes when the score can leave the s16 range; those and general scoring use the KP = 4 geometry
     const bool wide = (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
-    int kp;
-    if (wide || cs.general) kp = (p.band_w <= 16u * 512u) ? 4 : 0;
-    else kp = choose_kp(p.band_w);
-    if (kp == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
+    // bands beyond one CTA (16 warps) run on a thread-block cluster of 2, 4 or 8 CTAs
+    int kp, cl = 1;
+    if (wide || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
+    else {
+        kp = choose_kp(p.band_w);
+        if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
+    }
+    if (cl == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
+    if (cl > 1) t.flags |= (uint32_t)cl << TASK_CL_SHIFT;
     if (wide) t.flags |= TASK_S32;
     t.flags |= (uint32_t)kp << TASK_KP_SHIFT;
     const int steps_per_iter = steps_per_iter_of(t);
@@ -375,7 +417,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
 
     // per wave: order lists grouped by kernel variant and CTA width (warps)
     std::vector<uint32_t> order(n);
-    struct Group { int fam; int nwarp; int kp; size_t first, count; size_t smem; uint64_t work; };
+    struct Group { int fam; int nwarp; int kp; int cluster; size_t first, count; size_t smem; uint64_t work; };
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
@@ -384,24 +426,25 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const Task& t = tasks[k];
             if (t.flags & TASK_INVALID) continue;
             const int per_warp = 128 * kp_of(t);
-            const int nw = (t.band_w + per_warp - 1) / per_warp;
+            const int cl = cluster_of(t);
+            const int nw = cl > 1 ? 16 : (t.band_w + per_warp - 1) / per_warp;
             const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
-            by_w[nw + 1000 * kp_of(t) + 100000 * fam].push_back((uint32_t)k);
+            by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * cl].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
             size_t smem = 0; uint64_t work = 0;
-            const int nwarp = kv.first % 1000, kp = (kv.first / 1000) % 100, fam = kv.first / 100000;
+            const int nwarp = kv.first % 1000, kp = (kv.first / 1000) % 100, fam = (kv.first / 100000) % 100, cl = kv.first / 10000000;
             const int n_qimg = (fam == FAM_GEN || fam == FAM_S32_GEN) ? 2 : 1;            // general scoring stages two query images
             const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
                 smem = std::max(smem, (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
-                work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp));
+                work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
             if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
-            wave_groups[wv].push_back({ fam, nwarp, kp, pos, kv.second.size(), smem, work });
+            wave_groups[wv].push_back({ fam, nwarp, kp, cl, pos, kv.second.size(), smem, work });
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();
         }
@@ -432,7 +475,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const Group& gq = groups[gi];
-            launch_fwd(gq.fam, gq.kp, gq.nwarp, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
+            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
                        h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }

@@ -65,6 +65,8 @@ constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the score range 
 constexpr uint32_t TASK_S32 = 0x20000000u;       // pair runs on the 32-bit lane kernel (scores beyond the s16 range)
 constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP of the kernel variant the pair runs on
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;
+constexpr uint32_t TASK_CL_SHIFT = 16;           // bits 16..19: CTAs per cluster (0/1: no cluster)
+constexpr uint32_t TASK_CL_MASK = 0xF0000u;
 constexpr uint32_t NEGV = 0xC000C000u;   // s16x2 -16384: "minus infinity" for gap states
 constexpr uint32_t QNAN16 = 0x7E00u;     // fp16 NaN: sentinel base, never equal to anything
 
@@ -95,6 +97,42 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
 }
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---- thread-block clusters: bands wider than one CTA covers (16 warps) are split over the CTAs of a cluster; the
+// boundary mailboxes of neighbouring CTAs live in each other's shared memory (DSMEM) and the per-step CTA barrier
+// becomes a cluster barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one step's barrier / mailbox store, CTA-local or cluster-wide
+template <bool CL> __device__ __forceinline__ void step_barrier() { if (CL) cluster_sync_all(); else __syncthreads(); }
+template <bool CL> __device__ __forceinline__ void mailbox_store(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (CL) st_cluster_v4(addr, a, b, c, d); else sts_v4(addr, a, b, c, d);
+}
+// Mailbox addresses of this warp. A[w] receives lane 0 of warp w after an A-step and is read by warp w-1; the first
+// warp of a CTA inside a cluster writes to A[nwarp] of the previous CTA instead. B[w+1] receives lane 31 of warp w after a
+// B-step and is read by warp w+1; the last warp of a CTA writes to B[0] of the next CTA.
+template <bool CL>
+__device__ __forceinline__ void mailbox_targets(uint32_t s_mbA, uint32_t s_mbB, int warp, int nwarp, uint32_t crank, uint32_t csize,
+                                                uint32_t& s_myA, uint32_t& s_myB) {
+    if (CL) {
+        s_myA = (warp == 0 && crank > 0) ? mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1) : mapa_shared(s_mbA + 16u * (uint32_t)warp, crank);
+        s_myB = (warp == nwarp - 1 && crank + 1 < csize) ? mapa_shared(s_mbB, crank + 1) : mapa_shared(s_mbB + 16u * (uint32_t)(warp + 1), crank);
+    } else {
+        s_myA = s_mbA + 16u * (uint32_t)warp;
+        s_myB = s_mbB + 16u * (uint32_t)(warp + 1);
+    }
 }
 
 // Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
@@ -168,13 +206,16 @@ __device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) 
 
 constexpr int fwd_max_threads(int kp, bool multi) { return !multi ? 32 : (kp <= 8 ? 512 : 256); }
 
-template <int KP, bool MULTI, bool TWO>
+template <int KP, bool MULTI, bool TWO, bool CL = false>
 __global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+    static_assert(!CL || MULTI, "cluster variants are multi-warp");
     extern __shared__ __align__(16) uint8_t smem8[];
-    const Task tk = tasks[order[blockIdx.x]];
-    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
+    const int g = (int)crank * (int)blockDim.x + gl;          // thread index across the cluster: owner of diagonals g*4KP ...
     const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
     uint8_t* qimg = smem8;
     uint8_t* timg = smem8 + qbytes;
@@ -189,8 +230,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const uint32_t c_mat = pin(cs.mat), c_mis = pin(cs.mis), c_neg = pin(NEGV);
 
     stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
-    if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * g, c_noe1, c_noe2, c_neg, c_neg); }
-    __syncthreads();
+    if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); }
+    step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -217,8 +258,9 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
     const int pitch = tk.band_w >> 1;                        // bytes per traceback row (one step)
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
-    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
-    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    uint32_t s_myA, s_myB;
+    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
@@ -260,8 +302,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 if (active) store_row<KP>(tbp, HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) sts_v4(s_myA, P1[0], P2[0], F1[0], F2[0]);
-                    __syncthreads();
+                    if (lane == 0) mailbox_store<CL>(s_myA, P1[0], P2[0], F1[0], F2[0]);
+                    step_barrier<CL>();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -304,8 +346,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 if (active) store_row<KP>(tbp, HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) sts_v4(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
-                    __syncthreads();
+                    if (lane == 31) mailbox_store<CL>(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
+                    step_barrier<CL>();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t nb = lds_u8(s_q + (uint32_t)__vimin_s32_relu(qpos, qmax));
@@ -330,18 +372,18 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 // ---------------------------------------------------------------------------------------------
 // Byte layout of the traceback rows (written by svp_fwd_kernel<KP>): row = step s = (i + j) - r_begin,
 // pitch = band_w / 2 bytes; inside a row thread g owns bytes [g*2KP, (g+1)*2KP); the byte of its slot
-// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (4, 8, 12 or 16).
+// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (a power of two: 4, 8 or 16).
 struct TbView {
     const uint8_t* base;      // arena + tb_off
     const uint32_t* seqs32;   // packed sequences (global)
     int band_lo, band_w, r_begin, pitch, m, n, kp;
-    uint32_t magic;           // ceil(2^24 / (4*kp)): x / (4*kp) == (x * magic) >> 24 for x < 65536
+    int shift;                // log2(4*kp): the diagonals of one thread are a power of two (kp = 4, 8, 16)
     uint64_t q_word, t_word;  // word offsets of the packed sequences
     bool rc;
 
     // offset of diagonal x (band-relative) inside a row
     __device__ __forceinline__ int col(int x) const {
-        const int g = (int)(((uint32_t)x * magic) >> 24);
+        const int g = x >> shift;
         const int c = (x - g * 4 * kp) >> 1;
         const int half = c >= kp ? 1 : 0, k = c - half * kp;
         return g * 2 * kp + (k >> 1) * 4 + (k & 1) * 2 + half;
@@ -410,7 +452,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
     TbView v;
     v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
     v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
-    v.kp = KP; v.magic = (1u << 24) / (uint32_t)(4 * KP) + 1u;
+    v.kp = KP; v.shift = 31 - __clz(4 * KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
     const int d_hi = tk.band_lo + tk.band_w - 1;
 

@@ -85,14 +85,17 @@ __device__ __forceinline__ void stage_sequences_gen(const Task& tk, const uint8_
 // ---------------------------------------------------------------------------------------------
 // forward DP, s16x2 lanes, general scoring (KP = 4 geometry)
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool TWO>
+template <bool MULTI, bool TWO, bool CL = false>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                 uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+    static_assert(!CL || MULTI, "cluster variants are multi-warp");
     constexpr int KP = 4;
     extern __shared__ __align__(16) uint8_t smem8[];
-    const Task tk = tasks[order[blockIdx.x]];
-    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
+    const int g = (int)crank * (int)blockDim.x + gl;
     const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
     uint8_t* qsel = smem8;
     uint8_t* qsel2 = smem8 + qbytes;
@@ -111,8 +114,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     const uint32_t c_neg = pin(NEGV);
 
     stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
-    if (MULTI && g <= nwarp) { sts_v4(s_mbA + 16u * g, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * g, 0u, 0u, c_neg, c_neg); }
-    __syncthreads();
+    if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, 0u, 0u, c_neg, c_neg); }
+    step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -137,8 +140,9 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
-    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
-    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    uint32_t s_myA, s_myB;
+    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
 
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> uint32_t {
         const uint32_t sel = q | t;
@@ -184,8 +188,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 if (active) store_row<KP>(tbp, HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) sts_v4(s_myA, HA[0], 0u, F1[0], F2[0]);
-                    __syncthreads();
+                    if (lane == 0) mailbox_store<CL>(s_myA, HA[0], 0u, F1[0], F2[0]);
+                    step_barrier<CL>();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -227,8 +231,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 if (active) store_row<KP>(tbp, HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) sts_v4(s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
-                    __syncthreads();
+                    if (lane == 31) mailbox_store<CL>(s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
+                    step_barrier<CL>();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t off = (uint32_t)__vimin_s32_relu(qpos, qmax);
@@ -254,14 +258,17 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
 // 2K = 16 diagonals = the geometry of the s16 kernels with KP = 4, and the row bytes are written in their byte
 // order. One loop iteration is 2K = 16 steps = two end-cell blocks of 2*KP = 8 steps.
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool TWO, bool GEN>
+template <bool MULTI, bool TWO, bool GEN, bool CL = false>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                  uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+    static_assert(!CL || MULTI, "cluster variants are multi-warp");
     constexpr int K = 8, KPG = K / 2;
     extern __shared__ __align__(16) uint8_t smem8[];
-    const Task tk = tasks[order[blockIdx.x]];
-    const int g = threadIdx.x, lane = g & 31, warp = g >> 5, nwarp = blockDim.x >> 5;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
+    const int g = (int)crank * (int)blockDim.x + gl;
     const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
     uint8_t* qimg = smem8;                                   // GEN: qsel
     uint8_t* qimg2 = smem8 + qbytes;                         // GEN only: qsel2
@@ -281,11 +288,11 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
 
     if (GEN) stage_sequences_gen(tk, seqs, qimg, qimg2, timg, qbytes, tbytes);
     else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
-    if (MULTI && g <= nwarp) {
-        sts_v4(s_mbA + 16u * g, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-        sts_v4(s_mbB + 16u * g, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+    if (MULTI && gl <= nwarp) {
+        sts_v4(s_mbA + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+        sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
     }
-    __syncthreads();
+    step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (2 * K);
     const bool active = g < n_thr_active;
@@ -311,8 +318,9 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * K;
-    const uint32_t s_myA = s_mbA + 16u * warp, s_upA = s_mbA + 16u * (warp + 1);
-    const uint32_t s_myB = s_mbB + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    uint32_t s_myA, s_myB;
+    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
 
     // bytes of slots c = 0..7 in the shared row order: word0 = slots [0,4,1,5], word1 = slots [2,6,3,7]
     auto store8 = [&](const int (&Hs)[K]) {
@@ -365,8 +373,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 if (active) store8(HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) sts_v4(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
-                    __syncthreads();
+                    if (lane == 0) mailbox_store<CL>(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
+                    step_barrier<CL>();
                 }
                 T[u % K] = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));     // logical T[k] <- T[k+1]; new base in slot K-1
                 ++tpos;
@@ -392,8 +400,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 if (active) store8(HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) sts_v4(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
-                    __syncthreads();
+                    if (lane == 31) mailbox_store<CL>(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
+                    step_barrier<CL>();
                 }
                 const uint32_t qo = (uint32_t)__vimin_s32_relu(qpos, qmax);                 // logical Q[k] <- Q[k-1]; new base in slot 0
                 Q[(K - 1 - u) % K] = lds_u8(s_q + qo);

@@ -262,3 +262,76 @@ def test_long_reads_general_scoring():
     with Aligner(device=0, tb_bytes=2 << 30, scoring=scoring) as g:
         gres, _ = run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
     assert gres["score"].max() > 4000
+
+
+def test_alignment_on_high_band_columns(gpu, oracle):
+    """Alignments that run through band columns >= 8192 (KP = 8) / >= 4096 (KP = 4 geometry): the traceback's
+    diagonal -> byte-column mapping must not wrap (regression: a 32-bit multiply-shift did)."""
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(61)
+    t1 = randseq(rng, 12000)
+    q1 = mutate(rng, t1[8000:11000])                  # diagonal ~ +8000, band column ~ 11000 of 15008
+    t2 = randseq(rng, 6000)
+    q2 = mutate(rng, t2[4900:5900])                   # diagonal ~ +4900, band column ~ 5900 of 7008
+    seqs, names = [t1, q1, t2, q2], ["t1", "q1", "t2", "q2"]
+    specs = []
+    for q, t in ((1, 0), (3, 2)):
+        lo, w = ava.full_band(len(seqs[q]), len(seqs[t]))
+        specs += [(q, t, lo, w, 0)]
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert gres["score"].min() > 1000
+    scoring = SCORINGS["last_like_asym"]
+    with Aligner(device=0, tb_bytes=2 << 30, scoring=scoring) as g:
+        gres, _ = run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
+    assert gres["score"].min() > 1000 and not gres["status"].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# thread-block clusters: bands wider than one CTA
+# ---------------------------------------------------------------------------------------------
+
+def test_wide_band_cluster_fast_path(gpu, oracle):
+    """Full-matrix bands of 26k and 43k diagonals on the s16x2 fast path: clusters of 2 and 4 CTAs."""
+    rng = np.random.default_rng(71)
+    t1 = randseq(rng, 20000)
+    t2 = randseq(rng, 40000)
+    seqs = [t1, mutate(rng, t1[12000:17500]), revcomp(mutate(rng, t1[300:6200])), t2, mutate(rng, t2[33000:36000]), mutate(rng, t2[100:3100])]
+    names = ["t1", "a", "b", "t2", "c", "d"]
+    specs = []
+    for q, t, rc in ((1, 0, 0), (2, 0, 1), (4, 3, 0), (5, 3, 0)):
+        lo, w = ava.full_band(len(seqs[q]), len(seqs[t]))
+        specs.append((q, t, lo, w, PAIR_REVCOMP if rc else 0))
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert gres["score"].min() > 3000 and not gres["status"].any()
+
+
+def test_wide_band_cluster_long_reads(gpu, oracle):
+    """32-bit lanes + cluster: 18 kb reads whose haplotypes differ by a 9 kb insertion (band |dlen| + 512 > 8192)."""
+    rng = np.random.default_rng(72)
+    tmpl = randseq(rng, 18000)
+    ins = randseq(rng, 9000)
+    a = mutate(rng, tmpl, sub=0.01, ins=0.005, dele=0.005)        # accurate reads: bridging the 9 kb gap (cost 9024) pays off
+    b = mutate(rng, tmpl[:9000] + ins + tmpl[9000:], sub=0.01, ins=0.005, dele=0.005)
+    seqs, names = [a, b, revcomp(a)], ["a", "b", "a_rc"]
+    lo, w = ava.offset_band(len(a), len(b), slack=256, granule=32)
+    assert w > 8192
+    specs = [(0, 1, lo, w, 0), (2, 1, lo, w, PAIR_REVCOMP), (1, 0, -(lo + w - 1), w, 0)]
+    gres, gcig = run_both(gpu, oracle, names, seqs, specs)
+    assert not gres["status"].any() and gres["n_del_bp"][0] >= 9000 and gres["n_ins_bp"][2] >= 9000
+
+
+def test_wide_band_cluster_general_scoring():
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    scoring = SCORINGS["matrix_two_piece_asym"]
+    rng = np.random.default_rng(73)
+    t = randseq(rng, 14000)
+    seqs, names = [t, mutate(rng, t[9000:12500]), mutate(rng, t[200:3000])], ["t", "a", "b"]
+    specs = []
+    for q in (1, 2):
+        lo, w = ava.full_band(len(seqs[q]), len(t))
+        specs.append((q, 0, lo, w, 0))
+    with Aligner(device=0, tb_bytes=4 << 30, scoring=scoring) as g:
+        gres, _ = run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
+    assert not gres["status"].any()
