@@ -41,8 +41,8 @@ def reference_windows(cons: Consensus, chrom_lengths: dict[str, int], margin_fra
 
 
 def align_consensuses_to_reference(engine, consensuses: dict[str, Consensus], fetch: Callable[[str, int, int], str],
-                                   chrom_lengths: dict[str, int], band_w: int = 4096, min_score: int = ava.MIN_DP_SCORE
-                                   ) -> list[AlignedRecord]:
+                                   chrom_lengths: dict[str, int], band_w: int = 4096, min_score: int = ava.MIN_DP_SCORE,
+                                   margin_frac: float = 0.10, min_margin: int = 500) -> list[AlignedRecord]:
     """Align every padded consensus to its reference window(s). `fetch(chrom, start, end)` returns reference bases.
     Records carry chromosome names and chromosome coordinates, sorted by (chromosome, position) like the
     coordinate-sorted BAM of the reference's call."""
@@ -52,7 +52,7 @@ def align_consensuses_to_reference(engine, consensuses: dict[str, Consensus], fe
             raise ValueError(f"Consensus {cid} has no consensus_padding. This should not happen. Please check the input data.")
         seq = cons.consensus_padding.sequence
         core_lo, core_hi = cons.consensus_padding.consensus_interval_on_sequence_with_padding
-        for chrom, w_start, w_end in reference_windows(cons, chrom_lengths):
+        for chrom, w_start, w_end in reference_windows(cons, chrom_lengths, margin_frac, min_margin):
             regions = [r for r in cons.original_regions if r[0] == chrom]
             r_start, r_end = min(r[1] for r in regions), max(r[2] for r in regions)
             target_names.append(chrom)

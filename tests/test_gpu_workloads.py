@@ -1,0 +1,103 @@
+"""BASELINE configs 3-5 on the CUDA path: bit-exact against the oracle at sizes the oracle's full-band matrix fits,
+and — at the configs' full sizes (reads up to 50 kb, bands beyond 16k diagonals, 50 kb consensuses) — the
+size-independent consistency properties of tests/consistency.py on every pair."""
+import numpy as np
+import pytest
+
+from consistency import check_result
+from svirlpool_b200 import consensus_align, synth, workloads
+from svirlpool_b200._abi import cigartuples
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("score", "status", "q_beg", "q_end", "t_beg", "t_end", "n_match", "n_mismatch", "n_ins_ops", "n_ins_bp",
+              "n_del_ops", "n_del_bp", "cigar_len", "cells")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from svirlpool_b200.aligner import Aligner
+    a = Aligner(device=0, preset="map-ont", tb_bytes=24 << 30)
+    yield a
+    a.close()
+
+
+def align(engine, b):
+    return engine.align_batch(b["packed"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+
+
+def assert_parity(b, gpu, oracle):
+    gres, gcig = align(gpu, b)
+    ores, ocig = align(oracle, b)
+    for f in INT_FIELDS:
+        bad = np.nonzero(gres[f] != ores[f])[0]
+        assert len(bad) == 0, f"{f}: {len(bad)} mismatches, first at pair {bad[0]}: gpu={gres[bad[0]]} oracle={ores[bad[0]]} pair={b['pairs'][bad[0]]}"
+    for k in range(len(gres)):
+        assert cigartuples(gcig, gres[k]) == cigartuples(ocig, ores[k]), f"CIGAR differs at pair {k}"
+    np.testing.assert_allclose(gres["sv_dist"], ores["sv_dist"], rtol=1e-6, atol=0)
+    return gres, gcig
+
+
+def assert_consistent(b, gres, gcig, scoring, allow_status=0):
+    assert not (gres["status"] & ~np.uint32(1 | allow_status)).any(), f"unexpected status bits: {np.unique(gres['status'])}"
+    for k in range(len(gres)):
+        check_result(b["packed"], b["off"], b["lens"], b["pairs"][k], gres[k], gcig, scoring)
+
+
+def test_config3_reduced_parity(gpu, oracle):
+    b = workloads.batch_config3([0, 1, 2], n_reads=6, scale=0.3)
+    gres, gcig = assert_parity(b, gpu, oracle)
+    assert_consistent(b, gres, gcig, gpu.scoring)
+
+
+def test_config3_full_size_parity_long_reads(gpu, oracle):
+    """Region 16: haplotypes 21.7 / 24.8 kb (32-bit lanes), band 3.6k: the oracle still fits."""
+    b = workloads.batch_config3([16], n_reads=5)
+    assert b["lens"].min() > 16_000
+    gres, gcig = assert_parity(b, gpu, oracle)
+    assert gres["score"].max() > 16_000
+
+
+def test_config3_full_size_wide_bands_consistency(gpu):
+    """Region 6: haplotypes 15.6 / 33.5 kb, |dlen| = 17.9 kb -> bands beyond 16k diagonals on 32-bit lanes = clusters of 4
+    CTAs; 8 reads = 28 pairs incl. same-haplotype narrow ones. No oracle at this size: consistency properties."""
+    b = workloads.batch_config3([6], n_reads=8)
+    assert b["pairs"]["band_w"].max() > 16_384
+    gres, gcig = align(gpu, b)
+    assert_consistent(b, gres, gcig, gpu.scoring)
+    assert (gres["status"] == 0).all() and gres["score"].min() > 5_000
+
+
+def test_config4_reduced_parity(gpu, oracle):
+    b = workloads.batch_config4([0, 1, 2, 3], scale=0.3, max_reads=8, band_w=1024)
+    gres, gcig = assert_parity(b, gpu, oracle)
+    assert_consistent(b, gres, gcig, gpu.scoring)
+
+
+def test_config4_full_size_locus(gpu, oracle):
+    """Locus 1: core 12.6 kb, padded consensus 52.6 kb vs a 56.6 kb reference window (band 4096, both strands), plus
+    the all-vs-all of 10 of its reads: parity for the consensus pairs, consistency for everything."""
+    b = workloads.batch_config4([1], max_reads=10)
+    gres, gcig = align(gpu, b)
+    assert_consistent(b, gres, gcig, gpu.scoring)
+    cons_pairs = np.nonzero(b["lens"][b["pairs"]["q"]] > 50_000)[0]
+    assert len(cons_pairs) == 2
+    sub = dict(b)
+    sub["pairs"] = b["pairs"][cons_pairs].copy()
+    assert_parity(sub, gpu, oracle)
+    best = gres[cons_pairs][np.argmax(gres[cons_pairs]["score"])]
+    assert best["score"] > 90_000 and best["q_end"] - best["q_beg"] > 52_000
+
+
+def test_config5_skewed_locus_through_the_chain(gpu):
+    """A long-tail trio locus through align -> annotate -> core interval: the core maps back to the candidate region."""
+    lid = next(k for k in range(400) if synth.locus_config4(k, seed_base=40_000, skew=True).region.meta["core"] > 20_000)
+    loc = synth.locus_config4(lid, seed_base=40_000, skew=True, max_reads=4)
+    cons = workloads.consensus_objects(loc)
+    ref = synth.codes_to_str(loc.ref_window)
+    fetch = lambda c, s, e: ref[s - loc.window_start:e - loc.window_start]
+    recs = consensus_align.align_consensuses_to_reference(gpu, cons, fetch, {loc.chrom: loc.window_start + len(ref)}, min_margin=0)
+    ann = consensus_align.annotate_alignments(recs, "S")
+    cores = consensus_align.core_intervals_on_reference(cons, ann)
+    for cid in cons:
+        assert any(abs(a - loc.core_interval[0]) <= 10 for _i, _c, a, _b, _lo, _hi in cores[cid])
