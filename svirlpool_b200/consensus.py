@@ -73,3 +73,23 @@ def align_reads_to_consensus(engine, samplename: str, reads: dict[str, str], con
     records = ava.map_queries(engine, reads, consensus_name, consensus_seq)
     signals = [parse_ReadAlignmentSignals_from_alignment(samplename, r, min_signal_size, min_bnd_size) for r in records]
     return records, signals
+
+
+def final_consensus(engine, samplename: str, min_indel_size: int, min_bnd_size: int, reads: dict[str, str], consensus_sequence: str,
+                    ID: str, crIDs: list[int], original_regions: list[tuple[str, int, int]]):
+    """The reference's final_consensus (consensus.py:821-916) with the `minimap2 -x map-ont -Y --sam-hit-only
+    --secondary=no` subprocess replaced by the CUDA engine: the cluster's cut reads are aligned to the finished
+    consensus; their SV signals (the consensus' "distortions") and reference intervals go into the Consensus record.
+    Returns None when no read aligns, as the reference does. In-memory inputs instead of FASTA paths."""
+    from . import consensus_class
+    if not consensus_sequence:
+        raise ValueError("consensus sequence is empty. Cannot proceed.")
+    if not reads:
+        raise ValueError("reads are empty. Cannot proceed.")
+    records, signals = align_reads_to_consensus(engine, samplename, reads, ID, consensus_sequence,
+                                                min_signal_size=min_indel_size, min_bnd_size=min_bnd_size)
+    if not records:
+        return None
+    intervals = [(r.reference_start, r.reference_end, r.query_name, r.is_forward) for r in records]
+    return consensus_class.Consensus(ID=ID, crIDs=list(crIDs), original_regions=list(original_regions), consensus_sequence=consensus_sequence,
+                                     cut_read_alignment_signals=signals, intervals_cutread_alignments=intervals)

@@ -54,6 +54,27 @@ def read_fasta(path) -> dict[str, str]:
     return {k: "".join(v) for k, v in seqs.items()}
 
 
+def read_fasta_records(path):
+    """(id, description, sequence) per FASTA record, with Bio.SeqIO's conventions: id = first word of the header,
+    description = the whole header line."""
+    rid, desc, chunks = None, None, []
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            if line[0] == ">":
+                if rid is not None:
+                    yield rid, desc, "".join(chunks)
+                desc = line[1:].strip()
+                rid = desc.split()[0] if desc else ""
+                chunks = []
+            elif rid is not None:
+                chunks.append(line.strip())
+    if rid is not None:
+        yield rid, desc, "".join(chunks)
+
+
 def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", threads: int = 3, aln_args: str = "",
                              logfile=None, timeout: float | None = None, engine=None) -> None:
     """Drop-in for svirlpool.util.util.align_reads_with_minimap (util/util.py:162-238): FASTA path(s) in,

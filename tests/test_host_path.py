@@ -193,3 +193,24 @@ def test_file_seam_align_reads_with_minimap(tmp_path, golden, oracle):
     assert back[0].query_sequence == util.reverse_complement(next(iter(case["reads"].values())))
     ds = consensus_lib.parse_directed_signals_from_ava(bam, 12, 100)
     assert ds[0].signals == [SVsignal(480, 500, 500, 500, 20, 1)]
+
+
+def test_final_consensus_record(oracle):
+    """final_consensus (consensus.py:821-916): reads of one haplotype aligned to their consensus; the indel carried by a
+    read of the OTHER haplotype shows up as a distortion of the consensus."""
+    from svirlpool_b200 import consensus, synth
+    from svirlpool_b200.util import reverse_complement
+    region = synth.region_config2(11, n_reads=8, mean_len=1800, sd_len=60)
+    reads = region.read_strings()
+    hap0 = [n for n, h in zip(region.names, region.haplotypes) if h == 0]
+    other = [n for n, h in zip(region.names, region.haplotypes) if h == 1][:1]
+    strand = dict(zip(region.names, region.strands))
+    cseq = reads[hap0[0]] if strand[hap0[0]] == "+" else reverse_complement(reads[hap0[0]])
+    use = {n: reads[n] for n in hap0 + other}
+    c = consensus.final_consensus(oracle, "S", 8, 100, use, cseq, "11.0", [11], [("chr1", 1000, 2800)])
+    assert c is not None and c.get_used_readnames() == set(use)
+    assert {f for _s, _e, n, f in c.intervals_cutread_alignments if n == hap0[0]} == {strand[hap0[0]] == "+"}
+    big = [d for d in c.get_consensus_distortions() if d.readname == other[0] and d.size >= 40]
+    assert len(big) == 1 and big[0].size == abs(region.sv_size) and big[0].type == (0 if region.sv_size > 0 else 1)
+    assert c.get_max_cutread_coverage() >= len(hap0)
+    assert consensus.final_consensus(oracle, "S", 8, 100, {"x": "ACGT" * 30}, cseq, "11.0", [11], []) is None
