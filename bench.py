@@ -225,6 +225,8 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout; stdout carries exactly one JSON line, so route them to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/svirlpool_b200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
