@@ -117,6 +117,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // one step's barrier / mailbox store, CTA-local or cluster-wide
 template <bool CL> __device__ __forceinline__ void step_barrier() { if (CL) cluster_sync_all(); else __syncthreads(); }
+// (Tried and measured slower on B200, 1740 vs 1824 GCUPS on config 2: replacing the CTA barrier of the multi-warp kernels by
+// pairwise producer/consumer named barriers between neighbouring warps — bar.arrive by the producer, bar.sync by the
+// consumer, one barrier per direction per pair because a barrier only counts arrivals. The kernel then reserves all 16
+// named barriers and issues two barrier instructions per step.)
 template <bool CL> __device__ __forceinline__ void mailbox_store(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     if (CL) st_cluster_v4(addr, a, b, c, d); else sts_v4(addr, a, b, c, d);
 }
