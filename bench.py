@@ -117,29 +117,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def build_batch(region_ids: list[int]):
-    """Packed reads + pair descriptors of a list of config-2 regions."""
-    from svirlpool_b200 import synth
-    from svirlpool_b200._abi import PAIR_DTYPE, pack_codes
-    from svirlpool_b200.ava import cigar_cap_for
-    seqs, specs = [], []
-    for rid in region_ids:
-        reg = synth.region_config2(rid)
-        base = len(seqs)
-        seqs += reg.reads
-        specs += [(base + q, base + t, lo, w, fl) for (q, t, lo, w, fl) in synth.region_pairs(reg, SLACK, GRANULE)]
-    packed, off, lens = pack_codes(seqs)
-    pairs = np.zeros(len(specs), dtype=PAIR_DTYPE)
-    arr = np.array(specs, dtype=np.int64)
-    pairs["q"], pairs["t"], pairs["band_lo"], pairs["band_w"], pairs["flags"] = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3], arr[:, 4]
-    caps = np.array([cigar_cap_for(int(lens[q]), int(lens[t])) for q, t in arr[:, :2]], dtype=np.int64)
-    offs = np.concatenate(([0], np.cumsum(caps)[:-1]))
-    pairs["cigar_off"], pairs["cigar_cap"] = offs, caps
-    return {"packed": packed, "off": off, "lens": lens, "pairs": pairs, "cigar_words": int(caps.sum()), "n_regions": len(region_ids),
-            "seq_bytes": int(((lens.astype(np.int64) + 3) // 4).sum())}
+WORKLOADS = {
+    "config2": "config2: 10k regions x 30 ONT-like reads x 8 kb, all-vs-all (435 pairs/region), map-ont scoring",
+    "config3": "config3: tandem-repeat regions, 20 spanning reads of 10-50 kb, haplotypes 2-20 kb apart, all-vs-all, band |dlen|+512 (32-bit lanes, clusters)",
+    "config4": "config4: HG002-shape loci (core log-normal 3 kb, coverage Poisson 30), all-vs-all + padded consensus -> reference window on both strands",
+}
 
 
-def regions_for_step(step: int, world: int, per_gpu: int) -> list[list[int]]:
+def build_batch(region_ids: list[int], workload: str = "config2"):
+    """Packed reads + pair descriptors of a list of regions of the workload (svirlpool_b200.workloads)."""
+    from svirlpool_b200 import workloads
+    if workload == "config3":
+        return workloads.batch_config3(region_ids)
+    if workload == "config4":
+        return workloads.batch_config4(region_ids)
+    return workloads.batch_config2(region_ids, SLACK, GRANULE)
+
+
+def regions_for_step(step: int, world: int, per_gpu: int, workload: str = "config2") -> list[list[int]]:
     """Region ids of one step, assigned to ranks by the size-balanced scheduler (LPT on estimated cells)."""
     from svirlpool_b200 import scheduler, synth
     first = (step * world * per_gpu) % N_REGIONS_CONFIG
@@ -148,6 +143,13 @@ def regions_for_step(step: int, world: int, per_gpu: int) -> list[list[int]]:
         return [ids]
     costs = []
     for rid in ids:
+        if workload == "config3":
+            h0, h1 = synth.region_config3(rid, n_reads=1).meta["hap_lengths"]
+            costs.append(h1 * (h1 - h0 + 512))
+            continue
+        if workload == "config4":
+            costs.append(synth.locus_cost(synth.locus_config4(rid)))
+            continue
         length, sv = synth.region_config2_shape(rid)
         costs.append(length * (abs(sv) // 2 + 2 * SLACK + GRANULE))
     bins = scheduler.lpt_assign(costs, world)
@@ -203,12 +205,15 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--regions", type=int, default=96, help="regions per GPU per step")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the one the metric is quoted on)")
+    ap.add_argument("--regions", type=int, default=None, help="regions per GPU per step (default 96; 8 for config3, 48 for config4)")
     ap.add_argument("--distinct-batches", type=int, default=3, help="distinct synthetic batches cycled over the steps")
     ap.add_argument("--ref-regions", type=int, default=2, help="regions per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-sample-regions", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.regions is None:
+        args.regions = {"config2": 96, "config3": 8, "config4": 48}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
@@ -234,8 +239,8 @@ def main() -> None:
     n_distinct = max(1, min(args.distinct_batches, args.warmup + args.steps))
     batches = []
     for s in range(n_distinct):
-        mine = regions_for_step(s, world, args.regions)[rank]
-        b = build_batch(mine)
+        mine = regions_for_step(s, world, args.regions, args.workload)[rank]
+        b = build_batch(mine, args.workload)
         b["d_packed"] = torch.from_numpy(b["packed"]).to(dev)
         pin = torch.empty(b["packed"].nbytes, dtype=torch.uint8, pin_memory=True)
         pin.numpy()[:] = b["packed"]
@@ -323,12 +328,14 @@ def main() -> None:
         ap_ = alu_pipe_peak(clocks.get("sm_mhz"))
         n_fwd = max(int(agg["fwd_launches"]), 1)
         line = {
-            "metric": METRIC, "value": cells / elapsed / 1e9, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
+            "metric": METRIC if args.workload == "config2" else f"gcups_{args.workload}", "value": cells / elapsed / 1e9, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2" if args.workload == "config2" else "s16x2+s32",
             "data": "synthetic", "regions_per_s": regions_all / elapsed,
-            "config": {"workload": "config2: 10k regions x 30 ONT-like reads x 8 kb, all-vs-all (435 pairs/region), map-ont scoring",
-                       "regions_per_step_per_gpu": args.regions, "distinct_batches": n_distinct, "region_seeds": "10000+r",
-                       "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE}", "sharding": "LPT by estimated cells, no collective",
+            "config": {"workload": WORKLOADS[args.workload],
+                       "regions_per_step_per_gpu": args.regions, "distinct_batches": n_distinct,
+                       "region_seeds": {"config2": "10000+r", "config3": "20000+r", "config4": "30000+r"}[args.workload],
+                       "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE}" if args.workload != "config3" else "|dlen|+512", "sharding": "LPT by estimated cells, no collective",
                        "l2": "inputs+traceback per step >> 126 MB L2 (traceback arena rewritten every step)",
                        "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it"},
             "wall_ms_per_step": wall_elapsed / args.steps * 1e3,
@@ -351,7 +358,7 @@ def main() -> None:
                                       "note": "the kernel is integer-ALU-bound, not HBM-bound (DESIGN.md §5); frac uses the stricter of the two denominators"}},
             "kernel_ms": {"fwd": agg["fwd_ms"], "traceback": agg["tb_ms"], "device_total": agg["total_ms"], "waves": agg["waves"]},
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "config2":
             cb = cpu_arm(args.cpu_sample_regions, os.cpu_count() or 1)
             line["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
         print(json.dumps(line), flush=True)
