@@ -230,9 +230,20 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout; stdout carries exactly one JSON line, so route them to a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/svirlpool_b200_nccl.%h.%p.log")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version / debug lines on stdout when it creates the communicator; stdout must carry exactly one
+        # JSON line, so stdout points at stderr until the communicator exists (first collective)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     dev = torch.device("cuda", local)
 
     # ---- synthetic input: a few distinct batches, pre-packed, pinned on the host and resident in HBM ----
