@@ -44,7 +44,8 @@ extern "C" {
 #define SVP_ST_NOHIT         1u  /* best local score == 0: no alignment ("unmapped") */
 #define SVP_ST_CIGAR_OVF     2u  /* CIGAR longer than the pair's slot; counts/coords still valid */
 #define SVP_ST_SCORE_OVF     4u  /* score range exceeded the kernel's lane type (must not happen) */
-#define SVP_ST_BAD_PAIR      8u  /* pair descriptor invalid (index, band) */
+#define SVP_ST_BAD_PAIR      8u  /* pair descriptor invalid (index, band), or band wider than a cluster covers */
+#define SVP_ST_TOO_LONG     16u  /* the pair's sequences do not fit the kernels' shared-memory images (m + n beyond ~226 k bases) */
 
 /* CIGAR op codes: BAM encoding, word = len << 4 | op */
 #define SVP_CIGAR_M 0u

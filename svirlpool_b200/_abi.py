@@ -9,7 +9,7 @@ import numpy as np
 ABI_VERSION = 1
 
 SVP_OK, SVP_ERR_ARG, SVP_ERR_CUDA, SVP_ERR_NOMEM, SVP_ERR_UNSUPPORTED, SVP_ERR_NODEVICE = 0, -1, -2, -3, -4, -5
-ST_OK, ST_NOHIT, ST_CIGAR_OVF, ST_SCORE_OVF, ST_BAD_PAIR = 0, 1, 2, 4, 8
+ST_OK, ST_NOHIT, ST_CIGAR_OVF, ST_SCORE_OVF, ST_BAD_PAIR, ST_TOO_LONG = 0, 1, 2, 4, 8, 16
 PAIR_REVCOMP = 1
 
 SCORING_DTYPE = np.dtype([

@@ -385,6 +385,13 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     h->stats = svp_stats{};
     const size_t n = tasks.size();
     if (n == 0) return SVP_OK;
+    // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
+    for (Task& t : tasks) {
+        if (t.flags & TASK_INVALID) continue;
+        const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
+        const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
+        if (need > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
+    }
     // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
     // the traceback of wave w overlaps the forward pass of wave w+1
     const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
@@ -421,21 +428,26 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        std::map<int, std::vector<uint32_t>> by_w;
+        std::map<int64_t, std::vector<uint32_t>> by_w;
         for (size_t k = waves[wv].first; k < waves[wv].second; ++k) {
-            const Task& t = tasks[k];
+            Task& t = tasks[k];
             if (t.flags & TASK_INVALID) continue;
             const int per_warp = 128 * kp_of(t);
             const int cl = cluster_of(t);
             const int nw = cl > 1 ? 16 : (t.band_w + per_warp - 1) / per_warp;
             const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
-            by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * cl].push_back((uint32_t)k);
+            // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (powers of two from
+            // 16 KB) so that a few long pairs do not cut the occupancy of the short ones sharing their launch.
+            const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
+            int cls = 0;
+            while (((size_t)16384 << cls) < need) ++cls;
+            by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * (int64_t)cl + 1000000000 * (int64_t)cls].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
             size_t smem = 0; uint64_t work = 0;
-            const int nwarp = kv.first % 1000, kp = (kv.first / 1000) % 100, fam = (kv.first / 100000) % 100, cl = kv.first / 10000000;
+            const int nwarp = (int)(kv.first % 1000), kp = (int)((kv.first / 1000) % 100), fam = (int)((kv.first / 100000) % 100), cl = (int)((kv.first / 10000000) % 100);
             const int n_qimg = (fam == FAM_GEN || fam == FAM_S32_GEN) ? 2 : 1;            // general scoring stages two query images
             const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
@@ -443,7 +455,6 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
                 smem = std::max(smem, (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
                 work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
-            if (smem > (size_t)h->max_smem_optin) return fail(h, SVP_ERR_UNSUPPORTED, "sequences too long for shared-memory staging");
             wave_groups[wv].push_back({ fam, nwarp, kp, cl, pos, kv.second.size(), smem, work });
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();

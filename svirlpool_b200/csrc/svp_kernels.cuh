@@ -61,7 +61,7 @@ struct Consts {             // scoring in the forms the kernels use (svp_align.c
 };
 
 constexpr uint32_t TASK_INVALID = 0x80000000u;   // Task.flags: descriptor rejected by the planner
-constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the score range exceeds s16
+constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the two sequences do not fit the shared-memory images
 constexpr uint32_t TASK_S32 = 0x20000000u;       // pair runs on the 32-bit lane kernel (scores beyond the s16 range)
 constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP of the kernel variant the pair runs on
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;
@@ -448,7 +448,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
     res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
     if (tk.flags & TASK_INVALID) {
         res.cells = 0;
-        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_SCORE_OVF : SVP_ST_BAD_PAIR;
+        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_TOO_LONG : SVP_ST_BAD_PAIR;
         results[tk.pair_index] = res;
         return;
     }

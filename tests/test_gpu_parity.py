@@ -335,3 +335,49 @@ def test_wide_band_cluster_general_scoring():
     with Aligner(device=0, tb_bytes=4 << 30, scoring=scoring) as g:
         gres, _ = run_both(g, OracleEngine(scoring=scoring), names, seqs, specs)
     assert not gres["status"].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the batch interface
+# ---------------------------------------------------------------------------------------------
+
+def test_empty_batch_and_single_base(gpu, oracle):
+    from svirlpool_b200._abi import PAIR_DTYPE
+    batch = ava.PairBatch.build(["a", "b"], ["ACGT" * 10, "ACGT" * 10], [])
+    res, cig = gpu.align_batch(batch.packed, batch.seq_off, batch.seq_len, np.zeros(0, dtype=PAIR_DTYPE), 1)
+    assert len(res) == 0
+    seqs = ["A", "A", "C", "ACGTACGTAC"]
+    specs = [(0, 1, -31, 64, 0), (0, 2, -31, 64, 0), (0, 3, -31, 64, 0), (3, 0, -31, 64, PAIR_REVCOMP)]
+    gres, _ = run_both(gpu, oracle, ["a", "a2", "c", "d"], seqs, specs)
+    assert list(gres["score"]) == [2, 0, 2, 2] and list(gres["status"]) == [0, 1, 0, 0]
+
+
+def test_cigar_overflow_is_flagged_and_retried(gpu, oracle):
+    rng = np.random.default_rng(81)
+    tmpl = randseq(rng, 1500)
+    seqs = [mutate(rng, tmpl), mutate(rng, tmpl)]
+    lo, w = ava.offset_band(len(seqs[0]), len(seqs[1]), slack=100, granule=32)
+    tight = ava.PairBatch.build(["a", "b"], seqs, [(0, 1, lo, w, 0)], cap_fn=lambda m, n: 8)
+    res, _ = gpu.align_batch(tight.packed, tight.seq_off, tight.seq_len, tight.pairs, tight.cigar_words)
+    ores, _ = oracle.align_batch(tight.packed, tight.seq_off, tight.seq_len, tight.pairs, tight.cigar_words)
+    assert res[0]["status"] == 2 == ores[0]["status"] and res[0]["cigar_len"] == 0
+    for f in ("score", "q_beg", "q_end", "t_beg", "t_end", "n_match", "n_mismatch", "n_ins_bp", "n_del_bp"):
+        assert res[0][f] == ores[0][f]                      # counts and coordinates stay valid
+    full, cig = ava.run_batch(gpu, tight)                   # the driver retries with worst-case slots
+    assert full[0]["status"] == 0 and full[0]["cigar_len"] > 100
+    assert sum(n for op, n in cigartuples(cig, full[0]) if op in (0, 1)) == full[0]["q_end"] - full[0]["q_beg"]
+
+
+def test_pairs_beyond_the_kernel_limits_are_flagged_per_pair(gpu):
+    """A band wider than a cluster of 8 CTAs covers -> SVP_ST_BAD_PAIR; sequences that do not fit the shared-memory images ->
+    SVP_ST_TOO_LONG; the other pairs of the batch are aligned normally."""
+    rng = np.random.default_rng(82)
+    short = randseq(rng, 500)
+    long_a = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 130_000)])
+    long_b = long_a[:120_000]
+    seqs, names = [short, mutate(rng, short), long_a, long_b], ["s", "s2", "la", "lb"]
+    specs = [(0, 1, -499, 1024, 0), (2, 3, -512, 1024, 0), (0, 2, -499, 131_072 + 64, 0)]
+    batch = ava.PairBatch.build(names, seqs, specs, cap_fn=lambda m, n: 4096)
+    res, _ = gpu.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    assert res[0]["status"] == 0 and res[0]["score"] > 400
+    assert res[1]["status"] == 16 and res[2]["status"] == 8
