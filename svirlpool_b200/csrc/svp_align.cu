@@ -289,10 +289,21 @@ static void launch_cluster(Kern kern, int cluster, unsigned n_pairs, unsigned th
     cudaLaunchKernelEx(&cfg, kern, tasks, order, seqs, arena, bests, cs);
 }
 
-static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
+static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
                        const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
     const bool multi = nwarp > 1;
     const unsigned thr = (unsigned)nwarp * 32u;
+    if (ring) {              // sliding-window variant of the 32-bit lane kernel (plain or cluster launch)
+        const bool gen = fam == FAM_S32_GEN;
+#define SVP_RING(M, T, G) if (multi == M && two == T && gen == G) { \
+            if (cluster > 1) { if (M) launch_cluster(svp_fwd32_kernel<true, T, G, true, true>, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); } \
+            else svp_fwd32_kernel<M, T, G, false, true><<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs); \
+            return; }
+        SVP_RING(false, true, false) SVP_RING(true, true, false) SVP_RING(false, false, false) SVP_RING(true, false, false)
+        SVP_RING(false, true, true) SVP_RING(true, true, true) SVP_RING(false, false, true) SVP_RING(true, false, true)
+#undef SVP_RING
+        return;
+    }
     if (cluster > 1) {       // 16-warp CTAs, `cluster` of them per pair
 #define SVP_CL(COND, ...) if (COND) { launch_cluster(__VA_ARGS__, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
         SVP_CL(fam == FAM_FAST && two, svp_fwd_kernel<8, true, true, true>) SVP_CL(fam == FAM_FAST && !two, svp_fwd_kernel<8, true, false, true>)
@@ -334,7 +345,7 @@ struct Plan {
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
 };
 
-static void plan_pair(const Consts& cs, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+static void plan_pair(const Consts& cs, size_t max_smem, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
@@ -351,7 +362,12 @@ static void plan_pair(const Consts& cs, const svp_pair& p, uint32_t index, const
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
     // kernel variant: 32-bit lanes when the score can leave the s16 range; those and general scoring use the KP = 4 geometry
-    const bool wide = (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
+    // sequences that do not fit whole shared-memory images (with the widest CTA's mailboxes) run on the sliding-window
+    // variant of the 32-bit lane kernel, whatever their score range
+    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + 2 * 17 * sizeof(uint4);
+    static const bool force_ring = [] { const char* e = getenv("SVP_FORCE_RING"); return e && atoi(e); }();   // test aid
+    const bool ring = force_ring || image_need > max_smem;
+    const bool wide = ring || (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
     // bands beyond one CTA (16 warps) run on a thread-block cluster of 2, 4 or 8 CTAs
     int kp, cl = 1;
     if (wide || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
@@ -362,6 +378,7 @@ static void plan_pair(const Consts& cs, const svp_pair& p, uint32_t index, const
     if (cl == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
     if (cl > 1) t.flags |= (uint32_t)cl << TASK_CL_SHIFT;
     if (wide) t.flags |= TASK_S32;
+    if (ring) t.flags |= TASK_RING;
     t.flags |= (uint32_t)kp << TASK_KP_SHIFT;
     const int steps_per_iter = steps_per_iter_of(t);
     const int64_t m = t.m, n = t.n, lo = p.band_lo, hi = lo + (int64_t)p.band_w - 1;
@@ -387,7 +404,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     if (n == 0) return SVP_OK;
     // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
     for (Task& t : tasks) {
-        if (t.flags & TASK_INVALID) continue;
+        if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
         const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
         if (need > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
@@ -424,7 +441,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
 
     // per wave: order lists grouped by kernel variant and CTA width (warps)
     std::vector<uint32_t> order(n);
-    struct Group { int fam; int nwarp; int kp; int cluster; size_t first, count; size_t smem; uint64_t work; };
+    struct Group { int fam; int nwarp; int kp; int cluster; bool ring; size_t first, count; size_t smem; uint64_t work; };
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
@@ -438,9 +455,12 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
             // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (powers of two from
             // 16 KB) so that a few long pairs do not cut the occupancy of the short ones sharing their launch.
-            const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
+            const bool ring = (t.flags & TASK_RING) != 0;
+            const size_t need = ring ? (size_t)(cs.general ? 3 : 2) * ring_bytes(nw * 32, 8) + (size_t)2 * (nw + 1) * sizeof(uint4)
+                                     : (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
             int cls = 0;
             while (((size_t)16384 << cls) < need) ++cls;
+            if (ring) cls = 50;                       // its own group: the sliding-window kernel
             by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * (int64_t)cl + 1000000000 * (int64_t)cls].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
@@ -448,14 +468,16 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
             size_t smem = 0; uint64_t work = 0;
             const int nwarp = (int)(kv.first % 1000), kp = (int)((kv.first / 1000) % 100), fam = (int)((kv.first / 100000) % 100), cl = (int)((kv.first / 10000000) % 100);
+            const bool ring = kv.first / 1000000000 == 50;
             const int n_qimg = (fam == FAM_GEN || fam == FAM_S32_GEN) ? 2 : 1;            // general scoring stages two query images
             const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
-                smem = std::max(smem, (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
+                smem = std::max(smem, ring ? (size_t)(n_qimg + 1) * ring_bytes(nwarp * 32, 8) + (size_t)2 * (nwarp + 1) * sizeof(uint4)
+                                           : (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
                 work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
-            wave_groups[wv].push_back({ fam, nwarp, kp, cl, pos, kv.second.size(), smem, work });
+            wave_groups[wv].push_back({ fam, nwarp, kp, cl, ring, pos, kv.second.size(), smem, work });
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();
         }
@@ -486,7 +508,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const Group& gq = groups[gi];
-            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
+            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, gq.ring, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
                        h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }
@@ -530,7 +552,7 @@ extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seq
         return fail(h, SVP_ERR_ARG, "null argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, (size_t)h->max_smem_optin, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
     return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
 }
 
@@ -549,7 +571,7 @@ extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t
     CUDA_TRY(h, cudaMemsetAsync((uint8_t*)h->d_seqs.p + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, (size_t)h->max_smem_optin, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
     int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
     if (rc != SVP_OK) return rc;
     if (n_pairs) {

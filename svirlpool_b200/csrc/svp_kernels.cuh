@@ -62,6 +62,7 @@ struct Consts {             // scoring in the forms the kernels use (svp_align.c
 
 constexpr uint32_t TASK_INVALID = 0x80000000u;   // Task.flags: descriptor rejected by the planner
 constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the two sequences do not fit the shared-memory images
+constexpr uint32_t TASK_RING = 0x10000000u;      // ... on its sliding-window variant (sequences too long for whole shared-memory images)
 constexpr uint32_t TASK_S32 = 0x20000000u;       // pair runs on the 32-bit lane kernel (scores beyond the s16 range)
 constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP of the kernel variant the pair runs on
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;

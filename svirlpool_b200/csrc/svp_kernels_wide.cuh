@@ -254,11 +254,52 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sliding sequence windows (RING): pairs whose two sequences do not fit the shared-memory images (m + n beyond ~226 k
+// bases: a 185 kb padded consensus against its reference window) keep only the part of each sequence the CTA's
+// anti-diagonal currently touches. At any time the bases ENTERING the registers of a CTA lie within blockDim * K
+// consecutive positions of each sequence, advancing by K positions per loop iteration, so a power-of-two ring of
+// R >= blockDim*K + 4K + RING_CHUNK bytes per image, refilled with the next RING_CHUNK positions every
+// RING_CHUNK / K iterations, always holds them. The ring is indexed by the VIRTUAL position (pos & (R-1), two's
+// complement), positions outside [1, len] hold the pad code, so no clamping is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int RING_CHUNK = 256;
+__host__ __device__ __forceinline__ int ring_bytes(int n_threads, int k) {
+    int r = 1024;
+    while (r < n_threads * k + 4 * k + RING_CHUNK) r *= 2;
+    return r;
+}
+// code (0..3) of oriented query position p / target position p (1-based), or -1 outside the sequence
+__device__ __forceinline__ int packed_code(const uint32_t* __restrict__ src, int len, int p, bool rc) {
+    if (p < 1 || p > len) return -1;
+    const unsigned o = rc ? (unsigned)(len - p) : (unsigned)(p - 1);
+    const int c = (int)((__ldg(src + (o >> 4)) >> ((o & 15u) * 2u)) & 3u);
+    return rc ? 3 - c : c;
+}
+template <bool GEN>
+__device__ __forceinline__ void ring_fill(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qring, uint8_t* q2ring, uint8_t* tring,
+                                          int mask, int q_first, int t_first, int count) {
+    const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
+    const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
+    const bool rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    for (int x = threadIdx.x; x < count; x += blockDim.x) {
+        const int qc = packed_code(qsrc, tk.m, q_first + x, rc), tc = packed_code(tsrc, tk.n, t_first + x, false);
+        if (GEN) {
+            qring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? GEN_PAD : (uint32_t)(qc & 1) << 2);
+            q2ring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? GEN_PAD2 : 0x80u | 0x44u * (uint32_t)(qc >> 1));
+            tring[(t_first + x) & mask] = (uint8_t)(tc < 0 ? GEN_PAD : (uint32_t)tc);
+        } else {
+            qring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? 0x7E : 0x3C + qc);
+            tring[(t_first + x) & mask] = (uint8_t)(tc < 0 ? 0x7D : 0x3C + tc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward DP, 32-bit lanes: one cell per register, K = 8 registers per state array per set; the thread owns
 // 2K = 16 diagonals = the geometry of the s16 kernels with KP = 4, and the row bytes are written in their byte
 // order. One loop iteration is 2K = 16 steps = two end-cell blocks of 2*KP = 8 steps.
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool TWO, bool GEN, bool CL = false>
+template <bool MULTI, bool TWO, bool GEN, bool CL = false, bool RING = false>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                  uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
@@ -269,13 +310,15 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
     const int g = (int)crank * (int)blockDim.x + gl;
-    const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
+    const int ring = ring_bytes((int)blockDim.x, K), rmask = ring - 1;
+    const int qbytes = RING ? ring : seq_image_bytes(tk.m), tbytes = RING ? ring : seq_image_bytes(tk.n);
     uint8_t* qimg = smem8;                                   // GEN: qsel
     uint8_t* qimg2 = smem8 + qbytes;                         // GEN only: qsel2
     uint8_t* timg = smem8 + (GEN ? 2 : 1) * qbytes;
-    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + SEQ_PAD - 1;
-    const uint32_t s_q2 = (uint32_t)__cvta_generic_to_shared(qimg2) + SEQ_PAD - 1;
-    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + SEQ_PAD - 1;
+    // whole images: base + clamped 1-based position; rings: base + (virtual position & mask)
+    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + (RING ? 0 : SEQ_PAD - 1);
+    const uint32_t s_q2 = (uint32_t)__cvta_generic_to_shared(qimg2) + (RING ? 0 : SEQ_PAD - 1);
+    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + (RING ? 0 : SEQ_PAD - 1);
     const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(timg + tbytes);
     const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
     const int NEG = -(1 << 29);
@@ -286,8 +329,14 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const int c_mat = (int)pin((uint32_t)cs.s_match), c_mis = (int)pin((uint32_t)cs.s_mismatch), c_neg = (int)pin((uint32_t)NEG);
     const uint32_t r0 = pin(cs.tab[0]), r1 = pin(cs.tab[1]), r2 = pin(cs.tab[2]), r3 = pin(cs.tab[3]);
 
-    if (GEN) stage_sequences_gen(tk, seqs, qimg, qimg2, timg, qbytes, tbytes);
+    // lowest virtual positions the CTA touches at iteration 0 (thread gl = 0 has the largest I0 and the smallest J0)
+    const int g_first = (int)crank * (int)blockDim.x;
+    const int ring_q0 = (tk.r_begin - (tk.band_lo + (g_first + (int)blockDim.x - 1) * 2 * K)) / 2 - K;
+    const int ring_t0 = (tk.r_begin + (tk.band_lo + g_first * 2 * K)) / 2 - 1;
+    if (RING) ring_fill<GEN>(tk, seqs, qimg, qimg2, timg, rmask, ring_q0, ring_t0, ring);
+    else if (GEN) stage_sequences_gen(tk, seqs, qimg, qimg2, timg, qbytes, tbytes);
     else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
+    if (RING) __syncthreads();
     if (MULTI && gl <= nwarp) {
         sts_v4(s_mbA + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
         sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
@@ -309,10 +358,10 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     #pragma unroll
     for (int k = 0; k < K; ++k) {
         HA[k] = 0; HB[k] = 0; E1[k] = c_neg; E2[k] = c_neg; F1[k] = c_neg; F2[k] = c_neg;
-        const uint32_t qo = (uint32_t)__vimin_s32_relu(I0 - k, qmax);
+        const uint32_t qo = RING ? (uint32_t)((I0 - k) & rmask) : (uint32_t)__vimin_s32_relu(I0 - k, qmax);
         Q[k] = lds_u8(s_q + qo);
         Q2[k] = GEN ? sel2_of(lds_u8(s_q2 + qo)) : 0u;
-        T[k] = lds_u8(s_t + (uint32_t)__vimin_s32_relu(J0 + k, tmax));
+        T[k] = lds_u8(s_t + (RING ? (uint32_t)((J0 + k) & rmask) : (uint32_t)__vimin_s32_relu(J0 + k, tmax)));
     }
     int qpos = I0 + 1, tpos = J0 + K;
     int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
@@ -350,6 +399,10 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
+        if (RING && it && (it & (RING_CHUNK / K - 1)) == 0) {       // the next chunk of both windows (needed from the next iteration on)
+            ring_fill<GEN>(tk, seqs, qimg, qimg2, timg, rmask, ring_q0 + ring + (it - RING_CHUNK / K) * K, ring_t0 + ring + (it - RING_CHUNK / K) * K, RING_CHUNK);
+            if (!MULTI) __syncwarp();
+        }
         #pragma unroll
         for (int u = 0; u < K; ++u) {
             // =============================== A-step ===========================================
@@ -376,7 +429,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                     if (lane == 0) mailbox_store<CL>(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
                     step_barrier<CL>();
                 }
-                T[u % K] = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));     // logical T[k] <- T[k+1]; new base in slot K-1
+                T[u % K] = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));     // logical T[k] <- T[k+1]; new base in slot K-1
                 ++tpos;
             }
             // =============================== B-step ===========================================
@@ -403,7 +456,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                     if (lane == 31) mailbox_store<CL>(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
                     step_barrier<CL>();
                 }
-                const uint32_t qo = (uint32_t)__vimin_s32_relu(qpos, qmax);                 // logical Q[k] <- Q[k-1]; new base in slot 0
+                const uint32_t qo = RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax);   // logical Q[k] <- Q[k-1]; new base in slot 0
                 Q[(K - 1 - u) % K] = lds_u8(s_q + qo);
                 if (GEN) Q2[(K - 1 - u) % K] = sel2_of(lds_u8(s_q2 + qo));
                 ++qpos;

@@ -368,16 +368,54 @@ def test_cigar_overflow_is_flagged_and_retried(gpu, oracle):
     assert sum(n for op, n in cigartuples(cig, full[0]) if op in (0, 1)) == full[0]["q_end"] - full[0]["q_beg"]
 
 
-def test_pairs_beyond_the_kernel_limits_are_flagged_per_pair(gpu):
-    """A band wider than a cluster of 8 CTAs covers -> SVP_ST_BAD_PAIR; sequences that do not fit the shared-memory images ->
-    SVP_ST_TOO_LONG; the other pairs of the batch are aligned normally."""
+def test_band_beyond_cluster_limit_is_flagged_per_pair(gpu):
+    """A band wider than a cluster of 8 CTAs covers -> SVP_ST_BAD_PAIR; the other pairs of the batch are aligned normally."""
     rng = np.random.default_rng(82)
     short = randseq(rng, 500)
-    long_a = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 130_000)])
-    long_b = long_a[:120_000]
-    seqs, names = [short, mutate(rng, short), long_a, long_b], ["s", "s2", "la", "lb"]
-    specs = [(0, 1, -499, 1024, 0), (2, 3, -512, 1024, 0), (0, 2, -499, 131_072 + 64, 0)]
+    long_a = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 140_000)])
+    seqs, names = [short, mutate(rng, short), long_a], ["s", "s2", "la"]
+    specs = [(0, 1, -499, 1024, 0), (0, 2, -499, 131_072 + 64, 0)]
     batch = ava.PairBatch.build(names, seqs, specs, cap_fn=lambda m, n: 4096)
     res, _ = gpu.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
-    assert res[0]["status"] == 0 and res[0]["score"] > 400
-    assert res[1]["status"] == 16 and res[2]["status"] == 8
+    assert res[0]["status"] == 0 and res[0]["score"] > 400 and res[1]["status"] == 8
+
+
+def test_sequences_beyond_shared_memory_sliding_window(gpu, oracle):
+    """130 kb vs 120 kb (the size of the reference's INV.15 consensus record, 185 kb query): the images do not fit shared
+    memory, the pair runs on the sliding-window variant of the 32-bit lane kernel. Bit-exact against the oracle."""
+    rng = np.random.default_rng(83)
+    codes = rng.integers(0, 4, 130_000)
+    a = "".join(np.array(list("ACGT"))[codes])
+    edit = codes[:120_000].copy()
+    pos = rng.choice(120_000, 2400, replace=False)
+    edit[pos] = (edit[pos] + 1 + rng.integers(0, 3, len(pos))) & 3                   # 2 % substitutions
+    b = "".join(np.array(list("ACGT"))[edit])
+    b = b[:40_000] + b[40_300:90_000] + randseq(rng, 500) + b[90_000:]                 # a 300 bp deletion and a 500 bp insertion
+    seqs, names = [a, b, revcomp(b)], ["a", "b", "b_rc"]
+    specs = [(1, 0, -768, 1536, 0), (2, 0, -768, 1536, PAIR_REVCOMP), (0, 1, -768, 1536, 0)]
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert not gres["status"].any() and gres["score"].min() > 200_000 and (gres["n_ins_bp"] + gres["n_del_bp"]).min() >= 800
+
+
+@pytest.mark.parametrize("scoring_name", [None, "matrix_two_piece_asym"])
+def test_forced_sliding_window_equals_whole_images(oracle, monkeypatch, scoring_name):
+    """SVP_FORCE_RING pushes ordinary pairs (single-warp, multi-warp and cluster CTAs, both scoring paths) through the
+    sliding-window kernel: same results as the oracle."""
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_FORCE_RING", "1")
+    rng = np.random.default_rng(84)
+    names, seqs, specs = noisy_batch(rng, 6, 3000, 512)
+    n2, s2, p2 = noisy_batch(rng, 3, 1500, 96)
+    off = len(seqs)
+    specs = specs + [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in p2]
+    seqs = seqs + s2
+    t = randseq(rng, 12_000)
+    seqs += [t, mutate(rng, t[7000:10_000])]
+    lo, w = ava.full_band(len(seqs[-1]), len(t))                                     # 15k diagonals: a cluster of 2 CTAs
+    specs.append((len(seqs) - 1, len(seqs) - 2, lo, w, 0))
+    names = [f"r{k}" for k in range(len(seqs))]
+    kw = {"preset": "map-ont"} if scoring_name is None else {"scoring": SCORINGS[scoring_name]}
+    with Aligner(device=0, tb_bytes=2 << 30, **kw) as g:
+        gres, _ = run_both(g, OracleEngine(**kw) if scoring_name else oracle, names, seqs, specs)
+    assert not gres["status"].any()
