@@ -152,7 +152,7 @@ class Aligner:
 
     def _align_batch(self, packed, seq_off, seq_len, pairs, cigar_words, copy: bool):
         assert pairs.dtype == PAIR_DTYPE and packed.dtype == np.uint8
-        res = self._res_buf.view(len(pairs))
+        res = self._res_buf.view(len(pairs))[:len(pairs)]
         cig = self._cig_buf.view(cigar_words)
         self._check(self.lib.svp_align_batch(self._h, ptr(packed), packed.nbytes, ptr(seq_off), ptr(seq_len), len(seq_len),
                                              ptr(pairs), len(pairs), ptr(res), ptr(cig), len(cig)))

@@ -453,13 +453,14 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int cl = cluster_of(t);
             const int nw = cl > 1 ? 16 : (t.band_w + per_warp - 1) / per_warp;
             const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
-            // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (powers of two from
-            // 16 KB) so that a few long pairs do not cut the occupancy of the short ones sharing their launch.
+            // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (<= 32 KB, then powers
+            // of two) so that a few long pairs do not cut the occupancy of the short ones sharing their launch; finer classes
+            // were measured slower on config 2 (more, smaller launches: 1716 vs 1824 GCUPS).
             const bool ring = (t.flags & TASK_RING) != 0;
             const size_t need = ring ? (size_t)(cs.general ? 3 : 2) * ring_bytes(nw * 32, 8) + (size_t)2 * (nw + 1) * sizeof(uint4)
                                      : (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
             int cls = 0;
-            while (((size_t)16384 << cls) < need) ++cls;
+            while (((size_t)32768 << cls) < need) ++cls;
             if (ring) cls = 50;                       // its own group: the sliding-window kernel
             by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * (int64_t)cl + 1000000000 * (int64_t)cls].push_back((uint32_t)k);
         }
