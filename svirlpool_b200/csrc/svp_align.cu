@@ -482,30 +482,38 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
             pos += kv.second.size();
         }
-        // biggest group first, so the small ones fill the machine behind it
-        std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
+        // group order (env SVP_GROUP_ORDER, tuning aid): 0 = biggest group first, so the small ones fill the machine behind it;
+        // 1 = groups with the longest-running CTAs (most work per pair) first, the many short CTAs fill the tail
+        static const int group_order = [] { const char* e = getenv("SVP_GROUP_ORDER"); return e ? atoi(e) : 1; }();
+        if (group_order == 1)
+            std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
+        else
+            std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
     }
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(h->d_order.p, order.data(), pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     const Task* d_tasks = (const Task*)h->d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)h->d_order.p;
     uint2* d_bests = (uint2*)h->d_bests.p;
-    // events: per wave [fwd start, fwd end, tb end, aux join 0, aux join 1]; plus two for the whole call
-    const size_t EV_PER_WAVE = 5, n_ev = waves.size() * EV_PER_WAVE + 2;
+    // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]; plus two for the whole call
+    constexpr int MAX_FWD_STREAMS = 6;
+    const size_t EV_PER_WAVE = 3 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE + 2;
     while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
     cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
-    // forward passes of consecutive waves stay in stream order (letting them overlap was measured slower: the
-    // earlier wave finishes later and so does its traceback); inside a wave the groups use three streams
-    cudaStream_t sets[2][3] = { { st, h->stream_aux[0], h->stream_aux[1] }, { st, h->stream_aux[0], h->stream_aux[1] } };
+    // forward passes of consecutive waves stay in stream order (letting them overlap on separate stream sets was measured
+    // slower twice, 1810 vs 1915 GCUPS: the earlier wave finishes later and so does its traceback); inside a wave the groups
+    // run on up to four streams (2..6 measure the same, one stream 10 % slower), groups with the longest-running CTAs first
+    // (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail of the wave)
+    cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4] };
+    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), 6); }();
     cudaStream_t sT = h->stream_tb;
     CUDA_TRY(h, cudaEventRecord(ev_t0, st));
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        cudaStream_t* sF = sets[wv & 1];
         if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(sF[0], EV(wv - 2, 2), 0));      // this arena half is free again
         CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sF[0]));
         const std::vector<Group>& groups = wave_groups[wv];
-        const int n_streams = (int)std::min<size_t>(3, groups.size());
+        const int n_streams = (int)std::min<size_t>((size_t)max_streams, groups.size());
         for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const Group& gq = groups[gi];
