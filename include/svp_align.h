@@ -128,6 +128,16 @@ int svp_align_batch(svp_handle* h,
                     svp_result* results,
                     uint32_t* cigar_buf, size_t cigar_words);
 
+/* Summary variant for consumers that need no CIGARs (the consensus_lib similarity matrix with unit density weights:
+ * score, intervals, counts and sv_dist are all it reads; consensus_lib.py:353-413, consensus.py:1276-1305): identical
+ * to svp_align_batch() but nothing except the result rows is copied back. cigar_words still sizes the device scratch
+ * the traceback writes (svp_pair.cigar_off / cigar_cap); result.cigar_off is meaningless on return. */
+int svp_align_batch_summary(svp_handle* h,
+                            const uint8_t* packed_seqs, size_t packed_bytes,
+                            const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                            const svp_pair* pairs, uint32_t n_pairs,
+                            svp_result* results, size_t cigar_words);
+
 /* Device-resident variant: the bulk data — packed sequences in, results and CIGAR words out — are
  * DEVICE pointers on the handle's device (e.g. torch tensor data_ptr()); the launch plan (sequence
  * table and pair descriptors) stays in HOST memory. Every sequence must be readable up to the next

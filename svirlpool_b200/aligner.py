@@ -63,6 +63,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_align_batch.argtypes = batch_args
     lib.svp_align_batch_device.restype = C.c_int
     lib.svp_align_batch_device.argtypes = batch_args
+    lib.svp_align_batch_summary.restype = C.c_int
+    lib.svp_align_batch_summary.argtypes = batch_args[:9] + [C.c_size_t]
     if lib.svp_abi_version() != _abi.ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {lib.svp_abi_version()}, python {_abi.ABI_VERSION}")
     return lib
@@ -160,6 +162,16 @@ class Aligner:
         if copy:
             return res.copy(), cig[:max(used, 1)].copy()
         return res, cig[:max(used, 1)]
+
+    def align_batch_summary(self, packed: np.ndarray, seq_off: np.ndarray, seq_len: np.ndarray, pairs: np.ndarray,
+                            cigar_words: int, copy: bool = True) -> np.ndarray:
+        """Result rows only (svp_align_batch_summary): no CIGAR leaves the device. Enough for the similarity matrix with unit
+        density weights and the alignment-length matrix (consensus_lib.similarity_from_summary)."""
+        assert pairs.dtype == PAIR_DTYPE and packed.dtype == np.uint8
+        res = self._res_buf.view(len(pairs))[:len(pairs)]
+        self._check(self.lib.svp_align_batch_summary(self._h, ptr(packed), packed.nbytes, ptr(seq_off), ptr(seq_len), len(seq_len),
+                                                     ptr(pairs), len(pairs), ptr(res), int(cigar_words)))
+        return res.copy() if copy else res
 
     def align_batch_device(self, d_packed_ptr: int, packed_bytes: int, seq_off: np.ndarray, seq_len: np.ndarray,
                            pairs: np.ndarray, d_results_ptr: int, d_cigar_ptr: int, cigar_words: int) -> None:

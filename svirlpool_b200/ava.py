@@ -99,6 +99,35 @@ def run_batch(engine, batch: PairBatch) -> tuple[np.ndarray, np.ndarray]:
     return res, cig
 
 
+def run_summary(engine, batch: PairBatch) -> np.ndarray:
+    """Result rows only (Aligner.align_batch_summary: no CIGAR leaves the device). Pairs whose CIGAR slot overflowed —
+    their sv_dist is read off the CIGAR on the device — are re-run once with worst-case slots."""
+    fn = getattr(engine, "align_batch_summary", None)
+    run = (lambda b: fn(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)) if fn else \
+          (lambda b: engine.align_batch(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)[0])
+    res = run(batch)
+    ovf = np.nonzero(res["status"] & ST_CIGAR_OVF)[0]
+    if len(ovf):
+        specs = [(int(p["q"]), int(p["t"]), int(p["band_lo"]), int(p["band_w"]), int(p["flags"])) for p in batch.pairs[ovf]]
+        retry = PairBatch.build(batch.names, batch.seqs, specs, cap_fn=lambda m, n: m + n)
+        res[ovf] = run(retry)
+    return res
+
+
+def ava_summary(engine, reads: dict[str, str], strands: dict[str, str] | None = None, offsets: dict[str, int] | None = None,
+                slack: int = 300, granule: int = 32, full: bool = False) -> tuple[list[str], np.ndarray, np.ndarray, np.ndarray]:
+    """All-vs-all of one container without CIGARs: (read names, query index, target index, result rows), the input of
+    consensus_lib.similarity_from_summary()."""
+    names = list(reads)
+    seqs = [reads[k] for k in names]
+    specs, meta = ava_pair_specs(names, [len(s) for s in seqs], strands, offsets, slack, granule, full)
+    if not specs:
+        from ._abi import RESULT_DTYPE
+        return names, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=RESULT_DTYPE)
+    res = run_summary(engine, PairBatch.build(names, seqs, specs))
+    return names, np.array([m[0] for m in meta], dtype=np.int64), np.array([m[1] for m in meta], dtype=np.int64), res
+
+
 def record_from_result(res, cig: np.ndarray, query_name: str, target_name: str, query_len: int, revcomp: bool,
                        supplementary: bool = False, query_sequence: str | None = None,
                        query_offset: int = 0, query_total: int | None = None) -> AlignedRecord | None:

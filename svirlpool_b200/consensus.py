@@ -65,6 +65,18 @@ def ava_similarity(engine, reads: dict[str, str], strands: dict[str, str] | None
     return sim, order, records
 
 
+def ava_similarity_summary(engine, reads: dict[str, str], strands: dict[str, str] | None = None, min_bnd_size: int = 100,
+                           slack: int = 300, granule: int = 512) -> tuple[np.ndarray, list[str], np.ndarray]:
+    """ava_similarity() for the production setting (unit density weights) without CIGARs: the per-pair distance is reduced
+    on the GPU (svp_result.sv_dist), only result rows cross PCIe, and the matrices are assembled with numpy — bit-identical
+    to ava_similarity(..., densities_weight=0.0) and pairwise_alignment_lengths(). Returns (similarity, read names,
+    alignment-length matrix)."""
+    names, qi, ti, res = ava.ava_summary(engine, reads, strands=strands, slack=slack, granule=granule)
+    sim, aln_len = consensus_lib.similarity_from_summary(names, {n: len(s) for n, s in reads.items()}, qi, ti, res,
+                                                         min_bnd_size=min_bnd_size)
+    return sim, names, aln_len
+
+
 def align_reads_to_consensus(engine, samplename: str, reads: dict[str, str], consensus_name: str, consensus_seq: str,
                              min_signal_size: int = 8, min_bnd_size: int = 100
                              ) -> tuple[list[AlignedRecord], list[ReadAlignmentSignals]]:

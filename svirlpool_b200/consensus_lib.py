@@ -266,6 +266,14 @@ def pairwise_similarity_matrix(
         if _has_interior_bnd(ds.signals, ds.ref_length, bnd_margin=bnd_margin):
             interior_bnd[qi, ri] = True
 
+    return _similarity_from_directed(d_sum, d_count, interior_bnd, read_names, read_lengths, length_penalty_lambda), read_names
+
+
+def _similarity_from_directed(d_sum: np.ndarray, d_count: np.ndarray, interior_bnd: np.ndarray, read_names: list[str],
+                              read_lengths: Dict[str, int], length_penalty_lambda: float | None) -> np.ndarray:
+    """Directed distance sums / counts / interior-BND flags -> similarity matrix (second half of
+    pairwise_similarity_matrix, consensus_lib.py:497-592)."""
+    n = len(read_names)
     aligned = d_count > 0
     directed = np.where(aligned, d_sum / np.maximum(d_count, 1), 0.0)
     linked = aligned | aligned.T
@@ -291,7 +299,52 @@ def pairwise_similarity_matrix(
         similarity = np.where(np.isfinite(distance), np.exp(-(distance ** 2) / (2.0 * sigma ** 2)), 0.0)
     np.fill_diagonal(similarity, 1.0)
     similarity[(interior_bnd | interior_bnd.T) & off_diag] = 0.0
-    return similarity, read_names
+    return similarity
+
+
+def similarity_from_summary(read_names: list[str], read_lengths: Dict[str, int], q_index: np.ndarray, t_index: np.ndarray,
+                            results: np.ndarray, min_score: int = 80, min_bnd_size: int = 100, bnd_margin: int = 100,
+                            length_penalty_lambda: float | None = None) -> Tuple[np.ndarray, np.ndarray]:
+    """pairwise_similarity_matrix() and consensus.pairwise_alignment_lengths() for unit density weights (the reference's
+    production setting --densities-weight 0.0, consensus.py:3565-3572), computed from svp_result rows without CIGARs:
+
+      * the directed distance of an alignment = sum over indel runs >= min_signal_size of size_damping(size) * size, which the
+        traceback kernel accumulates per pair (svp_result.sv_dist; damping s0 = 30, alpha = 1.5 = the defaults here);
+      * its breakends: a clip >= min_bnd_size before / after the aligned part of the oriented query gives a BND at the
+        alignment's start / end on the target, and `_has_interior_bnd` tests it against the ALIGNED span
+        (`bnd_margin < pos < span - bnd_margin`, the reference's convention) — only a leading clip can satisfy it.
+
+    q_index / t_index: read index (into read_names) of every result row's query / target; several rows per read pair
+    (both orientations) are reduced to the best-scoring one, forward first on ties, like ava.ava_records(). Returns
+    (similarity, alignment-length matrix). Bit-identical to the record-based functions (tests/test_consensus_lib.py)."""
+    n = len(read_names)
+    res = results
+    ok = ((res["status"] & 1) == 0) & (res["score"] >= min_score) & (res["cigar_len"] > 0)
+    d_sum = np.zeros((n, n), dtype=np.float64)
+    d_count = np.zeros((n, n), dtype=np.int64)
+    interior = np.zeros((n, n), dtype=bool)
+    aln_len = np.zeros((n, n), dtype=int)
+    rows = np.flatnonzero(ok)
+    if len(rows):
+        # best row per (q, t): highest score, earliest row on ties
+        key = q_index[rows].astype(np.int64) * n + t_index[rows].astype(np.int64)
+        order = np.lexsort((rows, -res["score"][rows].astype(np.int64), key))
+        first = np.ones(len(order), dtype=bool)
+        first[1:] = key[order][1:] != key[order][:-1]
+        best = rows[order[first]]
+        q, t = q_index[best], t_index[best]
+        r = res[best]
+        d_sum[q, t] = r["sv_dist"]
+        d_count[q, t] = 1
+        lead = r["q_beg"].astype(np.int64)
+        span = (r["t_end"] - r["t_beg"]).astype(np.int64)
+        t_beg = r["t_beg"].astype(np.int64)
+        interior[q, t] = (lead >= min_bnd_size) & (t_beg > bnd_margin) & (t_beg < span - bnd_margin)
+        qlen = (r["q_end"] - r["q_beg"]).astype(int)
+        aln_len[q, t] = qlen
+        aln_len[t, q] = qlen
+    sim = _similarity_from_directed(d_sum, d_count, interior, list(read_names), read_lengths, length_penalty_lambda)
+    return sim, aln_len
 
 
 # ---------------------------------------------------------------------------------------------

@@ -565,13 +565,9 @@ extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seq
     return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
 }
 
-extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes,
-                               const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
-                               const svp_pair* pairs, uint32_t n_pairs, svp_result* results,
-                               uint32_t* cigar_buf, size_t cigar_words) {
-    if (!h) return SVP_ERR_ARG;
-    if (!packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !results || (!cigar_buf && cigar_words))
-        return fail(h, SVP_ERR_ARG, "null argument");
+static int align_host(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes, const uint64_t* seq_off, const uint32_t* seq_len,
+                      uint32_t n_seqs, const svp_pair* pairs, uint32_t n_pairs, svp_result* results, uint32_t* cigar_buf, size_t cigar_words,
+                      bool want_cigars) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t padded = ((packed_bytes + 15) & ~(size_t)15) + 64;
     CUDA_TRY(h, h->d_seqs.reserve(padded));
@@ -586,24 +582,46 @@ extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t
     if (n_pairs) {
         CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        // dense CIGAR layout in pair order; only the used words are copied back
-        std::vector<uint32_t> dense_off(n_pairs);
-        uint64_t total = 0;
-        for (uint32_t k = 0; k < n_pairs; ++k) { dense_off[k] = (uint32_t)total; total += results[k].cigar_len; }
-        if (total > cigar_words) return fail(h, SVP_ERR_ARG, "cigar_buf smaller than the CIGARs produced");
-        if (total) {
-            CUDA_TRY(h, h->d_dense.reserve(total * sizeof(uint32_t)));
-            CUDA_TRY(h, h->d_dense_off.reserve(n_pairs * sizeof(uint32_t)));
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_dense_off.p, dense_off.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-            const int wpb = 8;
-            svp_cigar_gather<<<(n_pairs + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>((const svp_result*)h->d_results.p, (const uint32_t*)h->d_dense_off.p,
-                                                                                  (const uint32_t*)h->d_cigar.p, (uint32_t*)h->d_dense.p, (int)n_pairs);
-            CUDA_TRY(h, cudaMemcpyAsync(cigar_buf, h->d_dense.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (want_cigars) {
+            // dense CIGAR layout in pair order; only the used words are copied back
+            std::vector<uint32_t> dense_off(n_pairs);
+            uint64_t total = 0;
+            for (uint32_t k = 0; k < n_pairs; ++k) { dense_off[k] = (uint32_t)total; total += results[k].cigar_len; }
+            if (total > cigar_words) return fail(h, SVP_ERR_ARG, "cigar_buf smaller than the CIGARs produced");
+            if (total) {
+                CUDA_TRY(h, h->d_dense.reserve(total * sizeof(uint32_t)));
+                CUDA_TRY(h, h->d_dense_off.reserve(n_pairs * sizeof(uint32_t)));
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_dense_off.p, dense_off.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+                const int wpb = 8;
+                svp_cigar_gather<<<(n_pairs + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>((const svp_result*)h->d_results.p, (const uint32_t*)h->d_dense_off.p,
+                                                                                      (const uint32_t*)h->d_cigar.p, (uint32_t*)h->d_dense.p, (int)n_pairs);
+                CUDA_TRY(h, cudaMemcpyAsync(cigar_buf, h->d_dense.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+            }
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            for (uint32_t k = 0; k < n_pairs; ++k) results[k].cigar_off = dense_off[k];
+        } else {
+            for (uint32_t k = 0; k < n_pairs; ++k) results[k].cigar_off = 0;
         }
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        for (uint32_t k = 0; k < n_pairs; ++k) results[k].cigar_off = dense_off[k];
         h->stats.reserved = 1;
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SVP_OK;
+}
+
+extern "C" int svp_align_batch(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes,
+                               const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                               const svp_pair* pairs, uint32_t n_pairs, svp_result* results,
+                               uint32_t* cigar_buf, size_t cigar_words) {
+    if (!h) return SVP_ERR_ARG;
+    if (!packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !results || (!cigar_buf && cigar_words))
+        return fail(h, SVP_ERR_ARG, "null argument");
+    return align_host(h, packed_seqs, packed_bytes, seq_off, seq_len, n_seqs, pairs, n_pairs, results, cigar_buf, cigar_words, true);
+}
+
+extern "C" int svp_align_batch_summary(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes,
+                                       const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                                       const svp_pair* pairs, uint32_t n_pairs, svp_result* results, size_t cigar_words) {
+    if (!h) return SVP_ERR_ARG;
+    if (!packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !results) return fail(h, SVP_ERR_ARG, "null argument");
+    return align_host(h, packed_seqs, packed_bytes, seq_off, seq_len, n_seqs, pairs, n_pairs, results, nullptr, cigar_words, false);
 }

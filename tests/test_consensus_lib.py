@@ -213,3 +213,30 @@ def test_coherent_length_groups_are_kept():
     names = ["solo"] + a + b
     rl = {"solo": 162, **{r: 1200 + 2 * k for k, r in enumerate(a)}, **{r: 1660 + 2 * k for k, r in enumerate(b)}}
     assert detect_outlier_reads(uniform(len(names)), names, rl, n_clusters=1) == {"solo"}
+
+
+def test_similarity_from_summary_equals_record_pipeline(oracle):
+    """The CIGAR-free path (svp_result rows -> similarity / alignment-length matrices) is bit-identical to the reference's
+    record pipeline with unit density weights, for known strands and for both-orientation (unknown strand) batches."""
+    from svirlpool_b200 import ava, consensus, consensus_lib, synth
+    for rid, strands_known in ((2, True), (5, False), (9, True)):
+        region = synth.region_config2(rid, n_reads=9, mean_len=1500, sd_len=80)
+        reads = region.read_strings()
+        strands = dict(zip(region.names, region.strands)) if strands_known else None
+        lengths = {n: len(s) for n, s in reads.items()}
+        recs = ava.ava_align(oracle, reads, strands=strands)
+        directed = consensus_lib.parse_directed_signals_from_ava(recs, 12, 100)
+        sim_a, names_a = consensus_lib.pairwise_similarity_matrix(directed, {}, lengths, all_read_names=list(reads), densities_weight=0.0)
+        len_a = consensus.pairwise_alignment_lengths(recs, list(reads))
+        names, qi, ti, res = ava.ava_summary(oracle, reads, strands=strands)
+        sim_b, len_b = consensus_lib.similarity_from_summary(names, lengths, qi, ti, res)
+        assert names == names_a
+        np.testing.assert_array_equal(sim_a, sim_b)
+        np.testing.assert_array_equal(len_a, len_b)
+    # a clipped alignment whose start lies inside the aligned span's margins marks the pair as unrelated (interior BND)
+    from svirlpool_b200._abi import RESULT_DTYPE
+    res = np.zeros(2, dtype=RESULT_DTYPE)
+    res["score"], res["cigar_len"] = 500, 3
+    res["q_beg"], res["q_end"], res["t_beg"], res["t_end"] = [150, 0], [900, 800], [120, 0], [900, 800]
+    sim, _ = consensus_lib.similarity_from_summary(["a", "b", "c"], {"a": 1000, "b": 1000, "c": 1000}, np.array([0, 0]), np.array([1, 2]), res)
+    assert sim[0, 1] == 0.0 and sim[0, 2] > 0.0

@@ -49,3 +49,16 @@ def test_ava_similarity_and_read_to_consensus_gpu(gpu, oracle):
     ro, so = consensus.align_reads_to_consensus(oracle, "S", hap0, "c0", cseq)
     assert [rec_key(r) for r in rg] == [rec_key(r) for r in ro]
     assert [s.unstructure() for s in sg] == [s.unstructure() for s in so]
+
+
+def test_summary_path_equals_record_path_gpu(gpu):
+    """CIGAR-free similarity (svp_align_batch_summary + numpy) == record pipeline, both on the CUDA engine."""
+    for rid in (4, 8):
+        region = synth.region_config2(rid, n_reads=12, mean_len=3000, sd_len=200)
+        reads = region.read_strings()
+        strands = dict(zip(region.names, region.strands))
+        sim_a, names_a, recs = consensus.ava_similarity(gpu, reads, strands=strands, densities_weight=0.0)
+        sim_b, names_b, len_b = consensus.ava_similarity_summary(gpu, reads, strands=strands)
+        assert names_a == names_b
+        np.testing.assert_array_equal(sim_a, sim_b)
+        np.testing.assert_array_equal(consensus.pairwise_alignment_lengths(recs, names_a), len_b)
