@@ -86,7 +86,7 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
     accepted for signature compatibility (seeding options have no counterpart; the call is bounded by the
     kernels, not by a child process). Failures raise aligner.AlignerError, a subprocess.CalledProcessError,
     which the reference's callers already catch. `engine`: an Aligner to reuse; default one per call.
-    A `.bai` index is not written."""
+    Like the reference (`samtools index`, util.py:232-238) a `.bai` is written next to the BAM."""
     from . import ava, sam
     from .aligner import Aligner
     paths = reads if isinstance(reads, list) else [reads]
@@ -111,7 +111,7 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
                 a = r.cigartuples[0][1] if r.cigartuples[0][0] == 5 else 0
                 r.query_sequence = r.query_sequence[a:a + r.query_alignment_length]
         cmd = f"svirlpool_b200 -x {tech} {aln_args}".strip()
-        sam.write_bam(bamout, sam.sort_records(records, lengths), lengths, command=cmd)
+        sam.write_bam(bamout, sam.sort_records(records, lengths), lengths, command=cmd, index=True)     # + <bamout>.bai
     finally:
         if own:
             engine.close()
