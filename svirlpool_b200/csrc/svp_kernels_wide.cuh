@@ -324,8 +324,10 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const int NEG = -(1 << 29);
     const int d_ne1 = (int)pin((uint32_t)-cs.d_ext1), d_noe1 = (int)pin((uint32_t)-(cs.d_open1 + cs.d_ext1));
     const int d_ne2 = (int)pin((uint32_t)-cs.d_ext2), d_noe2 = (int)pin((uint32_t)-(cs.d_open2 + cs.d_ext2));
-    const int i_ne1 = (int)pin((uint32_t)-cs.i_ext1), i_noe1 = (int)pin((uint32_t)-(cs.i_open1 + cs.i_ext1));
-    const int i_ne2 = (int)pin((uint32_t)-cs.i_ext2), i_noe2 = (int)pin((uint32_t)-(cs.i_open2 + cs.i_ext2));
+    // simple scoring has insertion == deletion costs: sharing the registers lets the compiler compute H + noe once per cell
+    // for its two consumers (the E of the cell to the right, the F of the cell below)
+    const int i_ne1 = GEN ? (int)pin((uint32_t)-cs.i_ext1) : d_ne1, i_noe1 = GEN ? (int)pin((uint32_t)-(cs.i_open1 + cs.i_ext1)) : d_noe1;
+    const int i_ne2 = GEN ? (int)pin((uint32_t)-cs.i_ext2) : d_ne2, i_noe2 = GEN ? (int)pin((uint32_t)-(cs.i_open2 + cs.i_ext2)) : d_noe2;
     const int c_mat = (int)pin((uint32_t)cs.s_match), c_mis = (int)pin((uint32_t)cs.s_mismatch), c_neg = (int)pin((uint32_t)NEG);
     const uint32_t r0 = pin(cs.tab[0]), r1 = pin(cs.tab[1]), r2 = pin(cs.tab[2]), r3 = pin(cs.tab[3]);
 

@@ -101,3 +101,25 @@ def test_config5_skewed_locus_through_the_chain(gpu):
     cores = consensus_align.core_intervals_on_reference(cons, ann)
     for cid in cons:
         assert any(abs(a - loc.core_interval[0]) <= 10 for _i, _c, a, _b, _lo, _hi in cores[cid])
+
+
+def test_config2_full_step_determinism_and_consistency(gpu):
+    """One bench-sized step of config 2 (24 regions = 10 440 pairs here, several waves): two runs give identical result
+    rows and CIGARs (a checksum of checksums), the CIGAR-free summary call returns the same rows, and a seeded sample of
+    the pairs passes the CIGAR/score/count consistency properties."""
+    import zlib
+    b = workloads.batch_config2(list(range(200, 224)))
+    r1, c1 = align(gpu, b)
+    r2, c2 = align(gpu, b)
+    fields = [f for f in r1.dtype.names]
+    assert all(np.array_equal(r1[f], r2[f]) for f in fields)
+    used = int(r1["cigar_off"][-1] + r1["cigar_len"][-1])
+    assert zlib.crc32(c1[:used].tobytes()) == zlib.crc32(c2[:used].tobytes())
+    rs = gpu.align_batch_summary(b["packed"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+    assert all(np.array_equal(r1[f], rs[f]) for f in fields if f != "cigar_off")
+    assert (r1["status"] == 0).all() and int(r1["cells"].sum()) > 50e9
+    rng = np.random.default_rng(0)
+    for k in rng.choice(len(r1), 400, replace=False):
+        check_result(b["packed"], b["off"], b["lens"], b["pairs"][k], r1[k], c1, gpu.scoring)
+    # same-haplotype pairs carry no large indel, cross-haplotype pairs carry the planted one (sv_dist separates them)
+    assert (r1["sv_dist"] == 0).sum() > 0.3 * len(r1) and (r1["sv_dist"] > 40).sum() > 0.3 * len(r1)
