@@ -80,6 +80,8 @@ class PairBatch:
             cap = cap_fn(int(lens[q]), int(lens[t]))
             pairs[k] = (q, t, lo, w, fl, pos, cap, 0)
             pos += cap
+            if pos >= 1 << 32:
+                raise ValueError("CIGAR slots of one batch exceed 2^32 words (svp_pair.cigar_off is 32-bit): split the batch")
         return PairBatch(names, seqs, packed, off, lens, pairs, max(pos, 1))
 
 

@@ -26,6 +26,8 @@ def assemble(seqs: list[np.ndarray], specs: list[tuple[int, int, int, int, int]]
         caps = np.array([cigar_cap_for(int(lens[q]), int(lens[t])) for q, t in arr[:, :2]], dtype=np.int64)
         pairs["cigar_off"], pairs["cigar_cap"] = np.concatenate(([0], np.cumsum(caps)[:-1])), caps
         words = int(caps.sum())
+        if words >= 1 << 32:
+            raise ValueError("CIGAR slots of one batch exceed 2^32 words (svp_pair.cigar_off is 32-bit): split the batch")
     else:
         words = 1
     return {"packed": packed, "off": off, "lens": lens, "pairs": pairs, "cigar_words": words, "n_regions": n_regions,
