@@ -84,6 +84,7 @@ struct svp_handle {
     svp_stats stats{};
     std::string err;
     int max_smem_optin = 0;
+    int tbw_max = 2048;                         // waves with at most this many pairs use the warp-per-pair traceback (env SVP_TBW_MAX)
 };
 
 static thread_local std::string g_err;
@@ -190,6 +191,7 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
 #define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
 #define SVP_ATTR(K) SVP_SMEM(svp_fwd_kernel<K, false, true>); SVP_SMEM(svp_fwd_kernel<K, true, true>); \
                     SVP_SMEM(svp_fwd_kernel<K, false, false>); SVP_SMEM(svp_fwd_kernel<K, true, false>)
@@ -530,7 +532,12 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         const int nt = (int)(waves[wv].second - waves[wv].first);
         if (nt > 0) {
             const int tpb = 64;
-            svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+            // few pairs in the wave (one container per call; long tandem-repeat pairs): the warp-per-pair kernel walks 32 cells
+            // per memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass
+            if (nt <= h->tbw_max)
+                svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+            else
+                svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
             h->stats.tb_launches++;
         }
         CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));

@@ -397,6 +397,21 @@ struct TbView {
     __device__ __forceinline__ const uint8_t* addr(int i, int j) const {
         return base + (ptrdiff_t)((i + j) - r_begin) * pitch + col((j - i) - band_lo);
     }
+    // stored byte of H(i, j); 0 for cells before the matrix or before the first stored row (callers check the band)
+    __device__ __forceinline__ uint32_t lb(int i, int j) const {
+        if (i < 1 || j < 1 || (i + j) < r_begin) return 0;
+        return *addr(i, j);
+    }
+    // single bases (codes 0..3) at 1-based positions of the ORIENTED query / the target
+    __device__ __forceinline__ int qbase(int i) const {
+        const unsigned p = rc ? (unsigned)(m - i) : (unsigned)(i - 1);
+        const int c = (int)((__ldg(seqs32 + q_word + (p >> 4)) >> ((p & 15u) * 2u)) & 3u);
+        return rc ? 3 - c : c;
+    }
+    __device__ __forceinline__ int tbase(int j) const {
+        const unsigned p = (unsigned)(j - 1);
+        return (int)((__ldg(seqs32 + t_word + (p >> 4)) >> ((p & 15u) * 2u)) & 3u);
+    }
     // bases at 1-based positions p, p+1, ..., base t in bits 2t (positions beyond len: unspecified)
     __device__ __forceinline__ uint32_t window_asc(uint64_t word0, int len, int p) const {
         const int p0 = max(p - 1, 0);
@@ -642,6 +657,205 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
         res.sv_dist = dist;
     }
     results[tk.pair_index] = res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// traceback, one WARP per pair: the latency-optimised variant for waves with few pairs (a single container per call,
+// the way the reference's seam is driven; long tandem-repeat pairs). Every round lane l fetches the diagonal
+// predecessor byte and the base pair of cell (i-l, j-l), so 32 cells of a diagonal run cost ONE memory round trip
+// (the thread-per-pair kernel covers 8); the cells are then resolved in order by all lanes in lockstep. Gap search:
+// 32 candidates of the row and of the column per round. Same spec, same results as svp_tb_kernel;
+// the Z-trim start is kept as a snapshot of the walk at its lowest H instead of a replay.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ tb,
+               const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n_tasks) return;
+    const Task tk = tasks[wid];
+    svp_result res;
+    res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
+    res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
+    res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
+    if (tk.flags & TASK_INVALID) {
+        res.cells = 0;
+        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_TOO_LONG : SVP_ST_BAD_PAIR;
+        if (lane == 0) results[tk.pair_index] = res;
+        return;
+    }
+    const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
+    TbView v;
+    v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
+    v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
+    v.kp = KP; v.shift = 31 - __clz(4 * KP);
+    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    const int d_hi = tk.band_lo + tk.band_w - 1;
+
+    // ---- 1. end cell ---------------------------------------------------------------------------
+    const int n_ent = (tk.band_w / (4 * KP)) * 2;
+    int M = 0; uint32_t blk = 0xFFFFFFFFu;
+    for (int e = lane; e < n_ent; e += 32) {
+        const uint2 b = __ldg(bests + tk.best_off + e);
+        const int val = (int)b.x;
+        if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const int M2 = __shfl_xor_sync(0xffffffffu, M, o);
+        const uint32_t b2 = __shfl_xor_sync(0xffffffffu, blk, o);
+        if (M2 > M || (M2 == M && b2 < blk)) { M = M2; blk = b2; }
+    }
+    if (M <= 0) {
+        res.status = SVP_ST_NOHIT;
+        if (lane == 0) results[tk.pair_index] = res;
+        return;
+    }
+    if (!(tk.flags & TASK_S32) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    int end_s = 0x7FFFFFFF, end_x = -1;
+    const int NC = 2 * KP * KP;
+    for (int e0 = 0; e0 < n_ent; e0 += 32) {
+        const int e = e0 + lane;
+        bool hit = false;
+        if (e < n_ent) { const uint2 b = __ldg(bests + tk.best_off + e); hit = ((int)b.x == M) && (b.y == blk); }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+            const int ee = e0 + __ffs(mask) - 1; mask &= mask - 1;
+            const int xbase = (ee >> 1) * 4 * KP + (ee & 1) * 2 * KP;     // first diagonal (band-relative) of the half
+            const int s0 = (int)blk * 2 * KP;
+            int rel_row0 = 0, rel = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
+            uint32_t b_row0 = 0, bprev = 0;
+            for (int c0 = 0; c0 < NC; c0 += 32) {             // bytes fetched 32 at a time, chained by all lanes in lockstep
+                const int idx = c0 + lane;
+                uint32_t mine = 0;
+                if (idx < NC) {
+                    const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
+                    mine = v.base[(size_t)s * v.pitch + v.col(x)];
+                }
+                const int lim = min(32, NC - c0);
+                for (int l = 0; l < lim; ++l) {
+                    const uint32_t b = __shfl_sync(0xffffffffu, mine, l);
+                    const int id = c0 + l;
+                    if (id == 0) rel = 0;
+                    else if (id % KP == 0) rel = rel_row0 + sext8(b - b_row0);
+                    else rel = rel + sext8(b - bprev);
+                    if (id % KP == 0) { rel_row0 = rel; b_row0 = b; }
+                    bprev = b;
+                    const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
+                    if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
+                    else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
+                }
+            }
+            if (cand_s < end_s || (cand_s == end_s && cand_x > end_x)) { end_s = cand_s; end_x = cand_x; }
+        }
+    }
+    int i = ((tk.r_begin + end_s) - (tk.band_lo + end_x)) / 2, j = ((tk.r_begin + end_s) + (tk.band_lo + end_x)) / 2;
+    const int best_i = i, best_j = j;
+
+    // ---- 2. walk back --------------------------------------------------------------------------
+    int H = M;
+    uint32_t* slot = cigar + tk.cigar_off;
+    int wpos = (int)tk.cigar_cap;                    // runs are written right-aligned, backwards
+    uint32_t cur_op = 0, cur_len = 0; bool ovf = false, bad = false;
+    uint32_t n_match = 0, n_mis = 0, n_io = 0, n_ib = 0, n_do = 0, n_db = 0;
+    // snapshot at the lowest H of the walk: where the alignment starts if the walk is cut (Z-trim, §3.5) or ends at H = 0
+    int low = M + 1, low_i = i, low_j = j, low_wpos = wpos; uint32_t low_op = 0, low_len = 0; bool low_ovf = false;
+    uint32_t l_match = 0, l_mis = 0, l_io = 0, l_ib = 0, l_do = 0, l_db = 0;
+    const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
+
+#define SVP_PUSHW() do { if (cur_len) { if (wpos > 0) { --wpos; if (lane == 0) slot[wpos] = (cur_len << 4) | cur_op; } else ovf = true; } } while (0)
+#define SVP_EMITW(op, len) do { if (cur_len && cur_op == (op)) cur_len += (len); else { SVP_PUSHW(); cur_op = (op); cur_len = (len); } } while (0)
+#define SVP_SNAPW(hv) do { low = (hv); low_i = i; low_j = j; low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf; \
+        l_match = n_match; l_mis = n_mis; l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db; } while (0)
+
+    bool done = false;
+    while (!done) {
+        // ---- diagonal run: lane l holds the diagonal predecessor byte and the bases of cell (i-l, j-l) ----
+        const int ci = i - lane, cj = j - lane;
+        uint32_t bp = 0; int sub_l = 0, same_l = 0;
+        if (ci >= 1 && cj >= 1) {
+            bp = v.lb(ci - 1, cj - 1);
+            const int qc = v.qbase(ci), tc = v.tbase(cj);
+            same_l = qc == tc;
+            sub_l = (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
+        }
+        if (ci - 33 >= 1 && cj - 33 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - 33, cj - 33)));   // next round's byte
+        bool gap = false;
+        for (int l = 0; l < 32; ++l) {
+            if (H < low) SVP_SNAPW(H);
+            if (H == 0 || i < 1 || j < 1) { done = true; break; }
+            int dd = (j - i) - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+            if (H - low > zdrop + cs.zdrop_ext * dd) { done = true; break; }
+            const uint32_t b = __shfl_sync(0xffffffffu, bp, l);
+            const int sub = __shfl_sync(0xffffffffu, sub_l, l), same = __shfl_sync(0xffffffffu, same_l, l);
+            const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(b - (uint32_t)H) : 0;
+            if (H == Hd + sub) {
+                SVP_EMITW(SVP_CIGAR_M, 1u);
+                if (same) ++n_match; else ++n_mis;
+                --i; --j; H = Hd;
+            } else { gap = true; break; }
+        }
+        if (done || !gap) continue;
+        // ---- gap: the smallest k with H == H(i, j-k) - del(k), else H == H(i-k, j) - ins(k) ----
+        const int d = j - i;
+        int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
+        bool found = false, dead = false;
+        for (int k0 = 0; !found && !dead; k0 += 32) {
+            const int k = k0 + lane + 1;
+            const uint32_t bd = ((j - k >= 1) && (d - k >= tk.band_lo)) ? v.lb(i, j - k) : 0;
+            const uint32_t bi = ((i - k >= 1) && (d + k <= d_hi)) ? v.lb(i - k, j) : 0;
+            for (int l2 = 0; l2 < 32; ++l2) {
+                const int kk = k0 + l2 + 1;
+                const bool del_ok = (j - kk >= 1) && (d - kk >= tk.band_lo);
+                const bool ins_ok = (i - kk >= 1) && (d + kk <= d_hi);
+                if (!del_ok && !ins_ok) { dead = true; break; }
+                const uint32_t b1 = __shfl_sync(0xffffffffu, bd, l2), b2 = __shfl_sync(0xffffffffu, bi, l2);
+                if (del_ok) {
+                    Hrow += sext8(b1 - brow); brow = b1;
+                    if (H == Hrow - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, kk)) {
+                        SVP_EMITW(SVP_CIGAR_D, (uint32_t)kk); ++n_do; n_db += kk; j -= kk; H = Hrow; found = true; break;
+                    }
+                }
+                if (ins_ok) {
+                    Hcol += sext8(b2 - bcol); bcol = b2;
+                    if (H == Hcol - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, kk)) {
+                        SVP_EMITW(SVP_CIGAR_I, (uint32_t)kk); ++n_io; n_ib += kk; i -= kk; H = Hcol; found = true; break;
+                    }
+                }
+            }
+        }
+        if (!found) { bad = true; done = true; }
+    }
+    // the alignment starts at the lowest point of the walk
+    const int cut_low = low;
+    i = low_i; j = low_j; wpos = low_wpos; cur_op = low_op; cur_len = low_len; ovf = low_ovf;
+    SVP_PUSHW();
+#undef SVP_PUSHW
+#undef SVP_EMITW
+#undef SVP_SNAPW
+    if (bad) res.status |= SVP_ST_SCORE_OVF;
+    res.score = M - cut_low;
+    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
+    res.n_match = l_match; res.n_mismatch = l_mis; res.n_ins_ops = l_io; res.n_ins_bp = l_ib; res.n_del_ops = l_do; res.n_del_bp = l_db;
+    __syncwarp();
+    if (lane == 0) {
+        if (ovf) {
+            res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
+        } else {
+            res.cigar_len = tk.cigar_cap - (uint32_t)wpos;
+            res.cigar_off = tk.cigar_off + (uint32_t)wpos;
+            double dist = 0.0;
+            for (uint32_t a = (uint32_t)wpos; a < tk.cigar_cap; ++a) {
+                const uint32_t w = slot[a];
+                const uint32_t op = w & 15u, len = w >> 4;
+                if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
+                    const double sz = (double)len;
+                    dist += (1.0 - exp(-pow(sz / 30.0, 1.5))) * sz;
+                }
+            }
+            res.sv_dist = dist;
+        }
+        results[tk.pair_index] = res;
+    }
 }
 
 }  // namespace svp

@@ -419,3 +419,24 @@ def test_forced_sliding_window_equals_whole_images(oracle, monkeypatch, scoring_
     with Aligner(device=0, tb_bytes=2 << 30, **kw) as g:
         gres, _ = run_both(g, OracleEngine(**kw) if scoring_name else oracle, names, seqs, specs)
     assert not gres["status"].any()
+
+
+@pytest.mark.parametrize("tbw_max", ["0", "1000000"])
+def test_both_traceback_kernels(oracle, monkeypatch, tbw_max):
+    """The thread-per-pair (bulk) and the warp-per-pair (few pairs per wave) traceback kernels implement the same walk:
+    SVP_TBW_MAX forces one or the other for a mixed batch incl. a Z-trimmed inversion, long gaps and reverse strands."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_TBW_MAX", tbw_max)
+    rng = np.random.default_rng(91)
+    names, seqs, specs = noisy_batch(rng, 10, 2500, 544)
+    ref = randseq(rng, 6000)
+    inv = ref[:2000] + revcomp(ref[2000:4000]) + ref[4000:]
+    off = len(seqs)
+    seqs += [ref, inv, mutate(rng, ref[:1500] + ref[2100:], sub=0.01, ins=0.005, dele=0.005)]
+    for q in (off + 1, off + 2):
+        lo, w = ava.full_band(len(seqs[q]), len(ref))
+        specs += [(q, off, lo, w, 0), (q, off, lo, w, PAIR_REVCOMP)]
+    names = [f"r{k}" for k in range(len(seqs))]
+    with Aligner(device=0, tb_bytes=2 << 30) as g:
+        gres, _ = run_both(g, oracle, names, seqs, specs)
+    assert gres["n_del_bp"].max() >= 600
