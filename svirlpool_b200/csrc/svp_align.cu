@@ -503,8 +503,10 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
     cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
-    // forward passes of consecutive waves stay in stream order (letting them overlap on separate stream sets was measured
-    // slower twice, 1810 vs 1915 GCUPS: the earlier wave finishes later and so does its traceback); inside a wave the groups
+    // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower three times — on
+    // separate stream sets (1810 vs 1915 GCUPS) and on priority-tiered stream sets where the older wave keeps precedence for
+    // CTA slots (1815-1857 vs 1938): the traceback, which cannot preempt resident forward CTAs, finishes later and with it
+    // the arena half the wave after next is waiting for. Inside a wave the groups
     // run on up to four streams (2..6 measure the same, one stream 10 % slower), groups with the longest-running CTAs first
     // (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail of the wave)
     cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4] };
