@@ -10,12 +10,13 @@
 //   VIADDMNMX.S16x2 / VIMNMX3.S16x2(.RELU) / VIADD.16x2; match/mismatch comes from one HSET2.EQ
 //   on fp16-coded bases. Neighbour diagonals that belong to the adjacent thread travel by
 //   __shfl_up/__shfl_down (one register per state array per step), to the adjacent warp through
-//   a 16-byte shared-memory mailbox and one CTA barrier per step. Sequences are staged 2-bit
-//   packed in shared memory (cp.async 16-byte copies). Per step each thread streams the low byte
-//   of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
+//   a 16-byte shared-memory mailbox and one CTA barrier per step (cluster barrier + DSMEM mailboxes
+//   when the band spans several CTAs). The 2-bit packed sequences are read with coalesced 128-bit
+//   loads and staged in shared memory as one code byte per base. Per step each thread streams the
+//   low byte of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
 //
-// Traceback    svp_tb_kernel<KP>
-//   One thread per pair. Rebuilds exact H values along the path from the stored low bytes
+// Traceback    svp_tb_kernel (one thread per pair, bulk) / svp_tbw_kernel (one warp per pair, small waves)
+//   Rebuilds exact H values along the path from the stored low bytes
 //   (neighbouring H differ by less than 128); latency-bound, overlapped with the
 //   next wave's forward pass on a second stream.
 #pragma once
@@ -164,13 +165,23 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
 __device__ __forceinline__ void stage_sequences(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qimg, uint8_t* timg,
                                                 int qbytes, int tbytes) {
     const int g = threadIdx.x;
-    const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
-    for (int w = g; w < (tk.n + 15) >> 4; w += blockDim.x)
-        *reinterpret_cast<uint4*>(timg + SEQ_PAD + 16 * w) = expand16(__ldg(tsrc + w));
+    // 128-bit coalesced loads of the 2-bit packed reads (every sequence starts on and is readable up to a 16-byte boundary):
+    // one load = 64 bases = four 16-byte groups of the image
+    auto stage64 = [&](const uint8_t* src, uint8_t* img, int len) {
+        const uint4* v = reinterpret_cast<const uint4*>(src);
+        for (int w = g; w < (len + 63) >> 6; w += blockDim.x) {
+            const uint4 p = __ldg(v + w);
+            uint4* dst = reinterpret_cast<uint4*>(img + SEQ_PAD + 64 * w);
+            const int groups = min(4, ((len + 15) >> 4) - 4 * w);      // do not run over the image's end
+            const uint32_t word[4] = { p.x, p.y, p.z, p.w };
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < groups) dst[k] = expand16(word[k]);
+        }
+    };
+    stage64(seqs + tk.t_off, timg, tk.n);
     const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
     if (!(tk.flags & SVP_PAIR_REVCOMP)) {
-        for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x)
-            *reinterpret_cast<uint4*>(qimg + SEQ_PAD + 16 * w) = expand16(__ldg(qsrc + w));
+        stage64(seqs + tk.q_off, qimg, tk.m);
     } else {
         // oriented base p = complement of original base m-1-p
         for (int w = g; w < (tk.m + 15) >> 4; w += blockDim.x) {
