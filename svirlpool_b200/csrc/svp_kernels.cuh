@@ -119,6 +119,17 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // one step's barrier / mailbox store, CTA-local or cluster-wide
 template <bool CL> __device__ __forceinline__ void step_barrier() { if (CL) cluster_sync_all(); else __syncthreads(); }
+// Split-phase step synchronisation. A step ends with step_arrive() right after the mailbox store; the NEXT step calls
+// step_wait() only just before the one cell that reads a neighbour's mailbox, which is the last cell it computes (slot 0 of
+// an A-step, the last slot of a B-step). In a cluster the ~380-cycle barrier.cluster latency then hides behind the step's
+// other cells (arrive.release / wait.acquire); inside one CTA arrive is the plain CTA barrier and wait is empty. The A and
+// B mailboxes alternate, so a slot is rewritten only after a barrier phase its reader has arrived at behind its read.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// (Inside one CTA a split-phase mbarrier — arrive after the mailbox store, try_wait before the edge cell — was tried as
+// well: correct, 2 % slower than the plain CTA barrier on config 2, so CTA-local kernels keep __syncthreads.)
+template <bool CL> __device__ __forceinline__ void step_arrive() { if (CL) cluster_arrive(); else __syncthreads(); }
+template <bool CL> __device__ __forceinline__ void step_wait() { if (CL) cluster_wait(); }
 // (Tried and measured slower on B200, 1740 vs 1824 GCUPS on config 2: replacing the CTA barrier of the multi-warp kernels by
 // pairwise producer/consumer named barriers between neighbouring warps — bar.arrive by the producer, bar.sync by the
 // consumer, one barrier per direction per pair because a barrier only counts arrivals. The kernel then reserves all 16
@@ -248,6 +259,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); }
     step_barrier<CL>();
+    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -288,14 +300,20 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 uint32_t sE1 = __shfl_up_sync(0xffffffffu, E1[KP - 1], 1);
                 uint32_t sP2 = 0, sE2 = 0;
                 if (TWO) { sP2 = __shfl_up_sync(0xffffffffu, P2[KP - 1], 1); sE2 = __shfl_up_sync(0xffffffffu, E2[KP - 1], 1); }
-                uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                if (MULTI) mb = lds_v4(s_loB);
-                sP1 = lo_edge ? mb.x : sP1; sE1 = lo_edge ? mb.z : sE1;
-                if (TWO) { sP2 = lo_edge ? mb.y : sP2; sE2 = lo_edge ? mb.w : sE2; }
-                const uint32_t P1m = __byte_perm(sP1, P1[KP - 1], 0x5432), E1m = __byte_perm(sE1, E1[KP - 1], 0x5432);
-                const uint32_t P2m = TWO ? __byte_perm(sP2, P2[KP - 1], 0x5432) : 0u, E2m = TWO ? __byte_perm(sE2, E2[KP - 1], 0x5432) : 0u;
+                // slot 0 is computed last: it alone needs the lower neighbour (shuffle, or the mailbox on lane 0), so the wait for
+                // the previous step's barrier sits right before it; its own-thread halves are the values from before this step
+                const uint32_t oP1 = P1[KP - 1], oE1 = E1[KP - 1], oP2 = P2[KP - 1], oE2 = E2[KP - 1];
+                uint32_t P1m = 0, E1m = 0, P2m = 0, E2m = 0;
                 #pragma unroll
                 for (int k = KP - 1; k >= 0; --k) {
+                    if (k == 0) {
+                        uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        sP1 = lo_edge ? mb.x : sP1; sE1 = lo_edge ? mb.z : sE1;
+                        if (TWO) { sP2 = lo_edge ? mb.y : sP2; sE2 = lo_edge ? mb.w : sE2; }
+                        P1m = __byte_perm(sP1, oP1, 0x5432); E1m = __byte_perm(sE1, oE1, 0x5432);
+                        if (TWO) { P2m = __byte_perm(sP2, oP2, 0x5432); E2m = __byte_perm(sE2, oE2, 0x5432); }
+                    }
                     const uint32_t p1l = k ? P1[k ? k - 1 : 0] : P1m, e1l = k ? E1[k ? k - 1 : 0] : E1m;
                     const uint32_t e1 = __viaddmax_s16x2(e1l, c_ne1, p1l);
                     const uint32_t f1 = __viaddmax_s16x2(F1[k], c_ne1, P1[k]);
@@ -319,7 +337,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 0) mailbox_store<CL>(s_myA, P1[0], P2[0], F1[0], F2[0]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -332,14 +350,18 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 uint32_t sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1);
                 uint32_t sP2 = 0, sF2 = 0;
                 if (TWO) { sP2 = __shfl_down_sync(0xffffffffu, P2[0], 1); sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1); }
-                uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                if (MULTI) mb = lds_v4(s_upA);
-                sP1 = hi_edge ? mb.x : sP1; sF1 = hi_edge ? mb.z : sF1;
-                if (TWO) { sP2 = hi_edge ? mb.y : sP2; sF2 = hi_edge ? mb.w : sF2; }
-                const uint32_t P1p = __byte_perm(P1[0], sP1, 0x5432), F1p = __byte_perm(F1[0], sF1, 0x5432);
-                const uint32_t P2p = TWO ? __byte_perm(P2[0], sP2, 0x5432) : 0u, F2p = TWO ? __byte_perm(F2[0], sF2, 0x5432) : 0u;
+                const uint32_t oP1 = P1[0], oF1 = F1[0], oP2 = P2[0], oF2 = F2[0];
+                uint32_t P1p = 0, F1p = 0, P2p = 0, F2p = 0;
                 #pragma unroll
                 for (int k = 0; k < KP; ++k) {
+                    if (k == KP - 1) {         // the last slot alone needs the upper neighbour
+                        uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        sP1 = hi_edge ? mb.x : sP1; sF1 = hi_edge ? mb.z : sF1;
+                        if (TWO) { sP2 = hi_edge ? mb.y : sP2; sF2 = hi_edge ? mb.w : sF2; }
+                        P1p = __byte_perm(oP1, sP1, 0x5432); F1p = __byte_perm(oF1, sF1, 0x5432);
+                        if (TWO) { P2p = __byte_perm(oP2, sP2, 0x5432); F2p = __byte_perm(oF2, sF2, 0x5432); }
+                    }
                     const uint32_t p1u = (k < KP - 1) ? P1[(k + 1) % KP] : P1p, f1u = (k < KP - 1) ? F1[(k + 1) % KP] : F1p;
                     const uint32_t e1 = __viaddmax_s16x2(E1[k], c_ne1, P1[k]);
                     const uint32_t f1 = __viaddmax_s16x2(f1u, c_ne1, p1u);
@@ -363,7 +385,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 31) mailbox_store<CL>(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t nb = lds_u8(s_q + (uint32_t)__vimin_s32_relu(qpos, qmax));
@@ -377,6 +399,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
         if (diff >> 16) blk_hi = (uint32_t)it;
         snap = best;
     }
+    if (CL) cluster_wait();                    // the last step's arrive: no CTA leaves while a neighbour may still write its mailbox
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);

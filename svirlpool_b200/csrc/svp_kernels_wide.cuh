@@ -116,6 +116,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, 0u, 0u, c_neg, c_neg); }
     step_barrier<CL>();
+    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -159,14 +160,18 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 uint32_t sE1 = __shfl_up_sync(0xffffffffu, E1[KP - 1], 1);
                 uint32_t sE2 = 0;
                 if (TWO) sE2 = __shfl_up_sync(0xffffffffu, E2[KP - 1], 1);
-                uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
-                if (MULTI) mb = lds_v4(s_loB);
-                sH = lo_edge ? mb.x : sH; sE1 = lo_edge ? mb.z : sE1;
-                if (TWO) sE2 = lo_edge ? mb.w : sE2;
-                const uint32_t Hm = __byte_perm(sH, HB[KP - 1], 0x5432), E1m = __byte_perm(sE1, E1[KP - 1], 0x5432);
-                const uint32_t E2m = TWO ? __byte_perm(sE2, E2[KP - 1], 0x5432) : 0u;
+                const uint32_t oE1 = E1[KP - 1], oE2 = E2[KP - 1];      // HB is not written in an A-step
+                uint32_t Hm = 0, E1m = 0, E2m = 0;
                 #pragma unroll
                 for (int k = KP - 1; k >= 0; --k) {
+                    if (k == 0) {              // slot 0, computed last, alone needs the lower neighbour: wait as late as possible
+                        uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        sH = lo_edge ? mb.x : sH; sE1 = lo_edge ? mb.z : sE1;
+                        if (TWO) sE2 = lo_edge ? mb.w : sE2;
+                        Hm = __byte_perm(sH, HB[KP - 1], 0x5432); E1m = __byte_perm(sE1, oE1, 0x5432);
+                        if (TWO) E2m = __byte_perm(sE2, oE2, 0x5432);
+                    }
                     const uint32_t hl = k ? HB[k ? k - 1 : 0] : Hm, e1l = k ? E1[k ? k - 1 : 0] : E1m;
                     const uint32_t e1 = __viaddmax_s16x2(e1l, d_ne1, __vadd2(hl, d_noe1));
                     const uint32_t f1 = __viaddmax_s16x2(F1[k], i_ne1, __vadd2(HB[k], i_noe1));
@@ -189,7 +194,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 0) mailbox_store<CL>(s_myA, HA[0], 0u, F1[0], F2[0]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -202,14 +207,18 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 uint32_t sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1);
                 uint32_t sF2 = 0;
                 if (TWO) sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
-                uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
-                if (MULTI) mb = lds_v4(s_upA);
-                sH = hi_edge ? mb.x : sH; sF1 = hi_edge ? mb.z : sF1;
-                if (TWO) sF2 = hi_edge ? mb.w : sF2;
-                const uint32_t Hp = __byte_perm(HA[0], sH, 0x5432), F1p = __byte_perm(F1[0], sF1, 0x5432);
-                const uint32_t F2p = TWO ? __byte_perm(F2[0], sF2, 0x5432) : 0u;
+                const uint32_t oF1 = F1[0], oF2 = F2[0];                // HA is not written in a B-step
+                uint32_t Hp = 0, F1p = 0, F2p = 0;
                 #pragma unroll
                 for (int k = 0; k < KP; ++k) {
+                    if (k == KP - 1) {         // the last slot alone needs the upper neighbour
+                        uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        sH = hi_edge ? mb.x : sH; sF1 = hi_edge ? mb.z : sF1;
+                        if (TWO) sF2 = hi_edge ? mb.w : sF2;
+                        Hp = __byte_perm(HA[0], sH, 0x5432); F1p = __byte_perm(oF1, sF1, 0x5432);
+                        if (TWO) F2p = __byte_perm(oF2, sF2, 0x5432);
+                    }
                     const uint32_t hu = (k < KP - 1) ? HA[(k + 1) % KP] : Hp, f1u = (k < KP - 1) ? F1[(k + 1) % KP] : F1p;
                     const uint32_t e1 = __viaddmax_s16x2(E1[k], d_ne1, __vadd2(HA[k], d_noe1));
                     const uint32_t f1 = __viaddmax_s16x2(f1u, i_ne1, __vadd2(hu, i_noe1));
@@ -232,7 +241,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 31) mailbox_store<CL>(s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t off = (uint32_t)__vimin_s32_relu(qpos, qmax);
@@ -247,6 +256,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
         if (diff >> 16) blk_hi = (uint32_t)it;
         snap = best;
     }
+    if (CL) cluster_wait();                    // the last step's arrive
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
@@ -344,6 +354,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
     }
     step_barrier<CL>();
+    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (2 * K);
     const bool active = g < n_thr_active;
@@ -411,12 +422,14 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
             {
                 int sH = __shfl_up_sync(0xffffffffu, HB[K - 1], 1), sE1 = __shfl_up_sync(0xffffffffu, E1[K - 1], 1), sE2 = 0;
                 if (TWO) sE2 = __shfl_up_sync(0xffffffffu, E2[K - 1], 1);
-                uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-                if (MULTI) mb = lds_v4(s_loB);
-                sH = lo_edge ? (int)mb.x : sH; sE1 = lo_edge ? (int)mb.z : sE1;
-                if (TWO) sE2 = lo_edge ? (int)mb.w : sE2;
                 #pragma unroll
                 for (int k = K - 1; k >= 0; --k) {
+                    if (k == 0) {              // the only cell that needs the lower neighbour: wait for its mailbox as late as possible
+                        uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        sH = lo_edge ? (int)mb.x : sH; sE1 = lo_edge ? (int)mb.z : sE1;
+                        if (TWO) sE2 = lo_edge ? (int)mb.w : sE2;
+                    }
                     const int hl = k ? HB[k ? k - 1 : 0] : sH, e1l = k ? E1[k ? k - 1 : 0] : sE1, e2l = k ? E2[k ? k - 1 : 0] : sE2;
                     const int hd = HA[k] + score(Q[(k - u + K) % K], Q2[(k - u + K) % K], T[(k + u) % K]);
                     int e1, e2, f1, f2;
@@ -429,7 +442,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 0) mailbox_store<CL>(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 T[u % K] = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));     // logical T[k] <- T[k+1]; new base in slot K-1
                 ++tpos;
@@ -438,12 +451,14 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
             {
                 int sH = __shfl_down_sync(0xffffffffu, HA[0], 1), sF1 = __shfl_down_sync(0xffffffffu, F1[0], 1), sF2 = 0;
                 if (TWO) sF2 = __shfl_down_sync(0xffffffffu, F2[0], 1);
-                uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-                if (MULTI) mb = lds_v4(s_upA);
-                sH = hi_edge ? (int)mb.x : sH; sF1 = hi_edge ? (int)mb.z : sF1;
-                if (TWO) sF2 = hi_edge ? (int)mb.w : sF2;
                 #pragma unroll
                 for (int k = 0; k < K; ++k) {
+                    if (k == K - 1) {          // the only cell that needs the upper neighbour
+                        uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        sH = hi_edge ? (int)mb.x : sH; sF1 = hi_edge ? (int)mb.z : sF1;
+                        if (TWO) sF2 = hi_edge ? (int)mb.w : sF2;
+                    }
                     const int hu = (k < K - 1) ? HA[(k + 1) % K] : sH, f1u = (k < K - 1) ? F1[(k + 1) % K] : sF1, f2u = (k < K - 1) ? F2[(k + 1) % K] : sF2;
                     const int hd = HB[k] + score(Q[(k - u + K) % K], Q2[(k - u + K) % K], T[(k + u + 1) % K]);
                     int e1, e2, f1, f2;
@@ -456,7 +471,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 tbp += pitch;
                 if (MULTI) {
                     if (lane == 31) mailbox_store<CL>(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
-                    step_barrier<CL>();
+                    step_arrive<CL>();
                 }
                 const uint32_t qo = RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax);   // logical Q[k] <- Q[k-1]; new base in slot 0
                 Q[(K - 1 - u) % K] = lds_u8(s_q + qo);
@@ -470,6 +485,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
             }
         }
     }
+    if (CL) cluster_wait();                    // the last step's arrive: no CTA leaves while a neighbour may still write its mailbox
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
