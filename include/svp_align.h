@@ -104,8 +104,8 @@ typedef struct svp_handle svp_handle;
 int         svp_abi_version(void);
 int         svp_device_count(void);
 int         svp_scoring_preset(const char* name, svp_scoring* out);
-/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default
- * 1/2 of free memory); the library processes a batch in waves that fit the arena. */
+/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default:
+ * 90 % of the free device memory); the library processes a batch in waves that fit half the arena. */
 int         svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out);
 void        svp_destroy(svp_handle* h);
 const char* svp_last_error(const svp_handle* h);

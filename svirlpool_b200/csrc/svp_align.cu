@@ -209,7 +209,11 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
 #undef SVP_SMEM
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
-    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>(free_b / 10 * 8, (size_t)128 << 30);
+    // default arena: 90 % of the free memory. Every wave boundary costs 3.5-5 ms of forward time (the drain of one wave and the
+    // ramp of the next; measured by sweeping the arena: 32 / 64 / 128 / 160 GB -> 1377 / 1728 / 1912 / 2006 GCUPS on config 2),
+    // so the arena — i.e. the wave — should be as large as the device allows.
+    size_t want = max_tb_bytes ? max_tb_bytes : free_b / 10 * 9;
+    if (!max_tb_bytes) if (const char* e = getenv("SVP_ARENA_GB")) want = std::min<size_t>((size_t)std::max(atoi(e), 1) << 30, free_b / 20 * 19);   // tuning aid
     want = (want + 255) & ~(size_t)255;
     if (cudaMalloc((void**)&h->arena, want) != cudaSuccess) { cudaGetLastError(); return bail(SVP_ERR_NOMEM, "cannot allocate the traceback arena"); }
     h->arena_bytes = want;
@@ -503,10 +507,10 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
     cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
-    // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower three times — on
+    // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower four times — on
     // separate stream sets (1810 vs 1915 GCUPS) and on priority-tiered stream sets where the older wave keeps precedence for
-    // CTA slots (1815-1857 vs 1938): the traceback, which cannot preempt resident forward CTAs, finishes later and with it
-    // the arena half the wave after next is waiting for. Inside a wave the groups
+    // CTA slots (2 or 3 tiers of 2 streams, within the 8 hardware queues: 1810-1909 vs 1923-1962): the union of the forward
+    // intervals gets longer, not shorter, and the traceback is delayed. Inside a wave the groups
     // run on up to four streams (2..6 measure the same, one stream 10 % slower), groups with the longest-running CTAs first
     // (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail of the wave)
     cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4] };
