@@ -805,16 +805,22 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
     while (!done) {
         // ---- diagonal run: lane l holds the diagonal predecessor byte and the bases of cell (i-l, j-l) ----
         const int ci = i - lane, cj = j - lane;
-        uint32_t bp = 0; int sub_l = 0, same_l = 0;
+        const int d0 = j - i;
+        const bool del_band = d0 - 1 >= tk.band_lo, ins_band = d0 + 1 <= d_hi;
+        uint32_t bp = 0, bl = 0, bu = 0; int sub_l = 0, same_l = 0;
         if (ci >= 1 && cj >= 1) {
             bp = v.lb(ci - 1, cj - 1);
+            if (del_band) bl = v.lb(ci, cj - 1);          // left / up neighbours: a 1-base gap is resolved from this round's loads
+            if (ins_band) bu = v.lb(ci - 1, cj);
             const int qc = v.qbase(ci), tc = v.tbase(cj);
             same_l = qc == tc;
             sub_l = (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
         }
         if (ci - 33 >= 1 && cj - 33 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - 33, cj - 33)));   // next round's byte
         bool gap = false;
+        int l_gap = 0;
         for (int l = 0; l < 32; ++l) {
+            l_gap = l;
             if (H < low) SVP_SNAPW(H);
             if (H == 0 || i < 1 || j < 1) { done = true; break; }
             int dd = (j - i) - (low_j - low_i); dd = dd < 0 ? -dd : dd;
@@ -829,6 +835,16 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
             } else { gap = true; break; }
         }
         if (done || !gap) continue;
+        {   // 1-base gap at the cell the run stopped at (deletion first, as in the search below)
+            const uint32_t b1 = __shfl_sync(0xffffffffu, bl, l_gap), b2 = __shfl_sync(0xffffffffu, bu, l_gap);
+            const int Hl = H + sext8(b1 - (uint32_t)H), Hu = H + sext8(b2 - (uint32_t)H);
+            if (del_band && j - 1 >= 1 && H == Hl - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1)) {
+                SVP_EMITW(SVP_CIGAR_D, 1u); ++n_do; ++n_db; --j; H = Hl; continue;
+            }
+            if (ins_band && i - 1 >= 1 && H == Hu - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1)) {
+                SVP_EMITW(SVP_CIGAR_I, 1u); ++n_io; ++n_ib; --i; H = Hu; continue;
+            }
+        }
         // ---- gap: the smallest k with H == H(i, j-k) - del(k), else H == H(i-k, j) - ins(k) ----
         const int d = j - i;
         int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
