@@ -540,7 +540,9 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int tpb = 64;
             // few pairs in the wave (one container per call; long tandem-repeat pairs): the warp-per-pair kernel walks 32 cells
             // per memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass
-            if (nt <= h->tbw_max)
+            // ... and the last wave of a call has no forward pass left to share the machine with: its traceback is pure latency
+            static const bool last_wave_warp = [] { const char* e = getenv("SVP_TBW_LAST"); return e ? atoi(e) != 0 : true; }();
+            if (nt <= h->tbw_max || (last_wave_warp && wv + 1 == waves.size()))
                 svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
             else
                 svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
