@@ -215,7 +215,13 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     size_t want = max_tb_bytes ? max_tb_bytes : free_b / 10 * 9;
     if (!max_tb_bytes) if (const char* e = getenv("SVP_ARENA_GB")) want = std::min<size_t>((size_t)std::max(atoi(e), 1) << 30, free_b / 20 * 19);   // tuning aid
     want = (want + 255) & ~(size_t)255;
-    if (cudaMalloc((void**)&h->arena, want) != cudaSuccess) { cudaGetLastError(); return bail(SVP_ERR_NOMEM, "cannot allocate the traceback arena"); }
+    // the default size shrinks until the allocation succeeds (fragmentation, another process on the device); an explicit size does not
+    while (cudaMalloc((void**)&h->arena, want) != cudaSuccess) {
+        cudaGetLastError();
+        h->arena = nullptr;
+        if (max_tb_bytes || want < ((size_t)1 << 30)) return bail(SVP_ERR_NOMEM, "cannot allocate the traceback arena");
+        want = (want / 4 * 3 + 255) & ~(size_t)255;
+    }
     h->arena_bytes = want;
     *out = h;
     return SVP_OK;
