@@ -6,6 +6,8 @@ aligner calls replaced by the CUDA engine (/root/reference/src/svirlpool/localas
     ava_similarity                              :1362-1467   (AVA alignment + consensus_lib pipeline of
                                                               consensus_while_clustering, steps 1-4)
     align_reads_to_consensus                    :851-857 / :2089-2096 (map-ont of reads vs consensus)
+    final_consensus                             :821-916
+    get_read_alignment_intervals_in_region / _in_cr, get_max_extents_of_read_alignments_on_cr, trim_reads   :382-586
 
 Clustering, consensus assembly (lamassemble/racon) and padding stay with the reference's host code: they
 are outside the alignment path.
@@ -105,3 +107,70 @@ def final_consensus(engine, samplename: str, min_indel_size: int, min_bnd_size: 
     intervals = [(r.reference_start, r.reference_end, r.query_name, r.is_forward) for r in records]
     return consensus_class.Consensus(ID=ID, crIDs=list(crIDs), original_regions=list(original_regions), consensus_sequence=consensus_sequence,
                                      cut_read_alignment_signals=signals, intervals_cutread_alignments=intervals)
+
+
+# ---------------------------------------------------------------------------------------------
+# read cutting: the reads of a container are trimmed to its candidate regions before the all-vs-all
+# (consensus.py:382-586); the cut reads are what BASELINE config 2's "30 reads x 8 kb" are
+# ---------------------------------------------------------------------------------------------
+
+def get_read_alignment_intervals_in_region(region_start: int, regions_end: int, alignments: list, buffer_clipped_length: int
+                                           ) -> dict[str, list[tuple[int, int, str, int, int]]]:
+    """readname -> [(read_start, read_end, ref_chr, ref_start, ref_end)] of every alignment inside the region
+    (consensus.py:382-418): the read interval covering the region (reaching up to buffer_clipped_length into a clip when
+    the region extends beyond the alignment) and the reference interval that read interval maps back to."""
+    from . import util
+    out: dict[str, list[tuple[int, int, str, int, int]]] = {}
+    for aln in alignments:
+        read_start, read_end = util.get_interval_on_read_in_region(a=aln, start=region_start, end=regions_end,
+                                                                   buffer_clipped_length=buffer_clipped_length)
+        ref_start, ref_end = util.get_interval_on_ref_in_region(a=aln, start=read_start, end=read_end)
+        if read_start is not None and read_end is not None and read_end > read_start:
+            out.setdefault(aln.query_name, []).append((read_start, read_end, aln.reference_name, ref_start, ref_end))
+    return out
+
+
+def get_read_alignment_intervals_in_cr(crs: list, buffer_clipped_length: int, dict_alignments: dict[int, list]
+                                       ) -> dict[str, list[tuple[int, int, str, int, int]]]:
+    """Intervals over all candidate regions of a container (consensus.py:422-465). `crs` need .crID, .referenceStart,
+    .referenceEnd and .sv_signals; the clip buffer is at least the largest insertion signal of the container."""
+    extents = {cr.crID: (cr.referenceStart, cr.referenceEnd) for cr in crs}
+    max_ins = max([sv.size for cr in crs for sv in cr.sv_signals if sv.sv_type == 0], default=0)
+    used = max(buffer_clipped_length, max_ins)
+    out: dict[str, list[tuple[int, int, str, int, int]]] = {}
+    for crID, alns in dict_alignments.items():
+        for name, ivs in get_read_alignment_intervals_in_region(extents[crID][0], extents[crID][1], alns, used).items():
+            out.setdefault(name, []).extend(ivs)
+    return out
+
+
+def get_max_extents_of_read_alignments_on_cr(dict_all_intervals: dict[str, list[tuple[int, int, str, int, int]]]
+                                             ) -> dict[str, tuple[int, int, str, int, str, int]]:
+    """readname -> (min read_start, max read_end, chr of min ref_start, min ref_start, chr of max ref_end, max ref_end)
+    (consensus.py:468-496)."""
+    out = {}
+    for name, ivs in dict_all_intervals.items():
+        lo = min((ref_start, ref_chr) for _s, _e, ref_chr, ref_start, _re in ivs)
+        hi = max((ref_end, ref_chr) for _s, _e, ref_chr, _rs, ref_end in ivs)
+        out[name] = (min(s for s, *_ in ivs), max(e for _s, e, *_ in ivs), lo[1], lo[0], hi[1], hi[0])
+    return out
+
+
+def trim_reads(dict_alignments: dict[int, list], intervals: dict[str, tuple[int, int, str, int, str, int]], read_records: dict[str, str]
+               ) -> dict[str, tuple[str, str]]:
+    """Cut every read to its interval (consensus.py:499-586). read_records: readname -> full sequence in ORIGINAL read
+    orientation (read_cache.ReadSequenceCache). Returns readname -> (cut sequence, description) with the reference's
+    description string (crID, cut positions on the read and on the reference)."""
+    cut: dict[str, tuple[str, str]] = {}
+    for crID, alns in dict_alignments.items():
+        for aln in alns:
+            name = aln.query_name
+            if name not in intervals or name in cut or name not in read_records:
+                continue
+            start, end, ref_start_chr, ref_start, ref_end_chr, ref_end = intervals[name]
+            first = (ref_start_chr, ref_start) if ref_start < ref_end else (ref_end_chr, ref_end)
+            last = (ref_start_chr, ref_start) if ref_start >= ref_end else (ref_end_chr, ref_end)
+            desc = (f"crID={crID},start={start},end={end},ref_start_chr={first[0]},ref_start={first[1]},"
+                    f"ref_end_chr={last[0]},ref_end={last[1]}")
+            cut[name] = (read_records[name][start:end], desc)
+    return cut

@@ -143,3 +143,58 @@ def test_packed_hand_over_feeds_the_aligner(tmp_path, oracle):
     assert np.array_equal(batch.packed, packed) and np.array_equal(batch.seq_off, off)
     res, cig = oracle.align_batch(packed, off, lens, batch.pairs, batch.cigar_words)
     assert (res["score"] > 150).all() and not res["status"].any()
+
+
+def test_read_cutting_from_bam_to_all_vs_all(tmp_path, oracle):
+    """BAM -> ReadSequenceCache -> intervals in the candidate region -> cut reads -> all-vs-all: the ingest chain of
+    consensus.py:348-586 without pysam. Reads overhang the candidate region on both sides; after cutting they span it."""
+    from svirlpool_b200 import ava, consensus, synth
+    from svirlpool_b200.datatypes import SVsignal
+    rng = np.random.default_rng(5)
+    chrom = "".join("ACGT"[c] for c in rng.integers(0, 4, 6000))
+    recs = []
+    for k in range(6):
+        lo, hi = int(rng.integers(200, 900)), int(rng.integers(4200, 5400))
+        seq = chrom[lo:hi]
+        if k % 2:                                           # a 40 bp deletion inside the region on half of the reads
+            seq = chrom[lo:2500] + chrom[2540:hi]
+            cigar = [(0, 2500 - lo), (2, 40), (0, hi - 2540)]
+        else:
+            cigar = [(0, hi - lo)]
+        if k == 4:                                          # one read is soft-clipped inside the region
+            cigar = [(4, 300)] + [(0, cigar[0][1] - 300)] + cigar[1:]
+            lo += 300
+        recs.append({"name": f"read{k}", "chr": "chr1", "start": lo, "seq": seq, "cigar": cigar, "flag": 16 if k == 3 else 0})
+    bam = _make_bam(tmp_path, recs)
+
+    @dataclass
+    class CR:
+        crID: int
+        chr: str
+        referenceStart: int
+        referenceEnd: int
+        sv_signals: list
+
+    cr = CR(3, "chr1", 2000, 3200, [SVsignal(2500, 2540, 0, 0, 40, 1)])
+    with ReadSequenceCache(bam) as cache:
+        alns, seqs = cache.fetch_for_cr(cr)
+    assert len(alns) == 6
+    intervals = consensus.get_read_alignment_intervals_in_cr([cr], buffer_clipped_length=100, dict_alignments={3: alns})
+    extents = consensus.get_max_extents_of_read_alignments_on_cr(intervals)
+    cut = consensus.trim_reads({3: alns}, extents, seqs)
+    assert set(cut) == {f"read{k}" for k in range(6)}
+    for k in range(6):
+        seq, desc = cut[f"read{k}"]
+        want = 1200 - (40 if k % 2 else 0)
+        assert abs(len(seq) - want) <= 1 and desc.startswith("crID=3,start=") and "ref_start_chr=chr1" in desc
+        rs, re_, _c0, ref_lo, _c1, ref_hi = extents[f"read{k}"]
+        assert (ref_lo, ref_hi) == (2000, 3200) and re_ - rs == len(seq)
+    # the reverse-strand read was cut in ORIGINAL read orientation: its cut equals the reverse complement of the region
+    region_rc = chrom[2000:3200][::-1].translate(str.maketrans("ACGT", "TGCA"))
+    assert cut["read3"][0] == (chrom[2000:2500] + chrom[2540:3200])[::-1].translate(str.maketrans("ACGT", "TGCA")) and len(region_rc) == 1200
+    reads = {n: s for n, (s, _d) in cut.items()}
+    strands = {f"read{k}": "-" if k == 3 else "+" for k in range(6)}
+    records = ava.ava_align(oracle, reads, strands=strands, slack=100)
+    assert len(records) == 15
+    big = [n for r in records for op, n in r.cigartuples if op in (1, 2) and n >= 30]
+    assert len(big) == 9 and set(big) == {40}               # 3 x 3 cross-haplotype pairs see the 40 bp indel
