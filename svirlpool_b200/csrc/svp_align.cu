@@ -376,7 +376,7 @@ static void plan_pair(const Consts& cs, size_t max_smem, const svp_pair& p, uint
     // kernel variant: 32-bit lanes when the score can leave the s16 range; those and general scoring use the KP = 4 geometry
     // sequences that do not fit whole shared-memory images (with the widest CTA's mailboxes) run on the sliding-window
     // variant of the 32-bit lane kernel, whatever their score range
-    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + 2 * 17 * sizeof(uint4);
+    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + 2 * 17 * sizeof(uint4) + 16;
     static const bool force_ring = [] { const char* e = getenv("SVP_FORCE_RING"); return e && atoi(e); }();   // test aid
     const bool ring = force_ring || image_need > max_smem;
     const bool wide = ring || (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
@@ -418,7 +418,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     for (Task& t : tasks) {
         if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-        const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
+        const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16;
         if (need > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
     }
     // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
@@ -469,8 +469,8 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             // of two) so that a few long pairs do not cut the occupancy of the short ones sharing their launch; finer classes
             // were measured slower on config 2 (more, smaller launches: 1716 vs 1824 GCUPS).
             const bool ring = (t.flags & TASK_RING) != 0;
-            const size_t need = ring ? (size_t)(cs.general ? 3 : 2) * ring_bytes(nw * 32, 8) + (size_t)2 * (nw + 1) * sizeof(uint4)
-                                     : (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4);
+            const size_t need = ring ? (size_t)(cs.general ? 3 : 2) * ring_bytes(nw * 32, 8) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16
+                                     : (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16;
             int cls = 0;
             while (((size_t)32768 << cls) < need) ++cls;
             if (ring) cls = 50;                       // its own group: the sliding-window kernel
@@ -486,8 +486,8 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
-                smem = std::max(smem, ring ? (size_t)(n_qimg + 1) * ring_bytes(nwarp * 32, 8) + (size_t)2 * (nwarp + 1) * sizeof(uint4)
-                                           : (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4));
+                smem = std::max(smem, ring ? (size_t)(n_qimg + 1) * ring_bytes(nwarp * 32, 8) + (size_t)2 * (nwarp + 1) * sizeof(uint4) + 16
+                                           : (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4) + 16);
                 work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
             wave_groups[wv].push_back({ fam, nwarp, kp, cl, ring, pos, kv.second.size(), smem, work });

@@ -10,8 +10,8 @@
 //   VIADDMNMX.S16x2 / VIMNMX3.S16x2(.RELU) / VIADD.16x2; match/mismatch comes from one HSET2.EQ
 //   on fp16-coded bases. Neighbour diagonals that belong to the adjacent thread travel by
 //   __shfl_up/__shfl_down (one register per state array per step), to the adjacent warp through
-//   a 16-byte shared-memory mailbox and one CTA barrier per step (cluster barrier + DSMEM mailboxes
-//   when the band spans several CTAs). The 2-bit packed sequences are read with coalesced 128-bit
+//   a 16-byte shared-memory mailbox and one CTA barrier per step (st.async + mbarrier links into the
+//   neighbouring CTA's shared memory when the band spans the CTAs of a cluster). The 2-bit packed sequences are read with coalesced 128-bit
 //   loads and staged in shared memory as one code byte per base. Per step each thread streams the
 //   low byte of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
 //
@@ -119,39 +119,71 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // one step's barrier / mailbox store, CTA-local or cluster-wide
 template <bool CL> __device__ __forceinline__ void step_barrier() { if (CL) cluster_sync_all(); else __syncthreads(); }
-// Split-phase step synchronisation. A step ends with step_arrive() right after the mailbox store; the NEXT step calls
-// step_wait() only just before the one cell that reads a neighbour's mailbox, which is the last cell it computes (slot 0 of
-// an A-step, the last slot of a B-step). In a cluster the ~380-cycle barrier.cluster latency then hides behind the step's
-// other cells (arrive.release / wait.acquire); inside one CTA arrive is the plain CTA barrier and wait is empty. The A and
-// B mailboxes alternate, so a slot is rewritten only after a barrier phase its reader has arrived at behind its read.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// (Inside one CTA a split-phase mbarrier — arrive after the mailbox store, try_wait before the edge cell — was tried as
-// well: correct, 2 % slower than the plain CTA barrier on config 2, so CTA-local kernels keep __syncthreads.)
-template <bool CL> __device__ __forceinline__ void step_arrive() { if (CL) cluster_arrive(); else __syncthreads(); }
-template <bool CL> __device__ __forceinline__ void step_wait() { if (CL) cluster_wait(); }
-// (Tried and measured slower on B200, 1740 vs 1824 GCUPS on config 2: replacing the CTA barrier of the multi-warp kernels by
-// pairwise producer/consumer named barriers between neighbouring warps — bar.arrive by the producer, bar.sync by the
-// consumer, one barrier per direction per pair because a barrier only counts arrivals. The kernel then reserves all 16
-// named barriers and issues two barrier instructions per step.)
-template <bool CL> __device__ __forceinline__ void mailbox_store(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    if (CL) st_cluster_v4(addr, a, b, c, d); else sts_v4(addr, a, b, c, d);
+// Step synchronisation. Inside a CTA: the mailbox stores of a step are followed by one CTA barrier. Between the CTAs of a
+// cluster there is NO barrier: the two warps that face a neighbouring CTA exchange their mailbox entries point to point with
+// st.async into the neighbour's shared memory, completing 16 transaction bytes on an mbarrier that lives next to the
+// destination slot (STAS + SYNCS in SASS). The receiving warp arms that mbarrier (arrive.expect_tx) and waits on its phase
+// only just before the one cell that reads the neighbour's entry — the last cell a step computes (slot 0 of an A-step, the
+// last slot of a B-step) — so the ~215-cycle DSMEM latency hides behind the step's other cells and no thread ever executes
+// a fence. (A cluster barrier per step with release/acquire semantics stalled every warp on the release fence: ncu showed
+// 5.3 warps per issue slot waiting on membar, profiles/ncu_cluster_r01.json; config 3 ran at 485 instead of 8xx GCUPS.)
+// A mailbox slot is safe to overwrite when its writer gets there: the exchange between two neighbours is a ping-pong (the
+// A entry travels down, the B entry up), so a writer produces entry t+1 only after it consumed the entry its reader sent
+// after reading entry t. One mbarrier phase per step; KP and K are even, so the phase parity of step u is u & 1.
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(addr), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(addr), "r"(bytes) : "memory");
 }
-// Mailbox addresses of this warp. A[w] receives lane 0 of warp w after an A-step and is read by warp w-1; the first
-// warp of a CTA inside a cluster writes to A[nwarp] of the previous CTA instead. B[w+1] receives lane 31 of warp w after a
-// B-step and is read by warp w+1; the last warp of a CTA writes to B[0] of the next CTA.
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    asm volatile("{ .reg .pred p;\n\tSVP_MBAR_WAIT: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SVP_MBAR_DONE;\n\tbra SVP_MBAR_WAIT;\n\tSVP_MBAR_DONE: }"
+                 :: "r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cmbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 :: "r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cmbar) : "memory");
+}
+// Per-warp view of the cluster links. lo: this warp is the first of a CTA that has a lower neighbour (it receives that
+// neighbour's B entry in its local slot B[0] and sends its A entry to the neighbour's slot A[nwarp]); up: last warp of a CTA
+// with an upper neighbour (receives A[nwarp], sends to the neighbour's B[0]).
+struct ClusterLink {
+    bool lo, up;
+    uint32_t bar_lo, bar_up;            // local mbarriers of the two inbound slots
+    uint32_t rem_A, rem_bar_A;          // lower neighbour's A[nwarp] slot and its mbarrier (cluster addresses)
+    uint32_t rem_B, rem_bar_B;          // upper neighbour's B[0] slot and its mbarrier
+};
 template <bool CL>
-__device__ __forceinline__ void mailbox_targets(uint32_t s_mbA, uint32_t s_mbB, int warp, int nwarp, uint32_t crank, uint32_t csize,
-                                                uint32_t& s_myA, uint32_t& s_myB) {
+__device__ __forceinline__ ClusterLink cluster_link(uint32_t s_mbA, uint32_t s_mbB, int warp, int nwarp, uint32_t crank, uint32_t csize) {
+    ClusterLink L{};
     if (CL) {
-        s_myA = (warp == 0 && crank > 0) ? mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1) : mapa_shared(s_mbA + 16u * (uint32_t)warp, crank);
-        s_myB = (warp == nwarp - 1 && crank + 1 < csize) ? mapa_shared(s_mbB, crank + 1) : mapa_shared(s_mbB + 16u * (uint32_t)(warp + 1), crank);
-    } else {
-        s_myA = s_mbA + 16u * (uint32_t)warp;
-        s_myB = s_mbB + 16u * (uint32_t)(warp + 1);
+        const uint32_t bars = s_mbB + 16u * (uint32_t)(nwarp + 1);      // two mbarriers behind the mailboxes
+        L.bar_lo = bars; L.bar_up = bars + 8u;
+        L.lo = warp == 0 && crank > 0;
+        L.up = warp == nwarp - 1 && crank + 1 < csize;
+        if (L.lo) { L.rem_A = mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1); L.rem_bar_A = mapa_shared(bars + 8u, crank - 1); }
+        if (L.up) { L.rem_B = mapa_shared(s_mbB, crank + 1); L.rem_bar_B = mapa_shared(bars, crank + 1); }
     }
+    return L;
 }
-
+// mbarriers of the CTA's two inbound slots; called by one thread before the initial cluster-wide barrier
+template <bool CL> __device__ __forceinline__ void cluster_link_init(uint32_t s_mbB, int nwarp) {
+    if (CL) { const uint32_t bars = s_mbB + 16u * (uint32_t)(nwarp + 1); mbar_init(bars, 1); mbar_init(bars + 8u, 1); mbar_fence_init(); }
+}
+// before the edge cell of an A-step (lower neighbour's entry, sent after its previous B-step: A-step s > 0 waits for
+// phase s - 1) / of a B-step (upper neighbour's entry, sent after its A-step of the same index: phase s)
+template <bool CL> __device__ __forceinline__ void link_wait_lo(const ClusterLink& L, int lane, uint32_t parity) {
+    if (CL && L.lo) { if (lane == 0) mbar_expect_tx(L.bar_lo, 16u); mbar_wait(L.bar_lo, parity); }
+}
+template <bool CL> __device__ __forceinline__ void link_wait_up(const ClusterLink& L, int lane, uint32_t parity) {
+    if (CL && L.up) { if (lane == 0) mbar_expect_tx(L.bar_up, 16u); mbar_wait(L.bar_up, parity); }
+}
+// mailbox stores of lane 0 after an A-step / of lane 31 after a B-step: local slot, or the neighbouring CTA's
+template <bool CL> __device__ __forceinline__ void mailbox_store_A(const ClusterLink& L, uint32_t s_local, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (CL && L.lo) st_async_v4(L.rem_A, a, b, c, d, L.rem_bar_A); else sts_v4(s_local, a, b, c, d);
+}
+template <bool CL> __device__ __forceinline__ void mailbox_store_B(const ClusterLink& L, uint32_t s_local, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (CL && L.up) st_async_v4(L.rem_B, a, b, c, d, L.rem_bar_B); else sts_v4(s_local, a, b, c, d);
+}
 // Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
 // base p (0-based) at byte SEQ_PAD + p, with 0x7E (NaN) in the bytes before and after; positions are
 // clamped into [SEQ_PAD-1, SEQ_PAD+len] so every out-of-range position reads a NaN: virtual cells
@@ -258,8 +290,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 
     stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); }
+    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
     step_barrier<CL>();
-    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -287,8 +319,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int pitch = tk.band_w >> 1;                        // bytes per traceback row (one step)
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
     const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    uint32_t s_myA, s_myB;
-    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
+    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
+    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
@@ -308,7 +340,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 for (int k = KP - 1; k >= 0; --k) {
                     if (k == 0) {
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1)); mb = lds_v4(s_loB); }
                         sP1 = lo_edge ? mb.x : sP1; sE1 = lo_edge ? mb.z : sE1;
                         if (TWO) { sP2 = lo_edge ? mb.y : sP2; sE2 = lo_edge ? mb.w : sE2; }
                         P1m = __byte_perm(sP1, oP1, 0x5432); E1m = __byte_perm(sE1, oE1, 0x5432);
@@ -336,8 +368,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 if (active) store_row<KP>(tbp, HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) mailbox_store<CL>(s_myA, P1[0], P2[0], F1[0], F2[0]);
-                    step_arrive<CL>();
+                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, P1[0], P2[0], F1[0], F2[0]);
+                    __syncthreads();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -356,7 +388,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 for (int k = 0; k < KP; ++k) {
                     if (k == KP - 1) {         // the last slot alone needs the upper neighbour
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1)); mb = lds_v4(s_upA); }
                         sP1 = hi_edge ? mb.x : sP1; sF1 = hi_edge ? mb.z : sF1;
                         if (TWO) { sP2 = hi_edge ? mb.y : sP2; sF2 = hi_edge ? mb.w : sF2; }
                         P1p = __byte_perm(oP1, sP1, 0x5432); F1p = __byte_perm(oF1, sF1, 0x5432);
@@ -384,8 +416,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 if (active) store_row<KP>(tbp, HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) mailbox_store<CL>(s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
-                    step_arrive<CL>();
+                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
+                    __syncthreads();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t nb = lds_u8(s_q + (uint32_t)__vimin_s32_relu(qpos, qmax));
@@ -399,7 +431,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
         if (diff >> 16) blk_hi = (uint32_t)it;
         snap = best;
     }
-    if (CL) cluster_wait();                    // the last step's arrive: no CTA leaves while a neighbour may still write its mailbox
+    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);

@@ -115,8 +115,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
 
     stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, 0u, 0u, c_neg, c_neg); }
+    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
     step_barrier<CL>();
-    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -142,8 +142,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
     const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    uint32_t s_myA, s_myB;
-    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
+    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
+    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> uint32_t {
         const uint32_t sel = q | t;
@@ -166,7 +166,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 for (int k = KP - 1; k >= 0; --k) {
                     if (k == 0) {              // slot 0, computed last, alone needs the lower neighbour: wait as late as possible
                         uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1)); mb = lds_v4(s_loB); }
                         sH = lo_edge ? mb.x : sH; sE1 = lo_edge ? mb.z : sE1;
                         if (TWO) sE2 = lo_edge ? mb.w : sE2;
                         Hm = __byte_perm(sH, HB[KP - 1], 0x5432); E1m = __byte_perm(sE1, oE1, 0x5432);
@@ -193,8 +193,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 if (active) store_row<KP>(tbp, HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) mailbox_store<CL>(s_myA, HA[0], 0u, F1[0], F2[0]);
-                    step_arrive<CL>();
+                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, HA[0], 0u, F1[0], F2[0]);
+                    __syncthreads();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
@@ -213,7 +213,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 for (int k = 0; k < KP; ++k) {
                     if (k == KP - 1) {         // the last slot alone needs the upper neighbour
                         uint4 mb = make_uint4(0u, 0u, c_neg, c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1)); mb = lds_v4(s_upA); }
                         sH = hi_edge ? mb.x : sH; sF1 = hi_edge ? mb.z : sF1;
                         if (TWO) sF2 = hi_edge ? mb.w : sF2;
                         Hp = __byte_perm(HA[0], sH, 0x5432); F1p = __byte_perm(oF1, sF1, 0x5432);
@@ -240,8 +240,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 if (active) store_row<KP>(tbp, HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) mailbox_store<CL>(s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
-                    step_arrive<CL>();
+                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
+                    __syncthreads();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t off = (uint32_t)__vimin_s32_relu(qpos, qmax);
@@ -256,7 +256,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
         if (diff >> 16) blk_hi = (uint32_t)it;
         snap = best;
     }
-    if (CL) cluster_wait();                    // the last step's arrive
+    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
@@ -353,8 +353,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         sts_v4(s_mbA + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
         sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
     }
+    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
     step_barrier<CL>();
-    if (CL) cluster_arrive();                  // arms the wait of the first step
 
     const int n_thr_active = tk.band_w / (2 * K);
     const bool active = g < n_thr_active;
@@ -381,8 +381,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * K;
     const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    uint32_t s_myA, s_myB;
-    mailbox_targets<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize, s_myA, s_myB);
+    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
+    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 
     // bytes of slots c = 0..7 in the shared row order: word0 = slots [0,4,1,5], word1 = slots [2,6,3,7]
     auto store8 = [&](const int (&Hs)[K]) {
@@ -426,7 +426,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 for (int k = K - 1; k >= 0; --k) {
                     if (k == 0) {              // the only cell that needs the lower neighbour: wait for its mailbox as late as possible
                         uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_loB); }
+                        if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1)); mb = lds_v4(s_loB); }
                         sH = lo_edge ? (int)mb.x : sH; sE1 = lo_edge ? (int)mb.z : sE1;
                         if (TWO) sE2 = lo_edge ? (int)mb.w : sE2;
                     }
@@ -441,8 +441,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 if (active) store8(HA);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 0) mailbox_store<CL>(s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
-                    step_arrive<CL>();
+                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
+                    __syncthreads();
                 }
                 T[u % K] = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));     // logical T[k] <- T[k+1]; new base in slot K-1
                 ++tpos;
@@ -455,7 +455,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 for (int k = 0; k < K; ++k) {
                     if (k == K - 1) {          // the only cell that needs the upper neighbour
                         uint4 mb = make_uint4(0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-                        if (MULTI) { step_wait<CL>(); mb = lds_v4(s_upA); }
+                        if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1)); mb = lds_v4(s_upA); }
                         sH = hi_edge ? (int)mb.x : sH; sF1 = hi_edge ? (int)mb.z : sF1;
                         if (TWO) sF2 = hi_edge ? (int)mb.w : sF2;
                     }
@@ -470,8 +470,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 if (active) store8(HB);
                 tbp += pitch;
                 if (MULTI) {
-                    if (lane == 31) mailbox_store<CL>(s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
-                    step_arrive<CL>();
+                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
+                    __syncthreads();
                 }
                 const uint32_t qo = RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax);   // logical Q[k] <- Q[k-1]; new base in slot 0
                 Q[(K - 1 - u) % K] = lds_u8(s_q + qo);
@@ -485,7 +485,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
             }
         }
     }
-    if (CL) cluster_wait();                    // the last step's arrive: no CTA leaves while a neighbour may still write its mailbox
+    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
         bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
         bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
