@@ -53,6 +53,16 @@ static inline int steps_per_iter_of(const Task& t) { return (t.flags & TASK_S32)
 static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * steps_per_iter_of(t) * (uint64_t)(t.band_w / 2); }
 static inline uint64_t best_entries_of(const Task& t) { return (uint64_t)(t.band_w / (4 * kp_of(t))) * 2; }
 
+// dynamic shared memory of a pair's CTA (nw warps): sequence images (whole, or the sliding windows of the RING variants) + mailboxes
+static inline size_t smem_need(const Task& t, const Consts& cs, int nw) {
+    const size_t n_qimg = cs.general ? 2 : 1;              // general scoring stages two query images
+    if (t.flags & TASK_RING) {
+        const int per_thread = (t.flags & TASK_S32) || cs.general ? 8 : 2 * kp_of(t);      // positions per thread
+        return (n_qimg + 1) * (size_t)ring_bytes(nw * 32, per_thread) + (size_t)mailbox_bytes(nw);
+    }
+    return n_qimg * (size_t)seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)mailbox_bytes(nw);
+}
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
@@ -84,6 +94,8 @@ struct svp_handle {
     svp_stats stats{};
     std::string err;
     int max_smem_optin = 0;
+    long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
+    bool force_ring = false;                    // test aid (env SVP_FORCE_RING): every pair on a sliding-window variant
     int tbw_max = 2048;                         // waves with at most this many pairs use the warp-per-pair traceback (env SVP_TBW_MAX)
 };
 
@@ -165,6 +177,11 @@ static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
     c.i_ne1 = pk16(-c.i_ext1); c.i_noe1 = pk16(-(c.i_open1 + c.i_ext1)); c.i_ne2 = pk16(-c.i_ext2); c.i_noe2 = pk16(-(c.i_open2 + c.i_ext2));
     for (int q = 0; q < 4; ++q) for (int t = 0; t < 4; ++t) c.tab[q] |= (uint32_t)(s.matrix[q * 4 + t] & 0xFF) << (8 * t);
     c.a_max = a_max;
+    // rebased s16x2 kernel (scores beyond the s16 range on the fast path): the values of a warp, relative to its offset, must
+    // stay inside +-RB_CLAMP between two rebases: (128*KP diagonals + RB_ITERS*2*KP steps) * Lip + 256 (svp_kernels.cuh)
+    const int lip = a_max + std::max(g1d, g1i);
+    c.rebase_ok = (simple && (128 * 8 + RB_ITERS * 16) * lip + 256 <= RB_CLAMP - 400) ? 1 : 0;
+    if (const char* e = getenv("SVP_NO_REBASE")) if (atoi(e)) c.rebase_ok = 0;          // test / tuning aid: long reads on the 32-bit lane kernel
     c.min_signal = s.min_signal_size; c.zdrop = s.zdrop; c.zdrop_ext = s.zdrop_ext;
     return SVP_OK;
 }
@@ -191,17 +208,23 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
+    if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
 #define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
-#define SVP_ATTR(K) SVP_SMEM(svp_fwd_kernel<K, false, true>); SVP_SMEM(svp_fwd_kernel<K, true, true>); \
-                    SVP_SMEM(svp_fwd_kernel<K, false, false>); SVP_SMEM(svp_fwd_kernel<K, true, false>)
+#define SVP_ATTR2(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>); \
+                           SVP_SMEM(svp_fwd_kernel<K, false, false, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, false, false, R, G>)
+#define SVP_ATTR(K) SVP_ATTR2(K, false, false); SVP_ATTR2(K, false, true); SVP_ATTR2(K, true, false); SVP_ATTR2(K, true, true)
     SVP_ATTR(4); SVP_ATTR(8);
+#define SVP_ATTRC(R, G) SVP_SMEM(svp_fwd_kernel<8, true, true, true, R, G>); SVP_SMEM(svp_fwd_kernel<8, true, false, true, R, G>)
+    SVP_ATTRC(false, false); SVP_ATTRC(false, true); SVP_ATTRC(true, false); SVP_ATTRC(true, true);
+#undef SVP_ATTRC
+#undef SVP_ATTR2
     SVP_SMEM(svp_fwdg_kernel<false, true>); SVP_SMEM(svp_fwdg_kernel<true, true>); SVP_SMEM(svp_fwdg_kernel<false, false>); SVP_SMEM(svp_fwdg_kernel<true, false>);
     SVP_SMEM(svp_fwd32_kernel<false, true, false>); SVP_SMEM(svp_fwd32_kernel<true, true, false>);
     SVP_SMEM(svp_fwd32_kernel<false, false, false>); SVP_SMEM(svp_fwd32_kernel<true, false, false>);
     SVP_SMEM(svp_fwd32_kernel<false, true, true>); SVP_SMEM(svp_fwd32_kernel<true, true, true>);
     SVP_SMEM(svp_fwd32_kernel<false, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true>);
-    SVP_SMEM(svp_fwd_kernel<8, true, true, true>); SVP_SMEM(svp_fwd_kernel<8, true, false, true>);
     SVP_SMEM(svp_fwdg_kernel<true, true, true>); SVP_SMEM(svp_fwdg_kernel<true, false, true>);
     SVP_SMEM(svp_fwd32_kernel<true, true, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, false, true>);
     SVP_SMEM(svp_fwd32_kernel<true, true, true, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true, true>);
@@ -284,7 +307,7 @@ static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
 }
 
 // kernel family of a pair
-enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3 };
+enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3, FAM_FAST_RB = 4 };
 
 template <typename Kern>
 static void launch_cluster(Kern kern, int cluster, unsigned n_pairs, unsigned thr, size_t smem, cudaStream_t st, const Task* tasks,
@@ -305,6 +328,23 @@ static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool 
                        const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
     const bool multi = nwarp > 1;
     const unsigned thr = (unsigned)nwarp * 32u;
+    if (fam == FAM_FAST || fam == FAM_FAST_RB) {        // s16x2 fast path: plain / rebased, whole images / sliding windows, one CTA / cluster
+        const bool rb = fam == FAM_FAST_RB;
+        if (cluster > 1) {
+#define SVP_FCL(T, R, G) if (two == T && rb == R && ring == G) { launch_cluster(svp_fwd_kernel<8, true, T, true, R, G>, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
+            SVP_FCL(true, false, false) SVP_FCL(true, false, true) SVP_FCL(true, true, false) SVP_FCL(true, true, true)
+            SVP_FCL(false, false, false) SVP_FCL(false, false, true) SVP_FCL(false, true, false) SVP_FCL(false, true, true)
+#undef SVP_FCL
+            return;
+        }
+#define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) { svp_fwd_kernel<K, M, T, false, R, G><<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs); return; }
+#define SVP_F4(K, M, T) SVP_F(K, M, T, false, false) SVP_F(K, M, T, false, true) SVP_F(K, M, T, true, false) SVP_F(K, M, T, true, true)
+        SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
+        SVP_F4(4, false, false) SVP_F4(4, true, false) SVP_F4(8, false, false) SVP_F4(8, true, false)
+#undef SVP_F4
+#undef SVP_F
+        return;
+    }
     if (ring) {              // sliding-window variant of the 32-bit lane kernel (plain or cluster launch)
         const bool gen = fam == FAM_S32_GEN;
 #define SVP_RING(M, T, G) if (multi == M && two == T && gen == G) { \
@@ -318,7 +358,6 @@ static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool 
     }
     if (cluster > 1) {       // 16-warp CTAs, `cluster` of them per pair
 #define SVP_CL(COND, ...) if (COND) { launch_cluster(__VA_ARGS__, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
-        SVP_CL(fam == FAM_FAST && two, svp_fwd_kernel<8, true, true, true>) SVP_CL(fam == FAM_FAST && !two, svp_fwd_kernel<8, true, false, true>)
         SVP_CL(fam == FAM_GEN && two, svp_fwdg_kernel<true, true, true>) SVP_CL(fam == FAM_GEN && !two, svp_fwdg_kernel<true, false, true>)
         SVP_CL(fam == FAM_S32 && two, svp_fwd32_kernel<true, true, false, true>) SVP_CL(fam == FAM_S32 && !two, svp_fwd32_kernel<true, false, false, true>)
         SVP_CL(fam == FAM_S32_GEN && two, svp_fwd32_kernel<true, true, true, true>) SVP_CL(fam == FAM_S32_GEN && !two, svp_fwd32_kernel<true, false, true, true>)
@@ -326,10 +365,6 @@ static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool 
         return;
     }
 #define SVP_ARGS <<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs)
-#define SVP_CASE(K, M, T) if (fam == FAM_FAST && kp == K && multi == M && two == T) { svp_fwd_kernel<K, M, T> SVP_ARGS; return; }
-    SVP_CASE(4, false, true) SVP_CASE(4, true, true) SVP_CASE(8, false, true) SVP_CASE(8, true, true)
-    SVP_CASE(4, false, false) SVP_CASE(4, true, false) SVP_CASE(8, false, false) SVP_CASE(8, true, false)
-#undef SVP_CASE
 #define SVP_CASE(M, T) if (fam == FAM_GEN && multi == M && two == T) { svp_fwdg_kernel<M, T> SVP_ARGS; return; }
     SVP_CASE(false, true) SVP_CASE(true, true) SVP_CASE(false, false) SVP_CASE(true, false)
 #undef SVP_CASE
@@ -357,7 +392,7 @@ struct Plan {
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
 };
 
-static void plan_pair(const Consts& cs, size_t max_smem, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+static void plan_pair(const svp_handle* h, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
@@ -373,23 +408,37 @@ static void plan_pair(const Consts& cs, size_t max_smem, const svp_pair& p, uint
     t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
-    // kernel variant: 32-bit lanes when the score can leave the s16 range; those and general scoring use the KP = 4 geometry
-    // sequences that do not fit whole shared-memory images (with the widest CTA's mailboxes) run on the sliding-window
-    // variant of the 32-bit lane kernel, whatever their score range
-    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + 2 * 17 * sizeof(uint4) + 16;
-    static const bool force_ring = [] { const char* e = getenv("SVP_FORCE_RING"); return e && atoi(e); }();   // test aid
-    const bool ring = force_ring || image_need > max_smem;
-    const bool wide = ring || (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
+    const Consts& cs = h->cs;
+    const size_t max_smem = (size_t)h->max_smem_optin;
+    const bool force_ring = h->force_ring;
+    const long ring_min = h->ring_min;
+    // kernel variant. General scoring and 32-bit lanes use the KP = 4 geometry. Sequences that do not fit whole shared-memory
+    // images (with the widest CTA's mailboxes) run on a sliding-window variant.
+    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)mailbox_bytes(16);
+    // sliding windows: always when whole images do not fit; on the fast path also when whole images would cost occupancy
+    // (more than SVP_RING_MIN bytes of images per warp of the CTA)
+    const bool beyond_s16 = (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
+    // scores beyond the s16 range: the rebased s16x2 fast path when the scoring allows it (simple scoring, bounded neighbour
+    // differences); else 32-bit lanes
+    const bool rebase = beyond_s16 && !cs.general && cs.rebase_ok && (int64_t)std::min(t.m, t.n) * cs.a_max < (1 << 30);
+    const bool wide = beyond_s16 && !rebase;
+    bool ring = force_ring || image_need > max_smem;
+    const bool wide32 = wide || (ring && cs.general);        // general scoring has no s16 sliding-window kernel: 32-bit lanes
     // bands beyond one CTA (16 warps) run on a thread-block cluster of 2, 4 or 8 CTAs
     int kp, cl = 1;
-    if (wide || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
+    if (wide32 || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
     else {
         kp = choose_kp(p.band_w);
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
+        if (!ring && cl) {
+            const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));
+            ring = ((long)seq_image_bytes(t.m) + (long)seq_image_bytes(t.n)) / nw > ring_min;
+        }
     }
     if (cl == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
     if (cl > 1) t.flags |= (uint32_t)cl << TASK_CL_SHIFT;
-    if (wide) t.flags |= TASK_S32;
+    if (wide32) t.flags |= TASK_S32;
+    if (rebase && !wide32) t.flags |= TASK_REBASE;
     if (ring) t.flags |= TASK_RING;
     t.flags |= (uint32_t)kp << TASK_KP_SHIFT;
     const int steps_per_iter = steps_per_iter_of(t);
@@ -418,8 +467,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     for (Task& t : tasks) {
         if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-        const size_t need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16;
-        if (need > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
+        if (smem_need(t, cs, nw) > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
     }
     // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
     // the traceback of wave w overlaps the forward pass of wave w+1
@@ -464,13 +512,12 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int per_warp = 128 * kp_of(t);
             const int cl = cluster_of(t);
             const int nw = cl > 1 ? 16 : (t.band_w + per_warp - 1) / per_warp;
-            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : FAM_FAST);
+            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : (t.flags & TASK_REBASE) ? FAM_FAST_RB : FAM_FAST);
             // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (<= 32 KB, then powers
             // of two) so that a few long pairs do not cut the occupancy of the short ones sharing their launch; finer classes
             // were measured slower on config 2 (more, smaller launches: 1716 vs 1824 GCUPS).
             const bool ring = (t.flags & TASK_RING) != 0;
-            const size_t need = ring ? (size_t)(cs.general ? 3 : 2) * ring_bytes(nw * 32, 8) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16
-                                     : (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nw + 1) * sizeof(uint4) + 16;
+            const size_t need = smem_need(t, cs, nw);
             int cls = 0;
             while (((size_t)32768 << cls) < need) ++cls;
             if (ring) cls = 50;                       // its own group: the sliding-window kernel
@@ -482,12 +529,10 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             size_t smem = 0; uint64_t work = 0;
             const int nwarp = (int)(kv.first % 1000), kp = (int)((kv.first / 1000) % 100), fam = (int)((kv.first / 100000) % 100), cl = (int)((kv.first / 10000000) % 100);
             const bool ring = kv.first / 1000000000 == 50;
-            const int n_qimg = (fam == FAM_GEN || fam == FAM_S32_GEN) ? 2 : 1;            // general scoring stages two query images
             const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : kv.second) {
                 const Task& t = tasks[k];
-                smem = std::max(smem, ring ? (size_t)(n_qimg + 1) * ring_bytes(nwarp * 32, 8) + (size_t)2 * (nwarp + 1) * sizeof(uint4) + 16
-                                           : (size_t)n_qimg * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)2 * (nwarp + 1) * sizeof(uint4) + 16);
+                smem = std::max(smem, smem_need(t, cs, nwarp));
                 work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
             wave_groups[wv].push_back({ fam, nwarp, kp, cl, ring, pos, kv.second.size(), smem, work });
@@ -582,7 +627,7 @@ extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seq
         return fail(h, SVP_ERR_ARG, "null argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, (size_t)h->max_smem_optin, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
     return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
 }
 
@@ -597,7 +642,7 @@ static int align_host(svp_handle* h, const uint8_t* packed_seqs, size_t packed_b
     CUDA_TRY(h, cudaMemsetAsync((uint8_t*)h->d_seqs.p + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
     std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h->cs, (size_t)h->max_smem_optin, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
     int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
     if (rc != SVP_OK) return rc;
     if (n_pairs) {

@@ -58,6 +58,7 @@ struct Consts {             // scoring in the forms the kernels use (svp_align.c
     int32_t  s_match, s_mismatch;
     int32_t  d_open1, d_ext1, d_open2, d_ext2, i_open1, i_ext1, i_open2, i_ext2;
     int32_t  a_max;         // largest matrix entry (score-range test)
+    int32_t  rebase_ok;     // the rebased s16x2 kernel is exact for this scoring (make_consts)
     int32_t  min_signal, zdrop, zdrop_ext;
 };
 
@@ -69,6 +70,7 @@ constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;
 constexpr uint32_t TASK_CL_SHIFT = 16;           // bits 16..19: CTAs per cluster (0/1: no cluster)
 constexpr uint32_t TASK_CL_MASK = 0xF0000u;
+constexpr uint32_t TASK_REBASE = 0x08000000u;    // pair runs on the s16x2 fast path with per-warp score offsets (scores beyond the s16 range)
 constexpr uint32_t NEGV = 0xC000C000u;   // s16x2 -16384: "minus infinity" for gap states
 constexpr uint32_t QNAN16 = 0x7E00u;     // fp16 NaN: sentinel base, never equal to anything
 
@@ -151,17 +153,28 @@ struct ClusterLink {
     uint32_t bar_lo, bar_up;            // local mbarriers of the two inbound slots
     uint32_t rem_A, rem_bar_A;          // lower neighbour's A[nwarp] slot and its mbarrier (cluster addresses)
     uint32_t rem_B, rem_bar_B;          // upper neighbour's B[0] slot and its mbarrier
+    uint32_t rem_wb_lo, rem_wb_up;      // score-offset slots (rebased kernel): lower neighbour's wb[nwarp+1], upper neighbour's wb[0]
 };
+// Shared memory behind the sequence images of a CTA with nwarp warps (all forward kernel families):
+//   A[0..nwarp], B[0..nwarp]  16-byte mailboxes          two mbarriers (cluster links)
+//   one 16-byte slot holding the "outside the band" constants (read by the last in-band thread when it is not lane 31)
+//   wb[0..nwarp+1]            per-warp score offsets of the rebased kernel (wb[0] / wb[nwarp+1]: the neighbouring CTAs' edge warps)
+__host__ __device__ __forceinline__ int mailbox_bytes(int nwarp) { return 2 * (nwarp + 1) * 16 + 16 + 16 + ((4 * (nwarp + 2) + 15) & ~15); }
+__device__ __forceinline__ uint32_t smem_bars(uint32_t s_mbA, int nwarp) { return s_mbA + 32u * (uint32_t)(nwarp + 1); }
+__device__ __forceinline__ uint32_t smem_cst(uint32_t s_mbA, int nwarp) { return smem_bars(s_mbA, nwarp) + 16u; }
+__device__ __forceinline__ uint32_t smem_wb(uint32_t s_mbA, int nwarp) { return smem_bars(s_mbA, nwarp) + 32u; }
 template <bool CL>
 __device__ __forceinline__ ClusterLink cluster_link(uint32_t s_mbA, uint32_t s_mbB, int warp, int nwarp, uint32_t crank, uint32_t csize) {
     ClusterLink L{};
     if (CL) {
-        const uint32_t bars = s_mbB + 16u * (uint32_t)(nwarp + 1);      // two mbarriers behind the mailboxes
+        const uint32_t bars = smem_bars(s_mbA, nwarp);                  // two mbarriers behind the mailboxes
+        const uint32_t wb = smem_wb(s_mbA, nwarp);
         L.bar_lo = bars; L.bar_up = bars + 8u;
         L.lo = warp == 0 && crank > 0;
         L.up = warp == nwarp - 1 && crank + 1 < csize;
-        if (L.lo) { L.rem_A = mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1); L.rem_bar_A = mapa_shared(bars + 8u, crank - 1); }
-        if (L.up) { L.rem_B = mapa_shared(s_mbB, crank + 1); L.rem_bar_B = mapa_shared(bars, crank + 1); }
+        if (L.lo) { L.rem_A = mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1); L.rem_bar_A = mapa_shared(bars + 8u, crank - 1);
+                    L.rem_wb_lo = mapa_shared(wb + 4u * (uint32_t)(nwarp + 1), crank - 1); }
+        if (L.up) { L.rem_B = mapa_shared(s_mbB, crank + 1); L.rem_bar_B = mapa_shared(bars, crank + 1); L.rem_wb_up = mapa_shared(wb, crank + 1); }
     }
     return L;
 }
@@ -169,6 +182,9 @@ __device__ __forceinline__ ClusterLink cluster_link(uint32_t s_mbA, uint32_t s_m
 template <bool CL> __device__ __forceinline__ void cluster_link_init(uint32_t s_mbB, int nwarp) {
     if (CL) { const uint32_t bars = s_mbB + 16u * (uint32_t)(nwarp + 1); mbar_init(bars, 1); mbar_init(bars + 8u, 1); mbar_fence_init(); }
 }
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+__device__ __forceinline__ void st_cluster_u32(uint32_t caddr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(caddr), "r"(v) : "memory"); }
 // before the edge cell of an A-step (lower neighbour's entry, sent after its previous B-step: A-step s > 0 waits for
 // phase s - 1) / of a B-step (upper neighbour's entry, sent after its A-step of the same index: phase s)
 template <bool CL> __device__ __forceinline__ void link_wait_lo(const ClusterLink& L, int lane, uint32_t parity) {
@@ -248,6 +264,40 @@ __device__ __forceinline__ void stage_sequences(const Task& tk, const uint8_t* _
     __syncthreads();
 }
 
+// Sliding sequence windows (RING variants): instead of whole images, a CTA keeps only the part of each sequence its
+// anti-diagonal currently touches. The bases ENTERING the registers of a CTA lie within blockDim * k consecutive
+// positions of each sequence (k = positions per thread), advancing by a fixed number of positions per loop iteration,
+// so a power-of-two ring of R >= blockDim*k + 4k + RING_CHUNK bytes per image, refilled with the next RING_CHUNK
+// positions every RING_CHUNK / (positions per iteration) iterations, always holds them. The ring is indexed by the
+// VIRTUAL position (pos & (R-1), two's complement); positions outside [1, len] hold the pad code, so no clamping is
+// needed. Shared memory per CTA no longer grows with the read length (occupancy for long reads), and sequences of any
+// length fit.
+constexpr int RING_CHUNK = 256;
+__host__ __device__ __forceinline__ int ring_bytes(int n_threads, int k) {
+    int r = 1024;
+    while (r < n_threads * k + 4 * k + RING_CHUNK) r *= 2;
+    return r;
+}
+// code (0..3) of oriented query position p / target position p (1-based), or -1 outside the sequence
+__device__ __forceinline__ int packed_code(const uint32_t* __restrict__ src, int len, int p, bool rc) {
+    if (p < 1 || p > len) return -1;
+    const unsigned o = rc ? (unsigned)(len - p) : (unsigned)(p - 1);
+    const int c = (int)((__ldg(src + (o >> 4)) >> ((o & 15u) * 2u)) & 3u);
+    return rc ? 3 - c : c;
+}
+// fp16-coded windows of the fast path: `count` positions from q_first / t_first on
+__device__ __forceinline__ void ring_fill_fast(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qring, uint8_t* tring,
+                                               int mask, int q_first, int t_first, int count) {
+    const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
+    const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
+    const bool rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    for (int x = threadIdx.x; x < count; x += blockDim.x) {
+        const int qc = packed_code(qsrc, tk.m, q_first + x, rc), tc = packed_code(tsrc, tk.n, t_first + x, false);
+        qring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? 0x7E : 0x3C + qc);
+        tring[(t_first + x) & mask] = (uint8_t)(tc < 0 ? 0x7D : 0x3C + tc);
+    }
+}
+
 // low bytes of the 2*KP H values of one step -> this thread's 2*KP bytes of the traceback row
 template <int KP>
 __device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) {
@@ -265,7 +315,22 @@ __device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) 
 
 constexpr int fwd_max_threads(int kp, bool multi) { return !multi ? 32 : (kp <= 8 ? 512 : 256); }
 
-template <int KP, bool MULTI, bool TWO, bool CL = false>
+// Rebased variant (RB = true): the s16x2 fast path for pairs whose scores leave the s16 range (reads beyond ~16 kb).
+// Every warp keeps its state RELATIVE to a warp-uniform 32-bit offset `base` (a multiple of 256, so the stored low bytes
+// are those of the true H). H of in-band neighbours differs by at most Lip = A_max + dearest 1-base gap,
+// so the 128*KP diagonals of a warp span at most 128*KP*Lip, and between two rebases (RB_ITERS iterations = RB_ITERS*2KP
+// steps) a cell's value drifts by at most Lip per step: the relative values stay inside +-RB_CLAMP, no 16-bit add ever
+// wraps, and the result is bit-identical to 32-bit arithmetic (the host checks the bound for the scoring, plan_pair).
+// The zero floor of local alignment becomes max(-base, -RB_CLAMP) and rides as the third operand of the last VIMNMX3
+// (the RELU of the plain kernel), so the loop body costs the same. Values that arrive from the neighbouring warp
+// (mailbox) are shifted by the difference of the two offsets (4 VIADD.16x2 per step); "outside the band" is a
+// neighbour with offset 0. Offsets are exchanged through shared memory at every rebase (one extra barrier per
+// RB_ITERS iterations; a cluster barrier when the band spans CTAs). The running maximum is kept in 32 bits per
+// (thread, half) and refreshed once per iteration.
+constexpr int RB_ITERS = 16;
+constexpr int RB_CLAMP = 16000;
+
+template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false>
 __global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
@@ -275,22 +340,31 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
     const int g = (int)crank * (int)blockDim.x + gl;          // thread index across the cluster: owner of diagonals g*4KP ...
-    const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
+    const int ring = ring_bytes((int)blockDim.x, 2 * KP), rmask = ring - 1;
+    const int qbytes = RING ? ring : seq_image_bytes(tk.m), tbytes = RING ? ring : seq_image_bytes(tk.n);
     uint8_t* qimg = smem8;
     uint8_t* timg = smem8 + qbytes;
-    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + SEQ_PAD - 1;   // + clamped 1-based position
-    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + SEQ_PAD - 1;
+    // whole images: base + clamped 1-based position; rings: base + (virtual position & mask)
+    const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + (RING ? 0 : SEQ_PAD - 1);
+    const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + (RING ? 0 : SEQ_PAD - 1);
     // mailboxes (MULTI): A[w] = lane 0 of warp w after an A-step, A[nwarp] = constants;
     //                    B[w+1] = lane 31 of warp w after a B-step, B[0] = constants
     const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(smem8 + qbytes + tbytes);
     const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
+    const uint32_t s_cst = smem_cst(s_mbA, nwarp), s_wb = smem_wb(s_mbA, nwarp);
 
     const uint32_t c_ne1 = pin(cs.ne1), c_noe1 = pin(cs.noe1), c_ne2 = pin(cs.ne2), c_noe2 = pin(cs.noe2);
     const uint32_t c_mat = pin(cs.mat), c_mis = pin(cs.mis), c_neg = pin(NEGV);
 
-    stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
+    // lowest virtual positions this CTA touches at iteration 0 (its last thread has the smallest I0, its first the smallest J0)
+    const int g_first = (int)crank * (int)blockDim.x;
+    const int ring_q0 = (tk.r_begin - (tk.band_lo + (g_first + (int)blockDim.x - 1) * 4 * KP)) / 2 - 2 * KP;
+    const int ring_t0 = (tk.r_begin + (tk.band_lo + g_first * 4 * KP)) / 2 - 1;
+    if (RING) { ring_fill_fast(tk, seqs, qimg, timg, rmask, ring_q0, ring_t0, ring); __syncthreads(); }
+    else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); }
-    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
+    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg); }
+    if (MULTI && RB && gl < nwarp + 2) sts_u32(s_wb + 4u * gl, 0u);
     step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (4 * KP);
@@ -303,7 +377,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int qmax = tk.m + 1, tmax = tk.n + 1;
 
     auto code_at = [&](uint32_t sbase, int pos, int lim) -> uint32_t {   // fp16 code (16 bit) of a 1-based position
-        return lds_u8(sbase + (uint32_t)__vimin_s32_relu(pos, lim)) << 8;
+        return lds_u8(sbase + (RING ? (uint32_t)(pos & rmask) : (uint32_t)__vimin_s32_relu(pos, lim))) << 8;
     };
     // packed state, slot k in the low half, slot KP+k in the high half
     uint32_t HA[KP], HB[KP], P1[KP], P2[KP], E1[KP], E2[KP], F1[KP], F2[KP], Q[KP], T[KP];
@@ -315,15 +389,24 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
         T[k] = code_at(s_t, J0 + k, tmax) | (code_at(s_t, J0 + KP + k, tmax) << 16);
     }
     int qpos = I0 + 1, tpos = J0 + 2 * KP;                   // next bases to enter
-    uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
+    uint32_t best = RB ? 0x80008000u : 0u, snap = 0, blk_lo = 0, blk_hi = 0;
+    // rebased variant: warp-uniform score offset, 32-bit running maxima, the floor (0 relative to the offset) and the
+    // offset differences to the lower / upper neighbour warp as s16x2 constants
+    int base = 0, best_lo = 0, best_hi = 0, nb_lo = 0;
+    uint32_t c_floor = 0, dLo = 0, dLoF = 0, dUp = 0;
     const int pitch = tk.band_w >> 1;                        // bytes per traceback row (one step)
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
-    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
+    const uint32_t s_upA = (g == n_thr_active - 1) ? s_cst : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
     const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
     const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
+        if (RING && it && (it & (RING_CHUNK / KP - 1)) == 0) {      // the next chunk of both windows (needed from the next iteration on)
+            ring_fill_fast(tk, seqs, qimg, timg, rmask, ring_q0 + ring + (it - RING_CHUNK / KP) * KP, ring_t0 + ring + (it - RING_CHUNK / KP) * KP, RING_CHUNK);
+            if (!MULTI) __syncwarp();
+        }
         #pragma unroll
         for (int u = 0; u < KP; ++u) {
             // =============================== A-step ===========================================
@@ -341,6 +424,11 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     if (k == 0) {
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
                         if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1)); mb = lds_v4(s_loB); }
+                        if (RB) {              // the entry was written before the last rebase when this is the first step after it
+                            const uint32_t dl = (u == 0) ? dLoF : dLo;
+                            mb.x = __vadd2(mb.x, dl); mb.z = __vadd2(mb.z, dl);
+                            if (TWO) { mb.y = __vadd2(mb.y, dl); mb.w = __vadd2(mb.w, dl); }
+                        }
                         sP1 = lo_edge ? mb.x : sP1; sE1 = lo_edge ? mb.z : sE1;
                         if (TWO) { sP2 = lo_edge ? mb.y : sP2; sE2 = lo_edge ? mb.w : sE2; }
                         P1m = __byte_perm(sP1, oP1, 0x5432); E1m = __byte_perm(sE1, oE1, 0x5432);
@@ -350,16 +438,19 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     const uint32_t e1 = __viaddmax_s16x2(e1l, c_ne1, p1l);
                     const uint32_t f1 = __viaddmax_s16x2(F1[k], c_ne1, P1[k]);
                     const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u) % KP]);
-                    const uint32_t h = __vadd2(HA[k], (mk & c_mat) | (~mk & c_mis));
+                    const uint32_t sc = (mk & c_mat) | (~mk & c_mis);
+                    const uint32_t h = __vadd2(HA[k], sc);
                     uint32_t H;
                     if (TWO) {
                         const uint32_t p2l = k ? P2[k ? k - 1 : 0] : P2m, e2l = k ? E2[k ? k - 1 : 0] : E2m;
                         const uint32_t e2 = __viaddmax_s16x2(e2l, c_ne2, p2l);
                         const uint32_t f2 = __viaddmax_s16x2(F2[k], c_ne2, P2[k]);
-                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        if (RB) H = __vimax3_s16x2(__vimax3_s16x2(__viaddmax_s16x2(HA[k], sc, e1), f1, e2), f2, c_floor);
+                        else H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
                         E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, c_noe2);
                     } else {
-                        H = __vimax3_s16x2_relu(h, e1, f1);
+                        if (RB) H = __vimax3_s16x2(__viaddmax_s16x2(HA[k], sc, e1), f1, c_floor);
+                        else H = __vimax3_s16x2_relu(h, e1, f1);
                     }
                     HA[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
                 }
@@ -372,7 +463,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     __syncthreads();
                 }
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
-                const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
+                const uint32_t nb = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));
                 T[u % KP] = __byte_perm(T[u % KP], nb, 0x4232);
                 ++tpos;
             }
@@ -389,6 +480,10 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     if (k == KP - 1) {         // the last slot alone needs the upper neighbour
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
                         if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1)); mb = lds_v4(s_upA); }
+                        if (RB) {
+                            mb.x = __vadd2(mb.x, dUp); mb.z = __vadd2(mb.z, dUp);
+                            if (TWO) { mb.y = __vadd2(mb.y, dUp); mb.w = __vadd2(mb.w, dUp); }
+                        }
                         sP1 = hi_edge ? mb.x : sP1; sF1 = hi_edge ? mb.z : sF1;
                         if (TWO) { sP2 = hi_edge ? mb.y : sP2; sF2 = hi_edge ? mb.w : sF2; }
                         P1p = __byte_perm(oP1, sP1, 0x5432); F1p = __byte_perm(oF1, sF1, 0x5432);
@@ -398,16 +493,19 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     const uint32_t e1 = __viaddmax_s16x2(E1[k], c_ne1, P1[k]);
                     const uint32_t f1 = __viaddmax_s16x2(f1u, c_ne1, p1u);
                     const uint32_t mk = heq_mask(Q[(k - u + KP) % KP], T[(k + u + 1) % KP]);
-                    const uint32_t h = __vadd2(HB[k], (mk & c_mat) | (~mk & c_mis));
+                    const uint32_t sc = (mk & c_mat) | (~mk & c_mis);
+                    const uint32_t h = __vadd2(HB[k], sc);
                     uint32_t H;
                     if (TWO) {
                         const uint32_t p2u = (k < KP - 1) ? P2[(k + 1) % KP] : P2p, f2u = (k < KP - 1) ? F2[(k + 1) % KP] : F2p;
                         const uint32_t e2 = __viaddmax_s16x2(E2[k], c_ne2, P2[k]);
                         const uint32_t f2 = __viaddmax_s16x2(f2u, c_ne2, p2u);
-                        H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
+                        if (RB) H = __vimax3_s16x2(__vimax3_s16x2(__viaddmax_s16x2(HB[k], sc, e1), f1, e2), f2, c_floor);
+                        else H = __vimax3_s16x2_relu(__vimax3_s16x2(h, e1, f1), e2, f2);
                         E2[k] = e2; F2[k] = f2; P2[k] = __vadd2(H, c_noe2);
                     } else {
-                        H = __vimax3_s16x2_relu(h, e1, f1);
+                        if (RB) H = __vimax3_s16x2(__viaddmax_s16x2(HB[k], sc, e1), f1, c_floor);
+                        else H = __vimax3_s16x2_relu(h, e1, f1);
                     }
                     HB[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
                 }
@@ -420,21 +518,66 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     __syncthreads();
                 }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
-                const uint32_t nb = lds_u8(s_q + (uint32_t)__vimin_s32_relu(qpos, qmax));
+                const uint32_t nb = lds_u8(s_q + (RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax)));
                 Q[(KP - 1 - u) % KP] = __byte_perm(nb, Q[(KP - 1 - u) % KP], 0x5401);
                 ++qpos;
             }
         }
         // which iteration first reached the running maximum, per half (end-cell search)
-        const uint32_t diff = best ^ snap;
-        if (diff & 0xFFFFu) blk_lo = (uint32_t)it;
-        if (diff >> 16) blk_hi = (uint32_t)it;
-        snap = best;
+        if (!RB) {
+            const uint32_t diff = best ^ snap;
+            if (diff & 0xFFFFu) blk_lo = (uint32_t)it;
+            if (diff >> 16) blk_hi = (uint32_t)it;
+            snap = best;
+        } else {
+            const int lo = (int)(int16_t)(best & 0xFFFFu) + base, hi = ((int)best >> 16) + base;
+            if (lo > best_lo) { best_lo = lo; blk_lo = (uint32_t)it; }
+            if (hi > best_hi) { best_hi = hi; blk_hi = (uint32_t)it; }
+            best = 0x80008000u;
+            dLoF = dLo;
+            if (((it + 1) & (RB_ITERS - 1)) == 0 && it + 1 < tk.n_iter) {
+                // ---- rebase: the new offset is lane 0's current H of slot 0, rounded down to a multiple of 256 ----
+                const int h0 = __shfl_sync(0xffffffffu, (int)(int16_t)(HA[0] & 0xFFFFu), 0);
+                const int delta = h0 & ~255;
+                if (delta) {
+                    const uint32_t nd = pk(-delta);
+                    #pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        HA[k] = __vadd2(HA[k], nd); HB[k] = __vadd2(HB[k], nd); P1[k] = __vadd2(P1[k], nd);
+                        E1[k] = __vadd2(E1[k], nd); F1[k] = __vadd2(F1[k], nd);
+                        if (TWO) { P2[k] = __vadd2(P2[k], nd); E2[k] = __vadd2(E2[k], nd); F2[k] = __vadd2(F2[k], nd); }
+                    }
+                    base += delta;
+                    c_floor = pk(max(-base, -RB_CLAMP));
+                }
+                const int nb_lo_old = nb_lo;
+                int nb_up = 0;
+                if (MULTI) {
+                    if (lane == 0) {
+                        sts_u32(s_wb + 4u * (uint32_t)(warp + 1), (uint32_t)base);
+                        if (CL && link.lo) st_cluster_u32(link.rem_wb_lo, (uint32_t)base);
+                        if (CL && link.up) st_cluster_u32(link.rem_wb_up, (uint32_t)base);
+                    }
+                    step_barrier<CL>();
+                    nb_lo = (int)lds_u32(s_wb + 4u * (uint32_t)warp);
+                    nb_up = (int)lds_u32(s_wb + 4u * (uint32_t)(warp + 2));
+                }
+                if (g == n_thr_active - 1) nb_up = 0;
+                dLoF = pk(max(min(nb_lo_old - base, RB_CLAMP), -RB_CLAMP));
+                dLo = pk(max(min(nb_lo - base, RB_CLAMP), -RB_CLAMP));
+                dUp = pk(max(min(nb_up - base, RB_CLAMP), -RB_CLAMP));
+            }
+        }
     }
     if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
-        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
-        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
+        if (RB) {
+            bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
+            bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
+        } else {
+            bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
+            bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
+        }
     }
 }
 
@@ -555,7 +698,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
         results[tk.pair_index] = res;
         return;
     }
-    if (!(tk.flags & TASK_S32) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    if (!(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
     // every (thread, half) block that reached M in iteration blk: rebuild its 2KP x 2KP cells from the low bytes
     int end_s = 0x7FFFFFFF, end_x = -1;
     for (int e = 0; e < n_ent; ++e) {
@@ -776,7 +919,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
         if (lane == 0) results[tk.pair_index] = res;
         return;
     }
-    if (!(tk.flags & TASK_S32) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    if (!(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
     int end_s = 0x7FFFFFFF, end_x = -1;
     const int NC = 2 * KP * KP;
     for (int e0 = 0; e0 < n_ent; e0 += 32) {

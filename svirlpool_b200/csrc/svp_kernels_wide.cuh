@@ -115,7 +115,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
 
     stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
     if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, 0u, 0u, c_neg, c_neg); }
-    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
+    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(smem_cst(s_mbA, nwarp), 0u, 0u, c_neg, c_neg); }
     step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (4 * KP);
@@ -141,7 +141,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
-    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
+    const uint32_t s_upA = (g == n_thr_active - 1) ? smem_cst(s_mbA, nwarp) : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
     const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
     const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 
@@ -272,19 +273,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
 // RING_CHUNK / K iterations, always holds them. The ring is indexed by the VIRTUAL position (pos & (R-1), two's
 // complement), positions outside [1, len] hold the pad code, so no clamping is needed.
 // ---------------------------------------------------------------------------------------------
-constexpr int RING_CHUNK = 256;
-__host__ __device__ __forceinline__ int ring_bytes(int n_threads, int k) {
-    int r = 1024;
-    while (r < n_threads * k + 4 * k + RING_CHUNK) r *= 2;
-    return r;
-}
-// code (0..3) of oriented query position p / target position p (1-based), or -1 outside the sequence
-__device__ __forceinline__ int packed_code(const uint32_t* __restrict__ src, int len, int p, bool rc) {
-    if (p < 1 || p > len) return -1;
-    const unsigned o = rc ? (unsigned)(len - p) : (unsigned)(p - 1);
-    const int c = (int)((__ldg(src + (o >> 4)) >> ((o & 15u) * 2u)) & 3u);
-    return rc ? 3 - c : c;
-}
+// (RING_CHUNK, ring_bytes, packed_code: svp_kernels.cuh)
 template <bool GEN>
 __device__ __forceinline__ void ring_fill(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qring, uint8_t* q2ring, uint8_t* tring,
                                           int mask, int q_first, int t_first, int count) {
@@ -353,7 +342,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         sts_v4(s_mbA + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
         sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
     }
-    if (MULTI && gl == 0) cluster_link_init<CL>(s_mbB, nwarp);
+    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(smem_cst(s_mbA, nwarp), 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg); }
     step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (2 * K);
@@ -380,7 +369,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
     const int pitch = tk.band_w >> 1;
     uint8_t* tbp = tb + tk.tb_off + (size_t)g * K;
-    const uint32_t s_upA = s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
+    // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
+    const uint32_t s_upA = (g == n_thr_active - 1) ? smem_cst(s_mbA, nwarp) : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
     const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
     const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
 

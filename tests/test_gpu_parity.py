@@ -234,13 +234,64 @@ def test_forced_general_equals_fast_path(gpu, oracle, monkeypatch):
     assert_same(batch, gres, gcig, ores, ocig)
 
 
-@pytest.mark.parametrize("seed,length,band", [(51, 17000, 512), (52, 21000, 1056), (53, 30000, 2048)])
-def test_long_reads_32bit_lanes(gpu, oracle, seed, length, band):
-    """Reads beyond the s16 score range (match * min(m, n) > 32000) run on svp_fwd32_kernel."""
+@pytest.mark.parametrize("no_rebase", ["0", "1"])
+@pytest.mark.parametrize("seed,length,band", [(51, 17000, 512), (52, 21000, 1056), (53, 30000, 2048), (56, 60000, 544)])
+def test_long_reads_beyond_s16(oracle, monkeypatch, no_rebase, seed, length, band):
+    """Reads beyond the s16 score range (match * min(m, n) > 32000): the rebased s16x2 fast path (per-warp score offsets,
+    default) and the 32-bit lane kernel (SVP_NO_REBASE=1) both reproduce the oracle; scores up to ~70 000."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_NO_REBASE", no_rebase)
     rng = np.random.default_rng(seed)
-    names, seqs, specs = noisy_batch(rng, 4, length, band)
-    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    names, seqs, specs = noisy_batch(rng, 4 if length < 40000 else 2, length, band)
+    with Aligner(device=0, preset="map-ont", tb_bytes=4 << 30) as g:
+        gres, _ = run_both(g, oracle, names, seqs, specs)
     assert gres["score"].max() > 12000 and not (gres["status"] & 4).any()
+
+
+@pytest.mark.parametrize("ring_min", ["0", "1000000000"])
+def test_sliding_windows_and_whole_images_fast_path(oracle, monkeypatch, ring_min):
+    """The s16x2 fast path with sliding sequence windows for every pair (SVP_RING_MIN=0) and with whole shared-memory
+    images for every pair that fits (huge SVP_RING_MIN): single-warp, multi-warp, rebased (long reads) and cluster CTAs,
+    forward and reverse-complemented queries, all against the oracle."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_RING_MIN", ring_min)
+    rng = np.random.default_rng(58)
+    n1, s1, p1 = noisy_batch(rng, 6, 1500, 256)
+    n2, s2, p2 = noisy_batch(rng, 4, 6000, 1056)
+    n3, s3, p3 = noisy_batch(rng, 3, 9000, 2080, sv_every=1)
+    n4, s4, p4 = noisy_batch(rng, 2, 19000, 544)
+    seqs, specs = [], []
+    for sq, sp in ((s1, p1), (s2, p2), (s3, p3), (s4, p4)):
+        off = len(seqs)
+        seqs += sq
+        specs += [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in sp]
+    t1 = randseq(rng, 20000)
+    off = len(seqs)
+    seqs += [t1, mutate(rng, t1[12000:17500]), revcomp(mutate(rng, t1[300:6200]))]
+    for q, rc in ((off + 1, 0), (off + 2, 1)):
+        lo, w = ava.full_band(len(seqs[q]), len(t1))                   # 26k diagonals: a cluster of 2 CTAs
+        specs.append((q, off, lo, w, PAIR_REVCOMP if rc else 0))
+    with Aligner(device=0, preset="map-ont", tb_bytes=4 << 30) as g:
+        gres, _ = run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
+    assert not gres["status"].any()
+
+
+def test_rebased_kernel_low_error_reads_and_restarts(gpu, oracle):
+    """Rebased kernel: accurate 40 kb reads (scores ~75 000, offsets far beyond 32768), a pair whose alignment only starts
+    after 25 kb of unrelated sequence (cells at H = 0 next to nothing, then a fresh start while other pairs' warps sit at
+    high offsets), and a pair with a 1.2 kb deletion that moves the path across warps."""
+    rng = np.random.default_rng(57)
+    t = randseq(rng, 40000)
+    a = mutate(rng, t, sub=0.01, ins=0.005, dele=0.005)
+    b = randseq(rng, 25000) + mutate(rng, t[25000:], sub=0.02, ins=0.01, dele=0.01)
+    c = mutate(rng, t[:20000] + t[21200:], sub=0.02, ins=0.01, dele=0.01)
+    seqs, names = [t, a, b, c, revcomp(a)], ["t", "a", "b", "c", "a_rc"]
+    specs = []
+    for q, rc in ((1, 0), (2, 0), (3, 0), (4, 1)):
+        lo, w = ava.offset_band(len(seqs[q]), len(t), slack=700, granule=32)
+        specs.append((q, 0, lo, w, PAIR_REVCOMP if rc else 0))
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert gres["score"][0] > 65536 and gres["score"][3] == gres["score"][0] and gres["n_del_bp"][2] >= 1200 and not gres["status"].any()
 
 
 def test_long_reads_mixed_with_short(gpu, oracle):
@@ -321,6 +372,48 @@ def test_wide_band_cluster_long_reads(gpu, oracle):
     assert not gres["status"].any() and gres["n_del_bp"][0] >= 9000 and gres["n_ins_bp"][2] >= 9000
 
 
+def test_wide_band_cluster_rebased_long_reads(gpu, oracle):
+    """Rebased s16x2 kernel on a cluster: 22 kb reads whose haplotypes differ by a 16.6 kb insertion (band > 16384
+    diagonals = 2 CTAs at KP = 8); the score offsets of the edge warps travel through DSMEM at every rebase."""
+    rng = np.random.default_rng(74)
+    tmpl = randseq(rng, 22000)
+    ins = randseq(rng, 16600)
+    a = mutate(rng, tmpl, sub=0.01, ins=0.005, dele=0.005)
+    b = mutate(rng, tmpl[:11000] + ins + tmpl[11000:], sub=0.01, ins=0.005, dele=0.005)
+    seqs, names = [a, b], ["a", "b"]
+    lo, w = ava.offset_band(len(a), len(b), slack=256, granule=32)
+    assert w > 16384
+    specs = [(0, 1, lo, w, 0), (1, 0, -(lo + w - 1), w, 0)]
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert not gres["status"].any() and gres["n_del_bp"][0] >= 16000 and gres["score"].min() > 10000
+
+
+@pytest.mark.parametrize("variant", ["fast_cluster", "rebased_cluster", "s32_cluster", "general_cluster", "fast_one_cta"])
+def test_alignment_pressed_against_the_upper_band_edge(oracle, monkeypatch, variant):
+    """The target carries a 400-base insertion the band does not allow (upper edge 100 diagonals above the start), and the
+    band's thread count is not a multiple of 32, so the last in-band thread sits mid-warp with further (out-of-band) warps /
+    CTAs behind it: it must see the "outside the band" constants, not the cells those threads compute.
+    (Regression: in cluster launches it read the mailbox of the next, out-of-band warp.)"""
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(75)
+    long_reads = variant in ("rebased_cluster", "s32_cluster")
+    length = 17000 if long_reads else 3000
+    base = randseq(rng, length)
+    q = mutate(rng, base, sub=0.01, ins=0.005, dele=0.005)
+    t = base[:length // 2] + randseq(rng, 400) + base[length // 2:]
+    w = {"fast_cluster": 16384 + 544, "rebased_cluster": 16384 + 544, "s32_cluster": 8192 + 288, "general_cluster": 8192 + 288,
+         "fast_one_cta": 1024 + 544}[variant]
+    hi = 100
+    specs = [(0, 1, hi - w + 1, w, 0)]
+    if variant == "s32_cluster":
+        monkeypatch.setenv("SVP_NO_REBASE", "1")
+    kw = {"scoring": SCORINGS["matrix_two_piece_asym"]} if variant == "general_cluster" else {"preset": "map-ont"}
+    with Aligner(device=0, tb_bytes=4 << 30, **kw) as g:
+        gres, _ = run_both(g, OracleEngine(**kw), ["q", "t"], [q, t], specs)
+    assert gres["score"][0] > 500 and gres["t_end"][0] < length // 2 + 700
+
+
 def test_wide_band_cluster_general_scoring():
     from oracle_engine import OracleEngine
     from svirlpool_b200.aligner import Aligner
@@ -380,9 +473,13 @@ def test_band_beyond_cluster_limit_is_flagged_per_pair(gpu):
     assert res[0]["status"] == 0 and res[0]["score"] > 400 and res[1]["status"] == 8
 
 
-def test_sequences_beyond_shared_memory_sliding_window(gpu, oracle):
+@pytest.mark.parametrize("no_rebase", ["0", "1"])
+def test_sequences_beyond_shared_memory_sliding_window(oracle, monkeypatch, no_rebase):
     """130 kb vs 120 kb (the size of the reference's INV.15 consensus record, 185 kb query): the images do not fit shared
-    memory, the pair runs on the sliding-window variant of the 32-bit lane kernel. Bit-exact against the oracle."""
+    memory, the pair runs on a sliding-window variant — of the rebased s16x2 kernel (scores > 200 000 on 16-bit lanes), or
+    of the 32-bit lane kernel (SVP_NO_REBASE=1). Bit-exact against the oracle."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_NO_REBASE", no_rebase)
     rng = np.random.default_rng(83)
     codes = rng.integers(0, 4, 130_000)
     a = "".join(np.array(list("ACGT"))[codes])
@@ -393,7 +490,8 @@ def test_sequences_beyond_shared_memory_sliding_window(gpu, oracle):
     b = b[:40_000] + b[40_300:90_000] + randseq(rng, 500) + b[90_000:]                 # a 300 bp deletion and a 500 bp insertion
     seqs, names = [a, b, revcomp(b)], ["a", "b", "b_rc"]
     specs = [(1, 0, -768, 1536, 0), (2, 0, -768, 1536, PAIR_REVCOMP), (0, 1, -768, 1536, 0)]
-    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    with Aligner(device=0, preset="map-ont", tb_bytes=4 << 30) as g:
+        gres, _ = run_both(g, oracle, names, seqs, specs)
     assert not gres["status"].any() and gres["score"].min() > 200_000 and (gres["n_ins_bp"] + gres["n_del_bp"]).min() >= 800
 
 
