@@ -151,6 +151,30 @@ int svp_align_batch_device(svp_handle* h,
 
 /* Timing / accounting of the last svp_align_batch*() call on this handle (CUDA events on the
  * stream the kernels ran on). */
+/* ---- host-side batch builders (no device needed) ---------------------------------------------------------------
+ * What the reference does by writing all_reads.fasta for minimap2 (consensus.py:1362-1369) and letting
+ * `minimap2 -x ava-ont -X` choose the read pairs (util/util.py:181-183) is two calls here; their outputs are the
+ * arguments of svp_align_batch().
+ *
+ * svp_pack_bytes   bytes svp_pack_2bit() needs for these sequences (every sequence starts on a 16-byte boundary,
+ *                  16 readable bytes follow the last one).
+ * svp_pack_2bit    ASCII (ACGT, either case; anything else packs as A) -> 2 bits per base, base k of a sequence in bits
+ *                  2*(k%4) of its byte k/4; fills seq_off[k] with the byte offset of sequence k.
+ * svp_ava_pairs    pair list of one container's all-vs-all alignment: reads seq_base .. seq_base+n_reads-1 of the sequence
+ *                  table, every unordered pair once, query = the read that comes first in name_order (n_reads indices,
+ *                  the reads sorted by name; NULL = table order). strand: +1 / -1 per read when the strands are known
+ *                  (one orientation per pair), NULL or 0 = unknown (both orientations). offsets: start of each read on a
+ *                  common coordinate (band starts at their difference), or NULL. Bands as in DESIGN.md §3.1: around the
+ *                  line from the start diagonal to n - m, +-slack, rounded up to `granule` (multiple of 32); full != 0:
+ *                  the whole matrix. CIGAR slots are laid out from *cigar_words on, which is advanced. Returns
+ *                  SVP_ERR_NOMEM with *n_pairs = the number of pairs when pairs_cap is too small. */
+size_t svp_pack_bytes(const uint32_t* seq_len, uint32_t n_seqs);
+int    svp_pack_2bit(const char* const* seqs, const uint32_t* seq_len, uint32_t n_seqs,
+                     uint8_t* packed, size_t packed_bytes, uint64_t* seq_off);
+int    svp_ava_pairs(const uint32_t* seq_len, const uint32_t* name_order, const int8_t* strand, const int32_t* offsets,
+                     uint32_t seq_base, uint32_t n_reads, int32_t slack, int32_t granule, int full,
+                     svp_pair* pairs, uint32_t pairs_cap, uint32_t* n_pairs, uint64_t* cigar_words);
+
 typedef struct svp_stats {
     double   fwd_ms;        /* sum over waves of the forward DP kernel(s) */
     double   tb_ms;         /* sum over waves of the traceback kernel */

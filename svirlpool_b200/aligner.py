@@ -65,9 +65,62 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_align_batch_device.argtypes = batch_args
     lib.svp_align_batch_summary.restype = C.c_int
     lib.svp_align_batch_summary.argtypes = batch_args[:9] + [C.c_size_t]
+    lib.svp_pack_bytes.restype = C.c_size_t
+    lib.svp_pack_bytes.argtypes = [C.c_void_p, C.c_uint32]
+    lib.svp_pack_2bit.restype = C.c_int
+    lib.svp_pack_2bit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.svp_ava_pairs.restype = C.c_int
+    lib.svp_ava_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int,
+                                  C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     if lib.svp_abi_version() != _abi.ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {lib.svp_abi_version()}, python {_abi.ABI_VERSION}")
     return lib
+
+
+_LIB: C.CDLL | None = None
+
+
+def shared_library() -> C.CDLL:
+    """The process-wide handle of libsvp_align.so (host-side builders need no Aligner)."""
+    global _LIB
+    if _LIB is None:
+        _LIB = load_library()
+    return _LIB
+
+
+def pack_2bit_native(seqs: list[str | bytes]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """svp_pack_2bit: same layout and return value as _abi.pack_2bit (packed uint8, seq_off uint64, seq_len uint32)."""
+    lib = shared_library()
+    raw = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    n = len(raw)
+    lens = np.fromiter((len(b) for b in raw), dtype=np.uint32, count=n)
+    ptrs = (C.c_char_p * max(n, 1))(*raw)
+    total = lib.svp_pack_bytes(ptr(lens), n)
+    packed = np.empty(total, dtype=np.uint8)
+    off = np.zeros(n, dtype=np.uint64)
+    rc = lib.svp_pack_2bit(ptrs, ptr(lens), n, ptr(packed), total, ptr(off))
+    if rc != SVP_OK:
+        raise AlignerError(rc, "svp_pack_2bit failed")
+    return packed, off, lens
+
+
+def ava_pairs_native(seq_len: np.ndarray, name_order: np.ndarray | None, strand: np.ndarray | None, offsets: np.ndarray | None,
+                     seq_base: int, n_reads: int, slack: int, granule: int, full: bool, cigar_start: int = 0) -> tuple[np.ndarray, int]:
+    """svp_ava_pairs: the pair descriptors of one container's all-vs-all alignment and the next free CIGAR word."""
+    lib = shared_library()
+    cap = n_reads * (n_reads - 1) if strand is None else n_reads * (n_reads - 1) // 2
+    pairs = np.zeros(max(cap, 1), dtype=PAIR_DTYPE)
+    n_pairs = np.zeros(1, dtype=np.uint32)
+    words = np.array([cigar_start], dtype=np.uint64)
+    order = None if name_order is None else np.ascontiguousarray(name_order, dtype=np.uint32)
+    st = None if strand is None else np.ascontiguousarray(strand, dtype=np.int8)
+    offs = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int32)
+    rc = lib.svp_ava_pairs(ptr(np.ascontiguousarray(seq_len, dtype=np.uint32)), None if order is None else ptr(order),
+                           None if st is None else ptr(st), None if offs is None else ptr(offs), int(seq_base), int(n_reads),
+                           int(slack), int(granule), int(bool(full)), ptr(pairs), len(pairs), ptr(n_pairs), ptr(words))
+    if rc != SVP_OK:
+        raise AlignerError(rc, "svp_ava_pairs failed (invalid argument, or the CIGAR slots of the batch exceed 2^32 words)")
+    return pairs[:int(n_pairs[0])], int(words[0])
 
 
 def scoring_preset(name: str, lib: C.CDLL | None = None) -> np.ndarray:

@@ -76,13 +76,35 @@ class PairBatch:
         packed, off, lens = pack_2bit(seqs)
         pairs = np.zeros(len(pair_specs), dtype=PAIR_DTYPE)
         pos = 0
-        for k, (q, t, lo, w, fl) in enumerate(pair_specs):
-            cap = cap_fn(int(lens[q]), int(lens[t]))
-            pairs[k] = (q, t, lo, w, fl, pos, cap, 0)
-            pos += cap
+        if pair_specs:
+            arr = np.asarray(pair_specs, dtype=np.int64).reshape(len(pair_specs), 5)
+            m, n = lens[arr[:, 0]].astype(np.int64), lens[arr[:, 1]].astype(np.int64)
+            if cap_fn is cigar_cap_for:
+                caps = np.minimum(m + n, (m + n) // 3 + 64)
+            else:
+                caps = np.fromiter((cap_fn(int(a), int(b)) for a, b in zip(m, n)), dtype=np.int64, count=len(m))
+            pos = int(caps.sum())
             if pos >= 1 << 32:
                 raise ValueError("CIGAR slots of one batch exceed 2^32 words (svp_pair.cigar_off is 32-bit): split the batch")
+            pairs["q"], pairs["t"], pairs["band_lo"], pairs["band_w"], pairs["flags"] = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3], arr[:, 4]
+            pairs["cigar_off"], pairs["cigar_cap"] = np.cumsum(caps) - caps, caps
         return PairBatch(names, seqs, packed, off, lens, pairs, max(pos, 1))
+
+
+    @staticmethod
+    def build_ava(names: list[str], seqs: list[str], strands: dict[str, str] | None, offsets: dict[str, int] | None,
+                  slack: int, granule: int, full: bool) -> tuple["PairBatch", list[tuple[int, int, bool]]]:
+        """The all-vs-all batch of one container through the library's host-side builders (svp_pack_2bit, svp_ava_pairs):
+        the same buffers and pair order as ava_pair_specs() + build(), without the per-pair Python work. Returns the batch
+        and the (q, t, revcomp) list of its pairs."""
+        from .aligner import ava_pairs_native, pack_2bit_native
+        packed, off, lens = pack_2bit_native(seqs)
+        order = np.array(sorted(range(len(names)), key=lambda k: names[k]), dtype=np.uint32)
+        strand = None if strands is None else np.array([1 if strands[n] == "+" else -1 for n in names], dtype=np.int8)
+        offs = None if offsets is None else np.array([offsets[n] for n in names], dtype=np.int32)
+        pairs, words = ava_pairs_native(lens, order, strand, offs, 0, len(names), slack, granule, full)
+        meta = list(zip(pairs["q"].tolist(), pairs["t"].tolist(), (pairs["flags"] & PAIR_REVCOMP).astype(bool).tolist()))
+        return PairBatch(names, seqs, packed, off, lens, pairs, max(words, 1)), meta
 
 
 def run_batch(engine, batch: PairBatch) -> tuple[np.ndarray, np.ndarray]:
@@ -122,11 +144,11 @@ def ava_summary(engine, reads: dict[str, str], strands: dict[str, str] | None = 
     consensus_lib.similarity_from_summary()."""
     names = list(reads)
     seqs = [reads[k] for k in names]
-    specs, meta = ava_pair_specs(names, [len(s) for s in seqs], strands, offsets, slack, granule, full)
-    if not specs:
+    if len(names) < 2:
         from ._abi import RESULT_DTYPE
         return names, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=RESULT_DTYPE)
-    res = run_summary(engine, PairBatch.build(names, seqs, specs))
+    batch, meta = PairBatch.build_ava(names, seqs, strands, offsets, slack, granule, full)
+    res = run_summary(engine, batch)
     return names, np.array([m[0] for m in meta], dtype=np.int64), np.array([m[1] for m in meta], dtype=np.int64), res
 
 
@@ -199,10 +221,9 @@ def ava_align(engine, reads: dict[str, str], strands: dict[str, str] | None = No
     names = list(reads)
     seqs = [reads[k] for k in names]
     lens = [len(s) for s in seqs]
-    specs, meta = ava_pair_specs(names, lens, strands, offsets, slack, granule, full)
-    if not specs:
+    if len(names) < 2:
         return []
-    batch = PairBatch.build(names, seqs, specs)
+    batch, meta = PairBatch.build_ava(names, seqs, strands, offsets, slack, granule, full)
     res, cig = run_batch(engine, batch)
     return ava_records(names, lens, meta, res, cig, min_score)
 

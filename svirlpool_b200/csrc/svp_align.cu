@@ -84,7 +84,7 @@ struct svp_handle {
     svp_scoring scoring{};
     Consts cs{};
     cudaStream_t stream = nullptr;              // forward kernels + copies
-    cudaStream_t stream_aux[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
+    cudaStream_t stream_aux[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
                                                 // wave run concurrently, and consecutive waves use different stream sets
     cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
     std::vector<cudaEvent_t> events;            // pool, grown on demand
@@ -258,7 +258,8 @@ extern "C" void svp_destroy(svp_handle* h) {
     for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
-    for (cudaStream_t sx : { h->stream, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4], h->stream_tb }) if (sx) cudaStreamDestroy(sx);
+    for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
+    for (cudaStream_t sx : { h->stream, h->stream_tb }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
 
@@ -553,7 +554,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     const uint32_t* d_order = (const uint32_t*)h->d_order.p;
     uint2* d_bests = (uint2*)h->d_bests.p;
     // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]; plus two for the whole call
-    constexpr int MAX_FWD_STREAMS = 6;
+    constexpr int MAX_FWD_STREAMS = 8;
     const size_t EV_PER_WAVE = 3 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE + 2;
     while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
@@ -564,27 +565,37 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     // intervals gets longer, not shorter, and the traceback is delayed. Inside a wave the groups
     // run on up to four streams (2..6 measure the same, one stream 10 % slower), groups with the longest-running CTAs first
     // (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail of the wave)
-    cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4] };
-    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), 6); }();
+    cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4], h->stream_aux[5], h->stream_aux[6] };
+    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), 8); }();
     cudaStream_t sT = h->stream_tb;
+    // Waves of few, long-running CTAs (long reads, wide bands: config 3) end in a tail of a few CTAs on an otherwise idle
+    // machine; there the forward pass of the next wave starts at once on the other half of the streams (it writes the other
+    // arena half anyway) instead of waiting in stream order. SVP_WAVE_OVERLAP = 0 / 1 forces the choice, default: waves
+    // averaging fewer than overlap_max_pairs pairs.
+    static const int overlap_mode = [] { const char* e = getenv("SVP_WAVE_OVERLAP"); return e ? atoi(e) : -1; }();
+    static const long overlap_max_pairs = [] { const char* e = getenv("SVP_WAVE_OVERLAP_PAIRS"); return e ? atol(e) : 4096L; }();
+    const bool overlap = waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
     CUDA_TRY(h, cudaEventRecord(ev_t0, st));
+    if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(sF[MAX_FWD_STREAMS / 2], ev_t0, 0));      // the copies above precede every wave
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(sF[0], EV(wv - 2, 2), 0));      // this arena half is free again
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sF[0]));
+        cudaStream_t* sW = overlap ? sF + (wv & 1) * (MAX_FWD_STREAMS / 2) : sF;         // this wave's streams
+        const int avail = overlap ? MAX_FWD_STREAMS / 2 : max_streams;
+        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv - 2, 2), 0));      // this arena half is free again
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sW[0]));
         const std::vector<Group>& groups = wave_groups[wv];
-        const int n_streams = (int)std::min<size_t>((size_t)max_streams, groups.size());
-        for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sF[a], EV(wv, 0), 0));
+        const int n_streams = (int)std::min<size_t>((size_t)avail, groups.size());
+        for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], EV(wv, 0), 0));
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             const Group& gq = groups[gi];
-            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, gq.ring, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sF[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
+            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, gq.ring, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sW[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
                        h->arena, d_bests, cs);
             h->stats.fwd_launches++;
         }
         for (int a = 1; a < n_streams; ++a) {
-            CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sF[a]));
-            CUDA_TRY(h, cudaStreamWaitEvent(sF[0], EV(wv, 2 + a), 0));
+            CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sW[a]));
+            CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv, 2 + a), 0));
         }
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sF[0]));
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sW[0]));
         CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
         const int nt = (int)(waves[wv].second - waves[wv].first);
         if (nt > 0) {
@@ -607,11 +618,16 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     CUDA_TRY(h, cudaEventSynchronize(ev_t1));
     float tot = 0; cudaEventElapsedTime(&tot, ev_t0, ev_t1);
     h->stats.total_ms = tot;
+    // forward time = length of the union of the waves' forward intervals (they overlap when `overlap` is set)
+    float covered_to = 0;
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, EV(wv, 0), EV(wv, 1));      // forward pass of the wave (may overlap the previous wave's traceback)
+        float f0 = 0, f1 = 0, b = 0;
+        cudaEventElapsedTime(&f0, ev_t0, EV(wv, 0));         // forward pass of the wave (may overlap the previous wave's traceback)
+        cudaEventElapsedTime(&f1, ev_t0, EV(wv, 1));
         cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));      // its traceback (includes waiting for SM slots)
-        h->stats.fwd_ms += a; h->stats.tb_ms += b;
+        const float from = std::max(f0, covered_to);
+        if (f1 > from) { h->stats.fwd_ms += f1 - from; covered_to = f1; }
+        h->stats.tb_ms += b;
     }
     for (const Task& t : tasks) if (!(t.flags & TASK_INVALID)) { h->stats.cells += t.cells; h->stats.tb_bytes += tb_bytes_of(t); }
     CUDA_TRY(h, cudaGetLastError());

@@ -973,8 +973,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
 
 #define SVP_PUSHW() do { if (cur_len) { if (wpos > 0) { --wpos; if (lane == 0) slot[wpos] = (cur_len << 4) | cur_op; } else ovf = true; } } while (0)
 #define SVP_EMITW(op, len) do { if (cur_len && cur_op == (op)) cur_len += (len); else { SVP_PUSHW(); cur_op = (op); cur_len = (len); } } while (0)
-#define SVP_SNAPW(hv) do { low = (hv); low_i = i; low_j = j; low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf; \
-        l_match = n_match; l_mis = n_mis; l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db; } while (0)
+
 
     bool done = false;
     while (!done) {
@@ -992,22 +991,55 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
             sub_l = (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
         }
         if (ci - 33 >= 1 && cj - 33 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - 33, cj - 33)));   // next round's byte
+        // ---- the run is resolved by all lanes at once: lane l assumes cells 0..l-1 were diagonal moves, so its H is the
+        // incoming H minus the substitution scores before it (prefix sum); the first lane that stops (H = 0, matrix edge,
+        // Z-drop) or does not continue diagonally ends the run. The lowest-H snapshot (strict minimum, first occurrence)
+        // is a prefix minimum. Same walk as the cell-by-cell loop of svp_tb_kernel.
         bool gap = false;
         int l_gap = 0;
-        for (int l = 0; l < 32; ++l) {
-            l_gap = l;
-            if (H < low) SVP_SNAPW(H);
-            if (H == 0 || i < 1 || j < 1) { done = true; break; }
-            int dd = (j - i) - (low_j - low_i); dd = dd < 0 ? -dd : dd;
-            if (H - low > zdrop + cs.zdrop_ext * dd) { done = true; break; }
-            const uint32_t b = __shfl_sync(0xffffffffu, bp, l);
-            const int sub = __shfl_sync(0xffffffffu, sub_l, l), same = __shfl_sync(0xffffffffu, same_l, l);
-            const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(b - (uint32_t)H) : 0;
-            if (H == Hd + sub) {
-                SVP_EMITW(SVP_CIGAR_M, 1u);
-                if (same) ++n_match; else ++n_mis;
-                --i; --j; H = Hd;
-            } else { gap = true; break; }
+        {
+            int incl = sub_l, cnt_same = 0;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int Hl = H - (incl - sub_l);
+            int pmin = Hl;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pmin, o); if (lane >= o) pmin = min(pmin, v); }
+            const bool inb = ci >= 1 && cj >= 1;
+            const bool stop2 = (Hl == 0) || !inb;
+            int dd = d0 - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+            if (pmin < low) dd = 0;                                   // the snapshot moved onto this diagonal at or before this cell
+            const bool stop3 = Hl - min(low, pmin) > zdrop + cs.zdrop_ext * dd;
+            const int Hd = (ci - 1 >= 1 && cj - 1 >= 1) ? Hl + sext8(bp - (uint32_t)Hl) : 0;
+            const bool isdiag = inb && (Hl == Hd + sub_l);
+            const unsigned term = __ballot_sync(0xffffffffu, stop2 || stop3 || !isdiag);
+            const unsigned sameb = __ballot_sync(0xffffffffu, same_l != 0);
+            const int first = term ? __ffs(term) - 1 : 32;
+            const int K = first < 31 ? first : 31;
+            const int runmin = __shfl_sync(0xffffffffu, pmin, K);
+            if (runmin < low) {                                       // snapshot at the first cell of the run that reaches the new minimum
+                const unsigned upto = K == 31 ? 0xffffffffu : ((2u << K) - 1u);
+                const int ks = __ffs(__ballot_sync(0xffffffffu, Hl == runmin) & upto) - 1;
+                low = runmin; low_i = i - ks; low_j = j - ks;
+                low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf;
+                if (ks > 0) {                                         // CIGAR state after ks more M's
+                    if (low_len && low_op == SVP_CIGAR_M) low_len += (uint32_t)ks;
+                    else { if (low_len) { if (low_wpos > 0) --low_wpos; else low_ovf = true; } low_op = SVP_CIGAR_M; low_len = (uint32_t)ks; }
+                }
+                cnt_same = __popc(sameb & ((1u << ks) - 1u));
+                l_match = n_match + (uint32_t)cnt_same; l_mis = n_mis + (uint32_t)(ks - cnt_same);
+                l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db;
+            }
+            const int Hnext = first < 32 ? __shfl_sync(0xffffffffu, Hl, K) : __shfl_sync(0xffffffffu, Hl - sub_l, 31);
+            const bool fin = __shfl_sync(0xffffffffu, stop2 || stop3, K) && first < 32;
+            if (first > 0) {
+                SVP_EMITW(SVP_CIGAR_M, (uint32_t)first);
+                cnt_same = __popc(sameb & (first == 32 ? 0xffffffffu : ((1u << first) - 1u)));
+                n_match += (uint32_t)cnt_same; n_mis += (uint32_t)(first - cnt_same);
+                i -= first; j -= first; H = Hnext;
+            }
+            if (fin) done = true;
+            else if (first < 32) { gap = true; l_gap = first; }
         }
         if (done || !gap) continue;
         {   // 1-base gap at the cell the run stopped at (deletion first, as in the search below)
@@ -1056,7 +1088,6 @@ svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __res
     SVP_PUSHW();
 #undef SVP_PUSHW
 #undef SVP_EMITW
-#undef SVP_SNAPW
     if (bad) res.status |= SVP_ST_SCORE_OVF;
     res.score = M - cut_low;
     res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;

@@ -14,7 +14,7 @@ HEADER = (ROOT / "include" / "svp_align.h").read_text()
 
 
 def declared_functions():
-    return sorted(set(re.findall(r"\b(svp_[a-z_]+)\s*\(", HEADER)))
+    return sorted(set(re.findall(r"\b(svp_[a-z_0-9]+)\s*\(", HEADER)))
 
 
 def test_header_functions_match_export_list():
@@ -62,3 +62,53 @@ def test_pack_2bit_layout():
     codes = [np.array([0, 1, 2, 3, 0, 1], dtype=np.uint8), np.array([3, 3, 3, 3], dtype=np.uint8)]
     p2, o2, l2 = _abi.pack_codes(codes)
     assert p2[0] == packed[0] and p2[16] == 0xFF and o2.tolist() == [0, 16] and l2.tolist() == [6, 4]
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side builders of the library (svp_pack_2bit, svp_ava_pairs): no device needed
+# ---------------------------------------------------------------------------------------------
+
+def _random_reads(rng, n, lo, hi):
+    alphabet = np.array(list("ACGTacgtN"))
+    return ["".join(alphabet[rng.integers(0, len(alphabet), int(rng.integers(lo, hi)))]) for _ in range(n)]
+
+
+def test_native_pack_2bit_equals_numpy_packer():
+    rng = np.random.default_rng(5)
+    seqs = _random_reads(rng, 40, 1, 700) + ["A", "ACGT" * 16, "T" * 63, "G" * 64, "C" * 65]
+    p1, o1, l1 = _abi.pack_2bit(seqs)
+    p2, o2, l2 = aligner.pack_2bit_native(seqs)
+    assert np.array_equal(o1, o2) and np.array_equal(l1, l2) and p1.tobytes() == p2.tobytes()
+    p3, o3, l3 = aligner.pack_2bit_native([])
+    assert len(o3) == 0 and len(p3) == 16
+
+
+@pytest.mark.parametrize("strands_known", [False, True])
+@pytest.mark.parametrize("with_offsets", [False, True])
+@pytest.mark.parametrize("full", [False, True])
+def test_native_ava_pairs_equal_python_builder(strands_known, with_offsets, full):
+    """svp_ava_pairs + svp_pack_2bit (PairBatch.build_ava) produce exactly the buffers of ava_pair_specs() +
+    PairBatch.build(): same pairs, order, bands, flags and CIGAR slots."""
+    from svirlpool_b200 import ava
+    rng = np.random.default_rng(11 + 2 * strands_known + with_offsets)
+    seqs = _random_reads(rng, 13, 200, 3000)
+    names = [f"read_{int(k)}" for k in rng.permutation(len(seqs))]           # name order != table order
+    strands = {n: "+-"[int(rng.integers(2))] for n in names} if strands_known else None
+    offsets = {n: int(rng.integers(0, 400)) for n in names} if with_offsets else None
+    specs, meta = ava.ava_pair_specs(names, [len(s) for s in seqs], strands, offsets, 300, 64, full)
+    ref = ava.PairBatch.build(names, seqs, specs)
+    got, gmeta = ava.PairBatch.build_ava(names, seqs, strands, offsets, 300, 64, full)
+    assert gmeta == [(q, t, bool(rc)) for q, t, rc in meta]
+    assert got.pairs.tobytes() == ref.pairs.tobytes() and got.cigar_words == ref.cigar_words
+    assert got.packed.tobytes() == ref.packed.tobytes() and np.array_equal(got.seq_off, ref.seq_off)
+
+
+def test_native_ava_pairs_argument_errors():
+    lens = np.array([100, 200, 300], dtype=np.uint32)
+    with pytest.raises(aligner.AlignerError):
+        aligner.ava_pairs_native(lens, None, None, None, 0, 3, 300, 48, False)        # granule must be a multiple of 32
+    with pytest.raises(aligner.AlignerError):
+        aligner.ava_pairs_native(lens, np.array([0, 1, 7], dtype=np.uint32), None, None, 0, 3, 300, 32, False)   # order index out of range
+    pairs, words = aligner.ava_pairs_native(lens, None, np.array([1, -1, 1], dtype=np.int8), None, 0, 3, 300, 32, False, cigar_start=10)
+    assert len(pairs) == 3 and pairs["cigar_off"][0] == 10 and words == 10 + int(pairs["cigar_cap"].sum())
+    assert pairs["flags"].tolist() == [1, 0, 1]
