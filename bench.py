@@ -211,6 +211,8 @@ def main() -> None:
     ap.add_argument("--ref-regions", type=int, default=2, help="regions per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-sample-regions", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="HBM-resident steps as blocking calls instead of pipelined submits (svp_submit_batch_device)")
     args = ap.parse_args()
     if args.regions is None:
         args.regions = {"config2": 96, "config3": 8, "config4": 48}[args.workload]
@@ -269,29 +271,36 @@ def main() -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_device(k: int) -> dict:
+    # result / CIGAR buffers alternate between consecutive steps: the steps are SUBMITTED (svp_submit_batch_device) and
+    # overlap on the device — step k+1 is planned and its forward pass starts under step k's last traceback; every step is
+    # complete when the timed region ends (svp_sync before the closing mark). --no-pipeline: blocking calls, one at a time.
+    d_results2 = torch.empty_like(d_results) if args.pipeline else d_results
+    d_cigar2 = torch.empty_like(d_cigar) if args.pipeline else d_cigar
+
+    def step_device(k: int) -> None:
         b = batches[k % n_distinct]
-        al.align_batch_device(b["d_packed"].data_ptr(), b["packed"].nbytes, b["off"], b["lens"], b["pairs"],
-                              d_results.data_ptr(), d_cigar.data_ptr(), b["cigar_words"])
-        return al.stats()
+        res, cig = (d_results, d_cigar) if k % 2 == 0 else (d_results2, d_cigar2)
+        fn = al.submit_batch_device if args.pipeline else al.align_batch_device
+        fn(b["d_packed"].data_ptr(), b["packed"].nbytes, b["off"], b["lens"], b["pairs"], res.data_ptr(), cig.data_ptr(), b["cigar_words"])
 
     # ---- HBM-resident timing ------------------------------------------------------------------------
     for k in range(args.warmup):
         step_device(k)
+    al.sync()
     sync_all()
+    al.stats_total(reset=True)
     sampler = ClockSampler(local)
     t0 = time.perf_counter()
     al.timer_mark(0)                                   # device stopwatch: CUDA events on the stream the kernels are launched on
-    agg = {"fwd_ms": 0.0, "tb_ms": 0.0, "total_ms": 0.0, "cells": 0, "tb_bytes": 0, "fwd_launches": 0, "tb_launches": 0, "waves": 0}
     regions_done, seq_bytes = 0, 0
     for k in range(args.steps):
-        st = step_device(args.warmup + k)
-        for key in agg:
-            agg[key] += st[key]
+        step_device(args.warmup + k)
         regions_done += batches[(args.warmup + k) % n_distinct]["n_regions"]
         seq_bytes += batches[(args.warmup + k) % n_distinct]["seq_bytes"]
-    al.timer_mark(1)
+    al.timer_mark(1)                                   # recorded behind every submitted step's last traceback
+    al.sync()
     sync_all()
+    agg = {k: v for k, v in al.stats_total().items() if k != "reserved"}
     wall_elapsed = time.perf_counter() - t0
     elapsed = al.timer_elapsed_ms() / 1e3                # device time of the K steps, host gaps between calls included
     clocks = sampler.stop()
@@ -365,7 +374,9 @@ def main() -> None:
                        "region_seeds": {"config2": "10000+r", "config3": "20000+r", "config4": "30000+r"}[args.workload],
                        "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE}" if args.workload != "config3" else "|dlen|+512", "sharding": "LPT by estimated cells, no collective",
                        "l2": "inputs+traceback per step >> 126 MB L2 (traceback arena rewritten every step)",
-                       "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it"},
+                       "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it",
+                       "pipeline": ("steps submitted back to back (svp_submit_batch_device), step k+1's forward pass under step k's last traceback; "
+                                    "all K steps complete inside the timed region") if args.pipeline else "blocking calls"},
             "wall_ms_per_step": wall_elapsed / args.steps * 1e3,
             "e2e": {"value": e2e_cells_all / e2e_elapsed / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "regions_per_s": regions_all / e2e_elapsed,

@@ -175,6 +175,17 @@ int    svp_ava_pairs(const uint32_t* seq_len, const uint32_t* name_order, const 
                      uint32_t seq_base, uint32_t n_reads, int32_t slack, int32_t granule, int full,
                      svp_pair* pairs, uint32_t pairs_cap, uint32_t* n_pairs, uint64_t* cigar_words);
 
+/* Pipelined form of svp_align_batch_device: returns as soon as the batch is enqueued. Results (and the caller's buffers)
+ * belong to the library until svp_sync() returns. Consecutive submits overlap on the device: the next batch is planned on
+ * the host and its forward pass starts while the previous batch's last traceback is still running (two batches in flight at
+ * most; a third submit first waits for the oldest). svp_sync waits for every submitted batch. */
+int svp_submit_batch_device(svp_handle* h,
+                            const uint8_t* d_packed_seqs, size_t packed_bytes,
+                            const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                            const svp_pair* pairs, uint32_t n_pairs,
+                            svp_result* d_results, uint32_t* d_cigar_buf, size_t cigar_words);
+int svp_sync(svp_handle* h);
+
 typedef struct svp_stats {
     double   fwd_ms;        /* sum over waves of the forward DP kernel(s) */
     double   tb_ms;         /* sum over waves of the traceback kernel */
@@ -184,6 +195,8 @@ typedef struct svp_stats {
     uint32_t fwd_launches, tb_launches, waves, reserved;
 } svp_stats;
 int svp_get_stats(const svp_handle* h, svp_stats* out);
+/* sums over all completed batches since svp_create or the last call with reset != 0 (waits for submitted batches first) */
+int svp_get_stats_total(svp_handle* h, svp_stats* out, int reset);
 
 /* Device-side stopwatch for callers that time several calls as one region (bench.py): mark 0 and mark 1 are
  * CUDA events recorded on the handle's main stream, which every kernel and copy of a call is ordered before

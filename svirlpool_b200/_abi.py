@@ -37,7 +37,7 @@ assert STATS_DTYPE.itemsize == 56
 
 # every symbol include/svp_align.h declares (checked by tests/test_abi.py against the built library)
 EXPORTS = ("svp_abi_version", "svp_device_count", "svp_scoring_preset", "svp_create", "svp_destroy", "svp_pinned_alloc", "svp_pinned_free",
-           "svp_last_error", "svp_pack_bytes", "svp_pack_2bit", "svp_ava_pairs", "svp_align_batch", "svp_align_batch_summary", "svp_align_batch_device", "svp_get_stats", "svp_timer_mark", "svp_timer_elapsed_ms")
+           "svp_last_error", "svp_pack_bytes", "svp_pack_2bit", "svp_ava_pairs", "svp_align_batch", "svp_align_batch_summary", "svp_align_batch_device", "svp_submit_batch_device", "svp_sync", "svp_get_stats", "svp_get_stats_total", "svp_timer_mark", "svp_timer_elapsed_ms")
 
 
 def ptr(a: np.ndarray) -> C.c_void_p:

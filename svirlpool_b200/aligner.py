@@ -63,6 +63,12 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_align_batch.argtypes = batch_args
     lib.svp_align_batch_device.restype = C.c_int
     lib.svp_align_batch_device.argtypes = batch_args
+    lib.svp_submit_batch_device.restype = C.c_int
+    lib.svp_submit_batch_device.argtypes = batch_args
+    lib.svp_sync.restype = C.c_int
+    lib.svp_sync.argtypes = [C.c_void_p]
+    lib.svp_get_stats_total.restype = C.c_int
+    lib.svp_get_stats_total.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.svp_align_batch_summary.restype = C.c_int
     lib.svp_align_batch_summary.argtypes = batch_args[:9] + [C.c_size_t]
     lib.svp_pack_bytes.restype = C.c_size_t
@@ -232,6 +238,23 @@ class Aligner:
         self._check(self.lib.svp_align_batch_device(self._h, C.c_void_p(d_packed_ptr), packed_bytes, ptr(seq_off), ptr(seq_len),
                                                     len(seq_len), ptr(pairs), len(pairs), C.c_void_p(d_results_ptr),
                                                     C.c_void_p(d_cigar_ptr), int(cigar_words)))
+
+    def submit_batch_device(self, d_packed_ptr: int, packed_bytes: int, seq_off: np.ndarray, seq_len: np.ndarray,
+                            pairs: np.ndarray, d_results_ptr: int, d_cigar_ptr: int, cigar_words: int) -> None:
+        """Pipelined align_batch_device (svp_submit_batch_device): returns after the enqueue; results are complete after sync().
+        The device buffers must stay untouched until then; consecutive submits overlap on the device."""
+        self._check(self.lib.svp_submit_batch_device(self._h, C.c_void_p(d_packed_ptr), packed_bytes, ptr(seq_off), ptr(seq_len),
+                                                     len(seq_len), ptr(pairs), len(pairs), C.c_void_p(d_results_ptr),
+                                                     C.c_void_p(d_cigar_ptr), int(cigar_words)))
+
+    def sync(self) -> None:
+        self._check(self.lib.svp_sync(self._h))
+
+    def stats_total(self, reset: bool = False) -> dict:
+        """Sums over all completed batches since the handle was created or last reset."""
+        s = np.zeros(1, dtype=STATS_DTYPE)
+        self._check(self.lib.svp_get_stats_total(self._h, ptr(s), int(reset)))
+        return {k: s[0][k].item() for k in STATS_DTYPE.names}
 
     def timer_mark(self, which: int) -> None:
         """Record device stopwatch mark 0 / 1 on the handle's main stream (svp_timer_mark)."""

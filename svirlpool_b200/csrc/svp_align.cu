@@ -79,6 +79,19 @@ struct DevBuf {
 
 }  // namespace
 
+// Per-call state. Two sets alternate, so a submitted call (svp_submit_batch_device) can still be running — typically its last
+// wave's traceback — while the next call is planned and its forward pass starts.
+struct CallSet {
+    DevBuf d_tasks, d_order, d_bests;
+    Task* h_tasks = nullptr; size_t h_tasks_cap = 0;            // pinned staging of the task / order arrays
+    uint32_t* h_order = nullptr; size_t h_order_cap = 0;
+    std::vector<cudaEvent_t> events;                            // pool, grown on demand
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;               // first enqueue on the main stream / last traceback done
+    bool pending = false;                                       // enqueued, times not collected yet
+    size_t n_waves = 0;
+    svp_stats stats{};                                          // counts filled at submit, times at collection
+};
+
 struct svp_handle {
     int device = 0;
     svp_scoring scoring{};
@@ -87,11 +100,15 @@ struct svp_handle {
     cudaStream_t stream_aux[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
                                                 // wave run concurrently, and consecutive waves use different stream sets
     cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
-    std::vector<cudaEvent_t> events;            // pool, grown on demand
     cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
-    DevBuf d_tasks, d_order, d_bests, d_seqs, d_results, d_cigar, d_dense, d_dense_off;
-    svp_stats stats{};
+    CallSet sets[2];
+    uint64_t call_idx = 0;                      // calls planned so far (set = call_idx & 1)
+    uint64_t wave_idx = 0;                      // waves enqueued so far: wave w writes arena half (w & 1), across calls
+    cudaEvent_t half_free[2] = { nullptr, nullptr };   // traceback-done event of the last wave that used each arena half
+    DevBuf d_seqs, d_results, d_cigar, d_dense, d_dense_off;
+    svp_stats stats{};                          // the last collected call
+    svp_stats stats_total{};                    // sums over collected calls since the last reset (svp_get_stats_total)
     std::string err;
     int max_smem_optin = 0;
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
@@ -255,8 +272,14 @@ extern "C" void svp_destroy(svp_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->arena) cudaFree(h->arena);
-    for (DevBuf* b : { &h->d_tasks, &h->d_order, &h->d_bests, &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
-    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (DevBuf* b : { &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
+    for (CallSet& c : h->sets) {
+        for (DevBuf* b : { &c.d_tasks, &c.d_order, &c.d_bests }) b->release();
+        if (c.h_tasks) cudaFreeHost(c.h_tasks);
+        if (c.h_order) cudaFreeHost(c.h_order);
+        for (cudaEvent_t e : c.events) cudaEventDestroy(e);
+        for (cudaEvent_t e : { c.ev_t0, c.ev_t1 }) if (e) cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
     for (cudaStream_t sx : { h->stream, h->stream_tb }) if (sx) cudaStreamDestroy(sx);
@@ -273,9 +296,58 @@ extern "C" void svp_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char* svp_last_error(const svp_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
+// wait for a submitted call and collect its times
+static int collect_call(svp_handle* h, CallSet& c) {
+    if (!c.pending) return SVP_OK;
+    c.pending = false;
+    CUDA_TRY(h, cudaEventSynchronize(c.ev_t1));
+    constexpr size_t EV_PER_WAVE = 3 + 7;
+    auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
+    float tot = 0; cudaEventElapsedTime(&tot, c.ev_t0, c.ev_t1);
+    c.stats.total_ms = tot;
+    // forward time = length of the union of the waves' forward intervals (they overlap when waves are allowed to)
+    float covered_to = 0;
+    for (size_t wv = 0; wv < c.n_waves; ++wv) {
+        float f0 = 0, f1 = 0, b = 0;
+        cudaEventElapsedTime(&f0, c.ev_t0, EV(wv, 0));       // forward pass of the wave (may overlap the previous wave's traceback)
+        cudaEventElapsedTime(&f1, c.ev_t0, EV(wv, 1));
+        cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));      // its traceback (includes waiting for SM slots)
+        const float from = std::max(f0, covered_to);
+        if (f1 > from) { c.stats.fwd_ms += f1 - from; covered_to = f1; }
+        c.stats.tb_ms += b;
+    }
+    for (cudaEvent_t& hf : h->half_free)                     // this call's waves are done: the halves they used last are free
+        for (cudaEvent_t e : c.events) if (hf == e) { hf = nullptr; break; }
+    h->stats = c.stats;
+    svp_stats& T = h->stats_total;
+    T.fwd_ms += c.stats.fwd_ms; T.tb_ms += c.stats.tb_ms; T.total_ms += c.stats.total_ms; T.cells += c.stats.cells; T.tb_bytes += c.stats.tb_bytes;
+    T.fwd_launches += c.stats.fwd_launches; T.tb_launches += c.stats.tb_launches; T.waves += c.stats.waves;
+    CUDA_TRY(h, cudaGetLastError());
+    return SVP_OK;
+}
+
+extern "C" int svp_sync(svp_handle* h) {
+    if (!h) return SVP_ERR_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // older call first
+    for (int k = 0; k < 2; ++k) { int rc = collect_call(h, h->sets[(h->call_idx + k) & 1]); if (rc != SVP_OK) return rc; }
+    return SVP_OK;
+}
+
 extern "C" int svp_get_stats(const svp_handle* h, svp_stats* out) {
     if (!h || !out) return SVP_ERR_ARG;
+    int rc = svp_sync(const_cast<svp_handle*>(h));
+    if (rc != SVP_OK) return rc;
     *out = h->stats;
+    return SVP_OK;
+}
+
+extern "C" int svp_get_stats_total(svp_handle* h, svp_stats* out, int reset) {
+    if (!h) return SVP_ERR_ARG;
+    int rc = svp_sync(h);
+    if (rc != SVP_OK) return rc;
+    if (out) *out = h->stats_total;
+    if (reset) h->stats_total = svp_stats{};
     return SVP_OK;
 }
 
@@ -283,6 +355,8 @@ extern "C" int svp_timer_mark(svp_handle* h, int which) {
     if (!h || which < 0 || which > 1) return SVP_ERR_ARG;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (!h->marks[which]) CUDA_TRY(h, cudaEventCreate(&h->marks[which]));
+    // submitted calls end on the traceback stream: the mark comes after them
+    for (CallSet& c : h->sets) if (c.pending) CUDA_TRY(h, cudaStreamWaitEvent(h->stream, c.ev_t1, 0));
     CUDA_TRY(h, cudaEventRecord(h->marks[which], h->stream));
     return SVP_OK;
 }
@@ -458,20 +532,49 @@ static void plan_pair(const svp_handle* h, const svp_pair& p, uint32_t index, co
     t.n_iter = (int32_t)((steps + steps_per_iter - 1) / steps_per_iter);
 }
 
-static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar) {
+// pinned staging for the next call's task / order arrays; waits for the call that used this set two calls ago
+static int begin_call(svp_handle* h, size_t n, CallSet** out) {
+    CallSet& c = h->sets[h->call_idx & 1];
+    int rc = collect_call(h, c);
+    if (rc != SVP_OK) return rc;
+    if (n > c.h_tasks_cap) {
+        if (c.h_tasks) cudaFreeHost(c.h_tasks);
+        c.h_tasks = nullptr; c.h_tasks_cap = 0;
+        const size_t cap = n + n / 4 + 16;
+        CUDA_TRY(h, cudaHostAlloc((void**)&c.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
+        c.h_tasks_cap = cap;
+    }
+    if (n > c.h_order_cap) {
+        if (c.h_order) cudaFreeHost(c.h_order);
+        c.h_order = nullptr; c.h_order_cap = 0;
+        const size_t cap = n + n / 4 + 16;
+        CUDA_TRY(h, cudaHostAlloc((void**)&c.h_order, cap * sizeof(uint32_t), cudaHostAllocDefault));
+        c.h_order_cap = cap;
+    }
+    if (!c.ev_t0) { CUDA_TRY(h, cudaEventCreate(&c.ev_t0)); CUDA_TRY(h, cudaEventCreate(&c.ev_t1)); }
+    *out = &c;
+    return SVP_OK;
+}
+
+// Enqueue the planned pairs of call set `c` (c.h_tasks[0..n)). wait = true: return when the results are complete and the
+// call's times are collected; false: return after the enqueue (svp_submit_batch_device) — the next call's planning and
+// forward pass then run under this call's last traceback.
+static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar, bool wait) {
     const Consts& cs = h->cs;
     cudaStream_t st = h->stream;
-    h->stats = svp_stats{};
-    const size_t n = tasks.size();
-    if (n == 0) return SVP_OK;
+    Task* tasks = c.h_tasks;
+    c.stats = svp_stats{};
+    c.n_waves = 0;
+    if (n == 0) { h->stats = c.stats; return SVP_OK; }
     // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
-    for (Task& t : tasks) {
+    for (size_t k = 0; k < n; ++k) {
+        Task& t = tasks[k];
         if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
         if (smem_need(t, cs, nw) > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
     }
-    // waves: consecutive tasks whose traceback rows fit HALF the arena; wave w writes half (w & 1), so
-    // the traceback of wave w overlaps the forward pass of wave w+1
+    // waves: consecutive tasks whose traceback rows fit HALF the arena; the halves alternate from wave to wave (across calls),
+    // so the traceback of a wave overlaps the forward pass of the next one
     const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
     std::vector<std::pair<size_t, size_t>> waves;
     std::vector<uint64_t> wave_best;
@@ -486,22 +589,24 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
                 if (need > half) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds half the arena; create the handle with a larger max_tb_bytes");
             }
             if (used + need > half) { waves.emplace_back(first, k); wave_best.push_back(best_used); first = k; used = 0; best_used = 0; }
-            t.tb_off = (waves.size() & 1) * half + used; t.best_off = best_used;
+            t.tb_off = ((h->wave_idx + waves.size()) & 1) * half + used; t.best_off = best_used;
             used += need; best_used += nbest;
         }
         waves.emplace_back(first, n); wave_best.push_back(best_used);
     }
     uint64_t max_best = 1;
     for (uint64_t b : wave_best) max_best = std::max(max_best, b);
-    for (size_t wv = 1; wv < waves.size(); wv += 2)
-        for (size_t k = waves[wv].first; k < waves[wv].second; ++k) tasks[k].best_off += max_best;
-    CUDA_TRY(h, h->d_tasks.reserve(n * sizeof(Task)));
-    CUDA_TRY(h, h->d_order.reserve(n * sizeof(uint32_t)));
-    CUDA_TRY(h, h->d_bests.reserve(2 * max_best * sizeof(uint2)));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, tasks.data(), n * sizeof(Task), cudaMemcpyHostToDevice, st));
+    for (size_t wv = 0; wv < waves.size(); ++wv)
+        if ((h->wave_idx + wv) & 1)
+            for (size_t k = waves[wv].first; k < waves[wv].second; ++k) tasks[k].best_off += max_best;
+    CUDA_TRY(h, c.d_tasks.reserve(n * sizeof(Task)));
+    CUDA_TRY(h, c.d_order.reserve(n * sizeof(uint32_t)));
+    CUDA_TRY(h, c.d_bests.reserve(2 * max_best * sizeof(uint2)));
+    CUDA_TRY(h, cudaEventRecord(c.ev_t0, st));
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_tasks.p, tasks, n * sizeof(Task), cudaMemcpyHostToDevice, st));
 
     // per wave: order lists grouped by kernel variant and CTA width (warps)
-    std::vector<uint32_t> order(n);
+    uint32_t* order = c.h_order;
     struct Group { int fam; int nwarp; int kp; int cluster; bool ring; size_t first, count; size_t smem; uint64_t work; };
     std::vector<std::vector<Group>> wave_groups(waves.size());
     size_t pos = 0;
@@ -521,7 +626,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const size_t need = smem_need(t, cs, nw);
             int cls = 0;
             while (((size_t)32768 << cls) < need) ++cls;
-            if (ring) cls = 50;                       // its own group: the sliding-window kernel
+            if (ring) cls = 50;                       // their own groups: the sliding-window variants
             by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * (int64_t)cl + 1000000000 * (int64_t)cls].push_back((uint32_t)k);
         }
         for (auto& kv : by_w) {
@@ -537,7 +642,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
                 work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
             }
             wave_groups[wv].push_back({ fam, nwarp, kp, cl, ring, pos, kv.second.size(), smem, work });
-            std::copy(kv.second.begin(), kv.second.end(), order.begin() + pos);
+            std::copy(kv.second.begin(), kv.second.end(), order + pos);
             pos += kv.second.size();
         }
         // group order (env SVP_GROUP_ORDER, tuning aid): 0 = biggest group first, so the small ones fill the machine behind it;
@@ -548,17 +653,16 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
         else
             std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
     }
-    if (pos) CUDA_TRY(h, cudaMemcpyAsync(h->d_order.p, order.data(), pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
-    const Task* d_tasks = (const Task*)h->d_tasks.p;
-    const uint32_t* d_order = (const uint32_t*)h->d_order.p;
-    uint2* d_bests = (uint2*)h->d_bests.p;
-    // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]; plus two for the whole call
+    const Task* d_tasks = (const Task*)c.d_tasks.p;
+    const uint32_t* d_order = (const uint32_t*)c.d_order.p;
+    uint2* d_bests = (uint2*)c.d_bests.p;
+    // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]
     constexpr int MAX_FWD_STREAMS = 8;
-    const size_t EV_PER_WAVE = 3 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE + 2;
-    while (h->events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); h->events.push_back(e); }
-    auto EV = [&](size_t wv, int which) { return h->events[wv * EV_PER_WAVE + which]; };
-    cudaEvent_t ev_t0 = h->events[n_ev - 2], ev_t1 = h->events[n_ev - 1];
+    const size_t EV_PER_WAVE = 3 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE;
+    while (c.events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
+    auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
     // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower four times — on
     // separate stream sets (1810 vs 1915 GCUPS) and on priority-tiered stream sets where the older wave keeps precedence for
     // CTA slots (2 or 3 tiers of 2 streams, within the 8 hardware queues: 1810-1909 vs 1923-1962): the union of the forward
@@ -575,12 +679,15 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
     static const int overlap_mode = [] { const char* e = getenv("SVP_WAVE_OVERLAP"); return e ? atoi(e) : -1; }();
     static const long overlap_max_pairs = [] { const char* e = getenv("SVP_WAVE_OVERLAP_PAIRS"); return e ? atol(e) : 4096L; }();
     const bool overlap = waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
-    CUDA_TRY(h, cudaEventRecord(ev_t0, st));
-    if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(sF[MAX_FWD_STREAMS / 2], ev_t0, 0));      // the copies above precede every wave
+    cudaEvent_t ev_copied = nullptr;                     // the copies above precede every wave, whatever stream leads it
+    if (overlap) { while (c.events.size() < n_ev + 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
+                   ev_copied = c.events[n_ev]; CUDA_TRY(h, cudaEventRecord(ev_copied, st)); }
     for (size_t wv = 0; wv < waves.size(); ++wv) {
-        cudaStream_t* sW = overlap ? sF + (wv & 1) * (MAX_FWD_STREAMS / 2) : sF;         // this wave's streams
+        const int half_id = (int)((h->wave_idx + wv) & 1);
+        cudaStream_t* sW = overlap ? sF + half_id * (MAX_FWD_STREAMS / 2) : sF;         // this wave's streams
         const int avail = overlap ? MAX_FWD_STREAMS / 2 : max_streams;
-        if (wv >= 2) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv - 2, 2), 0));      // this arena half is free again
+        if (overlap && sW[0] != st) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], ev_copied, 0));
+        if (h->half_free[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], h->half_free[half_id], 0));      // this arena half is free again
         CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sW[0]));
         const std::vector<Group>& groups = wave_groups[wv];
         const int n_streams = (int)std::min<size_t>((size_t)avail, groups.size());
@@ -589,7 +696,7 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const Group& gq = groups[gi];
             launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, gq.ring, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sW[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
                        h->arena, d_bests, cs);
-            h->stats.fwd_launches++;
+            c.stats.fwd_launches++;
         }
         for (int a = 1; a < n_streams; ++a) {
             CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sW[a]));
@@ -602,36 +709,36 @@ static int run_plan(svp_handle* h, std::vector<Task>& tasks, const uint8_t* d_se
             const int tpb = 64;
             // few pairs in the wave (one container per call; long tandem-repeat pairs): the warp-per-pair kernel walks 32 cells
             // per memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass
-            // ... and the last wave of a call has no forward pass left to share the machine with: its traceback is pure latency
+            // ... and the last wave of a blocking call has no forward pass left to share the machine with: its traceback is pure latency
             static const bool last_wave_warp = [] { const char* e = getenv("SVP_TBW_LAST"); return e ? atoi(e) != 0 : true; }();
-            if (nt <= h->tbw_max || (last_wave_warp && wv + 1 == waves.size()))
+            if (nt <= h->tbw_max || (last_wave_warp && wait && wv + 1 == waves.size()))
                 svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
             else
                 svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-            h->stats.tb_launches++;
+            c.stats.tb_launches++;
         }
         CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));
-        h->stats.waves++;
+        h->half_free[half_id] = EV(wv, 2);
+        c.stats.waves++;
     }
-    CUDA_TRY(h, cudaStreamWaitEvent(st, EV(waves.size() - 1, 2), 0));
-    CUDA_TRY(h, cudaEventRecord(ev_t1, st));
-    CUDA_TRY(h, cudaEventSynchronize(ev_t1));
-    float tot = 0; cudaEventElapsedTime(&tot, ev_t0, ev_t1);
-    h->stats.total_ms = tot;
-    // forward time = length of the union of the waves' forward intervals (they overlap when `overlap` is set)
-    float covered_to = 0;
-    for (size_t wv = 0; wv < waves.size(); ++wv) {
-        float f0 = 0, f1 = 0, b = 0;
-        cudaEventElapsedTime(&f0, ev_t0, EV(wv, 0));         // forward pass of the wave (may overlap the previous wave's traceback)
-        cudaEventElapsedTime(&f1, ev_t0, EV(wv, 1));
-        cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));      // its traceback (includes waiting for SM slots)
-        const float from = std::max(f0, covered_to);
-        if (f1 > from) { h->stats.fwd_ms += f1 - from; covered_to = f1; }
-        h->stats.tb_ms += b;
-    }
-    for (const Task& t : tasks) if (!(t.flags & TASK_INVALID)) { h->stats.cells += t.cells; h->stats.tb_bytes += tb_bytes_of(t); }
+    h->wave_idx += waves.size();
+    CUDA_TRY(h, cudaEventRecord(c.ev_t1, sT));           // tracebacks run in wave order on one stream: the last one ends the call
+    c.n_waves = waves.size();
+    for (size_t k = 0; k < n; ++k) if (!(tasks[k].flags & TASK_INVALID)) { c.stats.cells += tasks[k].cells; c.stats.tb_bytes += tb_bytes_of(tasks[k]); }
+    c.pending = true;
+    h->call_idx++;
     CUDA_TRY(h, cudaGetLastError());
-    return SVP_OK;
+    if (!wait) return SVP_OK;
+    return collect_call(h, c);
+}
+
+static int plan_and_run(svp_handle* h, const uint8_t* d_seqs, size_t packed_bytes, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                        const svp_pair* pairs, uint32_t n_pairs, svp_result* d_results, uint32_t* d_cigar, size_t cigar_words, bool need_padding, bool wait) {
+    CallSet* c = nullptr;
+    int rc = begin_call(h, n_pairs, &c);
+    if (rc != SVP_OK) return rc;
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
+    return run_plan(h, *c, n_pairs, d_seqs, d_results, d_cigar, wait);
 }
 
 extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seqs, size_t packed_bytes,
@@ -642,9 +749,18 @@ extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seq
     if (!d_packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !d_results || (!d_cigar_buf && cigar_words))
         return fail(h, SVP_ERR_ARG, "null argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, true, tasks[k]);
-    return run_plan(h, tasks, d_packed_seqs, d_results, d_cigar_buf);
+    return plan_and_run(h, d_packed_seqs, packed_bytes, seq_off, seq_len, n_seqs, pairs, n_pairs, d_results, d_cigar_buf, cigar_words, true, true);
+}
+
+extern "C" int svp_submit_batch_device(svp_handle* h, const uint8_t* d_packed_seqs, size_t packed_bytes,
+                                       const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+                                       const svp_pair* pairs, uint32_t n_pairs, svp_result* d_results,
+                                       uint32_t* d_cigar_buf, size_t cigar_words) {
+    if (!h) return SVP_ERR_ARG;
+    if (!d_packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !d_results || (!d_cigar_buf && cigar_words))
+        return fail(h, SVP_ERR_ARG, "null argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return plan_and_run(h, d_packed_seqs, packed_bytes, seq_off, seq_len, n_seqs, pairs, n_pairs, d_results, d_cigar_buf, cigar_words, true, false);
 }
 
 static int align_host(svp_handle* h, const uint8_t* packed_seqs, size_t packed_bytes, const uint64_t* seq_off, const uint32_t* seq_len,
@@ -657,9 +773,10 @@ static int align_host(svp_handle* h, const uint8_t* packed_seqs, size_t packed_b
     CUDA_TRY(h, h->d_cigar.reserve(std::max<size_t>(cigar_words, 1) * sizeof(uint32_t)));
     CUDA_TRY(h, cudaMemsetAsync((uint8_t*)h->d_seqs.p + (packed_bytes & ~(size_t)15), 0, padded - (packed_bytes & ~(size_t)15), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
-    std::vector<Task> tasks(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, padded, cigar_words, false, tasks[k]);
-    int rc = run_plan(h, tasks, (const uint8_t*)h->d_seqs.p, (svp_result*)h->d_results.p, (uint32_t*)h->d_cigar.p);
+    // a submitted device-resident call may still read the handle's sequence / result buffers only if it came through this
+    // function, which always waits: nothing of ours is in flight on them here
+    int rc = plan_and_run(h, (const uint8_t*)h->d_seqs.p, padded, seq_off, seq_len, n_seqs, pairs, n_pairs, (svp_result*)h->d_results.p,
+                          (uint32_t*)h->d_cigar.p, cigar_words, false, true);
     if (rc != SVP_OK) return rc;
     if (n_pairs) {
         CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));

@@ -538,3 +538,47 @@ def test_both_traceback_kernels(oracle, monkeypatch, tbw_max):
     with Aligner(device=0, tb_bytes=2 << 30) as g:
         gres, _ = run_both(g, oracle, names, seqs, specs)
     assert gres["n_del_bp"].max() >= 600
+
+
+def test_pipelined_submits_equal_blocking_calls(oracle):
+    """svp_submit_batch_device x 4 back to back (two batches in flight, the arena halves and the per-call buffers alternate
+    across calls; a small arena forces several waves per call) followed by one svp_sync gives the rows and CIGARs of the
+    blocking host-buffer calls, which equal the oracle."""
+    import torch
+    from svirlpool_b200._abi import RESULT_DTYPE
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(101)
+    batches = []
+    for n_pairs, length, band in ((10, 2500, 512), (3, 3000, 1056), (14, 1800, 256), (1, 2000, 512)):
+        names, seqs, specs = noisy_batch(rng, n_pairs, length, band)
+        batches.append(ava.PairBatch.build(names, seqs, specs))
+    dev = torch.device("cuda", 0)
+    with Aligner(device=0, preset="map-ont", tb_bytes=24 << 20) as g:
+        expected = []
+        for b in batches:
+            res, cig = g.align_batch(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)
+            ores, ocig = oracle.align_batch(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)
+            assert_same(b, res, cig, ores, ocig)
+            expected.append((res, cig))
+        assert g.stats()["waves"] >= 1
+        bufs = []
+        g.stats_total(reset=True)
+        for b in batches:
+            d_packed = torch.from_numpy(b.packed).to(dev)
+            d_res = torch.zeros(len(b.pairs) * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            d_cig = torch.zeros(b.cigar_words, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            g.submit_batch_device(d_packed.data_ptr(), b.packed.nbytes, b.seq_off, b.seq_len, b.pairs, d_res.data_ptr(), d_cig.data_ptr(),
+                                  b.cigar_words)
+            bufs.append((d_packed, d_res, d_cig))
+        g.sync()
+        total = g.stats_total()
+        assert total["waves"] >= len(batches) + 2 and total["cells"] == sum(int(e[0]["cells"].sum()) for e in expected)
+        for b, (res, cig), (_p, d_res, d_cig) in zip(batches, expected, bufs):
+            got = d_res.cpu().numpy().view(RESULT_DTYPE)
+            gcig = d_cig.cpu().numpy().view(np.uint32)
+            for f in INT_FIELDS:
+                if f != "cigar_len":
+                    assert np.array_equal(got[f], res[f]), f
+            for k in range(len(got)):
+                assert cigartuples(gcig, got[k]) == cigartuples(cig, res[k])
