@@ -100,6 +100,8 @@ struct svp_handle {
     cudaStream_t stream_aux[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
                                                 // wave run concurrently, and consecutive waves use different stream sets
     cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
+    cudaStream_t stream_tb2 = nullptr;          // ... the warp-per-pair walks of a wave's long pairs, beside the bulk kernel
+    long tbw_long = 24000;                      // pairs with m + n beyond this are walked by a warp each, whatever the wave (env SVP_TBW_LONG)
     cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
     CallSet sets[2];
@@ -224,6 +226,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     for (cudaStream_t& sx : h->stream_aux)
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    if (cudaStreamCreateWithPriority(&h->stream_tb2, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    if (const char* e = getenv("SVP_TBW_LONG")) h->tbw_long = atol(e);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
@@ -282,7 +286,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     }
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
-    for (cudaStream_t sx : { h->stream, h->stream_tb }) if (sx) cudaStreamDestroy(sx);
+    for (cudaStream_t sx : { h->stream, h->stream_tb, h->stream_tb2 }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
 
@@ -301,7 +305,7 @@ static int collect_call(svp_handle* h, CallSet& c) {
     if (!c.pending) return SVP_OK;
     c.pending = false;
     CUDA_TRY(h, cudaEventSynchronize(c.ev_t1));
-    constexpr size_t EV_PER_WAVE = 3 + 7;
+    constexpr size_t EV_PER_WAVE = 4 + 7;
     auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
     float tot = 0; cudaEventElapsedTime(&tot, c.ev_t0, c.ev_t1);
     c.stats.total_ms = tot;
@@ -544,10 +548,10 @@ static int begin_call(svp_handle* h, size_t n, CallSet** out) {
         CUDA_TRY(h, cudaHostAlloc((void**)&c.h_tasks, cap * sizeof(Task), cudaHostAllocDefault));
         c.h_tasks_cap = cap;
     }
-    if (n > c.h_order_cap) {
+    if (2 * n > c.h_order_cap) {                 // forward launch order + the traceback lists of every wave
         if (c.h_order) cudaFreeHost(c.h_order);
         c.h_order = nullptr; c.h_order_cap = 0;
-        const size_t cap = n + n / 4 + 16;
+        const size_t cap = 2 * n + n / 2 + 16;
         CUDA_TRY(h, cudaHostAlloc((void**)&c.h_order, cap * sizeof(uint32_t), cudaHostAllocDefault));
         c.h_order_cap = cap;
     }
@@ -576,9 +580,33 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     // waves: consecutive tasks whose traceback rows fit HALF the arena; the halves alternate from wave to wave (across calls),
     // so the traceback of a wave overlaps the forward pass of the next one
     const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
+    uint64_t cap = half;                        // bytes a wave may use
+    bool serial = false;
     std::vector<std::pair<size_t, size_t>> waves;
     std::vector<uint64_t> wave_best;
     {
+        // a call that needs several waves gets waves of equal size (not full halves and a remainder): the traceback of a wave
+        // runs under the forward pass of the next one, and the wave after that waits for it
+        uint64_t total_need = 0, total_len = 0;
+        for (size_t k = 0; k < n; ++k)
+            if (!(tasks[k].flags & TASK_INVALID)) { total_need += (tb_bytes_of(tasks[k]) + 255) & ~(uint64_t)255; total_len += (uint64_t)tasks[k].m + tasks[k].n; }
+        // Two ways to run the tracebacks. CONCURRENT: waves of half the arena, the traceback of a wave runs under the forward pass
+        // of the next one. SERIAL: waves of the whole arena, each traceback runs alone on the warp-per-pair kernel (5-6 ms for 10 000
+        // pairs) before the next forward pass starts. A concurrent traceback slows the forward pass it shares the SMs with by 12 %
+        // (config 2) to 18-50 % (config 4: many short pairs), more than it takes alone, and whole-arena waves halve the number of
+        // wave boundaries; but waves of few, long pairs (config 3) have latency-bound tracebacks that need the overlap, and on
+        // config 2 (8 kb reads) the two modes measure the same (2068 serial, 2083-2110 concurrent). Hence: serial when a half-arena
+        // wave would hold at least serial_min_pairs pairs of, on average, less than serial_max_len bases (m + n); config 4: 1693 ->
+        // 1949 GCUPS. Env SVP_TB_SERIAL = 0 / 1 forces the choice.
+        static const int serial_mode = [] { const char* e = getenv("SVP_TB_SERIAL"); return e ? atoi(e) : -1; }();
+        static const long serial_min_pairs = [] { const char* e = getenv("SVP_TB_SERIAL_PAIRS"); return e ? atol(e) : 4096L; }();
+        static const long serial_max_len = [] { const char* e = getenv("SVP_TB_SERIAL_LEN"); return e ? atol(e) : 12000L; }();
+        const uint64_t n_w_half = std::max<uint64_t>(1, (total_need + half - 1) / half);
+        serial = serial_mode >= 0 ? serial_mode != 0 : ((long)(n / n_w_half) >= serial_min_pairs && (long)(total_len / std::max<size_t>(n, 1)) < serial_max_len);
+        if (serial) cap = h->arena_bytes & ~(uint64_t)255;
+        const uint64_t n_w = std::max<uint64_t>(1, (total_need + cap - 1) / cap);
+        static const bool balance = [] { const char* e = getenv("SVP_WAVE_BALANCE"); return e ? atoi(e) != 0 : true; }();
+        const uint64_t target = balance ? std::min(cap, total_need / n_w + total_need / (n_w * 50) + 4096) : cap;
         size_t first = 0; uint64_t used = 0, best_used = 0;
         for (size_t k = 0; k < n; ++k) {
             Task& t = tasks[k];
@@ -586,10 +614,10 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
             if (!(t.flags & TASK_INVALID)) {
                 need = (tb_bytes_of(t) + 255) & ~(uint64_t)255;
                 nbest = best_entries_of(t);
-                if (need > half) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds half the arena; create the handle with a larger max_tb_bytes");
+                if (need > cap) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds half the arena; create the handle with a larger max_tb_bytes");
             }
-            if (used + need > half) { waves.emplace_back(first, k); wave_best.push_back(best_used); first = k; used = 0; best_used = 0; }
-            t.tb_off = ((h->wave_idx + waves.size()) & 1) * half + used; t.best_off = best_used;
+            if (used + need > cap || (used >= target && need)) { waves.emplace_back(first, k); wave_best.push_back(best_used); first = k; used = 0; best_used = 0; }
+            t.tb_off = (serial ? 0 : ((h->wave_idx + waves.size()) & 1) * half) + used; t.best_off = best_used;
             used += need; best_used += nbest;
         }
         waves.emplace_back(first, n); wave_best.push_back(best_used);
@@ -600,7 +628,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         if ((h->wave_idx + wv) & 1)
             for (size_t k = waves[wv].first; k < waves[wv].second; ++k) tasks[k].best_off += max_best;
     CUDA_TRY(h, c.d_tasks.reserve(n * sizeof(Task)));
-    CUDA_TRY(h, c.d_order.reserve(n * sizeof(uint32_t)));
+    CUDA_TRY(h, c.d_order.reserve(2 * n * sizeof(uint32_t)));
     CUDA_TRY(h, c.d_bests.reserve(2 * max_best * sizeof(uint2)));
     CUDA_TRY(h, cudaEventRecord(c.ev_t0, st));
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tasks.p, tasks, n * sizeof(Task), cudaMemcpyHostToDevice, st));
@@ -653,6 +681,22 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         else
             std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
     }
+    // traceback lists: a wave that is not walked by the warp-per-pair kernel as a whole hands its long pairs (m + n beyond
+    // tbw_long: a 40-90 kb consensus against its reference window takes the thread-per-pair kernel 10 000 dependent rounds, tens
+    // of milliseconds during which the next wave but one waits for the arena half) to warps, the rest to the bulk kernel
+    struct TbList { size_t first_short, n_short, first_long, n_long; };
+    std::vector<TbList> tb_lists(waves.size());
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        TbList& L = tb_lists[wv];
+        L.first_short = pos;
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
+            if ((tasks[k].flags & TASK_INVALID) || (long)tasks[k].m + tasks[k].n <= h->tbw_long) order[pos++] = (uint32_t)k;
+        L.n_short = pos - L.first_short;
+        L.first_long = pos;
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
+            if (!(tasks[k].flags & TASK_INVALID) && (long)tasks[k].m + tasks[k].n > h->tbw_long) order[pos++] = (uint32_t)k;
+        L.n_long = pos - L.first_long;
+    }
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     const Task* d_tasks = (const Task*)c.d_tasks.p;
@@ -660,7 +704,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     uint2* d_bests = (uint2*)c.d_bests.p;
     // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]
     constexpr int MAX_FWD_STREAMS = 8;
-    const size_t EV_PER_WAVE = 3 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE;
+    const size_t EV_PER_WAVE = 4 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE;       // [fwd start, fwd end, tb end, long-walk end, joins]
     while (c.events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
     auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
     // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower four times — on
@@ -678,7 +722,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     // averaging fewer than overlap_max_pairs pairs.
     static const int overlap_mode = [] { const char* e = getenv("SVP_WAVE_OVERLAP"); return e ? atoi(e) : -1; }();
     static const long overlap_max_pairs = [] { const char* e = getenv("SVP_WAVE_OVERLAP_PAIRS"); return e ? atol(e) : 4096L; }();
-    const bool overlap = waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
+    const bool overlap = !serial && waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
     cudaEvent_t ev_copied = nullptr;                     // the copies above precede every wave, whatever stream leads it
     if (overlap) { while (c.events.size() < n_ev + 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
                    ev_copied = c.events[n_ev]; CUDA_TRY(h, cudaEventRecord(ev_copied, st)); }
@@ -688,6 +732,8 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         const int avail = overlap ? MAX_FWD_STREAMS / 2 : max_streams;
         if (overlap && sW[0] != st) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], ev_copied, 0));
         if (h->half_free[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], h->half_free[half_id], 0));      // this arena half is free again
+        const bool tb_serial = serial;           // whole-arena wave: every earlier traceback must be done
+        if (tb_serial && h->half_free[half_id ^ 1]) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], h->half_free[half_id ^ 1], 0));
         CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sW[0]));
         const std::vector<Group>& groups = wave_groups[wv];
         const int n_streams = (int)std::min<size_t>((size_t)avail, groups.size());
@@ -699,8 +745,8 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
             c.stats.fwd_launches++;
         }
         for (int a = 1; a < n_streams; ++a) {
-            CUDA_TRY(h, cudaEventRecord(EV(wv, 2 + a), sW[a]));
-            CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv, 2 + a), 0));
+            CUDA_TRY(h, cudaEventRecord(EV(wv, 3 + a), sW[a]));
+            CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv, 3 + a), 0));
         }
         CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sW[0]));
         CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
@@ -711,14 +757,29 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
             // per memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass
             // ... and the last wave of a blocking call has no forward pass left to share the machine with: its traceback is pure latency
             static const bool last_wave_warp = [] { const char* e = getenv("SVP_TBW_LAST"); return e ? atoi(e) != 0 : true; }();
-            if (nt <= h->tbw_max || (last_wave_warp && wait && wv + 1 == waves.size()))
-                svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-            else
-                svp_tb_kernel<<<(nt + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks + waves[wv].first, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-            c.stats.tb_launches++;
+            const TbList& L = tb_lists[wv];
+            if (nt <= h->tbw_max || tb_serial || (last_wave_warp && wait && wv + 1 == waves.size())) {
+                svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nullptr, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
+                c.stats.tb_launches++;
+            } else {
+                if (L.n_long) {              // the long walks first, on their own stream beside the bulk kernel
+                    CUDA_TRY(h, cudaStreamWaitEvent(h->stream_tb2, EV(wv, 1), 0));
+                    svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, 0, h->stream_tb2>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs, h->arena, d_bests,
+                                                                                           d_results, d_cigar, cs);
+                    CUDA_TRY(h, cudaEventRecord(EV(wv, 3), h->stream_tb2));
+                    c.stats.tb_launches++;
+                }
+                if (L.n_short) {
+                    svp_tb_kernel<<<((int)L.n_short + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_bests, d_results,
+                                                                                 d_cigar, cs);
+                    c.stats.tb_launches++;
+                }
+                if (L.n_long) CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 3), 0));
+            }
         }
         CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));
         h->half_free[half_id] = EV(wv, 2);
+        if (serial) h->half_free[half_id ^ 1] = EV(wv, 2);
         c.stats.waves++;
     }
     h->wave_idx += waves.size();

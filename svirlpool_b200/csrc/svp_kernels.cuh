@@ -662,11 +662,12 @@ __device__ __forceinline__ int sext8(uint32_t x) { return (int)(int8_t)(x & 0xFF
 //   * the Z-trim start (lowest H of the walk, §3.5) is only tracked as a position; the rare walk that is
 //     actually cut is replayed up to that position (same deterministic path) to rebuild CIGAR and counts.
 __global__ void __launch_bounds__(64)
-svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ tb,
-              const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+              const uint8_t* __restrict__ tb, const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar,
+              const Consts cs) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n_tasks) return;
-    const Task tk = tasks[tid];
+    const Task tk = tasks[order ? order[tid] : (uint32_t)tid];          // order: the wave's pairs this kernel walks (nullptr: tasks[0..n))
     svp_result res;
     res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
     res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
@@ -877,11 +878,12 @@ svp_tb_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __rest
 // the Z-trim start is kept as a snapshot of the walk at its lowest H instead of a replay.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-svp_tbw_kernel(const Task* __restrict__ tasks, int n_tasks, const uint8_t* __restrict__ seqs, const uint8_t* __restrict__ tb,
-               const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+               const uint8_t* __restrict__ tb, const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar,
+               const Consts cs) {
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= n_tasks) return;
-    const Task tk = tasks[wid];
+    const Task tk = tasks[order ? order[wid] : (uint32_t)wid];
     svp_result res;
     res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
     res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
