@@ -531,7 +531,7 @@ def test_serial_and_concurrent_traceback_scheduling(oracle, monkeypatch, serial)
     off = len(seqs)
     seqs += s2
     specs += [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in p2]
-    with Aligner(device=0, preset="map-ont", tb_bytes=40 << 20) as g:
+    with Aligner(device=0, preset="map-ont", tb_bytes=24 << 20) as g:
         run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
         assert g.stats()["waves"] >= 2
 
