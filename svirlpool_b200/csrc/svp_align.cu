@@ -25,7 +25,9 @@ static inline int max_warps_of(int kp) { return kp <= 8 ? 16 : 8; }
 // warp-instructions per step of the inner loop (SASS counts), used only to rank variants
 static inline int step_cost(int kp, int nwarp) { return 22 + kp * 25 / 2 + (nwarp > 1 ? 10 : 0); }
 static int g_kp_mask = -1;          // tuning aid: env SVP_KP_MASK, bit (KP/4 - 1) allows that KP (default: all)
-static inline int choose_kp(uint32_t band_w) {
+// latency = true (a call of few pairs, e.g. one container: the GPU is not full): the variant with the shortest step, i.e. more,
+// narrower warps per pair, instead of the one with the fewest issue slots
+static inline int choose_kp(uint32_t band_w, bool latency) {
     if (g_kp_mask < 0) { const char* e = getenv("SVP_KP_MASK"); g_kp_mask = e ? atoi(e) : 15; if (!(g_kp_mask & 15)) g_kp_mask = 15; }
     int best_kp = 0; long best_cost = 0;
     for (int kp : { 4, 8 }) {      // KP 12 / 16 single-warp variants were measured slower on B200 (150-250 registers per thread)
@@ -33,7 +35,7 @@ static inline int choose_kp(uint32_t band_w) {
         if (band_w % (uint32_t)(4 * kp)) continue;
         const int nw = (int)((band_w + 128 * kp - 1) / (128 * kp));
         if (nw > max_warps_of(kp)) continue;
-        const long cost = (long)nw * step_cost(kp, nw);
+        const long cost = latency ? (long)step_cost(kp, nw) : (long)nw * step_cost(kp, nw);
         if (!best_kp || cost < best_cost) { best_kp = kp; best_cost = cost; }
     }
     return best_kp;          // 0: band too wide for every variant
@@ -114,6 +116,9 @@ struct svp_handle {
     std::string err;
     int max_smem_optin = 0;
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
+    long latency_pairs = 0;                     // calls of at most this many pairs are planned for short steps (more, narrower warps) instead of fewest
+                                                // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call (435
+                                                // pairs x 8 kb: forward 2.4 ms on 2 x KP=4 warps with a barrier per step, 2.0 ms on one KP=8 warp)
     bool force_ring = false;                    // test aid (env SVP_FORCE_RING): every pair on a sliding-window variant
     int tbw_max = 2048;                         // waves with at most this many pairs use the warp-per-pair traceback (env SVP_TBW_MAX)
 };
@@ -231,6 +236,7 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
+    if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
     if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
 #define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
 #define SVP_ATTR2(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>); \
@@ -471,7 +477,7 @@ struct Plan {
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
 };
 
-static void plan_pair(const svp_handle* h, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
@@ -507,7 +513,7 @@ static void plan_pair(const svp_handle* h, const svp_pair& p, uint32_t index, co
     int kp, cl = 1;
     if (wide32 || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
     else {
-        kp = choose_kp(p.band_w);
+        kp = choose_kp(p.band_w, latency);
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
         if (!ring && cl) {
             const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));
@@ -798,7 +804,9 @@ static int plan_and_run(svp_handle* h, const uint8_t* d_seqs, size_t packed_byte
     CallSet* c = nullptr;
     int rc = begin_call(h, n_pairs, &c);
     if (rc != SVP_OK) return rc;
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
+    // few pairs: optionally favour short steps (see latency_pairs)
+    const bool latency = (long)n_pairs <= h->latency_pairs;
+    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
     return run_plan(h, *c, n_pairs, d_seqs, d_results, d_cigar, wait);
 }
 

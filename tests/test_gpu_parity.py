@@ -519,6 +519,23 @@ def test_forced_sliding_window_equals_whole_images(oracle, monkeypatch, scoring_
     assert not gres["status"].any()
 
 
+def test_latency_plan_small_calls(oracle, monkeypatch):
+    """Calls of at most SVP_LATENCY_PAIRS pairs (off by default: measured slower) are planned for short steps — KP = 4 warps
+    wherever the band allows — instead of fewest issue slots. Same results."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_LATENCY_PAIRS", "1024")
+    rng = np.random.default_rng(93)
+    names, seqs, specs = noisy_batch(rng, 8, 3000, 1024)             # KP = 8 single warp on the throughput plan, 2 x KP = 4 here
+    n2, s2, p2 = noisy_batch(rng, 3, 5000, 2080)
+    n3, s3, p3 = noisy_batch(rng, 2, 17000, 1056)                    # rebased, multi-warp
+    for sq, sp in ((s2, p2), (s3, p3)):
+        off = len(seqs)
+        seqs += sq
+        specs += [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in sp]
+    with Aligner(device=0, preset="map-ont", tb_bytes=2 << 30) as g:
+        run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
+
+
 @pytest.mark.parametrize("serial", ["0", "1"])
 def test_serial_and_concurrent_traceback_scheduling(oracle, monkeypatch, serial):
     """SVP_TB_SERIAL forces whole-arena waves whose tracebacks run alone (1) or half-arena waves whose tracebacks run under the
