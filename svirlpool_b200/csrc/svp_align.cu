@@ -768,6 +768,9 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
                 svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nullptr, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
                 c.stats.tb_launches++;
             } else {
+                // (launching the long walks EARLY — as soon as the forward launches that hold them are done, under the rest of the
+                // wave's forward pass — was measured slower: config 4 1927 -> 1861 GCUPS, the walks cost the forward pass more than
+                // their latency saves)
                 if (L.n_long) {              // the long walks first, on their own stream beside the bulk kernel
                     CUDA_TRY(h, cudaStreamWaitEvent(h->stream_tb2, EV(wv, 1), 0));
                     svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, 0, h->stream_tb2>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs, h->arena, d_bests,

@@ -112,3 +112,30 @@ def test_native_ava_pairs_argument_errors():
     pairs, words = aligner.ava_pairs_native(lens, None, np.array([1, -1, 1], dtype=np.int8), None, 0, 3, 300, 32, False, cigar_start=10)
     assert len(pairs) == 3 and pairs["cigar_off"][0] == 10 and words == 10 + int(pairs["cigar_cap"].sum())
     assert pairs["flags"].tolist() == [1, 0, 1]
+
+
+def test_native_ava_pairs_several_containers_in_one_table():
+    """A batch of containers the way INTEGRATION.md describes it: one sequence table over all reads, svp_ava_pairs per
+    container with its seq_base and the running CIGAR word count == the per-container Python builds, shifted."""
+    from svirlpool_b200 import ava
+    rng = np.random.default_rng(21)
+    containers = [_random_reads(rng, n, 300, 1500) for n in (5, 2, 9)]
+    all_seqs = [s for c in containers for s in c]
+    packed, off, lens = aligner.pack_2bit_native(all_seqs)
+    base, words, got = 0, 0, []
+    for reads in containers:
+        pairs, words = aligner.ava_pairs_native(lens, None, np.ones(len(reads), dtype=np.int8), None, base, len(reads), 300, 32, False, cigar_start=words)
+        got.append(pairs)
+        base += len(reads)
+    base, slot = 0, 0
+    for reads, pairs in zip(containers, got):
+        names = [f"r{k:03d}" for k in range(len(reads))]                     # table order == name order
+        specs, _ = ava.ava_pair_specs(names, [len(s) for s in reads], {n: "+" for n in names}, None, 300, 32, False)
+        ref = ava.PairBatch.build(names, reads, specs).pairs
+        assert np.array_equal(pairs["q"], ref["q"] + base) and np.array_equal(pairs["t"], ref["t"] + base)
+        for f in ("band_lo", "band_w", "flags", "cigar_cap"):
+            assert np.array_equal(pairs[f], ref[f]), f
+        assert np.array_equal(pairs["cigar_off"], ref["cigar_off"] + slot)
+        base += len(reads)
+        slot += int(ref["cigar_cap"].sum())
+    assert words == slot

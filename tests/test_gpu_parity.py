@@ -542,6 +542,7 @@ def test_serial_and_concurrent_traceback_scheduling(oracle, monkeypatch, serial)
     next wave's forward pass (0); a small arena makes several waves either way. Same results as the oracle."""
     from svirlpool_b200.aligner import Aligner
     monkeypatch.setenv("SVP_TB_SERIAL", serial)
+    monkeypatch.setenv("SVP_TBW_MAX", "0")            # small waves, too, split into bulk kernel + warp walks of the long pairs
     rng = np.random.default_rng(92)
     names, seqs, specs = noisy_batch(rng, 16, 2200, 512)
     n2, s2, p2 = noisy_batch(rng, 2, 14000, 544)                      # long pairs: the warp-per-pair walks beside the bulk kernel
