@@ -330,6 +330,9 @@ constexpr int fwd_max_threads(int kp, bool multi) { return !multi ? 32 : (kp <= 
 constexpr int RB_ITERS = 16;
 constexpr int RB_CLAMP = 16000;
 
+// (No minimum-CTAs bound on the single-warp variants: the sliding-window KP = 8 kernel compiles to 157 registers = 12 CTAs per
+// SM, profiles/ncu_fwd_r01_v5_small.json; capping it at 128 registers / 16 CTAs per SM was measured 2 % SLOWER on configs 2
+// and 4 — the kernel is bound by the ALU pipe, not by latency hiding.)
 template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false>
 __global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
