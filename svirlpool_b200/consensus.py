@@ -48,6 +48,34 @@ def pairwise_alignment_lengths(ava_alignments: list[AlignedRecord], read_names: 
     return out
 
 
+def _rank_in_cluster(matrix: np.ndarray, matrix_names: list[str], cluster_names: list[str], reduce: str) -> list[str]:
+    """Cluster reads ordered by their row statistic inside the cluster's sub-matrix, largest first: the mean over the
+    cluster (similarity, diagonal included; consensus.py:583-609) or the sum over the OTHER reads (alignment lengths,
+    consensus.py:612-637). Ties fall as numpy's argsort of the negated values leaves them, as in the reference."""
+    if len(cluster_names) == 1:
+        return list(cluster_names)
+    where = {name: k for k, name in enumerate(matrix_names)}
+    idx = np.array([where[n] for n in cluster_names])
+    sub = np.array(matrix[np.ix_(idx, idx)])
+    if reduce == "mean":
+        stat = sub.mean(axis=1)
+    else:
+        np.fill_diagonal(sub, 0)
+        stat = sub.sum(axis=1)
+    return [cluster_names[k] for k in np.argsort(-stat)]
+
+
+def find_representative_read(similarity_matrix: np.ndarray, pairwise_alignment_lengths_matrix: np.ndarray,
+                             sim_read_names: list[str], cluster_read_names: list[str]) -> str:
+    """The read a cluster is polished against in racon mode (consensus.py:640-660): every read of the cluster is ranked by
+    its mean similarity to the cluster and by the summed lengths of its alignments to the other reads; the read with the
+    smallest rank sum wins (first one on ties). Same signature as the reference."""
+    by_sim = _rank_in_cluster(similarity_matrix, sim_read_names, cluster_read_names, "mean")
+    by_len = _rank_in_cluster(pairwise_alignment_lengths_matrix, sim_read_names, cluster_read_names, "sum")
+    ranksums = np.array([by_sim.index(r) + by_len.index(r) for r in cluster_read_names], dtype=float)
+    return cluster_read_names[int(np.argmin(ranksums))]
+
+
 def ava_similarity(engine, reads: dict[str, str], strands: dict[str, str] | None = None, densities_weight: float = 0.0,
                    min_signal_size: int = 12, min_bnd_size: int = 100, slack: int = 300, granule: int = 512
                    ) -> tuple[np.ndarray, list[str], list[AlignedRecord]]:

@@ -97,6 +97,34 @@ def write_alignments_tsv(path: Path | str, annotated: list[tuple[str, int, int, 
             print(cid, qs, qe, json.dumps(aln.unstructure()), sep="\t", file=f)
 
 
+def write_partitioned_alignments(input_bam, output_paths: dict[int, Path], index_consensusIDs: dict[int, set[str]],
+                                 samplename: str) -> None:
+    """The reference's entry point of this step (consensus_align.py:661-735), same signature and file format: every mapped
+    consensus alignment -> one line `consensusID \t qstart \t qend \t JSON(datatypes.Alignment)` in the TSV of the partition
+    that owns its consensusID (so all alignments of a consensus land in one file). `input_bam` is a BAM/SAM path (read by
+    sam.read_alignments, no htslib) or an iterable of AlignedRecord straight from align_consensuses_to_reference().
+    Raises ValueError for a consensusID outside index_consensusIDs or a record without reference_end, like the reference."""
+    owner = {cid: k for k, ids in index_consensusIDs.items() for cid in ids}
+    if isinstance(input_bam, (str, Path)):
+        from . import sam
+        records = list(sam.read_alignments(input_bam))
+    else:
+        records = list(input_bam)
+    writers = {k: open(path, "w") for k, path in output_paths.items()}
+    try:
+        for rec in records:
+            if rec.is_unmapped:
+                continue
+            if rec.query_name not in owner:
+                raise ValueError(f"consensusID {rec.query_name} not found in index_consensusIDs. "
+                                 "This should not happen. Please check the input data.")
+        for cid, qstart, qend, aln in annotate_alignments(records, samplename):
+            print(cid, qstart, qend, json.dumps(aln.unstructure()), sep="\t", file=writers[owner[cid]])
+    finally:
+        for w in writers.values():
+            w.close()
+
+
 def core_intervals_on_reference(consensuses: dict[str, Consensus], annotated: list[tuple[str, int, int, Alignment]]
                                 ) -> dict[str, list[tuple[int, str, int, int, int, int]]]:
     """consensusID -> [(alignment index in (qstart, qend) order, chromosome, core start on ref, core end on ref,

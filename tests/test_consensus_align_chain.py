@@ -210,3 +210,34 @@ def check_chain(recs, cons, sv, strand):
         assert sorted(s.sv_type for s in flat if s.sv_type >= 3) == [3, 3, 4, 4] or len([s for s in flat if s.sv_type >= 3]) >= 2
         starts = sorted(c[2] for c in cores["7.0"])
         assert abs(starts[0] - 5000) <= 2 and len(cores["7.0"]) == 3
+
+
+def test_write_partitioned_alignments_reference_signature(oracle, tmp_path):
+    """consensus_align.write_partitioned_alignments (reference: consensus_align.py:661-735): records -> partition TSVs by the
+    owner of each consensusID, from an in-memory record list and from a BAM path alike; unknown consensusIDs raise."""
+    from svirlpool_b200 import sam
+    rng = np.random.default_rng(6)
+    chrom, cons = _consensus_case(rng, core_len=2400, sv="inv", strand="+")
+    recs = consensus_align.align_consensuses_to_reference(oracle, {cons.ID: cons}, lambda c, s, e: chrom[s:e], {"chrS": len(chrom)},
+                                                          band_w=1024)
+    assert len(recs) == 3
+    paths = {0: tmp_path / "p0.tsv", 1: tmp_path / "p1.tsv"}
+    consensus_align.write_partitioned_alignments(recs, paths, {0: {"other.0"}, 1: {cons.ID}}, "S")
+    assert paths[0].read_text() == ""
+    lines = paths[1].read_text().splitlines()
+    assert len(lines) == 3
+    expected = consensus_align.annotate_alignments(recs, "S")
+    for line, (cid, qs, qe, aln) in zip(lines, expected):
+        f = line.split("\t")
+        assert (f[0], int(f[1]), int(f[2])) == (cid, qs, qe)
+        back = Alignment.structure(json.loads(f[3]))
+        assert back.annotations == {"qstart": qs, "qend": qe, "qmid": (qs + qe) // 2}
+        assert back.to_record().cigartuples == aln.to_record().cigartuples
+    # the same through a coordinate-sorted BAM on disk (the file the reference's minimap2 call leaves behind)
+    bam = tmp_path / "consensus.bam"
+    sam.write_bam(bam, sam.sort_records(recs, {"chrS": len(chrom)}), {"chrS": len(chrom)}, index=True)
+    paths2 = {0: tmp_path / "q0.tsv"}
+    consensus_align.write_partitioned_alignments(bam, paths2, {0: {cons.ID}}, "S")
+    assert sorted(l.split("\t")[:3] for l in paths2[0].read_text().splitlines()) == sorted(l.split("\t")[:3] for l in lines)
+    with pytest.raises(ValueError):
+        consensus_align.write_partitioned_alignments(recs, {0: tmp_path / "r0.tsv"}, {0: {"nobody"}}, "S")

@@ -215,3 +215,28 @@ def test_final_consensus_record(oracle):
     assert len(big) == 1 and abs(big[0].size - abs(region.sv_size)) <= 10 and big[0].type == (0 if region.sv_size > 0 else 1)
     assert c.get_max_cutread_coverage() >= len(hap0)
     assert consensus.final_consensus(oracle, "S", 8, 100, {"x": "ACGT" * 30}, cseq, "11.0", [11], []) is None
+
+
+def test_find_representative_read_rank_sum_medoid():
+    """consensus.find_representative_read (reference: consensus.py:583-660): ranks by mean similarity inside the cluster and
+    by summed alignment lengths to the other cluster reads, smallest rank sum wins; reads outside the cluster do not count."""
+    names = ["a", "b", "c", "d", "x"]
+    sim = np.array([[1.0, 0.9, 0.8, 0.2, 0.0],
+                    [0.9, 1.0, 0.9, 0.3, 0.0],
+                    [0.8, 0.9, 1.0, 0.1, 0.0],
+                    [0.2, 0.3, 0.1, 1.0, 0.9],
+                    [0.0, 0.0, 0.0, 0.9, 1.0]])
+    lens = np.array([[0, 7000, 6500, 100, 0],
+                     [7000, 0, 7800, 200, 0],
+                     [6500, 7800, 0, 150, 0],
+                     [100, 200, 150, 0, 9000],
+                     [0, 0, 0, 9000, 0]])
+    before = lens.copy()
+    assert consensus.find_representative_read(sim, lens, names, ["a", "b", "c"]) == "b"
+    assert consensus.find_representative_read(sim, lens, names, ["c", "a", "b"]) == "b"        # cluster order does not matter here
+    assert consensus.find_representative_read(sim, lens, names, ["d", "x"]) in ("d", "x")
+    assert consensus.find_representative_read(sim, lens, names, ["x"]) == "x"
+    assert np.array_equal(lens, before)                                                         # inputs are not modified
+    # similarity and alignment length disagree (c: ranks 0 + 1, b: 2 + 0, a: 1 + 2): the smallest rank sum wins
+    sim2 = sim.copy(); sim2[0, 1] = sim2[1, 0] = 0.5; sim2[0, 2] = sim2[2, 0] = 0.95
+    assert consensus.find_representative_read(sim2, lens, names, ["a", "b", "c"]) == "c"
