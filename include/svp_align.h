@@ -186,6 +186,27 @@ int svp_submit_batch_device(svp_handle* h,
                             svp_result* d_results, uint32_t* d_cigar_buf, size_t cigar_words);
 int svp_sync(svp_handle* h);
 
+/* Host-only view of the planner (no device needed): how each pair of a batch would run — for capacity planning (traceback bytes
+ * = arena use, shared memory per CTA) and for tests of the planning rules. Same arguments as svp_align_batch. */
+#define SVP_PLAN_S32      1u   /* 32-bit lanes */
+#define SVP_PLAN_REBASE   2u   /* 16-bit lanes relative to per-warp score offsets (scores beyond the s16 range) */
+#define SVP_PLAN_WINDOWS  4u   /* sliding sequence windows instead of whole shared-memory images */
+#define SVP_PLAN_GENERAL  8u   /* general scoring kernels (4x4 matrix, separate insertion / deletion costs) */
+#define SVP_PLAN_INVALID 16u   /* descriptor rejected (SVP_ST_BAD_PAIR) */
+#define SVP_PLAN_TOO_LONG 32u  /* sequences do not fit the shared-memory images (SVP_ST_TOO_LONG) */
+typedef struct svp_pair_plan {
+    uint32_t flags;        /* SVP_PLAN_* */
+    uint32_t kp;           /* packed registers per state array: a thread owns 4*kp diagonals */
+    uint32_t warps;        /* warps per CTA */
+    uint32_t cluster;      /* CTAs per pair (thread-block cluster), 1 = none */
+    uint32_t smem_bytes;   /* dynamic shared memory of the CTA */
+    uint32_t reserved;
+    uint64_t cells;        /* DP cells of the spec (band ∩ matrix) */
+    uint64_t tb_bytes;     /* traceback bytes this pair occupies in the arena */
+} svp_pair_plan;
+int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, const uint64_t* seq_off, const uint32_t* seq_len,
+                   uint32_t n_seqs, const svp_pair* pairs, uint32_t n_pairs, size_t cigar_words, svp_pair_plan* out);
+
 typedef struct svp_stats {
     double   fwd_ms;        /* sum over waves of the forward DP kernel(s) */
     double   tb_ms;         /* sum over waves of the traceback kernel */

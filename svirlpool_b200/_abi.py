@@ -35,9 +35,13 @@ STATS_DTYPE = np.dtype([
 assert SCORING_DTYPE.itemsize == 112 and PAIR_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 72
 assert STATS_DTYPE.itemsize == 56
 
+PLAN_DTYPE = np.dtype([("flags", "<u4"), ("kp", "<u4"), ("warps", "<u4"), ("cluster", "<u4"), ("smem_bytes", "<u4"), ("reserved", "<u4"),
+                       ("cells", "<u8"), ("tb_bytes", "<u8")])
+PLAN_S32, PLAN_REBASE, PLAN_WINDOWS, PLAN_GENERAL, PLAN_INVALID, PLAN_TOO_LONG = 1, 2, 4, 8, 16, 32
+
 # every symbol include/svp_align.h declares (checked by tests/test_abi.py against the built library)
 EXPORTS = ("svp_abi_version", "svp_device_count", "svp_scoring_preset", "svp_create", "svp_destroy", "svp_pinned_alloc", "svp_pinned_free",
-           "svp_last_error", "svp_pack_bytes", "svp_pack_2bit", "svp_ava_pairs", "svp_align_batch", "svp_align_batch_summary", "svp_align_batch_device", "svp_submit_batch_device", "svp_sync", "svp_get_stats", "svp_get_stats_total", "svp_timer_mark", "svp_timer_elapsed_ms")
+           "svp_last_error", "svp_pack_bytes", "svp_pack_2bit", "svp_ava_pairs", "svp_plan_pairs", "svp_align_batch", "svp_align_batch_summary", "svp_align_batch_device", "svp_submit_batch_device", "svp_sync", "svp_get_stats", "svp_get_stats_total", "svp_timer_mark", "svp_timer_elapsed_ms")
 
 
 def ptr(a: np.ndarray) -> C.c_void_p:

@@ -78,6 +78,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.svp_ava_pairs.restype = C.c_int
     lib.svp_ava_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int,
                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.svp_plan_pairs.restype = C.c_int
+    lib.svp_plan_pairs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p]
     if lib.svp_abi_version() != _abi.ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {lib.svp_abi_version()}, python {_abi.ABI_VERSION}")
     return lib
@@ -127,6 +129,18 @@ def ava_pairs_native(seq_len: np.ndarray, name_order: np.ndarray | None, strand:
     if rc != SVP_OK:
         raise AlignerError(rc, "svp_ava_pairs failed (invalid argument, or the CIGAR slots of the batch exceed 2^32 words)")
     return pairs[:int(n_pairs[0])], int(words[0])
+
+
+def plan_pairs(scoring: np.ndarray, packed_bytes: int, seq_off: np.ndarray, seq_len: np.ndarray, pairs: np.ndarray,
+               cigar_words: int) -> np.ndarray:
+    """svp_plan_pairs: per pair the kernel family / geometry / memory the library would use (host only, no GPU)."""
+    lib = shared_library()
+    out = np.zeros(max(len(pairs), 1), dtype=_abi.PLAN_DTYPE)
+    rc = lib.svp_plan_pairs(ptr(scoring), int(packed_bytes), ptr(seq_off), ptr(seq_len), len(seq_len), ptr(pairs), len(pairs),
+                            int(cigar_words), ptr(out))
+    if rc != SVP_OK:
+        raise AlignerError(rc, (lib.svp_last_error(None) or b"").decode())
+    return out[:len(pairs)]
 
 
 def scoring_preset(name: str, lib: C.CDLL | None = None) -> np.ndarray:

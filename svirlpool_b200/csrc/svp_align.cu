@@ -210,6 +210,15 @@ static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
     return SVP_OK;
 }
 
+// tuning / test knobs read from the environment when a handle (or a planning-only pseudo handle) is set up
+static void read_env_knobs(svp_handle* h) {
+    if (const char* e = getenv("SVP_TBW_LONG")) h->tbw_long = atol(e);
+    if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
+    if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
+    if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
+    if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
+}
+
 extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out) {
     if (!scoring || !out) return fail(nullptr, SVP_ERR_ARG, "null argument");
     *out = nullptr;
@@ -232,12 +241,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaStreamCreateWithPriority(&h->stream_tb2, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
-    if (const char* e = getenv("SVP_TBW_LONG")) h->tbw_long = atol(e);
+    read_env_knobs(h);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
-    if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
-    if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
-    if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
 #define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
 #define SVP_ATTR2(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>); \
                            SVP_SMEM(svp_fwd_kernel<K, false, false, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, false, false, R, G>)
@@ -811,6 +816,36 @@ static int plan_and_run(svp_handle* h, const uint8_t* d_seqs, size_t packed_byte
     const bool latency = (long)n_pairs <= h->latency_pairs;
     for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
     return run_plan(h, *c, n_pairs, d_seqs, d_results, d_cigar, wait);
+}
+
+// Host-only view of the planner: how the pairs of a batch would run (no device needed; B200's shared-memory limit assumed).
+extern "C" int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, const uint64_t* seq_off, const uint32_t* seq_len,
+                              uint32_t n_seqs, const svp_pair* pairs, uint32_t n_pairs, size_t cigar_words, svp_pair_plan* out) {
+    if (!scoring || !seq_off || !seq_len || (!pairs && n_pairs) || (!out && n_pairs)) return fail(nullptr, SVP_ERR_ARG, "null argument");
+    svp_handle pseudo;                                   // never touches CUDA: only the fields plan_pair() reads
+    std::string why;
+    int rc = make_consts(*scoring, pseudo.cs, why);
+    if (rc != SVP_OK) return fail(nullptr, rc, why);
+    pseudo.max_smem_optin = 232448;                      // 227 KB: cudaDevAttrMaxSharedMemoryPerBlockOptin of sm_100
+    read_env_knobs(&pseudo);
+    const bool latency = (long)n_pairs <= pseudo.latency_pairs;
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+        Task t;
+        plan_pair(&pseudo, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, false, t);
+        svp_pair_plan& o = out[k];
+        memset(&o, 0, sizeof(o));
+        if (t.flags & TASK_INVALID) { o.flags = SVP_PLAN_INVALID; continue; }
+        const int kp = kp_of(t), cl = cluster_of(t);
+        const int nw = cl > 1 ? 16 : (t.band_w + 128 * kp - 1) / (128 * kp);
+        o.kp = (uint32_t)kp; o.warps = (uint32_t)nw; o.cluster = (uint32_t)cl;
+        o.flags = ((t.flags & TASK_S32) ? SVP_PLAN_S32 : 0u) | ((t.flags & TASK_REBASE) ? SVP_PLAN_REBASE : 0u) |
+                  ((t.flags & TASK_RING) ? SVP_PLAN_WINDOWS : 0u) | (pseudo.cs.general ? SVP_PLAN_GENERAL : 0u);
+        o.smem_bytes = (uint32_t)smem_need(t, pseudo.cs, nw);
+        if (!(t.flags & TASK_RING) && o.smem_bytes > (uint32_t)pseudo.max_smem_optin) o.flags |= SVP_PLAN_TOO_LONG;
+        o.cells = t.cells;
+        o.tb_bytes = tb_bytes_of(t);
+    }
+    return SVP_OK;
 }
 
 extern "C" int svp_align_batch_device(svp_handle* h, const uint8_t* d_packed_seqs, size_t packed_bytes,

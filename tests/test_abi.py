@@ -139,3 +139,76 @@ def test_native_ava_pairs_several_containers_in_one_table():
         base += len(reads)
         slot += int(ref["cigar_cap"].sum())
     assert words == slot
+
+
+# ---------------------------------------------------------------------------------------------
+# the planner, host only (svp_plan_pairs): which kernel family / geometry a pair gets
+# ---------------------------------------------------------------------------------------------
+
+def _plan(lens, specs, preset="map-ont", scoring=None):
+    from svirlpool_b200 import ava
+    lens = np.asarray(lens, dtype=np.uint32)
+    nbytes = ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
+    off = np.concatenate(([0], np.cumsum(nbytes)[:-1])).astype(np.uint64)
+    pairs = np.zeros(len(specs), dtype=_abi.PAIR_DTYPE)
+    pos = 0
+    for k, (q, t, lo, w) in enumerate(specs):
+        cap = ava.cigar_cap_for(int(lens[min(q, len(lens) - 1)]), int(lens[min(t, len(lens) - 1)]))
+        pairs[k] = (q, t, lo, w, 0, pos, cap, 0)
+        pos += cap
+    sc = scoring if scoring is not None else aligner.scoring_preset(preset)
+    return aligner.plan_pairs(sc, int(nbytes.sum()) + 16, off, lens, pairs, pos), pairs, lens
+
+
+def test_planner_kernel_families(monkeypatch):
+    from svirlpool_b200 import scheduler
+    from svirlpool_b200._abi import PLAN_GENERAL, PLAN_INVALID, PLAN_REBASE, PLAN_S32, PLAN_WINDOWS
+    for var in ("SVP_NO_REBASE", "SVP_RING_MIN", "SVP_FORCE_RING", "SVP_FORCE_GENERAL", "SVP_LATENCY_PAIRS", "SVP_KP_MASK"):
+        monkeypatch.delenv(var, raising=False)
+    lens = [8000, 8100, 1000, 1100, 20000, 21000, 130000, 120000]
+    specs = [(0, 1, -462, 1024),        # 8 kb reads, band 1024: one KP = 8 warp, windows (16 KB of images for one warp)
+             (2, 3, -206, 512),         # 1 kb reads, band 512: one KP = 4 warp, whole images
+             (0, 1, -1000, 2048),       # two KP = 8 warps
+             (0, 1, -700, 1536),        # three KP = 4 warps beat two KP = 8 warps
+             (4, 5, -500, 2048),        # 20 kb reads: scores leave the s16 range -> rebased 16-bit lanes
+             (0, 1, -7999, 20000),      # band beyond one CTA (16 384 diagonals): a cluster of 2 CTAs
+             (6, 7, -768, 1536),        # 130 kb x 120 kb: whole images cannot fit -> windows, rebased
+             (0, 1, -462, 1000),        # band not a multiple of 32
+             (0, 1, -7999, 131072 + 64),  # wider than a cluster of 8 CTAs covers
+             (0, 9, -462, 1024)]        # sequence index out of range
+    plan, pairs, L = _plan(lens, specs)
+    fam = [(int(p["flags"]), int(p["kp"]), int(p["warps"]), int(p["cluster"])) for p in plan]
+    assert fam[0] == (PLAN_WINDOWS, 8, 1, 1)
+    assert fam[1] == (0, 4, 1, 1)
+    assert fam[2] == (PLAN_WINDOWS, 8, 2, 1)
+    assert fam[3] == (PLAN_WINDOWS, 4, 3, 1)
+    assert fam[4] == (PLAN_REBASE | PLAN_WINDOWS, 8, 2, 1)
+    assert fam[5][1:] == (8, 16, 2) and not fam[5][0] & (PLAN_S32 | PLAN_REBASE)
+    assert fam[6] == (PLAN_REBASE | PLAN_WINDOWS, 4, 3, 1) and plan[6]["smem_bytes"] < 16384
+    assert [f[0] for f in fam[7:]] == [PLAN_INVALID] * 3
+    for k in range(7):                  # cells = the closed form the scheduler uses; 1 traceback byte per cell (+ virtual cells)
+        q, t, lo, w = specs[k]
+        cells = scheduler.band_cells(int(L[q]), int(L[t]), lo, w)
+        assert int(plan[k]["cells"]) == cells and cells <= int(plan[k]["tb_bytes"])
+        if k != 5:                      # (the band of pair 5 is mostly outside the matrix: its rows are mostly virtual cells)
+            assert int(plan[k]["tb_bytes"]) <= 1.35 * cells + 64 * w
+    # the same long pair on 32-bit lanes when the rebase is switched off, and under general scoring
+    monkeypatch.setenv("SVP_NO_REBASE", "1")
+    p2, _, _ = _plan(lens, [specs[4], specs[6]])
+    assert [int(x["flags"]) for x in p2] == [PLAN_S32, PLAN_S32 | PLAN_WINDOWS] and [int(x["kp"]) for x in p2] == [4, 4]
+    monkeypatch.delenv("SVP_NO_REBASE")
+    p3, _, _ = _plan(lens, [specs[1], specs[0]], preset="last")          # largest matrix entry 6: 8 kb reads already leave the s16 range
+    assert [int(x["flags"]) for x in p3] == [PLAN_GENERAL, PLAN_GENERAL | PLAN_S32] and [int(x["warps"]) for x in p3] == [1, 2]
+    # every pair on windows when asked to
+    monkeypatch.setenv("SVP_RING_MIN", "0")
+    p4, _, _ = _plan(lens, [specs[1]])
+    assert int(p4[0]["flags"]) == PLAN_WINDOWS
+
+
+def test_planner_rejects_unsupported_scoring():
+    s = aligner.scoring_preset("map-ont").copy()
+    s["matrix"][0][0] = 60                       # 2 * (60 + 6) > 127: one-byte traceback bound
+    lens = np.array([100, 100], dtype=np.uint32)
+    with pytest.raises(aligner.AlignerError) as e:
+        aligner.plan_pairs(s, 64, np.array([0, 32], dtype=np.uint64), lens, np.zeros(0, dtype=_abi.PAIR_DTYPE), 1)
+    assert e.value.returncode == _abi.SVP_ERR_UNSUPPORTED
