@@ -228,6 +228,48 @@ def ava_align(engine, reads: dict[str, str], strands: dict[str, str] | None = No
     return ava_records(names, lens, meta, res, cig, min_score)
 
 
+def ava_align_many(engine, containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None = None,
+                   offsets: list[dict[str, int] | None] | None = None, slack: int = 300, granule: int = 32, full: bool = False,
+                   min_score: int = MIN_DP_SCORE) -> list[list[AlignedRecord]]:
+    """All-vs-all alignment of MANY containers in one engine call — the shape the GPU wants (a crs_to_batches batch holds ~100
+    containers, candidateregions/crs_to_batches.py:61-146, and the reference aligns them one minimap2 process at a time,
+    consensus.py:3270-3348). One sequence table over all reads (svp_pack_2bit), one svp_ava_pairs call per container with its
+    seq_base and the running CIGAR word count, one align_batch; returns per container exactly what ava_align() returns for it."""
+    from .aligner import ava_pairs_native, pack_2bit_native
+    n_c = len(containers)
+    strands = strands if strands is not None else [None] * n_c
+    offsets = offsets if offsets is not None else [None] * n_c
+    all_names, all_seqs, spans = [], [], []
+    for reads in containers:
+        spans.append((len(all_seqs), len(reads)))
+        all_names += list(reads)
+        all_seqs += [reads[k] for k in reads]
+    packed, off, lens = pack_2bit_native(all_seqs)
+    chunks, bounds, words = [], [0], 0
+    for (base, n), st, of in zip(spans, strands, offsets):
+        names = all_names[base:base + n]
+        if n < 2:
+            bounds.append(bounds[-1])
+            continue
+        order = np.array(sorted(range(n), key=lambda k: names[k]), dtype=np.uint32)
+        strand = None if st is None else np.array([1 if st[x] == "+" else -1 for x in names], dtype=np.int8)
+        offs = None if of is None else np.array([of[x] for x in names], dtype=np.int32)
+        pairs, words = ava_pairs_native(lens, order, strand, offs, base, n, slack, granule, full, cigar_start=words)
+        chunks.append(pairs)
+        bounds.append(bounds[-1] + len(pairs))
+    if not chunks:
+        return [[] for _ in containers]
+    batch = PairBatch(all_names, all_seqs, packed, off, lens, np.concatenate(chunks), max(words, 1))
+    res, cig = run_batch(engine, batch)
+    out = []
+    for c, (base, n) in enumerate(spans):
+        lo, hi = bounds[c], bounds[c + 1]
+        p = batch.pairs[lo:hi]
+        meta = list(zip((p["q"] - base).tolist(), (p["t"] - base).tolist(), (p["flags"] & PAIR_REVCOMP).astype(bool).tolist()))
+        out.append(ava_records(all_names[base:base + n], lens[base:base + n].tolist(), meta, res[lo:hi], cig, min_score) if hi > lo else [])
+    return out
+
+
 def ava_records(names, lens, meta, res, cig, min_score: int = MIN_DP_SCORE) -> list[AlignedRecord]:
     best: dict[tuple[int, int], int] = {}
     for k, (q, t, rc) in enumerate(meta):

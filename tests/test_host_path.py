@@ -240,3 +240,31 @@ def test_find_representative_read_rank_sum_medoid():
     # similarity and alignment length disagree (c: ranks 0 + 1, b: 2 + 0, a: 1 + 2): the smallest rank sum wins
     sim2 = sim.copy(); sim2[0, 1] = sim2[1, 0] = 0.5; sim2[0, 2] = sim2[2, 0] = 0.95
     assert consensus.find_representative_read(sim2, lens, names, ["a", "b", "c"]) == "c"
+
+
+def test_ava_align_many_equals_per_container_calls(oracle):
+    """ava.ava_align_many: several containers through ONE engine call (one sequence table, svp_ava_pairs per container) return,
+    per container, the records of ava.ava_align — incl. a container with a single read and one with unknown strands."""
+    rng = np.random.default_rng(31)
+    containers, strands = [], []
+    for c, n_reads in enumerate((4, 1, 3, 5)):
+        tmpl = "".join("ACGT"[k] for k in rng.integers(0, 4, 900 + 100 * c))
+        reads, st = {}, {}
+        for r in range(n_reads):
+            seq = list(tmpl[int(rng.integers(0, 40)):len(tmpl) - int(rng.integers(0, 40))])
+            for pos in rng.choice(len(seq), 30, replace=False):
+                seq[pos] = "ACGT"[(("ACGT".index(seq[pos])) + 1 + int(rng.integers(3))) % 4]
+            s = "".join(seq)
+            rev = bool(rng.integers(2))
+            name = f"c{c}_read{int(rng.integers(1000)):03d}_{r}"
+            reads[name] = s.translate(str.maketrans("ACGT", "TGCA"))[::-1] if rev else s
+            st[name] = "-" if rev else "+"
+        containers.append(reads)
+        strands.append(None if c == 2 else st)
+    many = ava.ava_align_many(oracle, containers, strands)
+    assert len(many) == 4 and many[1] == []
+    for reads, st, got in zip(containers, strands, many):
+        one = ava.ava_align(oracle, reads, strands=st)
+        key = lambda r: (r.query_name, r.reference_name, r.reference_start, r.flag, r.cigartuples, r.tags)
+        assert [key(r) for r in got] == [key(r) for r in one]
+    assert sum(len(x) for x in many) >= 6 + 3 + 10
