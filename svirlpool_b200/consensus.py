@@ -137,6 +137,48 @@ def final_consensus(engine, samplename: str, min_indel_size: int, min_bnd_size: 
                                      cut_read_alignment_signals=signals, intervals_cutread_alignments=intervals)
 
 
+def add_cutread_alignments_to_consensus_inplace(alns: list[AlignedRecord], consensus, min_indel_size: int, min_bnd_size: int,
+                                                samplename: str) -> None:
+    """Append the SV signals and reference intervals of further read alignments to a Consensus record
+    (consensus.py:919-943; same signature)."""
+    consensus.cut_read_alignment_signals.extend(
+        parse_ReadAlignmentSignals_from_alignment(samplename, aln, min_indel_size, min_bnd_size) for aln in alns)
+    consensus.intervals_cutread_alignments.extend((aln.reference_start, aln.reference_end, aln.query_name, aln.is_forward) for aln in alns)
+
+
+def add_unaligned_reads_to_consensuses_inplace(engine, samplename: str, consensus_objects: dict, pool: dict[str, str],
+                                               min_indel_size: int, min_bnd_size: int) -> dict[str, str]:
+    """Re-home the reads no consensus used (consensus.py:2050-2131): every read of `pool` is aligned to EVERY consensus
+    sequence (the reference: one `minimap2 -x map-ont --secondary=no --sam-hit-only -U 25,75 -H` run of the reads against a
+    FASTA of all consensuses) and given to the consensus of its primary, i.e. best-scoring, alignment; that consensus receives
+    the read's alignment signals and intervals. One engine call per round for all reads x consensuses, both strands
+    (ava.map_jobs). Reads without a hit stay unassigned. Returns {read name: consensus ID} (the reference returns None and
+    works through the side effect only; the side effect is the same). `pool`: read name -> sequence."""
+    if len(consensus_objects) == 0:
+        raise AssertionError("consensus_sequences must contain at least one consensus object")
+    if len(pool) == 0:
+        return {}
+    ids = list(consensus_objects)
+    targets = [consensus_objects[c].consensus_sequence for c in ids]
+    jobs = [ava.MapJob(name=name, seq=seq, target=k) for name, seq in pool.items() for k in range(len(ids))]
+    records = ava.map_jobs(engine, jobs, ids, targets)
+    # a read's primary record per consensus; the consensus with the highest alignment score wins, the first one on ties
+    best: dict[str, tuple[int, int]] = {}
+    for rec in records:
+        if rec.is_unmapped or rec.is_supplementary:
+            continue
+        score, k = int(rec.tags.get("AS", 0)), ids.index(rec.reference_name)
+        cur = best.get(rec.query_name)
+        if cur is None or score > cur[0] or (score == cur[0] and k < cur[1]):
+            best[rec.query_name] = (score, k)
+    redistribution = {name: ids[k] for name, (_score, k) in best.items()}
+    for cid, cons in consensus_objects.items():
+        assigned = [rec for rec in records if redistribution.get(rec.query_name) == cid and rec.reference_name == cid]
+        if assigned:
+            add_cutread_alignments_to_consensus_inplace(assigned, cons, min_indel_size, min_bnd_size, samplename)
+    return redistribution
+
+
 # ---------------------------------------------------------------------------------------------
 # read cutting: the reads of a container are trimmed to its candidate regions before the all-vs-all
 # (consensus.py:382-586); the cut reads are what BASELINE config 2's "30 reads x 8 kb" are

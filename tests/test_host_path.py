@@ -268,3 +268,39 @@ def test_ava_align_many_equals_per_container_calls(oracle):
         key = lambda r: (r.query_name, r.reference_name, r.reference_start, r.flag, r.cigartuples, r.tags)
         assert [key(r) for r in got] == [key(r) for r in one]
     assert sum(len(x) for x in many) >= 6 + 3 + 10
+
+
+def test_add_unaligned_reads_to_consensuses_inplace(oracle):
+    """Unused reads are re-homed to the consensus they align best to (reference: consensus.py:2050-2131): reads of two
+    haplotypes that differ by a 60-base deletion go to their own consensus and carry no distortion there; an unrelated read stays
+    unassigned; signals and intervals are appended to what the consensus already holds."""
+    from svirlpool_b200 import consensus_class
+    rng = np.random.default_rng(41)
+    hap0 = "".join("ACGT"[k] for k in rng.integers(0, 4, 1500))
+    hap1 = hap0[:700] + hap0[760:]
+
+    def noisy(seq, n_sub=12):
+        s = list(seq)
+        for pos in rng.choice(len(s), n_sub, replace=False):
+            s[pos] = "ACGT"[(("ACGT".index(s[pos])) + 1 + int(rng.integers(3))) % 4]
+        return "".join(s)
+
+    cons = {cid: consensus_class.Consensus(ID=cid, crIDs=[3], original_regions=[("chr1", 1000, 2500)], consensus_sequence=seq)
+            for cid, seq in (("3.0", hap0), ("3.1", hap1))}
+    cons["3.0"].intervals_cutread_alignments.append((0, 1500, "old_read", True))
+    pool = {"r_h0_a": noisy(hap0[20:1480]), "r_h0_b": util.reverse_complement(noisy(hap0[:1450])), "r_h1_a": noisy(hap1[10:]),
+            "junk": "".join("ACGT"[k] for k in rng.integers(0, 4, 800))}
+    out = consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", cons, pool, min_indel_size=8, min_bnd_size=100)
+    assert out == {"r_h0_a": "3.0", "r_h0_b": "3.0", "r_h1_a": "3.1"}
+    assert cons["3.0"].get_used_readnames() == {"old_read", "r_h0_a", "r_h0_b"} and cons["3.1"].get_used_readnames() == {"r_h1_a"}
+    assert {i[2]: i[3] for i in cons["3.0"].intervals_cutread_alignments}["r_h0_b"] is False        # reverse-strand read
+    assert len(cons["3.0"].cut_read_alignment_signals) == 2 and len(cons["3.1"].cut_read_alignment_signals) == 1
+    assert cons["3.0"].get_consensus_distortions() == [] and cons["3.1"].get_consensus_distortions() == []
+    # against the wrong haplotype only, the same read shows the 60-base event
+    only0 = {"3.0": consensus_class.Consensus(ID="3.0", crIDs=[3], original_regions=[("chr1", 1000, 2500)], consensus_sequence=hap0)}
+    consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", only0, {"r_h1_a": pool["r_h1_a"]}, 8, 100)
+    d = only0["3.0"].get_consensus_distortions()
+    assert len(d) == 1 and d[0].size == 60 and d[0].type == 1 and abs(d[0].position - 700) <= 5
+    with pytest.raises(AssertionError):
+        consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", {}, pool, 8, 100)
+    assert consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", cons, {}, 8, 100) == {}
