@@ -228,13 +228,11 @@ def ava_align(engine, reads: dict[str, str], strands: dict[str, str] | None = No
     return ava_records(names, lens, meta, res, cig, min_score)
 
 
-def ava_align_many(engine, containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None = None,
-                   offsets: list[dict[str, int] | None] | None = None, slack: int = 300, granule: int = 32, full: bool = False,
-                   min_score: int = MIN_DP_SCORE) -> list[list[AlignedRecord]]:
-    """All-vs-all alignment of MANY containers in one engine call — the shape the GPU wants (a crs_to_batches batch holds ~100
-    containers, candidateregions/crs_to_batches.py:61-146, and the reference aligns them one minimap2 process at a time,
-    consensus.py:3270-3348). One sequence table over all reads (svp_pack_2bit), one svp_ava_pairs call per container with its
-    seq_base and the running CIGAR word count, one align_batch; returns per container exactly what ava_align() returns for it."""
+def build_ava_many(containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None, offsets: list[dict[str, int] | None] | None,
+                   slack: int, granule: int, full: bool) -> tuple[PairBatch | None, list[tuple[int, int]], list[int]]:
+    """One batch over MANY containers: one sequence table over all reads (svp_pack_2bit), one svp_ava_pairs call per container
+    with its seq_base and the running CIGAR word count. Returns (batch or None when no container has two reads,
+    [(first sequence, read count)] per container, pair index bounds per container)."""
     from .aligner import ava_pairs_native, pack_2bit_native
     n_c = len(containers)
     strands = strands if strands is not None else [None] * n_c
@@ -258,15 +256,47 @@ def ava_align_many(engine, containers: list[dict[str, str]], strands: list[dict[
         chunks.append(pairs)
         bounds.append(bounds[-1] + len(pairs))
     if not chunks:
+        return None, spans, bounds
+    return PairBatch(all_names, all_seqs, packed, off, lens, np.concatenate(chunks), max(words, 1)), spans, bounds
+
+
+def ava_align_many(engine, containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None = None,
+                   offsets: list[dict[str, int] | None] | None = None, slack: int = 300, granule: int = 32, full: bool = False,
+                   min_score: int = MIN_DP_SCORE) -> list[list[AlignedRecord]]:
+    """All-vs-all alignment of MANY containers in one engine call — the shape the GPU wants (a crs_to_batches batch holds ~100
+    containers, candidateregions/crs_to_batches.py:61-146, and the reference aligns them one minimap2 process at a time,
+    consensus.py:3270-3348). Returns per container exactly what ava_align() returns for it."""
+    batch, spans, bounds = build_ava_many(containers, strands, offsets, slack, granule, full)
+    if batch is None:
         return [[] for _ in containers]
-    batch = PairBatch(all_names, all_seqs, packed, off, lens, np.concatenate(chunks), max(words, 1))
     res, cig = run_batch(engine, batch)
     out = []
     for c, (base, n) in enumerate(spans):
         lo, hi = bounds[c], bounds[c + 1]
         p = batch.pairs[lo:hi]
         meta = list(zip((p["q"] - base).tolist(), (p["t"] - base).tolist(), (p["flags"] & PAIR_REVCOMP).astype(bool).tolist()))
-        out.append(ava_records(all_names[base:base + n], lens[base:base + n].tolist(), meta, res[lo:hi], cig, min_score) if hi > lo else [])
+        out.append(ava_records(batch.names[base:base + n], batch.seq_len[base:base + n].tolist(), meta, res[lo:hi], cig, min_score)
+                   if hi > lo else [])
+    return out
+
+
+def ava_summary_many(engine, containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None = None,
+                     offsets: list[dict[str, int] | None] | None = None, slack: int = 300, granule: int = 32, full: bool = False
+                     ) -> list[tuple[list[str], np.ndarray, np.ndarray, np.ndarray]]:
+    """ava_summary() for MANY containers in one CIGAR-free engine call: per container (read names, query index, target index,
+    result rows), indices local to the container."""
+    from ._abi import RESULT_DTYPE
+    batch, spans, bounds = build_ava_many(containers, strands, offsets, slack, granule, full)
+    res = run_summary(engine, batch) if batch is not None else np.zeros(0, dtype=RESULT_DTYPE)
+    out = []
+    for c, (base, n) in enumerate(spans):
+        lo, hi = bounds[c], bounds[c + 1]
+        names = list(containers[c])
+        if hi == lo:
+            out.append((names, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=RESULT_DTYPE)))
+            continue
+        p = batch.pairs[lo:hi]
+        out.append((names, p["q"].astype(np.int64) - base, p["t"].astype(np.int64) - base, res[lo:hi]))
     return out
 
 

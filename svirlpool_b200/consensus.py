@@ -107,6 +107,19 @@ def ava_similarity_summary(engine, reads: dict[str, str], strands: dict[str, str
     return sim, names, aln_len
 
 
+def ava_similarity_summary_many(engine, containers: list[dict[str, str]], strands: list[dict[str, str] | None] | None = None,
+                                min_bnd_size: int = 100, slack: int = 300, granule: int = 512
+                                ) -> list[tuple[np.ndarray, list[str], np.ndarray]]:
+    """ava_similarity_summary() for a whole batch of containers in ONE engine call (what a consensus job over a crs_to_batches
+    batch does on the GPU): per container (similarity matrix, read names, alignment-length matrix)."""
+    out = []
+    for reads, (names, qi, ti, res) in zip(containers, ava.ava_summary_many(engine, containers, strands, slack=slack, granule=granule)):
+        sim, aln_len = consensus_lib.similarity_from_summary(names, {n: len(s) for n, s in reads.items()}, qi, ti, res,
+                                                             min_bnd_size=min_bnd_size)
+        out.append((sim, names, aln_len))
+    return out
+
+
 def align_reads_to_consensus(engine, samplename: str, reads: dict[str, str], consensus_name: str, consensus_seq: str,
                              min_signal_size: int = 8, min_bnd_size: int = 100
                              ) -> tuple[list[AlignedRecord], list[ReadAlignmentSignals]]:

@@ -304,3 +304,19 @@ def test_add_unaligned_reads_to_consensuses_inplace(oracle):
     with pytest.raises(AssertionError):
         consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", {}, pool, 8, 100)
     assert consensus.add_unaligned_reads_to_consensuses_inplace(oracle, "S", cons, {}, 8, 100) == {}
+
+
+def test_similarity_of_many_containers_in_one_call(oracle):
+    """consensus.ava_similarity_summary_many == consensus.ava_similarity_summary per container (matrices bit-identical), and ==
+    the record pipeline ava_similarity(densities_weight=0)."""
+    regions = [synth.region_config2(r, n_reads=n, mean_len=1200, sd_len=60) for r, n in ((0, 6), (1, 1), (2, 5))]
+    containers = [reg.read_strings() for reg in regions]
+    strands = [dict(zip(reg.names, reg.strands)) for reg in regions]
+    many = consensus.ava_similarity_summary_many(oracle, containers, strands, granule=64)
+    assert len(many) == 3 and many[1][0].shape == (1, 1)
+    for reads, st, (sim, names, aln_len) in zip(containers, strands, many):
+        sim1, names1, len1 = consensus.ava_similarity_summary(oracle, reads, strands=st, granule=64)
+        assert names == names1 and np.array_equal(sim, sim1) and np.array_equal(aln_len, len1)
+        if len(reads) > 1:
+            sim2, names2, _recs = consensus.ava_similarity(oracle, reads, strands=st, densities_weight=0.0, granule=64)
+            assert names2 == names and np.allclose(sim, sim2, rtol=1e-12, atol=0)
