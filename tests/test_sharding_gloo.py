@@ -2,6 +2,8 @@
 engine and gather on rank 0; the result must equal the single-process run."""
 import os
 import pickle
+
+import numpy as np
 import subprocess
 import sys
 import textwrap
@@ -30,10 +32,17 @@ WORKER = textwrap.dedent("""
         sim, names, recs = consensus.ava_similarity(eng, reg.read_strings(), strands=dict(zip(reg.names, reg.strands)))
         return (rid, names, np.round(sim, 12).tolist(), [(r.query_name, r.reference_name, r.reference_start, r.cigarstring) for r in recs])
 
+    def work_many(rids):
+        regs = [synth.region_config2(rid, n_reads=5, mean_len=700, sd_len=200) for rid in rids]
+        res = consensus.ava_similarity_summary_many(eng, [r.read_strings() for r in regs], [dict(zip(r.names, r.strands)) for r in regs],
+                                                    granule=32)
+        return [(rid, names, np.round(sim, 12).tolist(), aln_len.tolist()) for rid, (sim, names, aln_len) in zip(rids, res)]
+
     out = sharding.run_sharded(ids, costs, work, dist if world > 1 else None)
+    out_many = sharding.run_sharded(ids, costs, None, dist if world > 1 else None, process_many=work_many)
     if out is not None:
         with open(sys.argv[1], "wb") as f:
-            pickle.dump({{"out": out, "bins": scheduler.lpt_assign(costs, max(world, 1))}}, f)
+            pickle.dump({{"out": out, "out_many": out_many, "bins": scheduler.lpt_assign(costs, max(world, 1))}}, f)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 """)
@@ -56,5 +65,9 @@ def run(tmp_path, world):
 def test_two_ranks_equal_one_rank(tmp_path):
     one, two = run(tmp_path, 1), run(tmp_path, 2)
     assert one["out"] == two["out"]
+    # one engine call per rank (process_many): same matrices whatever the sharding, and the similarity equals the record pipeline's
+    assert one["out_many"] == two["out_many"] and [r[0] for r in two["out_many"]] == [11, 12, 13, 14, 15]
+    for a, b in zip(one["out"], one["out_many"]):
+        assert a[1] == b[1] and np.allclose(np.array(a[2]), np.array(b[2]), rtol=1e-9, atol=1e-12)
     assert [r[0] for r in two["out"]] == [11, 12, 13, 14, 15]
     assert sorted(k for b in two["bins"] for k in b) == [0, 1, 2, 3, 4] and all(two["bins"])
