@@ -404,6 +404,28 @@ def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[
     return [r for _t, r in out]
 
 
+def map_queries_to_best_target(engine, queries: dict[str, str], targets: dict[str, str], min_score: int = MIN_DP_SCORE,
+                               min_flank: int = 40, max_rounds: int = 8, granule: int = 32
+                               ) -> tuple[list[AlignedRecord], dict[str, str]]:
+    """Every query vs EVERY target, keeping — like `minimap2 --secondary=no` against a multi-sequence reference
+    (consensus.py:2089-2096: reads vs a FASTA of all consensuses) — only the records on the target of the query's best-scoring
+    primary alignment (first target on ties); the primaries on the other targets would be secondary alignments there.
+    One engine call per round for all queries x targets. Returns (records sorted by (target, position), {query: target})."""
+    names = list(targets)
+    jobs = [MapJob(name=q, seq=seq, target=k) for q, seq in queries.items() for k in range(len(names))]
+    records = map_jobs(engine, jobs, names, [targets[n] for n in names], min_score, min_flank, max_rounds, granule)
+    best: dict[str, tuple[int, int]] = {}
+    for rec in records:
+        if rec.is_unmapped or rec.is_supplementary:
+            continue
+        score, k = int(rec.tags.get("AS", 0)), names.index(rec.reference_name)
+        cur = best.get(rec.query_name)
+        if cur is None or score > cur[0] or (score == cur[0] and k < cur[1]):
+            best[rec.query_name] = (score, k)
+    chosen = {q: names[k] for q, (_s, k) in best.items()}
+    return [rec for rec in records if chosen.get(rec.query_name) == rec.reference_name], chosen
+
+
 def map_queries(engine, queries: dict[str, str], target_name: str, target: str, min_score: int = MIN_DP_SCORE,
                 min_flank: int = 40, max_rounds: int = 8, granule: int = 32) -> list[AlignedRecord]:
     """Every query vs ONE target over the full matrix (reads -> consensus, consensus.py:851-857); see map_jobs()."""

@@ -171,22 +171,10 @@ def add_unaligned_reads_to_consensuses_inplace(engine, samplename: str, consensu
         raise AssertionError("consensus_sequences must contain at least one consensus object")
     if len(pool) == 0:
         return {}
-    ids = list(consensus_objects)
-    targets = [consensus_objects[c].consensus_sequence for c in ids]
-    jobs = [ava.MapJob(name=name, seq=seq, target=k) for name, seq in pool.items() for k in range(len(ids))]
-    records = ava.map_jobs(engine, jobs, ids, targets)
-    # a read's primary record per consensus; the consensus with the highest alignment score wins, the first one on ties
-    best: dict[str, tuple[int, int]] = {}
-    for rec in records:
-        if rec.is_unmapped or rec.is_supplementary:
-            continue
-        score, k = int(rec.tags.get("AS", 0)), ids.index(rec.reference_name)
-        cur = best.get(rec.query_name)
-        if cur is None or score > cur[0] or (score == cur[0] and k < cur[1]):
-            best[rec.query_name] = (score, k)
-    redistribution = {name: ids[k] for name, (_score, k) in best.items()}
+    records, redistribution = ava.map_queries_to_best_target(
+        engine, pool, {cid: cons.consensus_sequence for cid, cons in consensus_objects.items()})
     for cid, cons in consensus_objects.items():
-        assigned = [rec for rec in records if redistribution.get(rec.query_name) == cid and rec.reference_name == cid]
+        assigned = [rec for rec in records if rec.reference_name == cid]
         if assigned:
             add_cutread_alignments_to_consensus_inplace(assigned, cons, min_indel_size, min_bnd_size, samplename)
     return redistribution

@@ -81,10 +81,13 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
     coordinate-sorted BAM out, computed by the CUDA aligner instead of `minimap2 | samtools sort`.
 
     tech "ava-ont": all-vs-all of the reads (`reference` and `reads` are the same FASTA at the reference's
-    AVA call site, consensus.py:1378-1386); otherwise every read is mapped to every sequence of `reference`
-    (primary + supplementary records, `--secondary=no`). `threads`, `aln_args`, `logfile` and `timeout` are
-    accepted for signature compatibility (seeding options have no counterpart; the call is bounded by the
-    kernels, not by a child process). Failures raise aligner.AlignerError, a subprocess.CalledProcessError,
+    AVA call site, consensus.py:1378-1386); otherwise every read is mapped against every sequence of `reference` and keeps
+    the records on the sequence of its best primary alignment (primary + supplementary; what `--secondary=no` leaves of a
+    multi-sequence reference, consensus.py:2089-2096). Of `aln_args` only `-Y` has a counterpart (supplementary records
+    soft-clipped with the full read sequence instead of hard-clipped, consensus.py:851-857); `--sam-hit-only` and
+    `--secondary=no` are what the engine does anyway, seeding options (`-U`, `-H`, `-z`, `-r`) have none. `threads`,
+    `logfile` and `timeout` are accepted for signature compatibility (the call is bounded by the kernels, not by a child
+    process). Failures raise aligner.AlignerError, a subprocess.CalledProcessError,
     which the reference's callers already catch. `engine`: an Aligner to reuse; default one per call.
     Like the reference (`samtools index`, util.py:232-238) a `.bai` is written next to the BAM."""
     from . import ava, sam
@@ -102,12 +105,15 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
             records = ava.ava_align(engine, queries)
             lengths = {n: len(s) for n, s in queries.items()}
         else:
-            records = [r for name, seq in refs.items() for r in ava.map_queries(engine, queries, name, seq)]
+            records, _chosen = ava.map_queries_to_best_target(engine, queries, refs)
             lengths = {n: len(s) for n, s in refs.items()}
+        soft_supplementary = "-Y" in aln_args.split()
         for r in records:
             seq = queries[r.query_name]
             r.query_sequence = reverse_complement(seq) if r.is_reverse else seq
-            if r.is_supplementary:                      # hard-clipped records carry only the aligned part
+            if r.is_supplementary and soft_supplementary:
+                r.cigartuples = [(4 if op == 5 else op, n) for op, n in r.cigartuples]
+            elif r.is_supplementary:                    # hard-clipped records carry only the aligned part
                 a = r.cigartuples[0][1] if r.cigartuples[0][0] == 5 else 0
                 r.query_sequence = r.query_sequence[a:a + r.query_alignment_length]
         cmd = f"svirlpool_b200 -x {tech} {aln_args}".strip()

@@ -320,3 +320,33 @@ def test_similarity_of_many_containers_in_one_call(oracle):
         if len(reads) > 1:
             sim2, names2, _recs = consensus.ava_similarity(oracle, reads, strands=st, densities_weight=0.0, granule=64)
             assert names2 == names and np.allclose(sim, sim2, rtol=1e-12, atol=0)
+
+
+def test_file_seam_multi_reference_and_soft_supplementary(tmp_path, oracle):
+    """S1 seam against a FASTA of several sequences (reads vs all consensuses, consensus.py:2089-2096): `--secondary=no` keeps a
+    read's records on the sequence of its best primary alignment only; `-Y` makes supplementary records soft-clipped with the
+    full read sequence (consensus.py:851-857), without it they are hard-clipped."""
+    rng = np.random.default_rng(51)
+    a = "".join("ACGT"[k] for k in rng.integers(0, 4, 1600))
+    b = "".join("ACGT"[k] for k in rng.integers(0, 4, 1500))
+    inv = a[:500] + util.reverse_complement(a[500:1100]) + a[1100:]            # read with an inverted middle: 3 records on a
+    reads = {"on_a": a[100:1500], "on_b_rc": util.reverse_complement(b[50:1400]), "inv_a": inv}
+    ref_fa, reads_fa = tmp_path / "cons.fa", tmp_path / "reads.fa"
+    ref_fa.write_text(f">cA\n{a}\n>cB\n{b}\n")
+    reads_fa.write_text("".join(f">{n}\n{s}\n" for n, s in reads.items()))
+    out = {}
+    for tag, args in (("hard", "--secondary=no --sam-hit-only -U 25,75 -H"), ("soft", "-Y --sam-hit-only --secondary=no -U 10,25 -H")):
+        bam = tmp_path / f"{tag}.bam"
+        util.align_reads_with_minimap(reference=ref_fa, reads=reads_fa, bamout=bam, tech="map-ont", threads=1, aln_args=args, engine=oracle)
+        out[tag] = list(sam.read_alignments(bam))
+    for recs in out.values():
+        assert sorted((r.query_name, r.reference_name) for r in recs if not r.is_supplementary) == \
+               [("inv_a", "cA"), ("on_a", "cA"), ("on_b_rc", "cB")]
+        assert {r.reference_name for r in recs if r.query_name == "inv_a"} == {"cA"} and sum(r.query_name == "inv_a" for r in recs) == 3
+        assert next(r for r in recs if r.query_name == "on_b_rc").is_reverse
+    hard = [r for r in out["hard"] if r.is_supplementary]
+    soft = [r for r in out["soft"] if r.is_supplementary]
+    assert len(hard) == len(soft) == 2
+    assert all(5 in (r.cigartuples[0][0], r.cigartuples[-1][0]) and len(r.query_sequence) == r.query_alignment_length for r in hard)
+    assert all(4 in (r.cigartuples[0][0], r.cigartuples[-1][0]) and len(r.query_sequence) == len(inv) for r in soft)
+    assert [(r.reference_start, r.reference_end, r.is_reverse) for r in hard] == [(r.reference_start, r.reference_end, r.is_reverse) for r in soft]
