@@ -30,7 +30,7 @@ sys.path.insert(0, str(ROOT))
 
 N_REGIONS_CONFIG = 10_000
 METRIC = "gcups_ava_config2"
-SLACK, GRANULE = 300, 512
+SLACK, GRANULE = 300, 128
 
 
 def peaks() -> dict:

@@ -18,20 +18,23 @@ using namespace svp;
 namespace {
 
 // Kernel widths: KP packed registers per state array per thread = 4*KP diagonals per thread, 128*KP per
-// warp (KP = 4, 8, 12, 16 -> 512, 1024, 1536, 2048). A pair runs on the (KP, warps) combination that needs
-// the fewest issue slots for its band (choose_variant); single-warp CTAs need no barrier or mailbox.
+// warp (KP = 4 .. 8 -> 512, 640, 768, 896, 1024). A pair runs on the (KP, warps) combination that needs
+// the fewest issue slots for its band (choose_kp); single-warp CTAs need no mailbox. With only KP = 4 / 8 a band had
+// to be padded to 512 diagonals per warp: on config 2 (bands |dlen| + 600, median need 768) that was 30 % more cells
+// than the spec asks for.
 constexpr int S16_SCORE_LIMIT = 32000;
 static inline int max_warps_of(int kp) { return kp <= 8 ? 16 : 8; }
 // warp-instructions per step of the inner loop (SASS counts), used only to rank variants
 static inline int step_cost(int kp, int nwarp) { return 22 + kp * 25 / 2 + (nwarp > 1 ? 10 : 0); }
-static int g_kp_mask = -1;          // tuning aid: env SVP_KP_MASK, bit (KP/4 - 1) allows that KP (default: all)
+static int g_kp_mask = -1;          // tuning aid: env SVP_KP_MASK, bit (KP - 4) allows that KP (default: all)
 // latency = true (a call of few pairs, e.g. one container: the GPU is not full): the variant with the shortest step, i.e. more,
 // narrower warps per pair, instead of the one with the fewest issue slots
-static inline int choose_kp(uint32_t band_w, bool latency) {
-    if (g_kp_mask < 0) { const char* e = getenv("SVP_KP_MASK"); g_kp_mask = e ? atoi(e) : 15; if (!(g_kp_mask & 15)) g_kp_mask = 15; }
+static inline int choose_kp(uint32_t band_w, bool latency, bool two_piece) {
+    if (g_kp_mask < 0) { const char* e = getenv("SVP_KP_MASK"); g_kp_mask = e ? atoi(e) : 31; if (!(g_kp_mask & 31)) g_kp_mask = 31; }
     int best_kp = 0; long best_cost = 0;
-    for (int kp : { 4, 8 }) {      // KP 12 / 16 single-warp variants were measured slower on B200 (150-250 registers per thread)
-        if (!(g_kp_mask & (1 << (kp / 4 - 1)))) continue;
+    for (int kp : { 4, 5, 6, 7, 8 }) {      // KP 12 / 16 single-warp variants were measured slower on B200 (150-250 registers per thread)
+        if (!(g_kp_mask & (1 << (kp - 4)))) continue;
+        if ((kp & 3) && !two_piece) continue;          // one-piece simple scoring: KP = 4 / 8 only (fewer instantiations)
         if (band_w % (uint32_t)(4 * kp)) continue;
         const int nw = (int)((band_w + 128 * kp - 1) / (128 * kp));
         if (nw > max_warps_of(kp)) continue;
@@ -52,7 +55,10 @@ static inline int cluster_for(uint32_t band_w, int diag_per_warp) {
 }
 // steps per loop iteration of the kernel the pair runs on: 2*KP (s16 kernels), 16 (32-bit lane kernel, KP = 4 geometry)
 static inline int steps_per_iter_of(const Task& t) { return (t.flags & TASK_S32) ? 16 : 2 * kp_of(t); }
-static inline uint64_t tb_bytes_of(const Task& t) { return (uint64_t)t.n_iter * steps_per_iter_of(t) * (uint64_t)(t.band_w / 2); }
+// traceback rows of a pair: one row per step pair, one slot per thread (svp_kernels.cuh: store_pair)
+static inline uint64_t tb_bytes_of(const Task& t) {
+    return (uint64_t)t.n_iter * (steps_per_iter_of(t) / 2) * (uint64_t)(t.band_w / (4 * kp_of(t))) * (uint64_t)tb_slot_bytes(kp_of(t));
+}
 static inline uint64_t best_entries_of(const Task& t) { return (uint64_t)(t.band_w / (4 * kp_of(t))) * 2; }
 
 // dynamic shared memory of a pair's CTA (nw warps): sequence images (whole, or the sliding windows of the RING variants) + mailboxes
@@ -248,6 +254,11 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
                            SVP_SMEM(svp_fwd_kernel<K, false, false, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, false, false, R, G>)
 #define SVP_ATTR(K) SVP_ATTR2(K, false, false); SVP_ATTR2(K, false, true); SVP_ATTR2(K, true, false); SVP_ATTR2(K, true, true)
     SVP_ATTR(4); SVP_ATTR(8);
+#define SVP_ATTR2T(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>)
+#define SVP_ATTRT(K) SVP_ATTR2T(K, false, false); SVP_ATTR2T(K, false, true); SVP_ATTR2T(K, true, false); SVP_ATTR2T(K, true, true)
+    SVP_ATTRT(5); SVP_ATTRT(6); SVP_ATTRT(7);
+#undef SVP_ATTRT
+#undef SVP_ATTR2T
 #define SVP_ATTRC(R, G) SVP_SMEM(svp_fwd_kernel<8, true, true, true, R, G>); SVP_SMEM(svp_fwd_kernel<8, true, false, true, R, G>)
     SVP_ATTRC(false, false); SVP_ATTRC(false, true); SVP_ATTRC(true, false); SVP_ATTRC(true, true);
 #undef SVP_ATTRC
@@ -430,6 +441,7 @@ static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool 
 #define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) { svp_fwd_kernel<K, M, T, false, R, G><<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs); return; }
 #define SVP_F4(K, M, T) SVP_F(K, M, T, false, false) SVP_F(K, M, T, false, true) SVP_F(K, M, T, true, false) SVP_F(K, M, T, true, true)
         SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
+        SVP_F4(5, false, true) SVP_F4(5, true, true) SVP_F4(6, false, true) SVP_F4(6, true, true) SVP_F4(7, false, true) SVP_F4(7, true, true)
         SVP_F4(4, false, false) SVP_F4(4, true, false) SVP_F4(8, false, false) SVP_F4(8, true, false)
 #undef SVP_F4
 #undef SVP_F
@@ -518,7 +530,7 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     int kp, cl = 1;
     if (wide32 || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
     else {
-        kp = choose_kp(p.band_w, latency);
+        kp = choose_kp(p.band_w, latency, cs.two_piece != 0);
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
         if (!ring && cl) {
             const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));

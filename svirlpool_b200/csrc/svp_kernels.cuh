@@ -145,60 +145,91 @@ __device__ __forceinline__ void st_async_v4(uint32_t caddr, uint32_t a, uint32_t
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                  :: "r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cmbar) : "memory");
 }
-// Per-warp view of the cluster links. lo: this warp is the first of a CTA that has a lower neighbour (it receives that
-// neighbour's B entry in its local slot B[0] and sends its A entry to the neighbour's slot A[nwarp]); up: last warp of a CTA
-// with an upper neighbour (receives A[nwarp], sends to the neighbour's B[0]).
-struct ClusterLink {
-    bool lo, up;
-    uint32_t bar_lo, bar_up;            // local mbarriers of the two inbound slots
-    uint32_t rem_A, rem_bar_A;          // lower neighbour's A[nwarp] slot and its mbarrier (cluster addresses)
-    uint32_t rem_B, rem_bar_B;          // upper neighbour's B[0] slot and its mbarrier
-    uint32_t rem_wb_lo, rem_wb_up;      // score-offset slots (rebased kernel): lower neighbour's wb[nwarp+1], upper neighbour's wb[0]
-};
-// Shared memory behind the sequence images of a CTA with nwarp warps (all forward kernel families):
-//   A[0..nwarp], B[0..nwarp]  16-byte mailboxes          two mbarriers (cluster links)
+// Per-warp view of the step links. Every warp exchanges one 16-byte mailbox entry per step with each neighbouring warp:
+// its A entry (lane 0, after an A-step) travels DOWN to the warp below, its B entry (lane 31, after a B-step) UP to the warp
+// above. There is NO CTA barrier in the loop: every inbound slot has its own mbarrier, the writer completes one phase per step
+// pair, the reader waits for that phase only just before the one cell that consumes the entry (the last cell a step computes),
+// so a warp may run up to a whole step ahead of its neighbours. (One __syncthreads() per step made every warp wait for the
+// slowest of up to 16: ncu showed the multi-warp variants at 57-67 % of the ALU pipe with 1.1 warps per issue slot stalled on
+// the barrier, against 89 % for single-warp CTAs, profiles/ncu_fwd_r01_v6.json.)
+//   neighbour in the same CTA:        st.shared + mbarrier.arrive (release) by the writer lane, try_wait (acquire) by the reader
+//   neighbour in the next CTA of a cluster: st.async ... mbarrier::complete_tx::bytes into the neighbour's shared memory; the reader
+//                                     arms its mbarrier with arrive.expect_tx (STAS + SYNCS in SASS; no fence anywhere)
+// A slot is single-buffered: the exchange between two neighbours is a ping-pong, a writer produces entry t+1 only after it
+// consumed the entry its reader sent after reading entry t.
+// Shared memory behind the sequence images of a CTA (all forward kernel families), a fixed layout for up to 16 warps so
+// that every address is one per-warp register plus an immediate:
+//   A[0..16], B[0..16]        16-byte mailboxes (A[w]: written by warp w, read by warp w-1; B[w]: written by warp w-1, read by
+//                             warp w; A[nwarp] / B[0]: inbound slots of the cluster links)
+//   barA[0..16], barB[0..16]  one mbarrier per slot
 //   one 16-byte slot holding the "outside the band" constants (read by the last in-band thread when it is not lane 31)
-//   wb[0..nwarp+1]            per-warp score offsets of the rebased kernel (wb[0] / wb[nwarp+1]: the neighbouring CTAs' edge warps)
-__host__ __device__ __forceinline__ int mailbox_bytes(int nwarp) { return 2 * (nwarp + 1) * 16 + 16 + 16 + ((4 * (nwarp + 2) + 15) & ~15); }
-__device__ __forceinline__ uint32_t smem_bars(uint32_t s_mbA, int nwarp) { return s_mbA + 32u * (uint32_t)(nwarp + 1); }
-__device__ __forceinline__ uint32_t smem_cst(uint32_t s_mbA, int nwarp) { return smem_bars(s_mbA, nwarp) + 16u; }
-__device__ __forceinline__ uint32_t smem_wb(uint32_t s_mbA, int nwarp) { return smem_bars(s_mbA, nwarp) + 32u; }
+//   wb[0..17]                 per-warp score offsets of the rebased kernel (wb[0] / wb[nwarp+1]: the neighbouring CTAs' edge warps)
+constexpr uint32_t MB_SLOTS = 17, MB_A = 0, MB_B = MB_A + 16 * MB_SLOTS, MB_BARA = MB_B + 16 * MB_SLOTS, MB_BARB = MB_BARA + 8 * MB_SLOTS,
+                   MB_CST = MB_BARB + 8 * MB_SLOTS, MB_WB = MB_CST + 16, MB_BYTES = MB_WB + 80;
+__host__ __device__ __forceinline__ int mailbox_bytes(int) { return (int)MB_BYTES; }
+__device__ __forceinline__ uint32_t smem_cst(uint32_t s_mb, int) { return s_mb + MB_CST; }
+__device__ __forceinline__ uint32_t smem_wb(uint32_t s_mb, int) { return s_mb + MB_WB; }
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(addr) : "memory");
+}
+struct StepLink {
+    bool lo, up;                        // this warp has a lower / upper neighbour warp
+    bool rlo, rup;                      // ... and it lives in the neighbouring CTA of the cluster
+    uint32_t mw, bw;                    // s_mb + 16 * warp, s_mb + 8 * warp: this warp's mailbox / mbarrier slots at fixed offsets
+    uint32_t rem_A, rem_bar_A;          // lower neighbour CTA's A[nwarp] slot and its mbarrier (cluster addresses)
+    uint32_t rem_B, rem_bar_B;          // upper neighbour CTA's B[0] slot and its mbarrier
+    uint32_t rem_wb_lo, rem_wb_up;      // score-offset slots (rebased kernel): lower neighbour's wb[nwarp+1], upper neighbour's wb[0]
+    // inbound: B[warp] (from below), A[warp + 1] (from above); outbound: A[warp], B[warp + 1]
+    __device__ __forceinline__ uint32_t in_lo() const { return mw + MB_B; }
+    __device__ __forceinline__ uint32_t in_up() const { return mw + MB_A + 16u; }
+    __device__ __forceinline__ uint32_t out_A() const { return mw + MB_A; }
+    __device__ __forceinline__ uint32_t out_B() const { return mw + MB_B + 16u; }
+    __device__ __forceinline__ uint32_t bar_lo() const { return bw + MB_BARB; }
+    __device__ __forceinline__ uint32_t bar_up() const { return bw + MB_BARA + 8u; }
+    __device__ __forceinline__ uint32_t sig_A() const { return bw + MB_BARA; }
+    __device__ __forceinline__ uint32_t sig_B() const { return bw + MB_BARB + 8u; }
+};
 template <bool CL>
-__device__ __forceinline__ ClusterLink cluster_link(uint32_t s_mbA, uint32_t s_mbB, int warp, int nwarp, uint32_t crank, uint32_t csize) {
-    ClusterLink L{};
+__device__ __forceinline__ StepLink step_link(uint32_t s_mb, int warp, int nwarp, uint32_t crank, uint32_t csize) {
+    StepLink L{};
+    L.rlo = CL && warp == 0 && crank > 0;
+    L.rup = CL && warp == nwarp - 1 && crank + 1 < csize;
+    L.lo = warp > 0 || L.rlo;
+    L.up = warp < nwarp - 1 || L.rup;
+    L.mw = s_mb + 16u * (uint32_t)warp;
+    L.bw = s_mb + 8u * (uint32_t)warp;
     if (CL) {
-        const uint32_t bars = smem_bars(s_mbA, nwarp);                  // two mbarriers behind the mailboxes
-        const uint32_t wb = smem_wb(s_mbA, nwarp);
-        L.bar_lo = bars; L.bar_up = bars + 8u;
-        L.lo = warp == 0 && crank > 0;
-        L.up = warp == nwarp - 1 && crank + 1 < csize;
-        if (L.lo) { L.rem_A = mapa_shared(s_mbA + 16u * (uint32_t)nwarp, crank - 1); L.rem_bar_A = mapa_shared(bars + 8u, crank - 1);
-                    L.rem_wb_lo = mapa_shared(wb + 4u * (uint32_t)(nwarp + 1), crank - 1); }
-        if (L.up) { L.rem_B = mapa_shared(s_mbB, crank + 1); L.rem_bar_B = mapa_shared(bars, crank + 1); L.rem_wb_up = mapa_shared(wb, crank + 1); }
+        if (L.rlo) { L.rem_A = mapa_shared(s_mb + MB_A + 16u * (uint32_t)nwarp, crank - 1); L.rem_bar_A = mapa_shared(s_mb + MB_BARA + 8u * (uint32_t)nwarp, crank - 1);
+                     L.rem_wb_lo = mapa_shared(s_mb + MB_WB + 4u * (uint32_t)(nwarp + 1), crank - 1); }
+        if (L.rup) { L.rem_B = mapa_shared(s_mb + MB_B, crank + 1); L.rem_bar_B = mapa_shared(s_mb + MB_BARB, crank + 1); L.rem_wb_up = mapa_shared(s_mb + MB_WB, crank + 1); }
     }
     return L;
 }
-// mbarriers of the CTA's two inbound slots; called by one thread before the initial cluster-wide barrier
-template <bool CL> __device__ __forceinline__ void cluster_link_init(uint32_t s_mbB, int nwarp) {
-    if (CL) { const uint32_t bars = s_mbB + 16u * (uint32_t)(nwarp + 1); mbar_init(bars, 1); mbar_init(bars + 8u, 1); mbar_fence_init(); }
+// mbarriers of every slot (one arrival per phase: the writer lane's arrive, or — cluster links — the reader's arrive.expect_tx);
+// called by the first nwarp + 1 threads before the initial barrier
+template <bool CL> __device__ __forceinline__ void step_link_init(uint32_t s_mb, int idx) {
+    mbar_init(s_mb + MB_BARA + 8u * (uint32_t)idx, 1); mbar_init(s_mb + MB_BARB + 8u * (uint32_t)idx, 1);
+    if (CL) mbar_fence_init();
 }
 __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
 __device__ __forceinline__ void st_cluster_u32(uint32_t caddr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(caddr), "r"(v) : "memory"); }
-// before the edge cell of an A-step (lower neighbour's entry, sent after its previous B-step: A-step s > 0 waits for
-// phase s - 1) / of a B-step (upper neighbour's entry, sent after its A-step of the same index: phase s)
-template <bool CL> __device__ __forceinline__ void link_wait_lo(const ClusterLink& L, int lane, uint32_t parity) {
-    if (CL && L.lo) { if (lane == 0) mbar_expect_tx(L.bar_lo, 16u); mbar_wait(L.bar_lo, parity); }
+// before the edge cell of an A-step (lower neighbour's B entry of the previous step pair) / of a B-step (upper neighbour's A
+// entry of the same step pair); parity = parity of the step pair that produced the entry
+template <bool CL> __device__ __forceinline__ void link_wait_lo(const StepLink& L, int lane, uint32_t parity) {
+    if (L.lo) { if (CL && L.rlo && lane == 0) mbar_expect_tx(L.bar_lo(), 16u); mbar_wait(L.bar_lo(), parity); }
 }
-template <bool CL> __device__ __forceinline__ void link_wait_up(const ClusterLink& L, int lane, uint32_t parity) {
-    if (CL && L.up) { if (lane == 0) mbar_expect_tx(L.bar_up, 16u); mbar_wait(L.bar_up, parity); }
+template <bool CL> __device__ __forceinline__ void link_wait_up(const StepLink& L, int lane, uint32_t parity) {
+    if (L.up) { if (CL && L.rup && lane == 0) mbar_expect_tx(L.bar_up(), 16u); mbar_wait(L.bar_up(), parity); }
 }
-// mailbox stores of lane 0 after an A-step / of lane 31 after a B-step: local slot, or the neighbouring CTA's
-template <bool CL> __device__ __forceinline__ void mailbox_store_A(const ClusterLink& L, uint32_t s_local, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    if (CL && L.lo) st_async_v4(L.rem_A, a, b, c, d, L.rem_bar_A); else sts_v4(s_local, a, b, c, d);
+// mailbox stores of lane 0 after an A-step / of lane 31 after a B-step (called by that lane only)
+template <bool CL> __device__ __forceinline__ void mailbox_store_A(const StepLink& L, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (CL && L.rlo) st_async_v4(L.rem_A, a, b, c, d, L.rem_bar_A);
+    else if (L.lo) { sts_v4(L.out_A(), a, b, c, d); mbar_arrive(L.sig_A()); }
 }
-template <bool CL> __device__ __forceinline__ void mailbox_store_B(const ClusterLink& L, uint32_t s_local, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    if (CL && L.up) st_async_v4(L.rem_B, a, b, c, d, L.rem_bar_B); else sts_v4(s_local, a, b, c, d);
+template <bool CL> __device__ __forceinline__ void mailbox_store_B(const StepLink& L, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (CL && L.rup) st_async_v4(L.rem_B, a, b, c, d, L.rem_bar_B);
+    else if (L.up) { sts_v4(L.out_B(), a, b, c, d); mbar_arrive(L.sig_B()); }
 }
 // Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
 // base p (0-based) at byte SEQ_PAD + p, with 0x7E (NaN) in the bytes before and after; positions are
@@ -298,18 +329,27 @@ __device__ __forceinline__ void ring_fill_fast(const Task& tk, const uint8_t* __
     }
 }
 
-// low bytes of the 2*KP H values of one step -> this thread's 2*KP bytes of the traceback row
+// Traceback rows. One row = one STEP PAIR (an A-step and the B-step after it); inside a row thread g owns a slot of
+// tb_slot_bytes(KP) bytes holding the low bytes of its 4*KP H values: word k = [A slot k, B slot k, A slot KP+k, B slot KP+k],
+// i.e. the diagonals (2k, 2k+1, 2KP+2k, 2KP+2k+1) of the thread. A cell's left and up neighbours (the other set, one step
+// earlier) and its diagonal predecessor (same set, one step pair earlier) then lie in the same 32-byte sector of the previous
+// row — or, for a B cell, left / up in the cell's own sector — so a walk touches one new sector per cell instead of three
+// (the former one-row-per-step layout cost the traceback 270 DRAM bytes per path cell, profiles/ncu_tbw_r01_v3.json).
+// Slots are padded to a multiple of 8 bytes (KP = 5: 24, KP = 7: 32) so that the stores stay 8- or 16-byte vectors.
+__host__ __device__ constexpr int tb_slot_bytes(int kp) { return kp <= 4 ? 16 : (kp <= 6 ? 24 : 32); }
+// low bytes of the 2*KP A values and 2*KP B values of one step pair -> this thread's slot of the row
 template <int KP>
-__device__ __forceinline__ void store_row(uint8_t* p, const uint32_t (&Hs)[KP]) {
-    uint32_t w[KP / 2];
+__device__ __forceinline__ void store_pair(uint8_t* p, const uint32_t (&HA)[KP], const uint32_t (&HB)[KP]) {
+    constexpr int NW = tb_slot_bytes(KP) / 4;
+    uint32_t w[NW];
     #pragma unroll
-    for (int k = 0; k < KP / 2; ++k) w[k] = __byte_perm(Hs[2 * k], Hs[2 * k + 1], 0x6420);
-    if (KP % 8 == 0) {          // 16-byte aligned: g * 2KP is a multiple of 16
+    for (int k = 0; k < NW; ++k) w[k] = k < KP ? __byte_perm(HA[k < KP ? k : 0], HB[k < KP ? k : 0], 0x6240) : 0u;
+    if (NW % 4 == 0) {          // 16 / 32-byte slots: 16-byte aligned
         #pragma unroll
-        for (int k = 0; k < KP / 2; k += 4) __stcs(reinterpret_cast<uint4*>(p) + k / 4, make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]));
-    } else {                    // KP = 4, 12: 8-byte aligned
+        for (int k = 0; k < NW; k += 4) __stcs(reinterpret_cast<uint4*>(p) + k / 4, make_uint4(w[k], w[k + 1], w[k + 2], w[k + 3]));
+    } else {                    // 24-byte slots: 8-byte aligned
         #pragma unroll
-        for (int k = 0; k < KP / 2; k += 2) __stcs(reinterpret_cast<uint2*>(p) + k / 2, make_uint2(w[k], w[k + 1]));
+        for (int k = 0; k < NW; k += 2) __stcs(reinterpret_cast<uint2*>(p) + k / 2, make_uint2(w[k], w[k + 1]));
     }
 }
 
@@ -352,9 +392,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + (RING ? 0 : SEQ_PAD - 1);
     // mailboxes (MULTI): A[w] = lane 0 of warp w after an A-step, A[nwarp] = constants;
     //                    B[w+1] = lane 31 of warp w after a B-step, B[0] = constants
-    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(smem8 + qbytes + tbytes);
-    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
-    const uint32_t s_cst = smem_cst(s_mbA, nwarp), s_wb = smem_wb(s_mbA, nwarp);
+    const uint32_t s_mb = (uint32_t)__cvta_generic_to_shared(smem8 + qbytes + tbytes);
+    const uint32_t s_cst = s_mb + MB_CST, s_wb = s_mb + MB_WB;
 
     const uint32_t c_ne1 = pin(cs.ne1), c_noe1 = pin(cs.noe1), c_ne2 = pin(cs.ne2), c_noe2 = pin(cs.noe2);
     const uint32_t c_mat = pin(cs.mat), c_mis = pin(cs.mis), c_neg = pin(NEGV);
@@ -365,8 +404,9 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int ring_t0 = (tk.r_begin + (tk.band_lo + g_first * 4 * KP)) / 2 - 1;
     if (RING) { ring_fill_fast(tk, seqs, qimg, timg, rmask, ring_q0, ring_t0, ring); __syncthreads(); }
     else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
-    if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); }
-    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg); }
+    if (MULTI && gl <= nwarp) { sts_v4(s_mb + MB_A + 16u * gl, c_noe1, c_noe2, c_neg, c_neg); sts_v4(s_mb + MB_B + 16u * gl, c_noe1, c_noe2, c_neg, c_neg);
+                                step_link_init<CL>(s_mb, gl); }
+    if (MULTI && gl == 0) sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg);
     if (MULTI && RB && gl < nwarp + 2) sts_u32(s_wb + 4u * gl, 0u);
     step_barrier<CL>();
 
@@ -397,19 +437,21 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     // offset differences to the lower / upper neighbour warp as s16x2 constants
     int base = 0, best_lo = 0, best_hi = 0, nb_lo = 0;
     uint32_t c_floor = 0, dLo = 0, dLoF = 0, dUp = 0;
-    const int pitch = tk.band_w >> 1;                        // bytes per traceback row (one step)
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
+    const int pitch = n_thr_active * tb_slot_bytes(KP);      // bytes per traceback row (one step pair)
+    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KP);
+    const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
-    const uint32_t s_upA = (g == n_thr_active - 1) ? s_cst : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
-    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
+    const uint32_t s_upA = (g == n_thr_active - 1) ? s_cst : link.in_up(), s_loB = link.in_lo();
+    constexpr int RING_PER = RING_CHUNK / KP;                 // iterations between two window refills (RING_PER * KP positions each)
 
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
-        if (RING && it && (it & (RING_CHUNK / KP - 1)) == 0) {      // the next chunk of both windows (needed from the next iteration on)
-            ring_fill_fast(tk, seqs, qimg, timg, rmask, ring_q0 + ring + (it - RING_CHUNK / KP) * KP, ring_t0 + ring + (it - RING_CHUNK / KP) * KP, RING_CHUNK);
-            if (!MULTI) __syncwarp();
+        if (RING && it && (it % RING_PER) == 0) {                   // the next chunk of both windows (needed from the next iteration on)
+            if (MULTI) __syncthreads();                             // the warps of a CTA drift by up to a step per warp: line them up around the refill
+            ring_fill_fast(tk, seqs, qimg, timg, rmask, ring_q0 + ring + (it - RING_PER) * KP, ring_t0 + ring + (it - RING_PER) * KP, RING_PER * KP);
+            if (MULTI) __syncthreads(); else __syncwarp();
         }
+        const uint32_t pit = (KP & 1) ? (uint32_t)(it & 1) : 0u;    // parity of step pair it * KP + u = (u & 1) ^ pit
         #pragma unroll
         for (int u = 0; u < KP; ++u) {
             // =============================== A-step ===========================================
@@ -426,7 +468,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 for (int k = KP - 1; k >= 0; --k) {
                     if (k == 0) {
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                        if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1)); mb = lds_v4(s_loB); }
+                        if (MULTI) { if (it | u) link_wait_lo<CL>(link, lane, (uint32_t)((u & 1) ^ 1) ^ pit); mb = lds_v4(s_loB); }
                         if (RB) {              // the entry was written before the last rebase when this is the first step after it
                             const uint32_t dl = (u == 0) ? dLoF : dLo;
                             mb.x = __vadd2(mb.x, dl); mb.z = __vadd2(mb.z, dl);
@@ -458,13 +500,9 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     HA[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
                 }
                 #pragma unroll
-                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
-                if (active) store_row<KP>(tbp, HA);
-                tbp += pitch;
-                if (MULTI) {
-                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, P1[0], P2[0], F1[0], F2[0]);
-                    __syncthreads();
-                }
+                for (int k = 0; k + 1 < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
+                if (KP & 1) best = __vmaxs2(best, HA[KP - 1]);
+                if (MULTI && lane == 0) mailbox_store_A<CL>(link, P1[0], P2[0], F1[0], F2[0]);
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));
                 T[u % KP] = __byte_perm(T[u % KP], nb, 0x4232);
@@ -482,7 +520,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 for (int k = 0; k < KP; ++k) {
                     if (k == KP - 1) {         // the last slot alone needs the upper neighbour
                         uint4 mb = make_uint4(c_noe1, c_noe2, c_neg, c_neg);
-                        if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1)); mb = lds_v4(s_upA); }
+                        if (MULTI) { link_wait_up<CL>(link, lane, (uint32_t)(u & 1) ^ pit); mb = lds_v4(s_upA); }
                         if (RB) {
                             mb.x = __vadd2(mb.x, dUp); mb.z = __vadd2(mb.z, dUp);
                             if (TWO) { mb.y = __vadd2(mb.y, dUp); mb.w = __vadd2(mb.w, dUp); }
@@ -513,13 +551,11 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                     HB[k] = H; E1[k] = e1; F1[k] = f1; P1[k] = __vadd2(H, c_noe1);
                 }
                 #pragma unroll
-                for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
-                if (active) store_row<KP>(tbp, HB);
+                for (int k = 0; k + 1 < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
+                if (KP & 1) best = __vmaxs2(best, HB[KP - 1]);
+                if (MULTI && lane == 31) mailbox_store_B<CL>(link, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
+                if (active) store_pair<KP>(tbp, HA, HB);
                 tbp += pitch;
-                if (MULTI) {
-                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, P1[KP - 1], P2[KP - 1], E1[KP - 1], E2[KP - 1]);
-                    __syncthreads();
-                }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t nb = lds_u8(s_q + (RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax)));
                 Q[(KP - 1 - u) % KP] = __byte_perm(nb, Q[(KP - 1 - u) % KP], 0x5401);
@@ -558,8 +594,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 if (MULTI) {
                     if (lane == 0) {
                         sts_u32(s_wb + 4u * (uint32_t)(warp + 1), (uint32_t)base);
-                        if (CL && link.lo) st_cluster_u32(link.rem_wb_lo, (uint32_t)base);
-                        if (CL && link.up) st_cluster_u32(link.rem_wb_up, (uint32_t)base);
+                        if (CL && link.rlo) st_cluster_u32(link.rem_wb_lo, (uint32_t)base);
+                        if (CL && link.rup) st_cluster_u32(link.rem_wb_up, (uint32_t)base);
                     }
                     step_barrier<CL>();
                     nb_lo = (int)lds_u32(s_wb + 4u * (uint32_t)warp);
@@ -587,28 +623,34 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 // ---------------------------------------------------------------------------------------------
 // traceback
 // ---------------------------------------------------------------------------------------------
-// Byte layout of the traceback rows (written by svp_fwd_kernel<KP>): row = step s = (i + j) - r_begin,
-// pitch = band_w / 2 bytes; inside a row thread g owns bytes [g*2KP, (g+1)*2KP); the byte of its slot
-// c = half*KP + k sits at (k>>1)*4 + (k&1)*2 + half. kp is a runtime value here (a power of two: 4, 8 or 16).
+// Byte layout of the traceback rows (store_pair): row = step pair (s >> 1), s = (i + j) - r_begin; pitch = threads * slot bytes;
+// inside a row thread g = x / (4*kp) owns one slot; the byte of its diagonal x' = x - g*4kp (x = (j - i) - band_lo, parity of x' =
+// parity of s) sits at 4*k + 2*half + (x' & 1) with c = x' >> 1, half = c >= kp, k = c - half*kp. kp is a runtime value (4..8).
 struct TbView {
     const uint8_t* base;      // arena + tb_off
     const uint32_t* seqs32;   // packed sequences (global)
-    int band_lo, band_w, r_begin, pitch, m, n, kp;
-    int shift;                // log2(4*kp): the diagonals of one thread are a power of two (kp = 4, 8, 16)
+    int band_lo, band_w, r_begin, pitch, m, n, kp, slot;
+    uint32_t inv;             // ceil(2^32 / (4*kp)): x / (4*kp) = umulhi(x, inv), exact for x < 2^27
     uint64_t q_word, t_word;  // word offsets of the packed sequences
     bool rc;
 
+    __device__ __forceinline__ void set_geometry(int band_w_, int kp_) {
+        band_w = band_w_; kp = kp_; slot = tb_slot_bytes(kp_);
+        pitch = (band_w_ / (4 * kp_)) * slot;
+        inv = (uint32_t)(((1ull << 32) + 4u * (uint32_t)kp_ - 1u) / (4u * (uint32_t)kp_));
+    }
     // offset of diagonal x (band-relative) inside a row
     __device__ __forceinline__ int col(int x) const {
-        const int g = x >> shift;
-        const int c = (x - g * 4 * kp) >> 1;
+        const int g = (int)__umulhi((uint32_t)x, inv);
+        const int xr = x - g * 4 * kp;
+        const int c = xr >> 1;
         const int half = c >= kp ? 1 : 0, k = c - half * kp;
-        return g * 2 * kp + (k >> 1) * 4 + (k & 1) * 2 + half;
+        return g * slot + k * 4 + half * 2 + (xr & 1);
     }
+    // stored byte of step s, band-relative diagonal x (x and s have the same parity)
+    __device__ __forceinline__ const uint8_t* addr_sx(int s, int x) const { return base + (ptrdiff_t)(s >> 1) * pitch + col(x); }
     // address of the stored byte of cell (i, j) (callers make sure the cell is real and inside the band)
-    __device__ __forceinline__ const uint8_t* addr(int i, int j) const {
-        return base + (ptrdiff_t)((i + j) - r_begin) * pitch + col((j - i) - band_lo);
-    }
+    __device__ __forceinline__ const uint8_t* addr(int i, int j) const { return addr_sx((i + j) - r_begin, (j - i) - band_lo); }
     // stored byte of H(i, j); 0 for cells before the matrix or before the first stored row (callers check the band)
     __device__ __forceinline__ uint32_t lb(int i, int j) const {
         if (i < 1 || j < 1 || (i + j) < r_begin) return 0;
@@ -684,8 +726,8 @@ svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
     TbView v;
     v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
-    v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
-    v.kp = KP; v.shift = 31 - __clz(4 * KP);
+    v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
+    v.set_geometry(tk.band_w, KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
     const int d_hi = tk.band_lo + tk.band_w - 1;
 
@@ -715,7 +757,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order
         uint32_t bprev = 0, b_row0 = 0;
         for (int id = 0; id < 2 * KP * KP; ++id) {
             const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
-            const uint32_t bb = v.base[(size_t)s * v.pitch + v.col(x)];
+            const uint32_t bb = *v.addr_sx(s, x);
             if (id == 0) rel = 0;
             else if (id % KP == 0) rel = rel_row0 + sext8(bb - b_row0);
             else rel = rel + sext8(bb - bprev);
@@ -732,7 +774,7 @@ svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order
     // ---- 2. walk back --------------------------------------------------------------------------
     constexpr int S = 8, NSCAN = 6;
     uint32_t* slot = cigar + tk.cigar_off;
-    const ptrdiff_t two_rows = 2 * (ptrdiff_t)v.pitch;
+    const ptrdiff_t two_rows = (ptrdiff_t)v.pitch;            // two steps = one row (step pair)
     const int cost1d = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1);
     const int cost1i = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1);
     const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
@@ -779,12 +821,10 @@ svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order
             if (!in_scan && i - S - 1 >= 1 && j - S - 1 >= 1) {              // L2 prefetch for the next round
                 #pragma unroll
                 for (int k = S; k < 2 * S; k += 2) {
-                    const uint8_t* pk = pd - k * two_rows;
-                    if (pk - 2 * two_rows >= v.base) {
+                    const uint8_t* pk = pd - k * two_rows;      // the sector holding a cell's diagonal, left and up predecessors
+                    if (pk - two_rows >= v.base) {
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(pk));
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk + v.pitch));
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows));
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows + v.pitch));
                     }
                 }
             }
@@ -900,8 +940,8 @@ svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
     TbView v;
     v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
-    v.band_lo = tk.band_lo; v.band_w = tk.band_w; v.r_begin = tk.r_begin; v.pitch = tk.band_w >> 1; v.m = tk.m; v.n = tk.n;
-    v.kp = KP; v.shift = 31 - __clz(4 * KP);
+    v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
+    v.set_geometry(tk.band_w, KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
     const int d_hi = tk.band_lo + tk.band_w - 1;
 
@@ -943,7 +983,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 uint32_t mine = 0;
                 if (idx < NC) {
                     const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
-                    mine = v.base[(size_t)s * v.pitch + v.col(x)];
+                    mine = *v.addr_sx(s, x);
                 }
                 const int lim = min(32, NC - c0);
                 for (int l = 0; l < lim; ++l) {

@@ -1,6 +1,6 @@
 // svp_kernels_wide.cuh — the forward-DP variants beside the fast path of svp_kernels.cuh. Same decomposition
 // (one CTA per pair, a thread owns consecutive diagonals, even ones = set A, odd ones = set B, one anti-diagonal
-// per step, neighbours by shuffle / mailbox) and the same traceback rows, so svp_tb_kernel serves all of them.
+// per step, neighbours by shuffle / mailbox) and the same traceback rows, so the traceback kernels serve all of them.
 //
 //   svp_fwdg_kernel<MULTI, TWO>       s16x2 lanes, KP = 4 geometry, GENERAL scoring: a full 4x4 substitution
 //                                     matrix (the shape of a last-train / lamassemble .mat, consensus.py:777) and
@@ -105,8 +105,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(tsel) + SEQ_PAD - 1;
     // mailboxes (MULTI): A[w] = lane 0 of warp w after an A-step (H, -, F1, F2), A[nwarp] = constants;
     //                    B[w+1] = lane 31 of warp w after a B-step (H, -, E1, E2), B[0] = constants
-    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(smem8 + 2 * qbytes + tbytes);
-    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
+    const uint32_t s_mb = (uint32_t)__cvta_generic_to_shared(smem8 + 2 * qbytes + tbytes);
 
     const uint32_t d_ne1 = pin(cs.d_ne1), d_noe1 = pin(cs.d_noe1), d_ne2 = pin(cs.d_ne2), d_noe2 = pin(cs.d_noe2);
     const uint32_t i_ne1 = pin(cs.i_ne1), i_noe1 = pin(cs.i_noe1), i_ne2 = pin(cs.i_ne2), i_noe2 = pin(cs.i_noe2);
@@ -114,8 +113,9 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     const uint32_t c_neg = pin(NEGV);
 
     stage_sequences_gen(tk, seqs, qsel, qsel2, tsel, qbytes, tbytes);
-    if (MULTI && gl <= nwarp) { sts_v4(s_mbA + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mbB + 16u * gl, 0u, 0u, c_neg, c_neg); }
-    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(smem_cst(s_mbA, nwarp), 0u, 0u, c_neg, c_neg); }
+    if (MULTI && gl <= nwarp) { sts_v4(s_mb + MB_A + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mb + MB_B + 16u * gl, 0u, 0u, c_neg, c_neg);
+                                step_link_init<CL>(s_mb, gl); }
+    if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, c_neg, c_neg);
     step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (4 * KP);
@@ -139,12 +139,11 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     }
     int qpos = I0 + 1, tpos = J0 + 2 * KP;
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
-    const int pitch = tk.band_w >> 1;
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * (2 * KP);
+    const int pitch = n_thr_active * tb_slot_bytes(KP);      // bytes per traceback row (one step pair)
+    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KP);
+    const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
-    const uint32_t s_upA = (g == n_thr_active - 1) ? smem_cst(s_mbA, nwarp) : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
-    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
+    const uint32_t s_upA = (g == n_thr_active - 1) ? s_mb + MB_CST : link.in_up(), s_loB = link.in_lo();
 
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> uint32_t {
         const uint32_t sel = q | t;
@@ -191,12 +190,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 }
                 #pragma unroll
                 for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HA[k], HA[k + 1]);
-                if (active) store_row<KP>(tbp, HA);
-                tbp += pitch;
-                if (MULTI) {
-                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, HA[0], 0u, F1[0], F2[0]);
-                    __syncthreads();
-                }
+                if (MULTI && lane == 0) mailbox_store_A<CL>(link, HA[0], 0u, F1[0], F2[0]);
                 // T advances by one base: logical T[k] <- T[k+1]; the new base enters slot 2KP-1
                 const uint32_t nb = lds_u8(s_t + (uint32_t)__vimin_s32_relu(tpos, tmax));
                 T[u % KP] = __byte_perm(T[u % KP], nb, 0x5541);
@@ -238,12 +232,9 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
                 }
                 #pragma unroll
                 for (int k = 0; k < KP; k += 2) best = __vimax3_s16x2(best, HB[k], HB[k + 1]);
-                if (active) store_row<KP>(tbp, HB);
+                if (MULTI && lane == 31) mailbox_store_B<CL>(link, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
+                if (active) store_pair<KP>(tbp, HA, HB);
                 tbp += pitch;
-                if (MULTI) {
-                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, HB[KP - 1], 0u, E1[KP - 1], E2[KP - 1]);
-                    __syncthreads();
-                }
                 // Q advances by one base: logical Q[k] <- Q[k-1]; the new base enters slot 0
                 const uint32_t off = (uint32_t)__vimin_s32_relu(qpos, qmax);
                 const uint32_t nb = lds_u8(s_q + off), nb2 = lds_u8(s_q2 + off);
@@ -318,8 +309,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const uint32_t s_q = (uint32_t)__cvta_generic_to_shared(qimg) + (RING ? 0 : SEQ_PAD - 1);
     const uint32_t s_q2 = (uint32_t)__cvta_generic_to_shared(qimg2) + (RING ? 0 : SEQ_PAD - 1);
     const uint32_t s_t = (uint32_t)__cvta_generic_to_shared(timg) + (RING ? 0 : SEQ_PAD - 1);
-    const uint32_t s_mbA = (uint32_t)__cvta_generic_to_shared(timg + tbytes);
-    const uint32_t s_mbB = s_mbA + (uint32_t)(nwarp + 1) * 16u;
+    const uint32_t s_mb = (uint32_t)__cvta_generic_to_shared(timg + tbytes);
     const int NEG = -(1 << 29);
     const int d_ne1 = (int)pin((uint32_t)-cs.d_ext1), d_noe1 = (int)pin((uint32_t)-(cs.d_open1 + cs.d_ext1));
     const int d_ne2 = (int)pin((uint32_t)-cs.d_ext2), d_noe2 = (int)pin((uint32_t)-(cs.d_open2 + cs.d_ext2));
@@ -339,10 +329,11 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     else stage_sequences(tk, seqs, qimg, timg, qbytes, tbytes);
     if (RING) __syncthreads();
     if (MULTI && gl <= nwarp) {
-        sts_v4(s_mbA + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-        sts_v4(s_mbB + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+        sts_v4(s_mb + MB_A + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+        sts_v4(s_mb + MB_B + 16u * gl, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+        step_link_init<CL>(s_mb, gl);
     }
-    if (MULTI && gl == 0) { cluster_link_init<CL>(s_mbB, nwarp); sts_v4(smem_cst(s_mbA, nwarp), 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg); }
+    if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
     step_barrier<CL>();
 
     const int n_thr_active = tk.band_w / (2 * K);
@@ -367,18 +358,19 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     }
     int qpos = I0 + 1, tpos = J0 + K;
     int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
-    const int pitch = tk.band_w >> 1;
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * K;
+    const int pitch = n_thr_active * tb_slot_bytes(KPG);     // bytes per traceback row (one step pair)
+    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KPG);
+    const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
-    const uint32_t s_upA = (g == n_thr_active - 1) ? smem_cst(s_mbA, nwarp) : s_mbA + 16u * (warp + 1), s_loB = s_mbB + 16u * warp;
-    const uint32_t s_myA = s_mbA + 16u * warp, s_myB = s_mbB + 16u * (warp + 1);
-    const ClusterLink link = cluster_link<CL>(s_mbA, s_mbB, warp, nwarp, crank, csize);
+    const uint32_t s_upA = (g == n_thr_active - 1) ? s_mb + MB_CST : link.in_up(), s_loB = link.in_lo();
 
-    // bytes of slots c = 0..7 in the shared row order: word0 = slots [0,4,1,5], word1 = slots [2,6,3,7]
-    auto store8 = [&](const int (&Hs)[K]) {
-        const uint32_t a = __byte_perm((uint32_t)Hs[0], (uint32_t)Hs[4], 0x0040), b = __byte_perm((uint32_t)Hs[1], (uint32_t)Hs[5], 0x0040);
-        const uint32_t c = __byte_perm((uint32_t)Hs[2], (uint32_t)Hs[6], 0x0040), d = __byte_perm((uint32_t)Hs[3], (uint32_t)Hs[7], 0x0040);
-        __stcs(reinterpret_cast<uint2*>(tbp), make_uint2(__byte_perm(a, b, 0x5410), __byte_perm(c, d, 0x5410)));
+    // low bytes of a step pair in the shared row order (store_pair, KP = 4): word k = [A slot k, B slot k, A slot 4+k, B slot 4+k]
+    auto store16 = [&](const int (&A)[K], const int (&B)[K]) {
+        uint32_t w[KPG];
+        #pragma unroll
+        for (int k = 0; k < KPG; ++k)
+            w[k] = __byte_perm(__byte_perm((uint32_t)A[k], (uint32_t)B[k], 0x0040), __byte_perm((uint32_t)A[KPG + k], (uint32_t)B[KPG + k], 0x0040), 0x5410);
+        __stcs(reinterpret_cast<uint4*>(tbp), make_uint4(w[0], w[1], w[2], w[3]));
     };
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> int {
         if (GEN) {
@@ -403,8 +395,9 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     #pragma unroll 1
     for (int it = 0; it < tk.n_iter; ++it) {
         if (RING && it && (it & (RING_CHUNK / K - 1)) == 0) {       // the next chunk of both windows (needed from the next iteration on)
+            if (MULTI) __syncthreads();                             // the warps of a CTA drift by up to a step per warp: line them up around the refill
             ring_fill<GEN>(tk, seqs, qimg, qimg2, timg, rmask, ring_q0 + ring + (it - RING_CHUNK / K) * K, ring_t0 + ring + (it - RING_CHUNK / K) * K, RING_CHUNK);
-            if (!MULTI) __syncwarp();
+            if (MULTI) __syncthreads(); else __syncwarp();
         }
         #pragma unroll
         for (int u = 0; u < K; ++u) {
@@ -428,12 +421,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 }
                 #pragma unroll
                 for (int k = 0; k < KPG; k += 2) { best_lo = __vimax3_s32(best_lo, HA[k], HA[k + 1]); best_hi = __vimax3_s32(best_hi, HA[KPG + k], HA[KPG + k + 1]); }
-                if (active) store8(HA);
-                tbp += pitch;
-                if (MULTI) {
-                    if (lane == 0) mailbox_store_A<CL>(link, s_myA, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
-                    __syncthreads();
-                }
+                if (MULTI && lane == 0) mailbox_store_A<CL>(link, (uint32_t)HA[0], 0u, (uint32_t)F1[0], (uint32_t)F2[0]);
                 T[u % K] = lds_u8(s_t + (RING ? (uint32_t)(tpos & rmask) : (uint32_t)__vimin_s32_relu(tpos, tmax)));     // logical T[k] <- T[k+1]; new base in slot K-1
                 ++tpos;
             }
@@ -457,12 +445,9 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
                 }
                 #pragma unroll
                 for (int k = 0; k < KPG; k += 2) { best_lo = __vimax3_s32(best_lo, HB[k], HB[k + 1]); best_hi = __vimax3_s32(best_hi, HB[KPG + k], HB[KPG + k + 1]); }
-                if (active) store8(HB);
+                if (MULTI && lane == 31) mailbox_store_B<CL>(link, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
+                if (active) store16(HA, HB);
                 tbp += pitch;
-                if (MULTI) {
-                    if (lane == 31) mailbox_store_B<CL>(link, s_myB, (uint32_t)HB[K - 1], 0u, (uint32_t)E1[K - 1], (uint32_t)E2[K - 1]);
-                    __syncthreads();
-                }
                 const uint32_t qo = RING ? (uint32_t)(qpos & rmask) : (uint32_t)__vimin_s32_relu(qpos, qmax);   // logical Q[k] <- Q[k-1]; new base in slot 0
                 Q[(K - 1 - u) % K] = lds_u8(s_q + qo);
                 if (GEN) Q2[(K - 1 - u) % K] = sel2_of(lds_u8(s_q2 + qo));

@@ -28,7 +28,7 @@ def band_cells(m: int, n: int, band_lo: int, band_w: int) -> int:
     return below(band_lo + band_w - 1) - below(band_lo - 1)
 
 
-def region_cost(read_lengths: Sequence[int], slack: int = 300, granule: int = 512) -> int:
+def region_cost(read_lengths: Sequence[int], slack: int = 300, granule: int = 128) -> int:
     """Estimated cells of the all-vs-all of one region from read lengths only (band = |dlen| + 2*slack,
     rounded up to the granule, times the shorter read)."""
     ln = np.sort(np.asarray(read_lengths, dtype=np.int64))

@@ -133,7 +133,7 @@ def region_config2_shape(region_id: int, mean_len: int = 8000, sd_len: int = 800
     return length, -min(size, length - pos - 100)
 
 
-def region_pairs(region: Region, slack: int = 300, granule: int = 512) -> list[tuple[int, int, int, int, int]]:
+def region_pairs(region: Region, slack: int = 300, granule: int = 128) -> list[tuple[int, int, int, int, int]]:
     """AVA pair specs (q, t, band_lo, band_w, flags) of one region with local read indices: every
     unordered pair once, query = lexicographically smaller name, strand from the known read
     orientations, band = offset_band() from the known start offsets and the length difference."""
@@ -284,7 +284,7 @@ def locus_config4(region_id: int, seed_base: int = 30_000, skew: bool = False, s
                  core_interval=(start + c0, start + c1), consensus=cons)
 
 
-def locus_cost(locus: Locus, slack: int = 300, granule: int = 512) -> int:
+def locus_cost(locus: Locus, slack: int = 300, granule: int = 128) -> int:
     """Estimated DP cells of a locus: its all-vs-all plus its consensus -> window pairs (both strands)."""
     from .scheduler import region_cost
     cost = region_cost([len(r) for r in locus.region.reads], slack, granule)

@@ -34,7 +34,7 @@ def assemble(seqs: list[np.ndarray], specs: list[tuple[int, int, int, int, int]]
             "seq_bytes": int(((lens.astype(np.int64) + 3) // 4).sum())}
 
 
-def batch_config2(region_ids: list[int], slack: int = 300, granule: int = 512) -> dict:
+def batch_config2(region_ids: list[int], slack: int = 300, granule: int = 128) -> dict:
     seqs, specs = [], []
     for rid in region_ids:
         reg = synth.region_config2(rid)
@@ -71,7 +71,7 @@ def consensus_window_specs(locus: synth.Locus, q_index: list[int], t_index: int,
 
 
 def batch_config4(locus_ids: list[int], seed_base: int = 30_000, skew: bool = False, scale: float = 1.0, max_reads: int = 60,
-                  slack: int = 300, granule: int = 512, band_w: int = 4096) -> dict:
+                  slack: int = 300, granule: int = 128, band_w: int = 4096) -> dict:
     """All-vs-all of every locus' reads plus its consensus -> reference-window pairs (both strands)."""
     seqs, specs = [], []
     for lid in locus_ids:

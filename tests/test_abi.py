@@ -169,29 +169,34 @@ def test_planner_kernel_families(monkeypatch):
     specs = [(0, 1, -462, 1024),        # 8 kb reads, band 1024: one KP = 8 warp, windows (16 KB of images for one warp)
              (2, 3, -206, 512),         # 1 kb reads, band 512: one KP = 4 warp, whole images
              (0, 1, -1000, 2048),       # two KP = 8 warps
-             (0, 1, -700, 1536),        # three KP = 4 warps beat two KP = 8 warps
+             (0, 1, -700, 1536),        # two KP = 6 warps beat three KP = 4 warps and two KP = 8 warps
              (4, 5, -500, 2048),        # 20 kb reads: scores leave the s16 range -> rebased 16-bit lanes
              (0, 1, -7999, 20000),      # band beyond one CTA (16 384 diagonals): a cluster of 2 CTAs
              (6, 7, -768, 1536),        # 130 kb x 120 kb: whole images cannot fit -> windows, rebased
              (0, 1, -462, 1000),        # band not a multiple of 32
              (0, 1, -7999, 131072 + 64),  # wider than a cluster of 8 CTAs covers
-             (0, 9, -462, 1024)]        # sequence index out of range
+             (0, 9, -462, 1024),        # sequence index out of range
+             (0, 1, -270, 640),         # bands of 640 / 768 / 896 diagonals: one KP = 5 / 6 / 7 warp instead of a padded KP = 8 one
+             (0, 1, -334, 768),
+             (0, 1, -398, 896),
+             (0, 1, -286, 672)]         # 672 = 28 threads x 24 diagonals: a KP = 6 warp with four idle lanes
     plan, pairs, L = _plan(lens, specs)
     fam = [(int(p["flags"]), int(p["kp"]), int(p["warps"]), int(p["cluster"])) for p in plan]
     assert fam[0] == (PLAN_WINDOWS, 8, 1, 1)
     assert fam[1] == (0, 4, 1, 1)
     assert fam[2] == (PLAN_WINDOWS, 8, 2, 1)
-    assert fam[3] == (PLAN_WINDOWS, 4, 3, 1)
+    assert fam[3] == (PLAN_WINDOWS, 6, 2, 1)
     assert fam[4] == (PLAN_REBASE | PLAN_WINDOWS, 8, 2, 1)
     assert fam[5][1:] == (8, 16, 2) and not fam[5][0] & (PLAN_S32 | PLAN_REBASE)
-    assert fam[6] == (PLAN_REBASE | PLAN_WINDOWS, 4, 3, 1) and plan[6]["smem_bytes"] < 16384
-    assert [f[0] for f in fam[7:]] == [PLAN_INVALID] * 3
-    for k in range(7):                  # cells = the closed form the scheduler uses; 1 traceback byte per cell (+ virtual cells)
+    assert fam[6] == (PLAN_REBASE | PLAN_WINDOWS, 6, 2, 1) and plan[6]["smem_bytes"] < 16384
+    assert [f[0] for f in fam[7:10]] == [PLAN_INVALID] * 3
+    assert [f[1:] for f in fam[10:]] == [(5, 1, 1), (6, 1, 1), (7, 1, 1), (6, 1, 1)]
+    for k in (0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13):                  # cells = the closed form the scheduler uses; 1 traceback byte per cell (+ virtual cells)
         q, t, lo, w = specs[k]
         cells = scheduler.band_cells(int(L[q]), int(L[t]), lo, w)
         assert int(plan[k]["cells"]) == cells and cells <= int(plan[k]["tb_bytes"])
         if k != 5:                      # (the band of pair 5 is mostly outside the matrix: its rows are mostly virtual cells)
-            assert int(plan[k]["tb_bytes"]) <= 1.35 * cells + 64 * w
+            assert int(plan[k]["tb_bytes"]) <= 1.35 * cells + 64 * w        # incl. the padded row slots of KP = 5 (24 B for 20 cells) and 7
     # the same long pair on 32-bit lanes when the rebase is switched off, and under general scoring
     monkeypatch.setenv("SVP_NO_REBASE", "1")
     p2, _, _ = _plan(lens, [specs[4], specs[6]])

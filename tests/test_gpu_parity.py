@@ -617,3 +617,52 @@ def test_pipelined_submits_equal_blocking_calls(oracle):
                     assert np.array_equal(got[f], res[f]), f
             for k in range(len(got)):
                 assert cigartuples(gcig, got[k]) == cigartuples(cig, res[k])
+
+
+# ---------------------------------------------------------------------------------------------
+# band widths between 512 and 1024 diagonals per warp (KP = 5, 6, 7) and their multi-warp CTAs
+# ---------------------------------------------------------------------------------------------
+
+def fixed_band_batch(rng, n_pairs, length, band_w, err=(0.035, 0.03, 0.035)):
+    """Noisy pairs aligned in a band of exactly band_w diagonals centred on the end-to-end diagonal; every third pair carries an
+    insertion / deletion of up to a third of the band."""
+    seqs, specs = [], []
+    for p in range(n_pairs):
+        tmpl = randseq(rng, length + int(rng.integers(-50, 50)))
+        a, b = mutate(rng, tmpl, *err), mutate(rng, tmpl, *err)
+        if p % 3 == 0:
+            pos = len(b) // 2
+            sv = int(rng.integers(20, band_w // 3))
+            b = b[:pos] + (randseq(rng, sv) if p % 2 else "") + b[pos + (0 if p % 2 else sv):]
+        rc = bool(rng.integers(2))
+        seqs += [revcomp(a) if rc else a, b]
+        mid = (len(b) - len(a)) // 2
+        specs.append((2 * p, 2 * p + 1, mid - band_w // 2, band_w, PAIR_REVCOMP if rc else 0))
+    return [f"r{k}" for k in range(len(seqs))], seqs, specs
+
+
+@pytest.mark.parametrize("ring_min", ["0", "1000000000"])
+@pytest.mark.parametrize("band_w,kp,warps", [(640, 5, 1), (768, 6, 1), (896, 7, 1), (672, 6, 1), (1280, 5, 2), (1536, 6, 2), (1792, 7, 2),
+                                              (2304, 6, 3), (3200, 5, 5), (5376, 7, 6), (10752, 7, 12), (13440, 7, 15)])
+def test_band_widths_kp_5_6_7(oracle, monkeypatch, band_w, kp, warps, ring_min):
+    """Every KP = 5 / 6 / 7 geometry (single warp, CTAs of 2..16 warps whose warps are linked by mbarriers instead of a CTA
+    barrier; whole images and sliding windows) against the oracle, and the planner picks the geometry the test names."""
+    from svirlpool_b200 import aligner as al
+    monkeypatch.setenv("SVP_RING_MIN", ring_min)
+    rng = np.random.default_rng(band_w)
+    names, seqs, specs = fixed_band_batch(rng, 6, 2600 if band_w < 4000 else 4200, band_w)
+    batch = ava.PairBatch.build(names, seqs, specs)
+    plan = al.plan_pairs(al.scoring_preset("map-ont"), batch.packed.nbytes, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    assert {(int(p["kp"]), int(p["warps"])) for p in plan} == {(kp, warps)}
+    with al.Aligner(device=0, preset="map-ont", tb_bytes=4 << 30) as g:
+        gres, _ = run_both(g, oracle, names, seqs, specs)
+    assert not gres["status"].any() and gres["score"].min() > 800
+
+
+@pytest.mark.parametrize("band_w", [640, 768, 896, 1536, 2688])
+def test_band_widths_kp_5_6_7_long_reads_rebased(gpu, oracle, band_w):
+    """The same widths on the rebased kernel (18 kb reads: scores beyond the s16 range, per-warp score offsets)."""
+    rng = np.random.default_rng(1000 + band_w)
+    names, seqs, specs = fixed_band_batch(rng, 3, 18000, band_w, err=(0.02, 0.015, 0.015))
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
+    assert not gres["status"].any() and gres["score"].max() > 20000
