@@ -156,27 +156,178 @@ def regions_for_step(step: int, world: int, per_gpu: int, workload: str = "confi
     return [[ids[k] for k in b] for b in bins]
 
 
-def cpu_arm(sample_regions: int, threads: int) -> dict:
+def cpu_arm(sample_regions: int, threads: int, keep_rows: bool = False) -> dict:
     """The CPU oracle (port of the spec; the reference's own path is an external minimap2 binary that is
-    not available) on a bounded sample of the same workload, all host threads."""
+    not available) on a bounded sample of the same workload: regions 0 .. sample_regions-1 of config 2."""
     sys.path.insert(0, str(ROOT / "tests"))
     from oracle_engine import OracleEngine
     b = build_batch(list(range(sample_regions)))
     eng = OracleEngine("map-ont", threads=threads)
     t0 = time.perf_counter()
-    res, _ = eng.align_batch(b["packed"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+    res, cig = eng.align_batch(b["packed"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
     dt = time.perf_counter() - t0
     cells = int(res["cells"].sum())
-    return {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
-            "sample": f"{sample_regions} region(s) of config 2 ({len(res)} pairs, {cells / 1e9:.2f} Gcells) in {dt:.2f} s",
-            "regions_per_s": sample_regions / dt, "_seconds": dt, "_cells": cells}
+    out = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
+           "sample": f"{sample_regions} region(s) of config 2 ({len(res)} pairs, {cells / 1e9:.2f} Gcells) in {dt:.2f} s on {threads} thread(s)",
+           "regions_per_s": sample_regions / dt, "_seconds": dt, "_cells": cells}
+    if keep_rows:
+        out["_rows"] = (b, res, cig)
+    return out
+
+
+PARITY_FIELDS = ("score", "status", "q_beg", "q_end", "t_beg", "t_end", "n_match", "n_mismatch", "n_ins_ops", "n_ins_bp",
+                 "n_del_ops", "n_del_bp", "cigar_len", "cells")
+
+
+def parity_check(al, rows) -> dict:
+    """GPU rows of the CPU arm's sample against the oracle rows the CPU arm just produced (outside every timed region):
+    integer fields and CIGARs bit for bit, sv_dist within 1e-6 relative."""
+    from svirlpool_b200._abi import cigartuples
+    b, ores, ocig = rows
+    gres, gcig = al.align_batch(b["packed"], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+    bad = np.zeros(len(ores), dtype=bool)
+    for f in PARITY_FIELDS:
+        bad |= gres[f] != ores[f]
+    bad |= ~np.isclose(gres["sv_dist"], ores["sv_dist"], rtol=1e-6, atol=0)
+    for k in range(len(ores)):
+        if not bad[k] and cigartuples(gcig, gres[k]) != cigartuples(ocig, ores[k]):
+            bad[k] = True
+    return {"pairs": int(len(ores)), "mismatches": int(bad.sum()), "regions": f"config 2 regions 0..{b['n_regions'] - 1} at full size",
+            "fields": list(PARITY_FIELDS) + ["cigar", "sv_dist (rtol 1e-6)"], "against": "oracle/svp_oracle.c (the rows of the cpu_baseline leg)"}
+
+
+def cells_at_granule(region_ids: list[int], granule: int) -> int:
+    """Spec cells of the same regions with the bands rounded up to `granule` instead of the bench's GRANULE (host only)."""
+    from svirlpool_b200 import scheduler, synth
+    total = 0
+    for rid in region_ids:
+        reg = synth.region_config2(rid)
+        lens = [len(r) for r in reg.reads]
+        for (q, t, lo, w, _fl) in synth.region_pairs(reg, SLACK, granule):
+            total += scheduler.band_cells(lens[q], lens[t], lo, w)
+    return total
+
+
+# ---------------------------------------------------------------------------------------------
+# strong-scaling sub-records: the north-star workloads (configs 4 and 5) as FIXED pools sharded over the ranks
+# ---------------------------------------------------------------------------------------------
+SCALING_SETS = {
+    "config4": {"sets": [(30_000, False)], "what": "HG002-shape loci (seeds 30000+r): all-vs-all + padded consensus -> reference window, both strands"},
+    "config5": {"sets": [(40_000, True), (50_000, True), (60_000, True)],
+                "what": "trio: three sets (seeds 40000/50000/60000+r) with a Pareto(1.3) core-length tail, one joint pool"},
+}
+SCALING_CHUNK = 128          # loci per engine call
+
+
+def scaling_items(name: str, pool: int) -> list[tuple[int, int, bool]]:
+    sets = SCALING_SETS[name]["sets"]
+    per = pool // len(sets)
+    return [(sb, lid, skew) for sb, skew in sets for lid in range(per)]
+
+
+def _gen_chunk(items):
+    from svirlpool_b200 import workloads
+    return workloads.batch_loci(items)
+
+
+def prepare_scaling(pool: int, rank: int, world: int) -> dict:
+    """Host preparation (untimed, before CUDA is touched so that a fork pool is safe): LPT assignment of every pool by estimated
+    cells (synth.locus_cost_estimate: shape only, what a scheduler knows before aligning) and the packed batches of THIS rank's
+    loci, in chunks of SCALING_CHUNK loci per engine call."""
+    import multiprocessing as mp
+    from svirlpool_b200 import scheduler, synth
+    out = {}
+    jobs = []
+    for name in SCALING_SETS:
+        items = scaling_items(name, pool)
+        costs = [synth.locus_cost_estimate(lid, sb, skew) for sb, lid, skew in items]
+        mine = scheduler.lpt_assign(costs, world)[rank]
+        chunks = [[items[k] for k in mine[c:c + SCALING_CHUNK]] for c in range(0, len(mine), SCALING_CHUNK)]
+        out[name] = {"items": items, "costs": costs, "mine": mine, "first": len(jobs), "n_chunks": len(chunks)}
+        jobs += chunks
+    workers = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    if workers > 1 and len(jobs) > 1:
+        with mp.get_context("fork").Pool(workers) as pl:
+            batches = pl.map(_gen_chunk, jobs, chunksize=1)
+    else:
+        batches = [_gen_chunk(j) for j in jobs]
+    for name, d in out.items():
+        d["batches"] = batches[d["first"]:d["first"] + d["n_chunks"]]
+    return out
+
+
+def run_scaling(al, name: str, prep: dict, rank: int, world: int, dist, torch, dev) -> dict | None:
+    """One pass over the fixed pool: every rank aligns its loci through the host-buffer API (H2D, kernels, D2H of rows and
+    CIGARs inside the timed region), results are gathered on rank 0 through sharding.run_sharded (host-side gather, no
+    collective on the data path). Time = max over ranks of the device stopwatch."""
+    from svirlpool_b200 import scheduler, sharding
+    d = prep[name]
+    pins = []
+    for b in d["batches"]:
+        pin = torch.empty(b["packed"].nbytes, dtype=torch.uint8, pin_memory=True)
+        pin.numpy()[:] = b["packed"]
+        pins.append(pin.numpy())
+    if d["batches"]:                                   # warm-up: this rank's first chunk, untimed
+        b = d["batches"][0]
+        al.align_batch_nocopy(pins[0], b["off"], b["lens"], b["pairs"], b["cigar_words"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    al.stats_total(reset=True)
+    state = {}
+
+    def process_many(mine_items):
+        rows = []
+        t0 = time.perf_counter()
+        al.timer_mark(0)
+        for b, pin in zip(d["batches"], pins):
+            res, _cig = al.align_batch_nocopy(pin, b["off"], b["lens"], b["pairs"], b["cigar_words"])
+            pb = b["pair_bounds"]
+            cells = np.add.reduceat(res["cells"].astype(np.int64), pb[:-1])
+            score = np.add.reduceat(res["score"].astype(np.int64), pb[:-1])
+            bad = np.add.reduceat((res["status"] & ~np.uint32(1) != 0).astype(np.int64), pb[:-1])
+            rows += [{"pairs": int(pb[k + 1] - pb[k]), "cells": int(cells[k]), "score_sum": int(score[k]), "bad_status": int(bad[k])}
+                     for k in range(len(pb) - 1)]
+        al.timer_mark(1)
+        state["ms"] = al.timer_elapsed_ms() if d["batches"] else 0.0
+        state["wall_ms"] = (time.perf_counter() - t0) * 1e3
+        return rows
+
+    results = sharding.run_sharded(d["items"], d["costs"], process_many=process_many, dist=dist if world > 1 else None)
+    agg = al.stats_total()
+    vec = torch.tensor([state["ms"], agg["fwd_ms"], float(agg["cells"]), state["wall_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        allv = [torch.zeros_like(vec) for _ in range(world)]
+        dist.all_gather(allv, vec)
+        allv = torch.stack(allv).cpu().numpy()
+    else:
+        allv = vec.cpu().numpy()[None, :]
+    if rank != 0:
+        return None
+    ms = allv[:, 0]
+    t = float(ms.max()) / 1e3
+    cells = sum(r["cells"] for r in results)
+    bins = scheduler.lpt_assign(d["costs"], world)
+    actual = [r["cells"] for r in results]
+    fwd_gcups = float(allv[:, 2].sum()) / (float(allv[:, 1].max()) / 1e3) / 1e9 if allv[:, 1].max() > 0 else 0.0
+    ip = int_pipe_peak()
+    return {"workload": SCALING_SETS[name]["what"], "scaling": "strong", "loci": len(results), "pairs": sum(r["pairs"] for r in results),
+            "bad_status_pairs": sum(r["bad_status"] for r in results),
+            "seconds": t, "loci_per_s": len(results) / t, "gcups": cells / t / 1e9,
+            "int_pipe_frac": fwd_gcups / (ip["gcups"] * world), "fwd_gcups": fwd_gcups,
+            "lpt_imbalance_estimated": scheduler.imbalance(d["costs"], bins), "lpt_imbalance_actual_cells": scheduler.imbalance(actual, bins),
+            "rank_ms": [round(float(x), 2) for x in ms], "rank_busy_frac": [round(float(x / ms.max()), 4) for x in ms],
+            "rank_wall_ms": [round(float(x), 2) for x in allv[:, 3]],
+            "e2e": "host buffers -> svp_align_batch -> host buffers, H2D and D2H (rows + CIGARs) inside the timed region",
+            "engine_calls_per_rank": d["n_chunks"], "loci_per_call": SCALING_CHUNK,
+            "gather": "sharding.run_sharded (dist.gather_object of per-locus rows to rank 0)"}
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = args.threads or os.cpu_count() or 1
     total = args.warmup + args.steps
     for _ in range(args.warmup):
         cpu_arm(args.ref_regions, threads)
@@ -210,6 +361,9 @@ def main() -> None:
     ap.add_argument("--distinct-batches", type=int, default=3, help="distinct synthetic batches cycled over the steps")
     ap.add_argument("--ref-regions", type=int, default=2, help="regions per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-sample-regions", type=int, default=2)
+    ap.add_argument("--threads", type=int, default=0, help="host threads of the CPU arm (--impl reference); default: all")
+    ap.add_argument("--scaling-pool", type=int, default=None,
+                    help="loci of the strong-scaling sub-records (config 4: one set; config 5: the three trio sets together); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="HBM-resident steps as blocking calls instead of pipelined submits (svp_submit_batch_device)")
@@ -220,14 +374,18 @@ def main() -> None:
         run_reference(args)
         return
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.scaling_pool is None:
+        args.scaling_pool = 3072 if args.workload == "config2" else 0
+    scaling_prep = prepare_scaling(args.scaling_pool, rank, world) if args.scaling_pool > 0 else None     # fork pool: before CUDA / NCCL exist
+
     import torch
     import torch.distributed as dist
     from svirlpool_b200._abi import RESULT_DTYPE
     from svirlpool_b200.aligner import Aligner
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -341,6 +499,14 @@ def main() -> None:
     sync_all()
     sum_elapsed = max(al.timer_elapsed_ms() / 1e3, 1e-9)
 
+    # ---- strong scaling of the north-star workloads on fixed pools (configs 4 and 5) ------------------------------------
+    scaling = {}
+    if scaling_prep is not None:
+        for name in SCALING_SETS:
+            rec = run_scaling(al, name, scaling_prep, rank, world, dist, torch, dev)
+            if rec is not None:
+                scaling[name] = rec
+
     # ---- reduce over ranks: max time, summed work ---------------------------------------------------
     vec = torch.tensor([elapsed, e2e_elapsed, float(agg["cells"]), float(regions_done), float(e2e_cells), agg["fwd_ms"], agg["tb_ms"],
                         float(agg["fwd_launches"] + agg["tb_launches"]), float(agg["tb_bytes"] + seq_bytes), float(agg["fwd_launches"]),
@@ -372,10 +538,10 @@ def main() -> None:
             "config": {"workload": WORKLOADS[args.workload],
                        "regions_per_step_per_gpu": args.regions, "distinct_batches": n_distinct,
                        "region_seeds": {"config2": "10000+r", "config3": "20000+r", "config4": "30000+r"}[args.workload],
-                       "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE}" if args.workload != "config3" else "|dlen|+512", "sharding": "LPT by estimated cells, no collective",
-                       "l2": "inputs+traceback per step >> 126 MB L2 (traceback arena rewritten every step)",
+                       "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE} diagonals" if args.workload != "config3" else "|dlen|+512", "sharding": "LPT by estimated cells, no collective",
+                       "l2": "inputs+traceback rows per step >> 126 MB L2 (every pair writes 6-12 MB of rows)",
                        "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it",
-                       "pipeline": ("steps submitted back to back (svp_submit_batch_device), step k+1's forward pass under step k's last traceback; "
+                       "pipeline": ("steps submitted back to back (svp_submit_batch_device), step k+1's kernels start as step k's CTAs retire; "
                                     "all K steps complete inside the timed region") if args.pipeline else "blocking calls"},
             "wall_ms_per_step": wall_elapsed / args.steps * 1e3,
             "e2e": {"value": e2e_cells_all / e2e_elapsed / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d // args.steps,
@@ -390,19 +556,37 @@ def main() -> None:
                          "traffic_note": (f"DRAM bytes per forward launch = algorithmic bytes per launch x {tr['ratio']:.4f} "
                                           f"(dram__bytes_read+write / algorithmic, ncu --set full, {tr['source']})") if tr else None,
                          "algorithmic_bytes_per_launch": algo_bytes / n_fwd,
-                         "kernel": "svp_fwd_kernel (all CTA-width groups of a wave; they run concurrently on 3 streams)", "peak_source": pk["source"],
+                         "kernel": "svp_fwd_kernel (one launch per kernel variant and call, forward pass + in-kernel walk; the launches of a call run concurrently)", "peak_source": pk["source"],
                          "launches": int(agg["fwd_launches"]), "avg_launch_ms": agg["fwd_ms"] / n_fwd,
                          "algorithmic_bytes_per_cell": 1.0,
                          "int_pipe": {"achieved_gcups": fwd_gcups, "peak_gcups": ip["gcups"], "frac": fwd_gcups / ip["gcups"],
                                       "peak_source": ip["source"],
                                       "alu_pipe_14op": {"peak_gcups": ap_["gcups"], "frac": fwd_gcups / ap_["gcups"], **{k: ap_[k] for k in ("ipc_per_smsp", "sm_mhz", "int_ops_per_cell", "source")}},
                                       "note": "the kernel is integer-ALU-bound, not HBM-bound (DESIGN.md §5); frac uses the stricter of the two denominators"}},
-            "kernel_ms": {"fwd": agg["fwd_ms"], "traceback": agg["tb_ms"], "device_total": agg["total_ms"], "waves": agg["waves"]},
+            "kernel_ms": {"device_total": agg["total_ms"], "walk_share_ms": agg["tb_ms"], "launch_groups": agg["waves"],
+                          "note": "forward pass and walk of a pair run inside one kernel; walk_share_ms = kernel time x the CTAs' summed walk ns / (forward + walk ns)"},
         }
+        if scaling:
+            line["strong_scaling"] = scaling
+        if args.workload == "config2":
+            # the same step's cells with bands rounded up to 32 instead of GRANULE diagonals: the un-padded spec figure
+            ids0 = regions_for_step(0, world, args.regions, args.workload)[0]
+            c_g, c_32 = cells_at_granule(ids0[:8], GRANULE), cells_at_granule(ids0[:8], 32)
+            line["cells_granule32"] = {"ratio_to_counted_cells": c_32 / c_g, "gcups": line["value"] * c_32 / c_g,
+                                       "note": f"bands |dlen|+2*{SLACK} rounded up to 32 instead of {GRANULE} diagonals (8 regions of step 0); regions_per_s is granule-free"}
         if not args.no_cpu_baseline and world == 1 and args.workload == "config2":
-            cb = cpu_arm(args.cpu_sample_regions, os.cpu_count() or 1)
+            ncpu = os.cpu_count() or 1
+            cb = cpu_arm(args.cpu_sample_regions, ncpu, keep_rows=True)
+            rows = cb.pop("_rows")
             line["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
+            cb1 = cpu_arm(1, 1)                         # --threads 1: the reference's per-container setting (consensus.py:3270)
+            line["cpu_baseline"]["threads_1"] = {k: v for k, v in cb1.items() if not k.startswith("_")}
+            line["parity_checked"] = parity_check(al, rows)
         print(json.dumps(line), flush=True)
+        if line.get("parity_checked", {}).get("mismatches", 0):
+            print("bench.py: GPU rows differ from the oracle rows of the CPU arm", file=sys.stderr, flush=True)
+            al.close()
+            os._exit(1)
     al.close()
     if world > 1:
         dist.barrier()

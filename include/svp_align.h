@@ -104,8 +104,10 @@ typedef struct svp_handle svp_handle;
 int         svp_abi_version(void);
 int         svp_device_count(void);
 int         svp_scoring_preset(const char* name, svp_scoring* out);
-/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default:
- * 90 % of the free device memory); the library processes a batch in waves that fit half the arena. */
+/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default: 48 GB, at most 60 % of the free
+ * device memory). The arena holds the traceback rows of the pairs RESIDENT on the GPU (a pair's CTA takes a slice when it starts
+ * and returns it when its walk is done), not of the batch; a pair whose rows exceed the arena makes the call fail with
+ * SVP_ERR_NOMEM. Several handles / processes can share a device. */
 int         svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out);
 void        svp_destroy(svp_handle* h);
 const char* svp_last_error(const svp_handle* h);
@@ -177,8 +179,8 @@ int    svp_ava_pairs(const uint32_t* seq_len, const uint32_t* name_order, const 
 
 /* Pipelined form of svp_align_batch_device: returns as soon as the batch is enqueued. Results (and the caller's buffers)
  * belong to the library until svp_sync() returns. Consecutive submits overlap on the device: the next batch is planned on
- * the host and its forward pass starts while the previous batch's last traceback is still running (two batches in flight at
- * most; a third submit first waits for the oldest). svp_sync waits for every submitted batch. */
+ * the host and its CTAs start as those of the previous batch retire (two batches in flight at most; a third submit first
+ * waits for the oldest). svp_sync waits for every submitted batch. */
 int svp_submit_batch_device(svp_handle* h,
                             const uint8_t* d_packed_seqs, size_t packed_bytes,
                             const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
@@ -208,12 +210,15 @@ int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, const uint64
                    uint32_t n_seqs, const svp_pair* pairs, uint32_t n_pairs, size_t cigar_words, svp_pair_plan* out);
 
 typedef struct svp_stats {
-    double   fwd_ms;        /* sum over waves of the forward DP kernel(s) */
-    double   tb_ms;         /* sum over waves of the traceback kernel */
-    double   total_ms;      /* first launch -> last kernel end */
+    double   fwd_ms;        /* device time of the call's kernels (forward pass and walk of a pair run inside one kernel) */
+    double   tb_ms;         /* fwd_ms x the walks' share of the CTAs' summed phase times (informational) */
+    double   total_ms;      /* first enqueue -> last kernel end */
     uint64_t cells;         /* spec cells aligned */
     uint64_t tb_bytes;      /* traceback bytes written to HBM */
-    uint32_t fwd_launches, tb_launches, waves, reserved;
+    uint32_t fwd_launches;  /* kernels launched */
+    uint32_t tb_launches;   /* 0 (no separate traceback kernel) */
+    uint32_t waves;         /* launch groups (kernel variant x CTA width x size class) */
+    uint32_t reserved;
 } svp_stats;
 int svp_get_stats(const svp_handle* h, svp_stats* out);
 /* sums over all completed batches since svp_create or the last call with reset != 0 (waits for submitted batches first) */

@@ -116,7 +116,9 @@ def ava_pairs_native(seq_len: np.ndarray, name_order: np.ndarray | None, strand:
                      seq_base: int, n_reads: int, slack: int, granule: int, full: bool, cigar_start: int = 0) -> tuple[np.ndarray, int]:
     """svp_ava_pairs: the pair descriptors of one container's all-vs-all alignment and the next free CIGAR word."""
     lib = shared_library()
-    cap = n_reads * (n_reads - 1) if strand is None else n_reads * (n_reads - 1) // 2
+    # both orientations of a pair are emitted when either strand is unknown (NULL array, or a 0 entry)
+    known = strand is not None and bool(np.all(np.asarray(strand) != 0))
+    cap = n_reads * (n_reads - 1) // 2 if known else n_reads * (n_reads - 1)
     pairs = np.zeros(max(cap, 1), dtype=PAIR_DTYPE)
     n_pairs = np.zeros(1, dtype=np.uint32)
     words = np.array([cigar_start], dtype=np.uint64)

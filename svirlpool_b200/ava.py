@@ -19,10 +19,42 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._abi import PAIR_DTYPE, PAIR_REVCOMP, ST_CIGAR_OVF, ST_NOHIT, cigartuples, pack_2bit
+from ._abi import (PAIR_DTYPE, PAIR_REVCOMP, ST_BAD_PAIR, ST_CIGAR_OVF, ST_NOHIT, ST_SCORE_OVF, ST_TOO_LONG, SVP_ERR_UNSUPPORTED, cigartuples,
+                   pack_2bit)
 from .datatypes import CIGAR_H, CIGAR_S, AlignedRecord
 
 MIN_DP_SCORE = 80          # minimap2 -s default: hits below this peak DP score are not reported
+ST_FAILED = ST_BAD_PAIR | ST_TOO_LONG | ST_SCORE_OVF
+
+
+def check_status(res: np.ndarray, pairs: np.ndarray | None = None, where: str = "align_batch") -> None:
+    """Per-pair failure bits never degrade into 'no hit': a pair the kernels could not run (descriptor rejected, band wider than a
+    cluster covers, sequences beyond the descriptors, score range exceeded) raises AlignerError — a subprocess.CalledProcessError,
+    what the reference's callers catch around their aligner calls (consensus.py:1387-1396)."""
+    bad = np.nonzero(res["status"] & ST_FAILED)[0]
+    if len(bad) == 0:
+        return
+    from .aligner import AlignerError
+    k = int(bad[0])
+    detail = f"; first: pair {k} status {int(res['status'][k])}"
+    if pairs is not None:
+        detail += f" (q {int(pairs['q'][k])}, t {int(pairs['t'][k])}, band_lo {int(pairs['band_lo'][k])}, band_w {int(pairs['band_w'][k])})"
+    raise AlignerError(SVP_ERR_UNSUPPORTED, f"{where}: {len(bad)} of {len(res)} pairs could not be aligned "
+                       f"(BAD_PAIR {int((res['status'] & ST_BAD_PAIR != 0).sum())}, TOO_LONG {int((res['status'] & ST_TOO_LONG != 0).sum())}, "
+                       f"SCORE_OVF {int((res['status'] & ST_SCORE_OVF != 0).sum())}){detail}")
+
+
+def max_band_w(engine) -> int:
+    """Widest band the kernels cover for the engine's scoring: a cluster of 8 CTAs x 16 warps — 131 072 diagonals on the s16x2 fast
+    path (simple scoring), 65 536 on the general / 32-bit lane kernels (include/svp_align.h: SVP_ST_BAD_PAIR)."""
+    sc = getattr(engine, "scoring", None)
+    simple = True
+    if sc is not None:
+        m = np.asarray(sc["matrix"][0]).reshape(4, 4)
+        simple = bool((np.diag(m) == m[0, 0]).all() and (m[~np.eye(4, dtype=bool)] == m[0, 1]).all()
+                      and int(sc["del_open1"][0]) == int(sc["ins_open1"][0]) and int(sc["del_ext1"][0]) == int(sc["ins_ext1"][0])
+                      and int(sc["del_open2"][0]) == int(sc["ins_open2"][0]) and int(sc["del_ext2"][0]) == int(sc["ins_ext2"][0]))
+    return (131072 if simple else 65536) - 64
 
 
 def round_up(x: int, g: int) -> int:
@@ -110,6 +142,7 @@ class PairBatch:
 def run_batch(engine, batch: PairBatch) -> tuple[np.ndarray, np.ndarray]:
     """Align a batch; pairs whose CIGAR slot overflowed are re-run once with worst-case slots."""
     res, cig = engine.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    check_status(res, batch.pairs, "run_batch")
     ovf = np.nonzero(res["status"] & ST_CIGAR_OVF)[0]
     if len(ovf):
         specs = [(int(p["q"]), int(p["t"]), int(p["band_lo"]), int(p["band_w"]), int(p["flags"])) for p in batch.pairs[ovf]]
@@ -130,6 +163,7 @@ def run_summary(engine, batch: PairBatch) -> np.ndarray:
     run = (lambda b: fn(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)) if fn else \
           (lambda b: engine.align_batch(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)[0])
     res = run(batch)
+    check_status(res, batch.pairs, "run_summary")
     ovf = np.nonzero(res["status"] & ST_CIGAR_OVF)[0]
     if len(ovf):
         specs = [(int(p["q"]), int(p["t"]), int(p["band_lo"]), int(p["band_w"]), int(p["flags"])) for p in batch.pairs[ovf]]
@@ -336,14 +370,19 @@ class MapJob:
     band_w: int = 0
 
 
-def _job_band(sub_len: int, n: int, diag: int | None, band_w: int, granule: int) -> tuple[int, int]:
+def _job_band(sub_len: int, n: int, diag: int | None, band_w: int, granule: int, cap: int = 131008) -> tuple[int, int]:
+    """Band of one job: band_w diagonals around the expected one, or the whole matrix (nothing known / band_w <= 0) — never more
+    than the kernels cover (`cap`): a matrix wider than that keeps its middle `cap` diagonals (around the expected diagonal when
+    there is one)."""
     flo, fw = full_band(sub_len, n, granule)
-    if diag is None or band_w <= 0:
-        return flo, fw
-    w = round_up(band_w, granule)
+    w = fw if diag is None or band_w <= 0 else min(round_up(band_w, granule), fw)
+    if w > cap:
+        w = cap // granule * granule
     if w >= fw:
         return flo, fw
-    return diag - w // 2, w
+    centre = diag if diag is not None else flo + fw // 2
+    lo = min(max(centre - w // 2, flo), flo + fw - w)
+    return lo, w
 
 
 def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[str], min_score: int = MIN_DP_SCORE,
@@ -356,7 +395,8 @@ def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[
     # task: (job index, sub-sequence start, sub-sequence end) in ORIGINAL read coordinates
     tasks = [(k, 0, len(j.seq)) for k, j in enumerate(jobs) if len(j.seq) > 0]
     hits: dict[int, list] = {k: [] for k in range(len(jobs))}
-    for _ in range(max_rounds):
+    cap = max_band_w(engine)
+    for rnd in range(max_rounds):
         if not tasks:
             break
         names, seqs, specs = list(target_names), list(targets), []
@@ -366,15 +406,19 @@ def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[
             names.append(f"{job.name}:{a}-{b}")
             seqs.append(job.seq[a:b])
             n = len(targets[job.target])
-            lo_f, w_f = _job_band(b - a, n, None if job.diag_fwd is None else job.diag_fwd + a, job.band_w, granule)
-            lo_r, w_r = _job_band(b - a, n, None if job.diag_rev is None else job.diag_rev + (full - b), job.band_w, granule)
+            # An unaligned flank is searched over the WHOLE target, not in the band of the first round: what stopped the first hit
+            # may be an indel larger than half that band (a 6 kb deletion in a 4 kb band), and the flank then lies on a diagonal
+            # the band never reaches — minimap2, seeding against the genome, finds it. The target is a window, so the cost is bounded.
+            bw = job.band_w if rnd == 0 else 0
+            lo_f, w_f = _job_band(b - a, n, None if job.diag_fwd is None else job.diag_fwd + a, bw, granule, cap)
+            lo_r, w_r = _job_band(b - a, n, None if job.diag_rev is None else job.diag_rev + (full - b), bw, granule, cap)
             specs.append((len(seqs) - 1, job.target, lo_f, w_f, 0))
             specs.append((len(seqs) - 1, job.target, lo_r, w_r, PAIR_REVCOMP))
         batch = PairBatch.build(names, seqs, specs)
         res, cig = run_batch(engine, batch)
         nxt = []
         for i, (k, a, b) in enumerate(tasks):
-            fwd, rev = res[2 * i], res[2 * i + 1]
+            fwd, rev = res[2 * i], res[2 * i + 1]          # (run_batch raised on failure bits: what is left is NOHIT / CIGAR_OVF after its retry)
             fs = -1 if int(fwd["status"]) & ~ST_CIGAR_OVF else int(fwd["score"])
             rs = -1 if int(rev["status"]) & ~ST_CIGAR_OVF else int(rev["score"])
             pick, rc = (fwd, False) if fs >= rs else (rev, True)

@@ -22,7 +22,8 @@ from . import ava, consensus_align_lib, consensus_class, util
 from .consensus_class import Consensus
 from .datatypes import AlignedRecord, Alignment, MergedSVSignal
 
-MAX_BAND = 8192          # widest band of the 32-bit lane kernel (16 warps x 512 diagonals)
+MAX_BAND = 32768         # first-round band around the expected diagonal (clusters cover up to 131 072 diagonals); unaligned flanks are
+                         # then searched over the whole window (ava.map_jobs), so SVs larger than half this band still split properly
 
 
 def reference_windows(cons: Consensus, chrom_lengths: dict[str, int], margin_frac: float = 0.10, min_margin: int = 500

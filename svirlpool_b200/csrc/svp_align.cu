@@ -1,9 +1,12 @@
 // svp_align.cu — C-ABI of the alignment hot path (include/svp_align.h) on top of the sm_100a
-// kernels in svp_kernels.cuh. Host side: validate, plan pairs into waves that fit the traceback
-// arena, group a wave's pairs by CTA width, launch forward + traceback kernels, time them with
-// CUDA events on the launching stream. No CPU fallback: without a CUDA device every entry point
-// that computes returns SVP_ERR_NODEVICE.
+// kernels in svp_kernels.cuh. Host side: validate, plan every pair (kernel geometry, arena slice), group the
+// pairs of a call by kernel variant, launch ONE kernel per group — forward pass and traceback of a pair
+// run back to back inside its CTA, which takes its traceback rows from the device-side arena and returns
+// them — and time the call with CUDA events on the launching stream. No CPU fallback: without a CUDA
+// device every entry point that computes returns SVP_ERR_NODEVICE.
 #include <algorithm>
+#include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,35 +90,38 @@ struct DevBuf {
 
 }  // namespace
 
-// Per-call state. Two sets alternate, so a submitted call (svp_submit_batch_device) can still be running — typically its last
-// wave's traceback — while the next call is planned and its forward pass starts.
+// Per-call state. Two sets alternate, so a submitted call (svp_submit_batch_device) can still be running while the next call
+// is planned and its kernels are enqueued behind / beside it.
 struct CallSet {
-    DevBuf d_tasks, d_order, d_bests;
+    DevBuf d_tasks, d_order;
     Task* h_tasks = nullptr; size_t h_tasks_cap = 0;            // pinned staging of the task / order arrays
     uint32_t* h_order = nullptr; size_t h_order_cap = 0;
-    std::vector<cudaEvent_t> events;                            // pool, grown on demand
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;               // first enqueue on the main stream / last traceback done
+    std::vector<cudaEvent_t> events;                            // pool, grown on demand (stream joins)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;               // first enqueue on the main stream / last kernel done
     bool pending = false;                                       // enqueued, times not collected yet
-    size_t n_waves = 0;
     svp_stats stats{};                                          // counts filled at submit, times at collection
 };
+
+constexpr int N_FWD_STREAMS = 8;
 
 struct svp_handle {
     int device = 0;
     svp_scoring scoring{};
     Consts cs{};
-    cudaStream_t stream = nullptr;              // forward kernels + copies
-    cudaStream_t stream_aux[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // extra forward streams: the CTA-width groups of a
-                                                // wave run concurrently, and consecutive waves use different stream sets
-    cudaStream_t stream_tb = nullptr;           // traceback kernels (overlap the next wave's forward pass)
-    cudaStream_t stream_tb2 = nullptr;          // ... the warp-per-pair walks of a wave's long pairs, beside the bulk kernel
-    long tbw_long = 24000;                      // pairs with m + n beyond this are walked by a warp each, whatever the wave (env SVP_TBW_LONG)
+    cudaStream_t stream = nullptr;              // copies, joins, the first kernel group of a call
+    cudaStream_t stream_aux[N_FWD_STREAMS - 1] = {};   // the other groups of a call run beside it
     cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
+    // arena: n_sm per-SM pools of sm_region bytes each, then one global pool (svp_kernels.cuh: ArenaPool)
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
+    ArenaPool* d_pools = nullptr;
+    uint32_t n_sm = 0;                          // %nsmid of the device
+    uint64_t sm_region = 0, global_region = 0;
+    double global_frac = -1.0;                  // share of the arena given to the global pool (set_partition)
+    unsigned long long* d_clocks = nullptr;     // summed forward ns / traceback ns / pairs over all CTAs
+    unsigned long long clocks_seen[3] = { 0, 0, 0 };
+    int smem_per_sm = 233472;
     CallSet sets[2];
     uint64_t call_idx = 0;                      // calls planned so far (set = call_idx & 1)
-    uint64_t wave_idx = 0;                      // waves enqueued so far: wave w writes arena half (w & 1), across calls
-    cudaEvent_t half_free[2] = { nullptr, nullptr };   // traceback-done event of the last wave that used each arena half
     DevBuf d_seqs, d_results, d_cigar, d_dense, d_dense_off;
     svp_stats stats{};                          // the last collected call
     svp_stats stats_total{};                    // sums over collected calls since the last reset (svp_get_stats_total)
@@ -123,10 +129,8 @@ struct svp_handle {
     int max_smem_optin = 0;
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
     long latency_pairs = 0;                     // calls of at most this many pairs are planned for short steps (more, narrower warps) instead of fewest
-                                                // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call (435
-                                                // pairs x 8 kb: forward 2.4 ms on 2 x KP=4 warps with a barrier per step, 2.0 ms on one KP=8 warp)
+                                                // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call
     bool force_ring = false;                    // test aid (env SVP_FORCE_RING): every pair on a sliding-window variant
-    int tbw_max = 2048;                         // waves with at most this many pairs use the warp-per-pair traceback (env SVP_TBW_MAX)
 };
 
 static thread_local std::string g_err;
@@ -218,11 +222,82 @@ static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
 
 // tuning / test knobs read from the environment when a handle (or a planning-only pseudo handle) is set up
 static void read_env_knobs(svp_handle* h) {
-    if (const char* e = getenv("SVP_TBW_LONG")) h->tbw_long = atol(e);
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
-    if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
+}
+
+// kernel family of a pair
+enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3, FAM_FAST_RB = 4 };
+
+// Every forward kernel has the same signature; the variant a group of pairs runs on is looked up here (svp_create sets the
+// attributes of every entry, run_plan launches through it). nullptr: no such variant.
+using FwdKernel = void (*)(const Task*, const uint32_t*, const uint8_t*, const Arena, svp_result*, uint32_t*, const Consts);
+static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring, bool two) {
+    if (fam == FAM_FAST || fam == FAM_FAST_RB) {        // s16x2 fast path: plain / rebased, whole images / sliding windows, one CTA / cluster
+        const bool rb = fam == FAM_FAST_RB;
+        if (cluster) {
+            if (kp != 8) return nullptr;
+#define SVP_FCL(T, R, G) if (two == T && rb == R && ring == G) return svp_fwd_kernel<8, true, T, true, R, G>;
+            SVP_FCL(true, false, false) SVP_FCL(true, false, true) SVP_FCL(true, true, false) SVP_FCL(true, true, true)
+            SVP_FCL(false, false, false) SVP_FCL(false, false, true) SVP_FCL(false, true, false) SVP_FCL(false, true, true)
+#undef SVP_FCL
+            return nullptr;
+        }
+#define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) return svp_fwd_kernel<K, M, T, false, R, G>;
+#define SVP_F4(K, M, T) SVP_F(K, M, T, false, false) SVP_F(K, M, T, false, true) SVP_F(K, M, T, true, false) SVP_F(K, M, T, true, true)
+        SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
+        SVP_F4(5, false, true) SVP_F4(5, true, true) SVP_F4(6, false, true) SVP_F4(6, true, true) SVP_F4(7, false, true) SVP_F4(7, true, true)
+        SVP_F4(4, false, false) SVP_F4(4, true, false) SVP_F4(8, false, false) SVP_F4(8, true, false)
+#undef SVP_F4
+#undef SVP_F
+        return nullptr;
+    }
+    if (kp != 4) return nullptr;                        // general scoring and 32-bit lanes: KP = 4 geometry
+    if (fam == FAM_GEN) {                               // whole images only
+        if (ring) return nullptr;
+#define SVP_G(M, T, C) if (multi == M && two == T && cluster == C) return svp_fwdg_kernel<M, T, C>;
+        SVP_G(false, true, false) SVP_G(true, true, false) SVP_G(false, false, false) SVP_G(true, false, false) SVP_G(true, true, true) SVP_G(true, false, true)
+#undef SVP_G
+        return nullptr;
+    }
+    const bool gen = fam == FAM_S32_GEN;
+#define SVP_W(M, T, G, C, R) if (multi == M && two == T && gen == G && cluster == C && ring == R) return svp_fwd32_kernel<M, T, G, C, R>;
+#define SVP_W2(M, C, R) SVP_W(M, true, false, C, R) SVP_W(M, false, false, C, R) SVP_W(M, true, true, C, R) SVP_W(M, false, true, C, R)
+    SVP_W2(false, false, false) SVP_W2(true, false, false) SVP_W2(true, true, false)
+    SVP_W2(false, false, true) SVP_W2(true, false, true) SVP_W2(true, true, true)
+#undef SVP_W2
+#undef SVP_W
+    return nullptr;
+}
+
+__global__ void svp_nsmid_kernel(uint32_t* out) { uint32_t n; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n)); *out = n; }
+
+// result rows of the pairs the planner rejected (no CTA runs for them)
+__global__ void svp_invalid_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n, svp_result* __restrict__ results) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const Task tk = tasks[order[k]];
+    svp_result res;
+    memset(&res, 0, sizeof(res));
+    res.cigar_off = tk.cigar_off;
+    res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_TOO_LONG : SVP_ST_BAD_PAIR;
+    results[tk.pair_index] = res;
+}
+
+// Split the arena into n_sm per-SM regions and one global region of `global_frac` of it. The device must be idle.
+static int set_partition(svp_handle* h, double global_frac) {
+    const uint64_t total = h->arena_bytes & ~(uint64_t)255;
+    uint64_t glob = (uint64_t)((double)total * global_frac) & ~(uint64_t)255;
+    const uint64_t region = ((total - glob) / h->n_sm) & ~(uint64_t)255;
+    glob = total - region * h->n_sm;
+    std::vector<ArenaPool> pools(h->n_sm + 1);
+    memset(pools.data(), 0, pools.size() * sizeof(ArenaPool));
+    for (uint32_t k = 0; k < h->n_sm; ++k) { pools[k].base = (uint64_t)k * region; pools[k].bytes = region; }
+    pools[h->n_sm].base = (uint64_t)h->n_sm * region; pools[h->n_sm].bytes = glob;
+    CUDA_TRY(h, cudaMemcpy(h->d_pools, pools.data(), pools.size() * sizeof(ArenaPool), cudaMemcpyHostToDevice));
+    h->sm_region = region; h->global_region = glob; h->global_frac = global_frac;
+    return SVP_OK;
 }
 
 extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out) {
@@ -240,45 +315,37 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     h->device = device; h->scoring = *scoring; h->cs = cs;
     auto bail = [&](int code, const std::string& m) { g_err = m; svp_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaSetDevice failed");
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     for (cudaStream_t& sx : h->stream_aux)
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
-    if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
-    if (cudaStreamCreateWithPriority(&h->stream_tb2, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     read_env_knobs(h);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-#define SVP_SMEM(...) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin)
-#define SVP_ATTR2(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>); \
-                           SVP_SMEM(svp_fwd_kernel<K, false, false, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, false, false, R, G>)
-#define SVP_ATTR(K) SVP_ATTR2(K, false, false); SVP_ATTR2(K, false, true); SVP_ATTR2(K, true, false); SVP_ATTR2(K, true, true)
-    SVP_ATTR(4); SVP_ATTR(8);
-#define SVP_ATTR2T(K, R, G) SVP_SMEM(svp_fwd_kernel<K, false, true, false, R, G>); SVP_SMEM(svp_fwd_kernel<K, true, true, false, R, G>)
-#define SVP_ATTRT(K) SVP_ATTR2T(K, false, false); SVP_ATTR2T(K, false, true); SVP_ATTR2T(K, true, false); SVP_ATTR2T(K, true, true)
-    SVP_ATTRT(5); SVP_ATTRT(6); SVP_ATTRT(7);
-#undef SVP_ATTRT
-#undef SVP_ATTR2T
-#define SVP_ATTRC(R, G) SVP_SMEM(svp_fwd_kernel<8, true, true, true, R, G>); SVP_SMEM(svp_fwd_kernel<8, true, false, true, R, G>)
-    SVP_ATTRC(false, false); SVP_ATTRC(false, true); SVP_ATTRC(true, false); SVP_ATTRC(true, true);
-#undef SVP_ATTRC
-#undef SVP_ATTR2
-    SVP_SMEM(svp_fwdg_kernel<false, true>); SVP_SMEM(svp_fwdg_kernel<true, true>); SVP_SMEM(svp_fwdg_kernel<false, false>); SVP_SMEM(svp_fwdg_kernel<true, false>);
-    SVP_SMEM(svp_fwd32_kernel<false, true, false>); SVP_SMEM(svp_fwd32_kernel<true, true, false>);
-    SVP_SMEM(svp_fwd32_kernel<false, false, false>); SVP_SMEM(svp_fwd32_kernel<true, false, false>);
-    SVP_SMEM(svp_fwd32_kernel<false, true, true>); SVP_SMEM(svp_fwd32_kernel<true, true, true>);
-    SVP_SMEM(svp_fwd32_kernel<false, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true>);
-    SVP_SMEM(svp_fwdg_kernel<true, true, true>); SVP_SMEM(svp_fwdg_kernel<true, false, true>);
-    SVP_SMEM(svp_fwd32_kernel<true, true, false, true>); SVP_SMEM(svp_fwd32_kernel<true, false, false, true>);
-    SVP_SMEM(svp_fwd32_kernel<true, true, true, true>); SVP_SMEM(svp_fwd32_kernel<true, false, true, true>);
-#undef SVP_ATTR
-#undef SVP_SMEM
+    cudaDeviceGetAttribute(&h->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    // every variant: the largest dynamic shared memory (sequence images, or the residency ballast of run_plan) and the whole
+    // L1 / shared-memory array as shared memory (the kernels stream their stores and read the rows through L2)
+    for (int fam = 0; fam < 5; ++fam) for (int kp = 4; kp <= 8; ++kp) for (int m = 0; m < 2; ++m) for (int c = 0; c < 2; ++c)
+        for (int r = 0; r < 2; ++r) for (int t = 0; t < 2; ++t)
+            if (FwdKernel k = fwd_kernel(fam, kp, m != 0, c != 0, r != 0, t != 0)) {
+                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+                cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
+    if (cudaGetLastError() != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
+    // %nsmid: the range of the SM ids the per-SM arena pools are indexed with
+    uint32_t* d_n = nullptr;
+    if (cudaMalloc((void**)&d_n, sizeof(uint32_t)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
+    svp_nsmid_kernel<<<1, 1, 0, h->stream>>>(d_n);
+    uint32_t nsm = 0;
+    const cudaError_t e_n = cudaMemcpyAsync(&nsm, d_n, sizeof(nsm), cudaMemcpyDeviceToHost, h->stream);
+    const cudaError_t e_s = cudaStreamSynchronize(h->stream);
+    cudaFree(d_n);
+    if (e_n != cudaSuccess || e_s != cudaSuccess || nsm == 0) return bail(SVP_ERR_CUDA, "cannot query the SM count");
+    h->n_sm = nsm;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
-    // default arena: 90 % of the free memory. Every wave boundary costs 3.5-5 ms of forward time (the drain of one wave and the
-    // ramp of the next; measured by sweeping the arena: 32 / 64 / 128 / 160 GB -> 1377 / 1728 / 1912 / 2006 GCUPS on config 2),
-    // so the arena — i.e. the wave — should be as large as the device allows.
-    size_t want = max_tb_bytes ? max_tb_bytes : free_b / 10 * 9;
+    // Default arena: 48 GB, at most 60 % of the free memory. The arena holds the traceback rows of the pairs RESIDENT on the GPU
+    // only (a slice lives from the start of a pair's CTA to the end of its walk), so it does not grow with the batch: config 2
+    // keeps ~2000 pairs x 6-12 MB in flight. Several handles / processes can share a device.
+    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>((size_t)48 << 30, free_b / 10 * 6);
     if (!max_tb_bytes) if (const char* e = getenv("SVP_ARENA_GB")) want = std::min<size_t>((size_t)std::max(atoi(e), 1) << 30, free_b / 20 * 19);   // tuning aid
     want = (want + 255) & ~(size_t)255;
     // the default size shrinks until the allocation succeeds (fragmentation, another process on the device); an explicit size does not
@@ -289,6 +356,10 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         want = (want / 4 * 3 + 255) & ~(size_t)255;
     }
     h->arena_bytes = want;
+    if (cudaMalloc((void**)&h->d_pools, (h->n_sm + 1) * sizeof(ArenaPool)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
+    if (cudaMalloc((void**)&h->d_clocks, 4 * sizeof(unsigned long long)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
+    cudaMemset(h->d_clocks, 0, 4 * sizeof(unsigned long long));
+    if (set_partition(h, 0.25) != SVP_OK) return bail(SVP_ERR_CUDA, "cannot initialise the arena pools");
     *out = h;
     return SVP_OK;
 }
@@ -298,9 +369,11 @@ extern "C" void svp_destroy(svp_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->arena) cudaFree(h->arena);
+    if (h->d_pools) cudaFree(h->d_pools);
+    if (h->d_clocks) cudaFree(h->d_clocks);
     for (DevBuf* b : { &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (CallSet& c : h->sets) {
-        for (DevBuf* b : { &c.d_tasks, &c.d_order, &c.d_bests }) b->release();
+        for (DevBuf* b : { &c.d_tasks, &c.d_order }) b->release();
         if (c.h_tasks) cudaFreeHost(c.h_tasks);
         if (c.h_order) cudaFreeHost(c.h_order);
         for (cudaEvent_t e : c.events) cudaEventDestroy(e);
@@ -308,7 +381,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     }
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
-    for (cudaStream_t sx : { h->stream, h->stream_tb, h->stream_tb2 }) if (sx) cudaStreamDestroy(sx);
+    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -327,23 +400,17 @@ static int collect_call(svp_handle* h, CallSet& c) {
     if (!c.pending) return SVP_OK;
     c.pending = false;
     CUDA_TRY(h, cudaEventSynchronize(c.ev_t1));
-    constexpr size_t EV_PER_WAVE = 4 + 7;
-    auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
     float tot = 0; cudaEventElapsedTime(&tot, c.ev_t0, c.ev_t1);
     c.stats.total_ms = tot;
-    // forward time = length of the union of the waves' forward intervals (they overlap when waves are allowed to)
-    float covered_to = 0;
-    for (size_t wv = 0; wv < c.n_waves; ++wv) {
-        float f0 = 0, f1 = 0, b = 0;
-        cudaEventElapsedTime(&f0, c.ev_t0, EV(wv, 0));       // forward pass of the wave (may overlap the previous wave's traceback)
-        cudaEventElapsedTime(&f1, c.ev_t0, EV(wv, 1));
-        cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));      // its traceback (includes waiting for SM slots)
-        const float from = std::max(f0, covered_to);
-        if (f1 > from) { c.stats.fwd_ms += f1 - from; covered_to = f1; }
-        c.stats.tb_ms += b;
-    }
-    for (cudaEvent_t& hf : h->half_free)                     // this call's waves are done: the halves they used last are free
-        for (cudaEvent_t e : c.events) if (hf == e) { hf = nullptr; break; }
+    // forward pass and walk of a pair run inside one kernel: the kernel time of the call is split by the CTAs' own clocks
+    // (summed ns of the two phases since the last collection; a pipelined neighbour call's CTAs are in the same sums)
+    unsigned long long clk[3] = { 0, 0, 0 };
+    CUDA_TRY(h, cudaMemcpy(clk, h->d_clocks, sizeof(clk), cudaMemcpyDeviceToHost));
+    const double f_ns = (double)(clk[0] - h->clocks_seen[0]), t_ns = (double)(clk[1] - h->clocks_seen[1]);
+    for (int k = 0; k < 3; ++k) h->clocks_seen[k] = clk[k];
+    const double tb_share = (f_ns + t_ns) > 0 ? t_ns / (f_ns + t_ns) : 0.0;
+    c.stats.fwd_ms = tot;
+    c.stats.tb_ms = tot * tb_share;
     h->stats = c.stats;
     svp_stats& T = h->stats_total;
     T.fwd_ms += c.stats.fwd_ms; T.tb_ms += c.stats.tb_ms; T.total_ms += c.stats.total_ms; T.cells += c.stats.cells; T.tb_bytes += c.stats.tb_bytes;
@@ -407,12 +474,9 @@ static int64_t cells_below(int64_t m, int64_t n, int64_t x) {
     return total;
 }
 
-// kernel family of a pair
-enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3, FAM_FAST_RB = 4 };
-
-template <typename Kern>
-static void launch_cluster(Kern kern, int cluster, unsigned n_pairs, unsigned thr, size_t smem, cudaStream_t st, const Task* tasks,
-                           const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
+// one kernel = every pair of a call that runs on one variant (grid = pairs x CTAs per pair)
+static cudaError_t launch_group(FwdKernel kern, int cluster, unsigned n_pairs, unsigned thr, size_t smem, cudaStream_t st, const Task* tasks,
+                                const uint32_t* order, const uint8_t* seqs, const Arena& ar, svp_result* results, uint32_t* cigar, const Consts& cs) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_pairs * (unsigned)cluster, 1, 1);
     cfg.blockDim = dim3(thr, 1, 1);
@@ -421,60 +485,8 @@ static void launch_cluster(Kern kern, int cluster, unsigned n_pairs, unsigned th
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, tasks, order, seqs, arena, bests, cs);
-}
-
-static void launch_fwd(int fam, int kp, int nwarp, int cluster, bool ring, bool two, unsigned grid, size_t smem, cudaStream_t st, const Task* tasks,
-                       const uint32_t* order, const uint8_t* seqs, uint8_t* arena, uint2* bests, const Consts& cs) {
-    const bool multi = nwarp > 1;
-    const unsigned thr = (unsigned)nwarp * 32u;
-    if (fam == FAM_FAST || fam == FAM_FAST_RB) {        // s16x2 fast path: plain / rebased, whole images / sliding windows, one CTA / cluster
-        const bool rb = fam == FAM_FAST_RB;
-        if (cluster > 1) {
-#define SVP_FCL(T, R, G) if (two == T && rb == R && ring == G) { launch_cluster(svp_fwd_kernel<8, true, T, true, R, G>, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
-            SVP_FCL(true, false, false) SVP_FCL(true, false, true) SVP_FCL(true, true, false) SVP_FCL(true, true, true)
-            SVP_FCL(false, false, false) SVP_FCL(false, false, true) SVP_FCL(false, true, false) SVP_FCL(false, true, true)
-#undef SVP_FCL
-            return;
-        }
-#define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) { svp_fwd_kernel<K, M, T, false, R, G><<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs); return; }
-#define SVP_F4(K, M, T) SVP_F(K, M, T, false, false) SVP_F(K, M, T, false, true) SVP_F(K, M, T, true, false) SVP_F(K, M, T, true, true)
-        SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
-        SVP_F4(5, false, true) SVP_F4(5, true, true) SVP_F4(6, false, true) SVP_F4(6, true, true) SVP_F4(7, false, true) SVP_F4(7, true, true)
-        SVP_F4(4, false, false) SVP_F4(4, true, false) SVP_F4(8, false, false) SVP_F4(8, true, false)
-#undef SVP_F4
-#undef SVP_F
-        return;
-    }
-    if (ring) {              // sliding-window variant of the 32-bit lane kernel (plain or cluster launch)
-        const bool gen = fam == FAM_S32_GEN;
-#define SVP_RING(M, T, G) if (multi == M && two == T && gen == G) { \
-            if (cluster > 1) { if (M) launch_cluster(svp_fwd32_kernel<true, T, G, true, true>, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); } \
-            else svp_fwd32_kernel<M, T, G, false, true><<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs); \
-            return; }
-        SVP_RING(false, true, false) SVP_RING(true, true, false) SVP_RING(false, false, false) SVP_RING(true, false, false)
-        SVP_RING(false, true, true) SVP_RING(true, true, true) SVP_RING(false, false, true) SVP_RING(true, false, true)
-#undef SVP_RING
-        return;
-    }
-    if (cluster > 1) {       // 16-warp CTAs, `cluster` of them per pair
-#define SVP_CL(COND, ...) if (COND) { launch_cluster(__VA_ARGS__, cluster, grid, thr, smem, st, tasks, order, seqs, arena, bests, cs); return; }
-        SVP_CL(fam == FAM_GEN && two, svp_fwdg_kernel<true, true, true>) SVP_CL(fam == FAM_GEN && !two, svp_fwdg_kernel<true, false, true>)
-        SVP_CL(fam == FAM_S32 && two, svp_fwd32_kernel<true, true, false, true>) SVP_CL(fam == FAM_S32 && !two, svp_fwd32_kernel<true, false, false, true>)
-        SVP_CL(fam == FAM_S32_GEN && two, svp_fwd32_kernel<true, true, true, true>) SVP_CL(fam == FAM_S32_GEN && !two, svp_fwd32_kernel<true, false, true, true>)
-#undef SVP_CL
-        return;
-    }
-#define SVP_ARGS <<<grid, thr, smem, st>>>(tasks, order, seqs, arena, bests, cs)
-#define SVP_CASE(M, T) if (fam == FAM_GEN && multi == M && two == T) { svp_fwdg_kernel<M, T> SVP_ARGS; return; }
-    SVP_CASE(false, true) SVP_CASE(true, true) SVP_CASE(false, false) SVP_CASE(true, false)
-#undef SVP_CASE
-#define SVP_CASE(M, T, G) if (fam == (G ? FAM_S32_GEN : FAM_S32) && multi == M && two == T) { svp_fwd32_kernel<M, T, G> SVP_ARGS; return; }
-    SVP_CASE(false, true, false) SVP_CASE(true, true, false) SVP_CASE(false, false, false) SVP_CASE(true, false, false)
-    SVP_CASE(false, true, true) SVP_CASE(true, true, true) SVP_CASE(false, false, true) SVP_CASE(true, false, true)
-#undef SVP_CASE
-#undef SVP_ARGS
+    cfg.attrs = attr; cfg.numAttrs = cluster > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, tasks, order, seqs, ar, results, cigar, cs);
 }
 
 // CIGAR compaction for the host-buffer entry point: one warp per pair copies its (right-aligned) slot
@@ -516,7 +528,7 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     const long ring_min = h->ring_min;
     // kernel variant. General scoring and 32-bit lanes use the KP = 4 geometry. Sequences that do not fit whole shared-memory
     // images (with the widest CTA's mailboxes) run on a sliding-window variant.
-    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)mailbox_bytes(16);
+    const size_t image_need = (size_t)(cs.general ? 2 : 1) * seq_image_bytes(t.m) + (size_t)seq_image_bytes(t.n) + (size_t)mailbox_bytes(16) + 64;
     // sliding windows: always when whole images do not fit; on the fast path also when whole images would cost occupancy
     // (more than SVP_RING_MIN bytes of images per warp of the CTA)
     const bool beyond_s16 = (int64_t)std::min(t.m, t.n) * cs.a_max > S16_SCORE_LIMIT;
@@ -557,6 +569,8 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     const int64_t steps = rmax - rb + 1;
     t.r_begin = (int32_t)rb;
     t.n_iter = (int32_t)((steps + steps_per_iter - 1) / steps_per_iter);
+    t.tb_bytes = (tb_bytes_of(t) + 15) & ~(uint64_t)15;
+    t.slice_bytes = (t.tb_bytes + best_entries_of(t) * sizeof(uint2) + 255) & ~(uint64_t)255;
 }
 
 // pinned staging for the next call's task / order arrays; waits for the call that used this set two calls ago
@@ -584,234 +598,162 @@ static int begin_call(svp_handle* h, size_t n, CallSet** out) {
 }
 
 // Enqueue the planned pairs of call set `c` (c.h_tasks[0..n)). wait = true: return when the results are complete and the
-// call's times are collected; false: return after the enqueue (svp_submit_batch_device) — the next call's planning and
-// forward pass then run under this call's last traceback.
+// call's times are collected; false: return after the enqueue (svp_submit_batch_device) — the next call is planned while this
+// one runs, and its kernels start as CTA slots and arena slices free up.
+//
+// There are no waves. Every pair's CTA takes its traceback rows from the device-side arena when it starts and returns them when
+// its walk is done (svp_kernels.cuh: ArenaPool), so the arena bounds the pairs in flight, not the batch. What the host does:
+//   * classify the pairs: "regular" slices (at most a third of a per-SM region) come from the pool of the SM the CTA runs on,
+//     larger ones from the global pool; the split of the arena between the two follows the demand of the call;
+//   * group the pairs by kernel variant, CTA width, shared-memory class and slice-size class; one launch per group;
+//   * bound the residency: a regular group asks for at least 1.5 x slice / region of an SM's shared memory per CTA (ballast), so
+//     the block scheduler itself keeps the slices live on an SM within its region, with room for fragmentation — a CTA that still
+//     finds its pool full waits for a neighbour to finish (arena_alloc);
+//   * launch the groups with the longest-running CTAs first, round-robin over the streams, so that the many short single-warp
+//     CTAs fill the tail; consecutive calls rotate the streams and overlap freely.
 static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar, bool wait) {
     const Consts& cs = h->cs;
     cudaStream_t st = h->stream;
     Task* tasks = c.h_tasks;
     c.stats = svp_stats{};
-    c.n_waves = 0;
     if (n == 0) { h->stats = c.stats; return SVP_OK; }
     // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
     for (size_t k = 0; k < n; ++k) {
         Task& t = tasks[k];
         if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-        if (smem_need(t, cs, nw) > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;
+        if (smem_need(t, cs, nw) + 64 > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;      // (+ the kernels' static shared memory)
     }
-    // waves: consecutive tasks whose traceback rows fit HALF the arena; the halves alternate from wave to wave (across calls),
-    // so the traceback of a wave overlaps the forward pass of the next one
-    const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
-    uint64_t cap = half;                        // bytes a wave may use
-    bool serial = false;
-    std::vector<std::pair<size_t, size_t>> waves;
-    std::vector<uint64_t> wave_best;
+    // ---- arena partition: which share goes to the global pool ----------------------------------------------------------
     {
-        // a call that needs several waves gets waves of equal size (not full halves and a remainder): the traceback of a wave
-        // runs under the forward pass of the next one, and the wave after that waits for it
-        uint64_t total_need = 0, total_len = 0;
-        for (size_t k = 0; k < n; ++k)
-            if (!(tasks[k].flags & TASK_INVALID)) { total_need += (tb_bytes_of(tasks[k]) + 255) & ~(uint64_t)255; total_len += (uint64_t)tasks[k].m + tasks[k].n; }
-        // Two ways to run the tracebacks. CONCURRENT: waves of half the arena, the traceback of a wave runs under the forward pass
-        // of the next one. SERIAL: waves of the whole arena, each traceback runs alone on the warp-per-pair kernel (5-6 ms for 10 000
-        // pairs) before the next forward pass starts. A concurrent traceback slows the forward pass it shares the SMs with by 12 %
-        // (config 2) to 18-50 % (config 4: many short pairs), more than it takes alone, and whole-arena waves halve the number of
-        // wave boundaries; but waves of few, long pairs (config 3) have latency-bound tracebacks that need the overlap, and on
-        // config 2 (8 kb reads) the two modes measure the same (2068 serial, 2083-2110 concurrent). Hence: serial when a half-arena
-        // wave would hold at least serial_min_pairs pairs of, on average, less than serial_max_len bases (m + n); config 4: 1693 ->
-        // 1949 GCUPS. Env SVP_TB_SERIAL = 0 / 1 forces the choice.
-        static const int serial_mode = [] { const char* e = getenv("SVP_TB_SERIAL"); return e ? atoi(e) : -1; }();
-        static const long serial_min_pairs = [] { const char* e = getenv("SVP_TB_SERIAL_PAIRS"); return e ? atol(e) : 4096L; }();
-        static const long serial_max_len = [] { const char* e = getenv("SVP_TB_SERIAL_LEN"); return e ? atol(e) : 12000L; }();
-        const uint64_t n_w_half = std::max<uint64_t>(1, (total_need + half - 1) / half);
-        serial = serial_mode >= 0 ? serial_mode != 0 : ((long)(n / n_w_half) >= serial_min_pairs && (long)(total_len / std::max<size_t>(n, 1)) < serial_max_len);
-        if (serial) cap = h->arena_bytes & ~(uint64_t)255;
-        const uint64_t n_w = std::max<uint64_t>(1, (total_need + cap - 1) / cap);
-        static const bool balance = [] { const char* e = getenv("SVP_WAVE_BALANCE"); return e ? atoi(e) != 0 : true; }();
-        const uint64_t target = balance ? std::min(cap, total_need / n_w + total_need / (n_w * 50) + 4096) : cap;
-        size_t first = 0; uint64_t used = 0, best_used = 0;
-        for (size_t k = 0; k < n; ++k) {
-            Task& t = tasks[k];
-            uint64_t need = 0, nbest = 0;
-            if (!(t.flags & TASK_INVALID)) {
-                need = (tb_bytes_of(t) + 255) & ~(uint64_t)255;
-                nbest = best_entries_of(t);
-                if (need > cap) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds half the arena; create the handle with a larger max_tb_bytes");
+        uint64_t max_slice = 0;
+        for (size_t k = 0; k < n; ++k) if (!(tasks[k].flags & TASK_INVALID)) max_slice = std::max(max_slice, tasks[k].slice_bytes);
+        auto demand = [&](double gf, double& share, bool& fits) {
+            const uint64_t total = h->arena_bytes & ~(uint64_t)255;
+            const uint64_t glob = (uint64_t)((double)total * gf), region = (total - glob) / h->n_sm;
+            double huge = 0, all = 0;
+            for (size_t k = 0; k < n; ++k) {
+                if (tasks[k].flags & TASK_INVALID) continue;
+                all += (double)tasks[k].slice_bytes;
+                if (tasks[k].slice_bytes * 3 > region) huge += (double)tasks[k].slice_bytes;
             }
-            if (used + need > cap || (used >= target && need)) { waves.emplace_back(first, k); wave_best.push_back(best_used); first = k; used = 0; best_used = 0; }
-            t.tb_off = (serial ? 0 : ((h->wave_idx + waves.size()) & 1) * half) + used; t.best_off = best_used;
-            used += need; best_used += nbest;
+            share = all > 0 ? huge / all : 0.0;
+            fits = max_slice * 3 <= region || max_slice + 4096 <= glob;
+        };
+        double share = 0; bool fits = false;
+        demand(h->global_frac, share, fits);
+        if (!fits || std::fabs(std::min(std::max(share, 0.1), 0.9) - h->global_frac) > 0.3) {
+            double best_gf = -1, best_d = 1e9;
+            for (double gf : { 0.1, 0.25, 0.5, 0.75, 0.9 }) {
+                double sh; bool ok;
+                demand(gf, sh, ok);
+                const double d = std::fabs(std::min(std::max(sh, 0.1), 0.9) - gf);
+                if (ok && d < best_d) { best_d = d; best_gf = gf; }
+            }
+            if (best_gf < 0) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds the arena; create the handle with a larger max_tb_bytes");
+            if (best_gf != h->global_frac) {
+                for (CallSet& o : h->sets) { int rc = collect_call(h, o); if (rc != SVP_OK) return rc; }      // the device must be idle
+                CUDA_TRY(h, cudaDeviceSynchronize());
+                int rc = set_partition(h, best_gf);
+                if (rc != SVP_OK) return rc;
+            }
         }
-        waves.emplace_back(first, n); wave_best.push_back(best_used);
     }
-    uint64_t max_best = 1;
-    for (uint64_t b : wave_best) max_best = std::max(max_best, b);
-    for (size_t wv = 0; wv < waves.size(); ++wv)
-        if ((h->wave_idx + wv) & 1)
-            for (size_t k = waves[wv].first; k < waves[wv].second; ++k) tasks[k].best_off += max_best;
+    // ---- groups ---------------------------------------------------------------------------------------------------------
+    struct Group { int fam, nwarp, kp, cluster; bool ring, huge; size_t first, count, smem; uint64_t work, max_slice; };
+    std::vector<Group> groups;
+    uint32_t* order = c.h_order;
+    size_t pos = 0;
+    {
+        std::map<std::array<int64_t, 8>, std::vector<uint32_t>> by_key;
+        for (size_t k = 0; k < n; ++k) {
+            const Task& t = tasks[k];
+            if (t.flags & TASK_INVALID) continue;
+            const int cl = cluster_of(t);
+            const int nw = cl > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
+            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : (t.flags & TASK_REBASE) ? FAM_FAST_RB : FAM_FAST);
+            const bool ring = (t.flags & TASK_RING) != 0;
+            // shared memory of the pair's CTA: sequence images + mailboxes, in classes (<= 32 KB, then powers of two) so that a few long
+            // pairs do not cut the occupancy of the short ones sharing their launch; sliding-window variants have a fixed size
+            int smem_cls = 0;
+            if (!ring) while (((size_t)32768 << smem_cls) < smem_need(t, cs, nw)) ++smem_cls;
+            const bool huge = t.slice_bytes * 3 > h->sm_region;
+            // slice-size classes (x1.5 steps) keep the ballast of a regular group close to what each of its pairs needs
+            int size_cls = 0;
+            if (!huge) for (uint64_t b = (uint64_t)1 << 20; b < t.slice_bytes; b += b / 2) ++size_cls;
+            by_key[{ fam, kp_of(t), nw, cl, ring, smem_cls, huge, size_cls }].push_back((uint32_t)k);
+        }
+        for (auto& kv : by_key) {
+            std::vector<uint32_t>& v = kv.second;
+            // longest pairs first inside a group: the tail of the launch is short pairs
+            std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
+            Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, pos, v.size(), 0, 0, 0 };
+            const int lane_cost = (g.fam == FAM_S32 || g.fam == FAM_S32_GEN) ? 2 : 1;
+            for (uint32_t k : v) {
+                const Task& t = tasks[k];
+                g.smem = std::max(g.smem, smem_need(t, cs, g.nwarp));
+                g.max_slice = std::max(g.max_slice, t.slice_bytes);
+                g.work += (uint64_t)t.n_iter * g.nwarp * g.kp * lane_cost * (steps_per_iter_of(t) / (2 * g.kp)) * g.cluster;
+            }
+            if (!g.huge) {
+                // ballast: CTAs per SM <= smem_per_sm / (smem + 1 KB the system reserves per CTA); keep 1.5 x their slices within the SM's region
+                const double per_cta = 1.5 * (double)g.max_slice / (double)h->sm_region * (double)h->smem_per_sm;
+                const size_t ballast = per_cta > 1024.0 ? (size_t)per_cta - 1024 + 16 : 0;
+                g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - 64);
+            }
+            std::copy(v.begin(), v.end(), order + pos);
+            pos += v.size();
+            groups.push_back(g);
+        }
+        // groups with the longest-running CTAs (most work per pair) first, the many short CTAs fill the tail
+        std::sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
+    }
+    const size_t inv_first = pos;
+    for (size_t k = 0; k < n; ++k) if (tasks[k].flags & TASK_INVALID) order[pos++] = (uint32_t)k;
+    const size_t n_invalid = pos - inv_first;
+
     CUDA_TRY(h, c.d_tasks.reserve(n * sizeof(Task)));
-    CUDA_TRY(h, c.d_order.reserve(2 * n * sizeof(uint32_t)));
-    CUDA_TRY(h, c.d_bests.reserve(2 * max_best * sizeof(uint2)));
+    CUDA_TRY(h, c.d_order.reserve(std::max<size_t>(pos, 1) * sizeof(uint32_t)));
     CUDA_TRY(h, cudaEventRecord(c.ev_t0, st));
     CUDA_TRY(h, cudaMemcpyAsync(c.d_tasks.p, tasks, n * sizeof(Task), cudaMemcpyHostToDevice, st));
-
-    // per wave: order lists grouped by kernel variant and CTA width (warps)
-    uint32_t* order = c.h_order;
-    struct Group { int fam; int nwarp; int kp; int cluster; bool ring; size_t first, count; size_t smem; uint64_t work; };
-    std::vector<std::vector<Group>> wave_groups(waves.size());
-    size_t pos = 0;
-    for (size_t wv = 0; wv < waves.size(); ++wv) {
-        std::map<int64_t, std::vector<uint32_t>> by_w;
-        for (size_t k = waves[wv].first; k < waves[wv].second; ++k) {
-            Task& t = tasks[k];
-            if (t.flags & TASK_INVALID) continue;
-            const int per_warp = 128 * kp_of(t);
-            const int cl = cluster_of(t);
-            const int nw = cl > 1 ? 16 : (t.band_w + per_warp - 1) / per_warp;
-            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : (t.flags & TASK_REBASE) ? FAM_FAST_RB : FAM_FAST);
-            // shared memory of the pair's CTA: sequence images + mailboxes. Pairs are grouped by size class (<= 32 KB, then powers
-            // of two) so that a few long pairs do not cut the occupancy of the short ones sharing their launch; finer classes
-            // were measured slower on config 2 (more, smaller launches: 1716 vs 1824 GCUPS).
-            const bool ring = (t.flags & TASK_RING) != 0;
-            const size_t need = smem_need(t, cs, nw);
-            int cls = 0;
-            while (((size_t)32768 << cls) < need) ++cls;
-            if (ring) cls = 50;                       // their own groups: the sliding-window variants
-            by_w[nw + 1000 * kp_of(t) + 100000 * fam + 10000000 * (int64_t)cl + 1000000000 * (int64_t)cls].push_back((uint32_t)k);
-        }
-        for (auto& kv : by_w) {
-            // longest pairs first inside a group: the tail of the launch is short pairs
-            std::sort(kv.second.begin(), kv.second.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
-            size_t smem = 0; uint64_t work = 0;
-            const int nwarp = (int)(kv.first % 1000), kp = (int)((kv.first / 1000) % 100), fam = (int)((kv.first / 100000) % 100), cl = (int)((kv.first / 10000000) % 100);
-            const bool ring = kv.first / 1000000000 == 50;
-            const int lane_cost = (fam == FAM_S32 || fam == FAM_S32_GEN) ? 2 : 1;
-            for (uint32_t k : kv.second) {
-                const Task& t = tasks[k];
-                smem = std::max(smem, smem_need(t, cs, nwarp));
-                work += (uint64_t)t.n_iter * nwarp * kp * lane_cost * (steps_per_iter_of(t) / (2 * kp)) * cl;
-            }
-            wave_groups[wv].push_back({ fam, nwarp, kp, cl, ring, pos, kv.second.size(), smem, work });
-            std::copy(kv.second.begin(), kv.second.end(), order + pos);
-            pos += kv.second.size();
-        }
-        // group order (env SVP_GROUP_ORDER, tuning aid): 0 = biggest group first, so the small ones fill the machine behind it;
-        // 1 = groups with the longest-running CTAs (most work per pair) first, the many short CTAs fill the tail
-        static const int group_order = [] { const char* e = getenv("SVP_GROUP_ORDER"); return e ? atoi(e) : 1; }();
-        if (group_order == 1)
-            std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
-        else
-            std::sort(wave_groups[wv].begin(), wave_groups[wv].end(), [](const Group& a, const Group& b) { return a.work > b.work; });
-    }
-    // traceback lists: a wave that is not walked by the warp-per-pair kernel as a whole hands its long pairs (m + n beyond
-    // tbw_long: a 40-90 kb consensus against its reference window takes the thread-per-pair kernel 10 000 dependent rounds, tens
-    // of milliseconds during which the next wave but one waits for the arena half) to warps, the rest to the bulk kernel
-    struct TbList { size_t first_short, n_short, first_long, n_long; };
-    std::vector<TbList> tb_lists(waves.size());
-    for (size_t wv = 0; wv < waves.size(); ++wv) {
-        TbList& L = tb_lists[wv];
-        L.first_short = pos;
-        for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
-            if ((tasks[k].flags & TASK_INVALID) || (long)tasks[k].m + tasks[k].n <= h->tbw_long) order[pos++] = (uint32_t)k;
-        L.n_short = pos - L.first_short;
-        L.first_long = pos;
-        for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
-            if (!(tasks[k].flags & TASK_INVALID) && (long)tasks[k].m + tasks[k].n > h->tbw_long) order[pos++] = (uint32_t)k;
-        L.n_long = pos - L.first_long;
-    }
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-
     const Task* d_tasks = (const Task*)c.d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)c.d_order.p;
-    uint2* d_bests = (uint2*)c.d_bests.p;
-    // events: per wave [fwd start, fwd end, tb end, aux stream joins ...]
-    constexpr int MAX_FWD_STREAMS = 8;
-    const size_t EV_PER_WAVE = 4 + (MAX_FWD_STREAMS - 1), n_ev = waves.size() * EV_PER_WAVE;       // [fwd start, fwd end, tb end, long-walk end, joins]
-    while (c.events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
-    auto EV = [&](size_t wv, int which) { return c.events[wv * EV_PER_WAVE + which]; };
-    // forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower four times — on
-    // separate stream sets (1810 vs 1915 GCUPS) and on priority-tiered stream sets where the older wave keeps precedence for
-    // CTA slots (2 or 3 tiers of 2 streams, within the 8 hardware queues: 1810-1909 vs 1923-1962): the union of the forward
-    // intervals gets longer, not shorter, and the traceback is delayed. Inside a wave the groups
-    // run on up to four streams (2..6 measure the same, one stream 10 % slower), groups with the longest-running CTAs first
-    // (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail of the wave)
-    cudaStream_t sF[MAX_FWD_STREAMS] = { st, h->stream_aux[0], h->stream_aux[1], h->stream_aux[2], h->stream_aux[3], h->stream_aux[4], h->stream_aux[5], h->stream_aux[6] };
-    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), 8); }();
-    cudaStream_t sT = h->stream_tb;
-    // Waves of few, long-running CTAs (long reads, wide bands: config 3) end in a tail of a few CTAs on an otherwise idle
-    // machine; there the forward pass of the next wave starts at once on the other half of the streams (it writes the other
-    // arena half anyway) instead of waiting in stream order. SVP_WAVE_OVERLAP = 0 / 1 forces the choice, default: waves
-    // averaging fewer than overlap_max_pairs pairs.
-    static const int overlap_mode = [] { const char* e = getenv("SVP_WAVE_OVERLAP"); return e ? atoi(e) : -1; }();
-    static const long overlap_max_pairs = [] { const char* e = getenv("SVP_WAVE_OVERLAP_PAIRS"); return e ? atol(e) : 4096L; }();
-    const bool overlap = !serial && waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
-    cudaEvent_t ev_copied = nullptr;                     // the copies above precede every wave, whatever stream leads it
-    if (overlap) { while (c.events.size() < n_ev + 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.events.push_back(e); }
-                   ev_copied = c.events[n_ev]; CUDA_TRY(h, cudaEventRecord(ev_copied, st)); }
-    for (size_t wv = 0; wv < waves.size(); ++wv) {
-        const int half_id = (int)((h->wave_idx + wv) & 1);
-        cudaStream_t* sW = overlap ? sF + half_id * (MAX_FWD_STREAMS / 2) : sF;         // this wave's streams
-        const int avail = overlap ? MAX_FWD_STREAMS / 2 : max_streams;
-        if (overlap && sW[0] != st) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], ev_copied, 0));
-        if (h->half_free[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], h->half_free[half_id], 0));      // this arena half is free again
-        const bool tb_serial = serial;           // whole-arena wave: every earlier traceback must be done
-        if (tb_serial && h->half_free[half_id ^ 1]) CUDA_TRY(h, cudaStreamWaitEvent(sW[0], h->half_free[half_id ^ 1], 0));
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sW[0]));
-        const std::vector<Group>& groups = wave_groups[wv];
-        const int n_streams = (int)std::min<size_t>((size_t)avail, groups.size());
-        for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], EV(wv, 0), 0));
-        for (size_t gi = 0; gi < groups.size(); ++gi) {
-            const Group& gq = groups[gi];
-            launch_fwd(gq.fam, gq.kp, gq.nwarp, gq.cluster, gq.ring, cs.two_piece != 0, (unsigned)gq.count, gq.smem, sW[gi % (size_t)std::max(n_streams, 1)], d_tasks, d_order + gq.first, d_seqs,
-                       h->arena, d_bests, cs);
-            c.stats.fwd_launches++;
-        }
-        for (int a = 1; a < n_streams; ++a) {
-            CUDA_TRY(h, cudaEventRecord(EV(wv, 3 + a), sW[a]));
-            CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv, 3 + a), 0));
-        }
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sW[0]));
-        CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
-        const int nt = (int)(waves[wv].second - waves[wv].first);
-        if (nt > 0) {
-            const int tpb = 64;
-            // few pairs in the wave (one container per call; long tandem-repeat pairs): the warp-per-pair kernel walks 32 cells
-            // per memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass
-            // ... and the last wave of a blocking call has no forward pass left to share the machine with: its traceback is pure latency
-            static const bool last_wave_warp = [] { const char* e = getenv("SVP_TBW_LAST"); return e ? atoi(e) != 0 : true; }();
-            const TbList& L = tb_lists[wv];
-            if (nt <= h->tbw_max || tb_serial || (last_wave_warp && wait && wv + 1 == waves.size())) {
-                svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, 0, sT>>>(d_tasks + waves[wv].first, nullptr, nt, d_seqs, h->arena, d_bests, d_results, d_cigar, cs);
-                c.stats.tb_launches++;
-            } else {
-                // (launching the long walks EARLY — as soon as the forward launches that hold them are done, under the rest of the
-                // wave's forward pass — was measured slower: config 4 1927 -> 1861 GCUPS, the walks cost the forward pass more than
-                // their latency saves)
-                if (L.n_long) {              // the long walks first, on their own stream beside the bulk kernel
-                    CUDA_TRY(h, cudaStreamWaitEvent(h->stream_tb2, EV(wv, 1), 0));
-                    svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, 0, h->stream_tb2>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs, h->arena, d_bests,
-                                                                                           d_results, d_cigar, cs);
-                    CUDA_TRY(h, cudaEventRecord(EV(wv, 3), h->stream_tb2));
-                    c.stats.tb_launches++;
-                }
-                if (L.n_short) {
-                    svp_tb_kernel<<<((int)L.n_short + tpb - 1) / tpb, tpb, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_bests, d_results,
-                                                                                 d_cigar, cs);
-                    c.stats.tb_launches++;
-                }
-                if (L.n_long) CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 3), 0));
-            }
-        }
-        CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));
-        h->half_free[half_id] = EV(wv, 2);
-        if (serial) h->half_free[half_id ^ 1] = EV(wv, 2);
-        c.stats.waves++;
+
+    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : N_FWD_STREAMS; return std::min(std::max(v, 1), N_FWD_STREAMS); }();
+    cudaStream_t sF[N_FWD_STREAMS] = { st };
+    for (int a = 1; a < N_FWD_STREAMS; ++a) sF[a] = h->stream_aux[a - 1];
+    while (c.events.size() < (size_t)N_FWD_STREAMS + 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
+    const int n_streams = (int)std::min<size_t>((size_t)max_streams, std::max<size_t>(groups.size(), 1));
+    cudaEvent_t ev_copied = c.events[N_FWD_STREAMS];
+    CUDA_TRY(h, cudaEventRecord(ev_copied, st));
+    // consecutive calls start on different streams: the heavy first group of call k+1 does not queue behind the one of call k
+    const int rot = (int)(h->call_idx % (uint64_t)N_FWD_STREAMS);
+    auto stream_of = [&](size_t gi) { return sF[(gi + (size_t)rot) % (size_t)n_streams]; };
+    bool used[N_FWD_STREAMS] = {};
+    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks };
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const Group& g = groups[gi];
+        FwdKernel kern = fwd_kernel(g.fam, g.kp, g.nwarp > 1, g.cluster > 1, g.ring, cs.two_piece != 0);
+        if (!kern) return fail(h, SVP_ERR_UNSUPPORTED, "internal: no kernel variant for a planned group");
+        const int si = (int)((gi + (size_t)rot) % (size_t)n_streams);
+        if (sF[si] != st && !used[si]) CUDA_TRY(h, cudaStreamWaitEvent(sF[si], ev_copied, 0));
+        used[si] = true;
+        ar.use_global = g.huge ? 1u : 0u;
+        CUDA_TRY(h, launch_group(kern, g.cluster, (unsigned)g.count, (unsigned)g.nwarp * 32u, g.smem, stream_of(gi), d_tasks, d_order + g.first, d_seqs, ar,
+                                 d_results, d_cigar, cs));
+        c.stats.fwd_launches++;
     }
-    h->wave_idx += waves.size();
-    CUDA_TRY(h, cudaEventRecord(c.ev_t1, sT));           // tracebacks run in wave order on one stream: the last one ends the call
-    c.n_waves = waves.size();
-    for (size_t k = 0; k < n; ++k) if (!(tasks[k].flags & TASK_INVALID)) { c.stats.cells += tasks[k].cells; c.stats.tb_bytes += tb_bytes_of(tasks[k]); }
+    if (n_invalid)
+        svp_invalid_kernel<<<(unsigned)((n_invalid + 127) / 128), 128, 0, st>>>(d_tasks, d_order + inv_first, (int)n_invalid, d_results);
+    for (int a = 0; a < N_FWD_STREAMS; ++a) {
+        if (!used[a] || sF[a] == st) continue;
+        CUDA_TRY(h, cudaEventRecord(c.events[a], sF[a]));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, c.events[a], 0));
+    }
+    CUDA_TRY(h, cudaEventRecord(c.ev_t1, st));
+    c.stats.waves = (uint32_t)groups.size();
+    for (size_t k = 0; k < n; ++k) if (!(tasks[k].flags & TASK_INVALID)) { c.stats.cells += tasks[k].cells; c.stats.tb_bytes += tasks[k].tb_bytes; }
     c.pending = true;
     h->call_idx++;
     CUDA_TRY(h, cudaGetLastError());
@@ -853,9 +795,9 @@ extern "C" int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, c
         o.flags = ((t.flags & TASK_S32) ? SVP_PLAN_S32 : 0u) | ((t.flags & TASK_REBASE) ? SVP_PLAN_REBASE : 0u) |
                   ((t.flags & TASK_RING) ? SVP_PLAN_WINDOWS : 0u) | (pseudo.cs.general ? SVP_PLAN_GENERAL : 0u);
         o.smem_bytes = (uint32_t)smem_need(t, pseudo.cs, nw);
-        if (!(t.flags & TASK_RING) && o.smem_bytes > (uint32_t)pseudo.max_smem_optin) o.flags |= SVP_PLAN_TOO_LONG;
+        if (!(t.flags & TASK_RING) && o.smem_bytes + 64 > (uint32_t)pseudo.max_smem_optin) o.flags |= SVP_PLAN_TOO_LONG;
         o.cells = t.cells;
-        o.tb_bytes = tb_bytes_of(t);
+        o.tb_bytes = t.tb_bytes;
     }
     return SVP_OK;
 }

@@ -15,10 +15,11 @@
 //   loads and staged in shared memory as one code byte per base. Per step each thread streams the
 //   low byte of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
 //
-// Traceback    svp_tb_kernel (one thread per pair, bulk) / svp_tbw_kernel (one warp per pair, small waves)
-//   Rebuilds exact H values along the path from the stored low bytes
-//   (neighbouring H differ by less than 128); latency-bound, overlapped with the
-//   next wave's forward pass on a second stream.
+// Traceback    svp_traceback_warp, called by warp 0 of the pair's CTA right after its forward pass
+//   Rebuilds exact H values along the path from the stored low bytes (neighbouring H differ by less than
+//   128); latency-bound, hidden behind the forward passes of the other CTAs on the SM.
+// Arena        every pair takes its traceback rows from a device-side allocator when its CTA starts and
+//   gives them back when its walk is done (ArenaPool): memory in use = the pairs resident on the GPU.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -37,8 +38,8 @@ struct Task {               // one pair, prepared on the host (svp_align.cu: pla
     int32_t  n_iter;        // loop iterations; one iteration = 2*KP steps
     uint32_t flags;
     uint32_t pair_index;    // index into the caller's pair / result arrays
-    uint64_t tb_off;        // byte offset of this pair's traceback rows in the arena
-    uint64_t best_off;      // first entry of this pair in the per-thread best array
+    uint64_t tb_bytes;      // bytes of this pair's traceback rows; its per-thread best records (8 B each) follow them in the arena slice
+    uint64_t slice_bytes;   // rows + best records, a multiple of 256: what the pair takes from the arena
     uint64_t cells;         // spec cells (band ∩ matrix), copied into the result
     uint32_t cigar_off, cigar_cap;
 };
@@ -231,6 +232,118 @@ template <bool CL> __device__ __forceinline__ void mailbox_store_B(const StepLin
     if (CL && L.rup) st_async_v4(L.rem_B, a, b, c, d, L.rem_bar_B);
     else if (L.up) { sts_v4(L.out_B(), a, b, c, d); mbar_arrive(L.sig_B()); }
 }
+__device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
+                                                const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                                uint32_t* __restrict__ cigar, const Consts& cs);
+// ---------------------------------------------------------------------------------------------
+// Device-side arena. The traceback rows of a pair live from the start of its forward pass to the end of its walk, both inside
+// one CTA (cluster), so the arena only has to hold the pairs that are RESIDENT on the GPU: thread 0 of a pair's (first) CTA
+// takes a slice when the CTA starts and returns it when the walk is done. One pool per SM (a CTA allocates from the pool of
+// the SM it runs on: no contention beyond the ~16 CTAs of an SM) plus one global pool for slices too large for a per-SM
+// region (long reads in wide bands, clusters). A pool is a first-fit list of live slices under a spin lock; allocation waits
+// (nanosleep) when the pool is full — the holders are running CTAs that do not depend on the waiter, so it always ends. The
+// host bounds the residency per SM through the shared-memory request of every launch (svp_align.cu: ballast), so that the
+// slices live on an SM fit its region with room for fragmentation and the wait is the exception.
+// ---------------------------------------------------------------------------------------------
+constexpr int POOL_MAX = 48;
+struct ArenaPool {
+    uint32_t lock, n;                 // spin lock (0 free), live slices
+    uint64_t base, bytes;             // the pool's region: arena offset and size
+    uint64_t off[POOL_MAX], len[POOL_MAX];   // live slices, ascending by offset (relative to base)
+    unsigned long long waits;         // allocations that had to wait (statistics)
+};
+struct Arena {
+    uint8_t* base;
+    ArenaPool* pools;                 // pools[0 .. n_sm): per SM, pools[n_sm]: global
+    uint32_t n_sm;
+    uint32_t use_global;              // this launch's pairs allocate from the global pool
+    unsigned long long* clocks;       // [0] summed forward ns, [1] summed traceback ns, [2] pairs (statistics)
+};
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// one thread; returns the arena offset of a slice of `bytes` bytes (a multiple of 256) and the pool it came from
+__device__ __noinline__ uint64_t arena_alloc(const Arena& A, uint64_t bytes, uint32_t& pool_id) {
+    pool_id = A.use_global ? A.n_sm : min(smid(), A.n_sm - 1u);
+    ArenaPool* P = A.pools + pool_id;
+    volatile uint64_t* off = P->off; volatile uint64_t* len = P->len;
+    bool waited = false;
+    for (;;) {
+        while (atomicCAS(&P->lock, 0u, 1u) != 0u) __nanosleep(100);
+        __threadfence();
+        const uint32_t n = *(volatile uint32_t*)&P->n;
+        uint64_t prev_end = 0; int at = -1;
+        if (n < (uint32_t)POOL_MAX) {
+            for (uint32_t k = 0; k < n; ++k) {
+                if (off[k] - prev_end >= bytes) { at = (int)k; break; }
+                prev_end = off[k] + len[k];
+            }
+            if (at < 0 && P->bytes - prev_end >= bytes) at = (int)n;
+        }
+        if (at >= 0) {
+            for (int k = (int)n; k > at; --k) { off[k] = off[k - 1]; len[k] = len[k - 1]; }
+            off[at] = prev_end; len[at] = bytes;
+            *(volatile uint32_t*)&P->n = n + 1;
+            if (waited) P->waits += 1;
+            __threadfence();
+            atomicExch(&P->lock, 0u);
+            return P->base + prev_end;
+        }
+        __threadfence();
+        atomicExch(&P->lock, 0u);
+        waited = true;
+        __nanosleep(20000);
+    }
+}
+__device__ __noinline__ void arena_free(const Arena& A, uint32_t pool_id, uint64_t arena_off) {
+    ArenaPool* P = A.pools + pool_id;
+    volatile uint64_t* off = P->off; volatile uint64_t* len = P->len;
+    const uint64_t rel = arena_off - P->base;
+    while (atomicCAS(&P->lock, 0u, 1u) != 0u) __nanosleep(100);
+    __threadfence();
+    const uint32_t n = *(volatile uint32_t*)&P->n;
+    uint32_t k = 0;
+    while (k < n && off[k] != rel) ++k;
+    if (k < n) {
+        for (; k + 1 < n; ++k) { off[k] = off[k + 1]; len[k] = len[k + 1]; }
+        *(volatile uint32_t*)&P->n = n - 1;
+    }
+    __threadfence();
+    atomicExch(&P->lock, 0u);
+}
+// Start of a pair's CTA(s): thread 0 of the first CTA takes the slice and notes it in its shared memory (s_slice: uint64[3] =
+// arena offset, pool id, start time); after the caller's initial barrier every CTA of a cluster reads the offset from the first
+// CTA's shared memory (pair_rows; remote shared memory may only be touched once the cluster barrier has shown that CTA running).
+__device__ __forceinline__ void pair_begin(const Arena& A, const Task& tk, uint32_t crank, unsigned long long* s_slice) {
+    if (threadIdx.x == 0 && crank == 0) {
+        uint32_t pool_id;
+        s_slice[0] = arena_alloc(A, tk.slice_bytes, pool_id);
+        s_slice[1] = pool_id;
+        s_slice[2] = globaltimer_ns();
+    }
+}
+template <bool CL>
+__device__ __forceinline__ uint8_t* pair_rows(const Arena& A, uint32_t crank, const unsigned long long* s_slice) {
+    unsigned long long o;
+    if (CL && crank != 0) {
+        const uint32_t ra = mapa_shared((uint32_t)__cvta_generic_to_shared(s_slice), 0u);
+        asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(o) : "r"(ra) : "memory");
+    } else o = s_slice[0];
+    return A.base + o;
+}
+// End of a pair: called by warp 0 of the first CTA after the barrier that follows the forward pass.
+__device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                         uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice) {
+    const uint64_t o = s_slice[0];
+    const unsigned long long t1 = globaltimer_ns();
+    svp_traceback_warp(tk, A.base + o, reinterpret_cast<const uint2*>(A.base + o + tk.tb_bytes), seqs, results, cigar, cs);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        arena_free(A, (uint32_t)s_slice[1], o);
+        const unsigned long long t2 = globaltimer_ns();
+        atomicAdd(A.clocks + 0, t1 - s_slice[2]); atomicAdd(A.clocks + 1, t2 - t1); atomicAdd(A.clocks + 2, 1ull);
+    }
+}
+
 // Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
 // base p (0-based) at byte SEQ_PAD + p, with 0x7E (NaN) in the bytes before and after; positions are
 // clamped into [SEQ_PAD-1, SEQ_PAD+len] so every out-of-range position reads a NaN: virtual cells
@@ -376,9 +489,10 @@ constexpr int RB_CLAMP = 16000;
 template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false>
 __global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
-               uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+               const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
     static_assert(!CL || MULTI, "cluster variants are multi-warp");
     extern __shared__ __align__(16) uint8_t smem8[];
+    __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
     const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
@@ -408,7 +522,10 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg);
     if (MULTI && RB && gl < nwarp + 2) sts_u32(s_wb + 4u * gl, 0u);
+    pair_begin(ar, tk, crank, s_slice);
     step_barrier<CL>();
+    uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
+    uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -438,7 +555,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     int base = 0, best_lo = 0, best_hi = 0, nb_lo = 0;
     uint32_t c_floor = 0, dLo = 0, dLoF = 0, dUp = 0;
     const int pitch = n_thr_active * tb_slot_bytes(KP);      // bytes per traceback row (one step pair)
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KP);
+    uint8_t* tbp = rows + (size_t)g * tb_slot_bytes(KP);
     const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
     const uint32_t s_upA = (g == n_thr_active - 1) ? s_cst : link.in_up(), s_loB = link.in_lo();
@@ -608,16 +725,18 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
             }
         }
     }
-    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
         if (RB) {
-            bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
-            bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
+            bests[2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
+            bests[2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
         } else {
-            bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
-            bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
+            bests[2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
+            bests[2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
         }
     }
+    // rows and best records of every warp (CTA of the cluster) are complete; no CTA leaves while a neighbour may still store into its mailbox
+    step_barrier<CL>();
+    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -654,7 +773,7 @@ struct TbView {
     // stored byte of H(i, j); 0 for cells before the matrix or before the first stored row (callers check the band)
     __device__ __forceinline__ uint32_t lb(int i, int j) const {
         if (i < 1 || j < 1 || (i + j) < r_begin) return 0;
-        return *addr(i, j);
+        return __ldcg(addr(i, j));
     }
     // single bases (codes 0..3) at 1-based positions of the ORIENTED query / the target
     __device__ __forceinline__ int qbase(int i) const {
@@ -698,248 +817,27 @@ __device__ __forceinline__ int gap_cost2(int o1, int e1, int o2, int e2, int two
 
 __device__ __forceinline__ int sext8(uint32_t x) { return (int)(int8_t)(x & 0xFFu); }
 
-// One THREAD per pair, 32 independent walks per warp. A walk is a chain of dependent byte loads, so what
-// matters is the number of memory round trips and keeping the 32 lanes on ONE instruction stream:
-//   * a round = every lane issues all its loads (the diagonal/left/up predecessor bytes of the next S
-//     cells along its current diagonal, or — while it searches a gap longer than one — the next NSCAN
-//     cells of its row and column), then the loaded cells are processed by straight-line predicated
-//     code without data-dependent branches;
-//   * the Z-trim start (lowest H of the walk, §3.5) is only tracked as a position; the rare walk that is
-//     actually cut is replayed up to that position (same deterministic path) to rebuild CIGAR and counts.
-__global__ void __launch_bounds__(64)
-svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
-              const uint8_t* __restrict__ tb, const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar,
-              const Consts cs) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n_tasks) return;
-    const Task tk = tasks[order ? order[tid] : (uint32_t)tid];          // order: the wave's pairs this kernel walks (nullptr: tasks[0..n))
+// ---------------------------------------------------------------------------------------------
+// Traceback, run by ONE WARP right after the forward pass of its pair, inside the same CTA (warp 0 of the pair's first CTA):
+// the rows it reads are the ones this CTA (cluster) just wrote, and the pair's slice of the arena is free again as soon as the
+// walk is done — there are no waves and no second kernel. Every round lane l fetches the diagonal predecessor byte, the left / up
+// neighbour bytes and the base pair of cell (i-l, j-l), so 32 cells of a diagonal run cost ONE memory round trip; the run is then
+// resolved by all lanes at once (prefix sums of the substitution scores). Gap search: 32 candidates of the row and of the column
+// per round. The Z-trim start is kept as a snapshot of the walk at its lowest H.
+// All loads of rows / best records are ld.global.cg: they were written by this grid (by other SMs when the band spans a cluster),
+// and an arena slice is reused by later CTAs, so L1 must not serve them.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
+                                                const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                                uint32_t* __restrict__ cigar, const Consts& cs) {
+    const int lane = threadIdx.x & 31;
     svp_result res;
     res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
     res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
     res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
-    if (tk.flags & TASK_INVALID) {
-        res.cells = 0;
-        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_TOO_LONG : SVP_ST_BAD_PAIR;
-        results[tk.pair_index] = res;
-        return;
-    }
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
     TbView v;
-    v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
-    v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
-    v.set_geometry(tk.band_w, KP);
-    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
-    const int d_hi = tk.band_lo + tk.band_w - 1;
-
-    // ---- 1. end cell: maximum over the per-thread-half records, earliest iteration ------------
-    const int n_ent = (tk.band_w / (4 * KP)) * 2;
-    int M = 0; uint32_t blk = 0xFFFFFFFFu;
-    for (int e = 0; e < n_ent; ++e) {
-        const uint2 b = __ldg(bests + tk.best_off + e);
-        const int val = (int)b.x;
-        if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
-    }
-    if (M <= 0) {
-        res.status = SVP_ST_NOHIT;
-        results[tk.pair_index] = res;
-        return;
-    }
-    if (!(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
-    // every (thread, half) block that reached M in iteration blk: rebuild its 2KP x 2KP cells from the low bytes
-    int end_s = 0x7FFFFFFF, end_x = -1;
-    for (int e = 0; e < n_ent; ++e) {
-        const uint2 b = __ldg(bests + tk.best_off + e);
-        if ((int)b.x != M || b.y != blk) continue;
-        const int xbase = (e >> 1) * 4 * KP + (e & 1) * 2 * KP;      // first diagonal (band-relative) of the half
-        const int s0 = (int)blk * 2 * KP;
-        // cells id = 0 .. 2*KP*KP-1: step s0 + id/KP, diagonal xbase + 2*(id%KP) + (step odd); chained by neighbours
-        int rel = 0, rel_row0 = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
-        uint32_t bprev = 0, b_row0 = 0;
-        for (int id = 0; id < 2 * KP * KP; ++id) {
-            const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
-            const uint32_t bb = *v.addr_sx(s, x);
-            if (id == 0) rel = 0;
-            else if (id % KP == 0) rel = rel_row0 + sext8(bb - b_row0);
-            else rel = rel + sext8(bb - bprev);
-            if (id % KP == 0) { rel_row0 = rel; b_row0 = bb; }
-            bprev = bb;
-            if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
-            else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
-        }
-        if (cand_s < end_s || (cand_s == end_s && cand_x > end_x)) { end_s = cand_s; end_x = cand_x; }
-    }
-    const int best_i = ((tk.r_begin + end_s) - (tk.band_lo + end_x)) / 2;
-    const int best_j = ((tk.r_begin + end_s) + (tk.band_lo + end_x)) / 2;
-
-    // ---- 2. walk back --------------------------------------------------------------------------
-    constexpr int S = 8, NSCAN = 6;
-    uint32_t* slot = cigar + tk.cigar_off;
-    const ptrdiff_t two_rows = (ptrdiff_t)v.pitch;            // two steps = one row (step pair)
-    const int cost1d = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1);
-    const int cost1i = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1);
-    const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
-
-    int i, j, H, wpos, low, low_i, low_j, mrun, scan_k, Hrow, Hcol;
-    uint32_t brow, bcol, n_match, n_mis, n_io, n_ib, n_do, n_db;
-    bool ovf, bad = false;
-    int stop_i = -1, stop_j = -1;            // replay target (cut walk): stop when the walk reaches this cell
-    bool cut = false; int cut_low = 0;
-
-#define SVP_PUSH(op, len) do { if (wpos > 0) { --wpos; slot[wpos] = ((uint32_t)(len) << 4) | (op); } else ovf = true; } while (0)
-
-    for (int pass = 0; pass < 2; ++pass) {
-        i = best_i; j = best_j; H = M; wpos = (int)tk.cigar_cap; ovf = false;
-        low = M + 1; low_i = i; low_j = j; mrun = 0; scan_k = 0; Hrow = Hcol = 0; brow = bcol = 0;
-        n_match = n_mis = n_io = n_ib = n_do = n_db = 0;
-        bool done = false;
-        while (!done) {
-            const int d = j - i;
-            const bool in_scan = scan_k != 0;
-            // ---------------- loads of the round, all issued before any is used -----------------
-            const bool del_band = (d - 1 >= tk.band_lo), ins_band = (d + 1 <= d_hi);
-            const uint8_t* pd = v.addr(i - 1, j - 1);            // diagonal predecessor of cell 0 (stride: 2 rows per cell)
-            const uint8_t* pl = v.addr(i, j - 1);                // left neighbour of cell 0
-            const uint8_t* pu = v.addr(i - 1, j);                // up neighbour of cell 0
-            uint32_t bd[S], bl[S], bu[S];
-            #pragma unroll
-            for (int k = 0; k < S; ++k) {
-                const bool in_q = (i - k - 1 >= 1), in_t = (j - k - 1 >= 1);
-                bd[k] = (!in_scan && in_q && in_t) ? (uint32_t)*(pd - k * two_rows) : 0u;
-                bl[k] = (!in_scan && i - k >= 1 && in_t && del_band) ? (uint32_t)*(pl - k * two_rows) : 0u;
-                bu[k] = (!in_scan && in_q && j - k >= 1 && ins_band) ? (uint32_t)*(pu - k * two_rows) : 0u;
-            }
-            uint32_t br[NSCAN], bc[NSCAN]; bool okr[NSCAN], okc[NSCAN];
-            #pragma unroll
-            for (int t = 0; t < NSCAN; ++t) {
-                const int k = scan_k + t;
-                okr[t] = in_scan && (j - k >= 1) && (d - k >= tk.band_lo);
-                okc[t] = in_scan && (i - k >= 1) && (d + k <= d_hi);
-                br[t] = okr[t] ? (uint32_t)*v.addr(i, j - k) : 0u;
-                bc[t] = okc[t] ? (uint32_t)*v.addr(i - k, j) : 0u;
-            }
-            const uint32_t qwin = v.qwindow(i, S), twin = v.twindow(j, S);   // 2 bits per cell along the diagonal
-            if (!in_scan && i - S - 1 >= 1 && j - S - 1 >= 1) {              // L2 prefetch for the next round
-                #pragma unroll
-                for (int k = S; k < 2 * S; k += 2) {
-                    const uint8_t* pk = pd - k * two_rows;      // the sector holding a cell's diagonal, left and up predecessors
-                    if (pk - two_rows >= v.base) {
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk));
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows));
-                    }
-                }
-            }
-            // ---------------- gap scan (lanes in the scan state) ------------------------------------
-            if (in_scan) {
-                bool found = false, dead = false;
-                #pragma unroll
-                for (int t = 0; t < NSCAN; ++t) {
-                    const int k = scan_k + t;
-                    const int costd = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, k);
-                    const int costi = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, k);
-                    if (!found && !dead) {
-                        if (!okr[t] && !okc[t]) dead = true;
-                        if (okr[t]) {
-                            Hrow += sext8(br[t] - brow); brow = br[t];
-                            if (H == Hrow - costd) { SVP_PUSH(SVP_CIGAR_D, k); ++n_do; n_db += k; j -= k; H = Hrow; found = true; }
-                        }
-                        if (!found && okc[t]) {
-                            Hcol += sext8(bc[t] - bcol); bcol = bc[t];
-                            if (H == Hcol - costi) { SVP_PUSH(SVP_CIGAR_I, k); ++n_io; n_ib += k; i -= k; H = Hcol; found = true; }
-                        }
-                    }
-                }
-                if (found) scan_k = 0;
-                else if (dead) { bad = true; done = true; }
-                else scan_k += NSCAN;
-                continue;
-            }
-            // ---------------- H state: up to S cells along the diagonal, predicated -----------------
-            bool alive = true, gap_here = false;
-            uint32_t gl = 0, gu = 0;
-            #pragma unroll
-            for (int k = 0; k < S; ++k) {
-                // stop conditions of the current cell
-                int dd = d - (low_j - low_i); dd = dd < 0 ? -dd : dd;
-                const bool stop = alive && (H == 0 || i < 1 || j < 1 || (i == stop_i && j == stop_j) ||
-                                            (pass == 0 && H >= low && H - low > zdrop + cs.zdrop_ext * dd));
-                if (stop) { if (pass == 0 && H != 0 && i >= 1 && j >= 1) cut = true; done = true; alive = false; }
-                if (alive && H < low) { low = H; low_i = i; low_j = j; }
-                const uint32_t qc = (qwin >> (2 * k)) & 3u, tc = (twin >> (2 * k)) & 3u;
-                const bool same = qc == tc;
-                const int sub = (int)(int8_t)((cs.tab[qc] >> (8u * tc)) & 0xFFu);
-                const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(bd[k] - (uint32_t)H) : 0;
-                const bool isdiag = alive && (H == Hd + sub);
-                if (alive && !isdiag) { gap_here = true; gl = bl[k]; gu = bu[k]; alive = false; }
-                if (isdiag) { ++mrun; n_match += same ? 1u : 0u; n_mis += same ? 0u : 1u; --i; --j; H = Hd; }
-            }
-            if (done) continue;
-            if (gap_here) {
-                // the M run since the previous gap, then a gap of length 1 (deletion first) or the scan state
-                if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
-                const bool del_ok = (j - 1 >= 1) && del_band, ins_ok = (i - 1 >= 1) && ins_band;
-                const int Hl = H + sext8(gl - (uint32_t)H), Hu = H + sext8(gu - (uint32_t)H);
-                if (!del_ok && !ins_ok) { bad = true; done = true; }
-                else if (del_ok && H == Hl - cost1d) { SVP_PUSH(SVP_CIGAR_D, 1); ++n_do; ++n_db; --j; H = Hl; }
-                else if (ins_ok && H == Hu - cost1i) { SVP_PUSH(SVP_CIGAR_I, 1); ++n_io; ++n_ib; --i; H = Hu; }
-                else { scan_k = 2; Hrow = Hl; brow = gl; Hcol = Hu; bcol = gu; }
-            }
-        }
-        if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
-        if (!cut || pass == 1) break;
-        stop_i = low_i; stop_j = low_j; cut_low = low;   // replay the (deterministic) walk up to the lowest point
-    }
-#undef SVP_PUSH
-    if (bad) res.status |= SVP_ST_SCORE_OVF;
-    res.score = M - (cut ? cut_low : 0);
-    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
-    res.n_match = n_match; res.n_mismatch = n_mis; res.n_ins_ops = n_io; res.n_ins_bp = n_ib; res.n_del_ops = n_do; res.n_del_bp = n_db;
-    if (ovf) {
-        res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
-    } else {
-        res.cigar_len = tk.cigar_cap - (uint32_t)wpos;
-        res.cigar_off = tk.cigar_off + (uint32_t)wpos;
-        double dist = 0.0;
-        for (uint32_t a = (uint32_t)wpos; a < tk.cigar_cap; ++a) {
-            const uint32_t w = slot[a];
-            const uint32_t op = w & 15u, len = w >> 4;
-            if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
-                const double sz = (double)len;
-                dist += (1.0 - exp(-pow(sz / 30.0, 1.5))) * sz;
-            }
-        }
-        res.sv_dist = dist;
-    }
-    results[tk.pair_index] = res;
-}
-
-// ---------------------------------------------------------------------------------------------
-// traceback, one WARP per pair: the latency-optimised variant for waves with few pairs (a single container per call,
-// the way the reference's seam is driven; long tandem-repeat pairs). Every round lane l fetches the diagonal
-// predecessor byte and the base pair of cell (i-l, j-l), so 32 cells of a diagonal run cost ONE memory round trip
-// (the thread-per-pair kernel covers 8); the cells are then resolved in order by all lanes in lockstep. Gap search:
-// 32 candidates of the row and of the column per round. Same spec, same results as svp_tb_kernel;
-// the Z-trim start is kept as a snapshot of the walk at its lowest H instead of a replay.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
-               const uint8_t* __restrict__ tb, const uint2* __restrict__ bests, svp_result* __restrict__ results, uint32_t* __restrict__ cigar,
-               const Consts cs) {
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= n_tasks) return;
-    const Task tk = tasks[order ? order[wid] : (uint32_t)wid];
-    svp_result res;
-    res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
-    res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
-    res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
-    if (tk.flags & TASK_INVALID) {
-        res.cells = 0;
-        res.status = (tk.flags & TASK_TOO_LONG) ? SVP_ST_TOO_LONG : SVP_ST_BAD_PAIR;
-        if (lane == 0) results[tk.pair_index] = res;
-        return;
-    }
-    const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
-    TbView v;
-    v.base = tb + tk.tb_off; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
+    v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
     v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
     v.set_geometry(tk.band_w, KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
@@ -949,7 +847,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int n_ent = (tk.band_w / (4 * KP)) * 2;
     int M = 0; uint32_t blk = 0xFFFFFFFFu;
     for (int e = lane; e < n_ent; e += 32) {
-        const uint2 b = __ldg(bests + tk.best_off + e);
+        const uint2 b = __ldcg(bests + e);
         const int val = (int)b.x;
         if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
     }
@@ -970,7 +868,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     for (int e0 = 0; e0 < n_ent; e0 += 32) {
         const int e = e0 + lane;
         bool hit = false;
-        if (e < n_ent) { const uint2 b = __ldg(bests + tk.best_off + e); hit = ((int)b.x == M) && (b.y == blk); }
+        if (e < n_ent) { const uint2 b = __ldcg(bests + e); hit = ((int)b.x == M) && (b.y == blk); }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {
             const int ee = e0 + __ffs(mask) - 1; mask &= mask - 1;
@@ -983,7 +881,7 @@ svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                 uint32_t mine = 0;
                 if (idx < NC) {
                     const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
-                    mine = *v.addr_sx(s, x);
+                    mine = __ldcg(v.addr_sx(s, x));
                 }
                 const int lim = min(32, NC - c0);
                 for (int l = 0; l < lim; ++l) {

@@ -88,10 +88,11 @@ __device__ __forceinline__ void stage_sequences_gen(const Task& tk, const uint8_
 template <bool MULTI, bool TWO, bool CL = false>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
-                uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+                const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
     static_assert(!CL || MULTI, "cluster variants are multi-warp");
     constexpr int KP = 4;
     extern __shared__ __align__(16) uint8_t smem8[];
+    __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
     const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
@@ -116,7 +117,10 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     if (MULTI && gl <= nwarp) { sts_v4(s_mb + MB_A + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mb + MB_B + 16u * gl, 0u, 0u, c_neg, c_neg);
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, c_neg, c_neg);
+    pair_begin(ar, tk, crank, s_slice);
     step_barrier<CL>();
+    uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
+    uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
 
     const int n_thr_active = tk.band_w / (4 * KP);
     const bool active = g < n_thr_active;
@@ -140,7 +144,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     int qpos = I0 + 1, tpos = J0 + 2 * KP;
     uint32_t best = 0, snap = 0, blk_lo = 0, blk_hi = 0;
     const int pitch = n_thr_active * tb_slot_bytes(KP);      // bytes per traceback row (one step pair)
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KP);
+    uint8_t* tbp = rows + (size_t)g * tb_slot_bytes(KP);
     const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
     const uint32_t s_upA = (g == n_thr_active - 1) ? s_mb + MB_CST : link.in_up(), s_loB = link.in_lo();
@@ -248,11 +252,12 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
         if (diff >> 16) blk_hi = (uint32_t)it;
         snap = best;
     }
-    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
-        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
-        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
+        bests[2 * g]     = make_uint2((uint32_t)(int)(int16_t)(best & 0xFFFFu), blk_lo);
+        bests[2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
     }
+    step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
+    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,10 +297,11 @@ __device__ __forceinline__ void ring_fill(const Task& tk, const uint8_t* __restr
 template <bool MULTI, bool TWO, bool GEN, bool CL = false, bool RING = false>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
-                 uint8_t* __restrict__ tb, uint2* __restrict__ bests, const Consts cs) {
+                 const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
     static_assert(!CL || MULTI, "cluster variants are multi-warp");
     constexpr int K = 8, KPG = K / 2;
     extern __shared__ __align__(16) uint8_t smem8[];
+    __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
     const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
@@ -334,7 +340,10 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         step_link_init<CL>(s_mb, gl);
     }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
+    pair_begin(ar, tk, crank, s_slice);
     step_barrier<CL>();
+    uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
+    uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
 
     const int n_thr_active = tk.band_w / (2 * K);
     const bool active = g < n_thr_active;
@@ -359,7 +368,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     int qpos = I0 + 1, tpos = J0 + K;
     int best_lo = 0, best_hi = 0, snap_lo = 0, snap_hi = 0; uint32_t blk_lo = 0, blk_hi = 0;
     const int pitch = n_thr_active * tb_slot_bytes(KPG);     // bytes per traceback row (one step pair)
-    uint8_t* tbp = tb + tk.tb_off + (size_t)g * tb_slot_bytes(KPG);
+    uint8_t* tbp = rows + (size_t)g * tb_slot_bytes(KPG);
     const StepLink link = step_link<CL>(s_mb, warp, nwarp, crank, csize);
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
     const uint32_t s_upA = (g == n_thr_active - 1) ? s_mb + MB_CST : link.in_up(), s_loB = link.in_lo();
@@ -460,11 +469,12 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
             }
         }
     }
-    if (CL) cluster_sync_all();                // no CTA leaves while a neighbour may still store into its mailbox
     if (active) {
-        bests[tk.best_off + 2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
-        bests[tk.best_off + 2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
+        bests[2 * g]     = make_uint2((uint32_t)best_lo, blk_lo);
+        bests[2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
     }
+    step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
+    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
 }
 
 }  // namespace svp

@@ -284,6 +284,31 @@ def locus_config4(region_id: int, seed_base: int = 30_000, skew: bool = False, s
                  core_interval=(start + c0, start + c1), consensus=cons)
 
 
+def locus_shape(region_id: int, seed_base: int = 30_000, skew: bool = False, scale: float = 1.0, max_reads: int = 60) -> tuple[int, int, int, bool]:
+    """(core, pad, n_reads, two_haps) of locus_config4(region_id, ...) without generating its sequences — the same first draws
+    of the same generator; what a scheduler knows before it aligns (candidate-region span and coverage)."""
+    rng = np.random.Generator(np.random.PCG64(seed_base + region_id))
+    core = max(200, int(_core_length(rng, skew) * scale))
+    pad = min(2 * core, int(20_000 * scale))
+    n_reads = int(np.clip(rng.poisson(30), 4, max_reads))
+    two_haps = bool(rng.random() < 0.5)
+    return core, pad, n_reads, two_haps
+
+
+def locus_cost_estimate(region_id: int, seed_base: int = 30_000, skew: bool = False, slack: int = 300, band_w: int = 4096) -> int:
+    """Estimated DP cells of a locus from its shape alone: n(n-1)/2 read pairs of ~core + 300 bases in bands of ~2*slack + 200
+    diagonals (+ the planted SV between haplotypes), plus both strands of every padded consensus against its window."""
+    core, pad, n, two = locus_shape(region_id, seed_base, skew)
+    read = core + 300
+    pairs = n * (n - 1) // 2
+    band = 2 * slack + 200
+    if two:                                                       # half the pairs cross haplotypes: + the mean of the log-uniform SV size
+        top = max(51, min(2000, core // 3))
+        band += int(0.5 * (top - 50) / np.log(top / 50.0))
+    cons = (2 if two else 1) * 2 * (core + 2 * pad) * min(band_w, core + 2 * pad)
+    return pairs * read * min(band, 2 * read) + cons
+
+
 def locus_cost(locus: Locus, slack: int = 300, granule: int = 128) -> int:
     """Estimated DP cells of a locus: its all-vs-all plus its consensus -> window pairs (both strands)."""
     from .scheduler import region_cost

@@ -89,6 +89,28 @@ def batch_config4(locus_ids: list[int], seed_base: int = 30_000, skew: bool = Fa
     return assemble(seqs, specs, len(locus_ids))
 
 
+def batch_loci(items: list[tuple[int, int, bool]], slack: int = 300, granule: int = 128, band_w: int = 4096) -> dict:
+    """batch_config4() over loci of several sets: items = (seed_base, locus id, skew). Config 5 = the three trio sets
+    (seed bases 40 000 / 50 000 / 60 000, skew) in one pool."""
+    seqs, specs, bounds = [], [], [0]
+    for seed_base, lid, skew in items:
+        loc = synth.locus_config4(lid, seed_base=seed_base, skew=skew)
+        base = len(seqs)
+        seqs += loc.region.reads
+        specs += [(base + q, base + t, lo, w, fl) for (q, t, lo, w, fl) in synth.region_pairs(loc.region, slack, granule)]
+        t_index = len(seqs)
+        seqs.append(loc.ref_window)
+        q_index = []
+        for c in loc.consensus:
+            q_index.append(len(seqs))
+            seqs.append(c["padded"])
+        specs += consensus_window_specs(loc, q_index, t_index, band_w)
+        bounds.append(len(specs))
+    out = assemble(seqs, specs, len(items))
+    out["pair_bounds"] = np.array(bounds, dtype=np.int64)        # pairs of locus k: [pair_bounds[k], pair_bounds[k + 1])
+    return out
+
+
 def consensus_objects(locus: synth.Locus) -> dict[str, Consensus]:
     """The locus' padded consensuses as Consensus records (lower-case flanks, UPPER core), for the consensus_align chain."""
     out = {}

@@ -240,3 +240,29 @@ def test_similarity_from_summary_equals_record_pipeline(oracle):
     res["q_beg"], res["q_end"], res["t_beg"], res["t_end"] = [150, 0], [900, 800], [120, 0], [900, 800]
     sim, _ = consensus_lib.similarity_from_summary(["a", "b", "c"], {"a": 1000, "b": 1000, "c": 1000}, np.array([0, 0]), np.array([1, 2]), res)
     assert sim[0, 1] == 0.0 and sim[0, 2] > 0.0
+
+
+def test_parse_sv_signals_from_ava_alignments_pools_by_reference_read():
+    from svirlpool_b200 import consensus_lib
+    """a3 (consensus_lib.py:40-90): signals are collected under the REFERENCE read of every alignment, over all queries aligned
+    to it; unmapped records and records without CIGAR are skipped; alignments without signals leave no key."""
+    from svirlpool_b200.datatypes import AlignedRecord
+    recs = [
+        AlignedRecord("a", "b", 100, [(0, 500), (2, 40), (0, 300), (1, 25), (0, 200)]),                  # DEL 40 @600, INS 25 @940 on b
+        AlignedRecord("c", "b", 0, [(4, 150), (0, 400), (1, 10), (0, 100)]),                               # BNDL 150 on b; INS 10 is below 12
+        AlignedRecord("a", "c", 10, [(0, 1000)]),                                                           # no signal: no key for c
+        AlignedRecord("d", "a", 5, [(0, 300), (2, 12), (0, 300), (5, 120)], flag=16),                      # reverse strand: DEL 12 + BNDR 120 on a
+        AlignedRecord("u", None, 0, None, flag=4),
+    ]
+    out = consensus_lib.parse_sv_signals_from_ava_alignments(recs, 12, 100)
+    assert set(out) == {"a", "b"}
+    b = sorted(out["b"])
+    assert [(s.ref_start, s.ref_end, s.size, s.sv_type) for s in b] == [(0, 0, 150, 3), (600, 640, 40, 1), (940, 940, 25, 0)]
+    a = out["a"]
+    assert [(s.ref_start, s.ref_end, s.size, s.sv_type) for s in a] == [(617, 617, 120, 4), (305, 317, 12, 1)]
+    # the INS on b: read coordinates in original read orientation (forward: leading clip 0 + 500 + 300 consumed)
+    ins = next(s for s in b if s.sv_type == 0)
+    assert (ins.read_start, ins.read_end) == (800, 825)
+    # directed view of the same records: one entry per mapped alignment, ref_length = aligned reference span
+    ds = consensus_lib.parse_directed_signals_from_ava(recs, 12, 100)
+    assert [(d.query_name, d.ref_name, d.ref_length) for d in ds] == [("a", "b", 1040), ("c", "b", 500), ("a", "c", 1000), ("d", "a", 612)]

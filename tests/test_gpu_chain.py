@@ -62,3 +62,60 @@ def test_summary_path_equals_record_path_gpu(gpu):
         assert names_a == names_b
         np.testing.assert_array_equal(sim_a, sim_b)
         np.testing.assert_array_equal(consensus.pairwise_alignment_lengths(recs, names_a), len_b)
+
+
+# ---------------------------------------------------------------------------------------------
+# the host-path cases of tests/test_host_path.py (run there on the CPU oracle engine) on the CUDA engine: same inputs,
+# same expectations — A4 re-homing, the best-target mapping, both S1 file-seam cases, final_consensus, many containers per call
+# ---------------------------------------------------------------------------------------------
+
+def test_rehoming_of_unused_reads_gpu(gpu):
+    import test_host_path as hp
+    hp.test_add_unaligned_reads_to_consensuses_inplace(gpu)
+
+
+def test_file_seam_gpu(gpu, tmp_path, golden):
+    import test_host_path as hp
+    hp.test_file_seam_align_reads_with_minimap(tmp_path, golden, gpu)
+
+
+def test_file_seam_multi_reference_best_target_gpu(gpu, tmp_path):
+    import test_host_path as hp
+    hp.test_file_seam_multi_reference_and_soft_supplementary(tmp_path, gpu)
+
+
+def test_final_consensus_and_many_containers_gpu(gpu):
+    import test_host_path as hp
+    hp.test_final_consensus_record(gpu)
+    hp.test_ava_align_many_equals_per_container_calls(gpu)
+    hp.test_similarity_of_many_containers_in_one_call(gpu)
+
+
+def test_best_target_mapping_gpu_equals_oracle(gpu, oracle):
+    """ava.map_queries_to_best_target: identical records and identical target choice on both engines."""
+    from svirlpool_b200 import ava, util
+    rng = np.random.default_rng(77)
+    t0 = "".join("ACGT"[k] for k in rng.integers(0, 4, 2200))
+    t1 = t0[:900] + t0[1100:]                                        # the same locus minus 200 bases
+    t2 = "".join("ACGT"[k] for k in rng.integers(0, 4, 1800))
+    targets = {"c0": t0, "c1": t1, "c2": t2}
+    queries = {"q_full": t0[50:2100], "q_del": t1[30:1900], "q_rc": util.reverse_complement(t2[100:1700]),
+               "q_none": "".join("ACGT"[k] for k in rng.integers(0, 4, 700))}
+    rg, cg = ava.map_queries_to_best_target(gpu, queries, targets)
+    ro, co = ava.map_queries_to_best_target(oracle, queries, targets)
+    assert cg == co == {"q_full": "c0", "q_del": "c1", "q_rc": "c2"}
+    assert [rec_key(r) for r in rg] == [rec_key(r) for r in ro]
+
+
+def test_file_seam_default_engine_gpu(tmp_path, golden):
+    """S1 without an explicit engine: the process-wide Aligner (bounded arena) is created on first use and reused."""
+    from svirlpool_b200 import aligner, sam, util
+    case = next(c for c in golden["cases"] if c["name"] == "simulated.with_insertion")
+    ref_fa, reads_fa = tmp_path / "ref.fa", tmp_path / "reads.fa"
+    ref_fa.write_text(">ref\n" + case["reference"] + "\n")
+    reads_fa.write_text("".join(f">{n}\n{s}\n" for n, s in case["reads"].items()))
+    for k in range(2):
+        bam = tmp_path / f"out{k}.bam"
+        util.align_reads_with_minimap(reference=ref_fa, reads=reads_fa, bamout=bam, tech="map-ont", threads=1)
+        assert [r.cigarstring for r in sam.read_alignments(bam)] == ["499M20I501M"]
+    assert len(aligner._SHARED) == 1

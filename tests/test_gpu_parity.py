@@ -131,8 +131,8 @@ def test_invalid_pairs_are_flagged(gpu):
     assert res[1]["status"] == 8 and res[2]["status"] == 8
 
 
-def test_multiple_waves_small_arena(oracle):
-    """A 16 MiB arena forces several waves; results must not depend on the wave split."""
+def test_small_arena(oracle):
+    """A 16 MiB arena holds a handful of pairs at a time; results must not depend on it."""
     from svirlpool_b200.aligner import Aligner
     rng = np.random.default_rng(21)
     seqs, specs = [], []
@@ -143,7 +143,7 @@ def test_multiple_waves_small_arena(oracle):
         specs.append((2 * p, 2 * p + 1, lo, w, 0))
     with Aligner(device=0, tb_bytes=16 << 20) as small:
         run_both(small, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
-        assert small.stats()["waves"] > 1
+        assert small.stats()["fwd_launches"] >= 1
 
 
 # ---------------------------------------------------------------------------------------------
@@ -536,30 +536,39 @@ def test_latency_plan_small_calls(oracle, monkeypatch):
         run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
 
 
-@pytest.mark.parametrize("serial", ["0", "1"])
-def test_serial_and_concurrent_traceback_scheduling(oracle, monkeypatch, serial):
-    """SVP_TB_SERIAL forces whole-arena waves whose tracebacks run alone (1) or half-arena waves whose tracebacks run under the
-    next wave's forward pass (0); a small arena makes several waves either way. Same results as the oracle."""
+@pytest.mark.parametrize("arena_mb,streams", [(24, "1"), (24, "8"), (160, "8")])
+def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams):
+    """A small arena: the slices of short pairs come from the per-SM pools, the long pairs' from the global pool, and most CTAs
+    have to wait for a slice (arena_alloc) — results do not depend on who waited, nor on the number of launch streams."""
     from svirlpool_b200.aligner import Aligner
-    monkeypatch.setenv("SVP_TB_SERIAL", serial)
-    monkeypatch.setenv("SVP_TBW_MAX", "0")            # small waves, too, split into bulk kernel + warp walks of the long pairs
+    monkeypatch.setenv("SVP_FWD_STREAMS", streams)
     rng = np.random.default_rng(92)
-    names, seqs, specs = noisy_batch(rng, 16, 2200, 512)
-    n2, s2, p2 = noisy_batch(rng, 2, 14000, 544)                      # long pairs: the warp-per-pair walks beside the bulk kernel
+    names, seqs, specs = noisy_batch(rng, 48, 2200, 512)
+    n2, s2, p2 = noisy_batch(rng, 3, 14000, 544)                      # long pairs: slices beyond a per-SM region
     off = len(seqs)
     seqs += s2
     specs += [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in p2]
-    with Aligner(device=0, preset="map-ont", tb_bytes=24 << 20) as g:
-        run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
-        assert g.stats()["waves"] >= 2
+    with Aligner(device=0, preset="map-ont", tb_bytes=arena_mb << 20) as g:
+        for _ in range(2):
+            run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
+        assert g.stats()["waves"] >= 2                                 # launch groups
 
 
-@pytest.mark.parametrize("tbw_max", ["0", "1000000"])
-def test_both_traceback_kernels(oracle, monkeypatch, tbw_max):
-    """The thread-per-pair (bulk) and the warp-per-pair (few pairs per wave) traceback kernels implement the same walk:
-    SVP_TBW_MAX forces one or the other for a mixed batch incl. a Z-trimmed inversion, long gaps and reverse strands."""
-    from svirlpool_b200.aligner import Aligner
-    monkeypatch.setenv("SVP_TBW_MAX", tbw_max)
+def test_pair_beyond_the_arena_is_an_error():
+    """A pair whose traceback rows exceed the whole arena cannot run: the call fails with SVP_ERR_NOMEM (AlignerError), it is not
+    silently dropped."""
+    from svirlpool_b200 import aligner as al
+    rng = np.random.default_rng(94)
+    names, seqs, specs = noisy_batch(rng, 1, 9000, 1024)
+    b = ava.PairBatch.build(names, seqs, specs)
+    with al.Aligner(device=0, preset="map-ont", tb_bytes=4 << 20) as g:
+        with pytest.raises(al.AlignerError) as e:
+            g.align_batch(b.packed, b.seq_off, b.seq_len, b.pairs, b.cigar_words)
+        assert e.value.returncode == -3
+
+
+def test_walk_cases_zdrop_long_gaps_reverse_strands(gpu, oracle):
+    """The walk on a mixed batch incl. a Z-trimmed inversion, long gaps and reverse strands."""
     rng = np.random.default_rng(91)
     names, seqs, specs = noisy_batch(rng, 10, 2500, 544)
     ref = randseq(rng, 6000)
@@ -570,15 +579,26 @@ def test_both_traceback_kernels(oracle, monkeypatch, tbw_max):
         lo, w = ava.full_band(len(seqs[q]), len(ref))
         specs += [(q, off, lo, w, 0), (q, off, lo, w, PAIR_REVCOMP)]
     names = [f"r{k}" for k in range(len(seqs))]
-    with Aligner(device=0, tb_bytes=2 << 30) as g:
-        gres, _ = run_both(g, oracle, names, seqs, specs)
+    gres, _ = run_both(gpu, oracle, names, seqs, specs)
     assert gres["n_del_bp"].max() >= 600
 
 
+def test_two_handles_share_a_device(oracle):
+    """Two Aligner handles with the default (bounded) arena coexist on one GPU and give the same rows — the reference runs
+    several consensus jobs per node (main.smk:649-707)."""
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(95)
+    names, seqs, specs = noisy_batch(rng, 12, 2500, 544)
+    with Aligner(device=0, preset="map-ont") as g1, Aligner(device=0, preset="map-ont") as g2:
+        r1, _ = run_both(g1, oracle, names, seqs, specs)
+        r2, _ = run_both(g2, oracle, names, seqs, specs)
+        assert np.array_equal(r1["score"], r2["score"])
+
+
 def test_pipelined_submits_equal_blocking_calls(oracle):
-    """svp_submit_batch_device x 4 back to back (two batches in flight, the arena halves and the per-call buffers alternate
-    across calls; a small arena forces several waves per call) followed by one svp_sync gives the rows and CIGARs of the
-    blocking host-buffer calls, which equal the oracle."""
+    """svp_submit_batch_device x 4 back to back (two batches in flight, the per-call buffers alternate across calls; a small
+    arena makes their CTAs compete for slices) followed by one svp_sync gives the rows and CIGARs of the blocking host-buffer
+    calls, which equal the oracle."""
     import torch
     from svirlpool_b200._abi import RESULT_DTYPE
     from svirlpool_b200.aligner import Aligner

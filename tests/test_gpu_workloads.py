@@ -44,6 +44,40 @@ def assert_consistent(b, gres, gcig, scoring, allow_status=0):
         check_result(b["packed"], b["off"], b["lens"], b["pairs"][k], gres[k], gcig, scoring)
 
 
+@pytest.fixture(scope="module")
+def oracle_mt():
+    """The oracle on every host thread (full-size workloads: hundreds of 8 kb pairs)."""
+    import os
+    from oracle_engine import OracleEngine
+    return OracleEngine("map-ont", threads=os.cpu_count() or 1)
+
+
+def test_config2_full_size_parity(gpu, oracle_mt):
+    """The headline workload at its real shape: regions 0 and 1 of config 2 (30 reads x 8 kb, 435 pairs each, bands
+    |dlen| + 600 at granule 128 — the regions bench.py's CPU arm aligns), every pair bit-exact against the oracle."""
+    b = workloads.batch_config2([0, 1])
+    assert len(b["pairs"]) == 870 and b["lens"].mean() > 7000
+    gres, gcig = assert_parity(b, gpu, oracle_mt)
+    assert (gres["status"] == 0).all() and int(gres["cells"].sum()) > 5e9
+    assert len({int(w) for w in b["pairs"]["band_w"]}) > 4             # several kernel geometries in one batch
+
+
+def test_config5_reduced_parity(gpu, oracle_mt):
+    """Trio-shaped loci (Pareto length tail, seeds 40 000+) at reduced size: all-vs-all + consensus -> window pairs."""
+    b = workloads.batch_config4([0, 1, 2, 3, 5], seed_base=40_000, skew=True, scale=0.3, max_reads=8, band_w=1024)
+    gres, gcig = assert_parity(b, gpu, oracle_mt)
+    assert_consistent(b, gres, gcig, gpu.scoring)
+
+
+def test_config5_full_size_locus_parity(gpu, oracle_mt):
+    """One full-size locus of each trio set (seeds 40 000 / 50 000 / 60 000 + 1): every read pair and both strands of every
+    padded consensus against its reference window, bit-exact against the oracle."""
+    for seed_base in (40_000, 50_000, 60_000):
+        b = workloads.batch_config4([1], seed_base=seed_base, skew=True, max_reads=14)
+        gres, gcig = assert_parity(b, gpu, oracle_mt)
+        assert (gres["status"] & ~np.uint32(1) == 0).all() and gres["score"].max() > 5000
+
+
 def test_config3_reduced_parity(gpu, oracle):
     b = workloads.batch_config3([0, 1, 2], n_reads=6, scale=0.3)
     gres, gcig = assert_parity(b, gpu, oracle)
