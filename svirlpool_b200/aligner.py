@@ -177,6 +177,37 @@ class PinnedBuffer:
             self.ptr, self.cap = None, 0
 
 
+_SHARED: dict = {}
+
+
+def shared_aligner(preset: str = "map-ont", device: int | None = None) -> "Aligner":
+    """The process-wide Aligner for (device, preset), created on first use with the default bounded arena and closed at exit —
+    what the file seam (util.align_reads_with_minimap) uses when the caller passes no engine, so that repeated calls do not
+    pay a handle (and an arena allocation) each. device None: the current CUDA device."""
+    import atexit
+    key = (device, preset)
+    eng = _SHARED.get(key)
+    if eng is None or eng._h is None:
+        eng = Aligner(device=-1 if device is None else device, preset=preset)
+        if not _SHARED:
+            atexit.register(close_shared_aligners)
+        _SHARED[key] = eng
+    return eng
+
+
+def close_shared_aligners() -> None:
+    for eng in list(_SHARED.values()):
+        eng.close()
+    _SHARED.clear()
+
+
+def estimate_seconds(scoring: np.ndarray, batch, gcups: float = 800.0, overhead: float = 0.02) -> float:
+    """Device time a batch will take, from the planner alone (svp_plan_pairs: spec cells per pair; no GPU needed), at a conservative
+    rate — the budget check behind the `timeout` of the file seam."""
+    plan = plan_pairs(scoring, batch.packed.nbytes, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
+    return overhead + float(plan["cells"].sum()) / (gcups * 1e9)
+
+
 class Aligner:
     """One handle = one GPU + one scoring profile. Not thread-safe; one call at a time."""
 

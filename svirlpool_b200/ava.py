@@ -433,6 +433,9 @@ def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[
             if sub - qe >= min_flank:
                 nxt.append((k, a + qe, b))
         tasks = nxt
+    for _ in range(4):                                # collinear hits on either side of a large indel become one record
+        if not _join_collinear(engine, jobs, hits, target_names, targets, granule, cap):
+            break
     out = []
     for k, hs in hits.items():
         if not hs:
@@ -446,6 +449,66 @@ def map_jobs(engine, jobs: list[MapJob], target_names: list[str], targets: list[
                 out.append((job.target, rec))
     out.sort(key=lambda tr: (tr[0], tr[1].reference_start, tr[1].query_name))
     return [r for _t, r in out]
+
+
+def _oriented(full: int, hit) -> tuple[int, int, int, int]:
+    """(query begin, query end) on the ORIENTED full query and (target begin, target end) of a map_jobs hit."""
+    _score, rc, a, b, row, _cig = hit
+    off = (full - b) if rc else a
+    return off + int(row["q_beg"]), off + int(row["q_end"]), int(row["t_beg"]), int(row["t_end"])
+
+
+def _join_collinear(engine, jobs: list[MapJob], hits: dict[int, list], target_names: list[str], targets: list[str], granule: int, cap: int,
+                    slack: int = 300, tol: int = 50) -> bool:
+    """Two hits of a query that follow each other on the same strand in the same order on query and target — the two sides of a
+    deletion / insertion larger than the first round's band — are re-aligned as ONE piece in a band that spans both diagonals, and
+    replaced by that alignment when it covers both and scores higher than either: the event then is a D / I run of the CIGAR
+    (long-gap cost 24 + len for minimap2's scoring), as in minimap2's chained alignment, not a pair of breakends. One join per
+    query and call; returns whether anything was joined."""
+    cands = []
+    for k, hs in hits.items():
+        full = len(jobs[k].seq)
+        order = sorted(range(len(hs)), key=lambda i: _oriented(full, hs[i])[0])
+        for x, y in zip(order, order[1:]):
+            if hs[x][1] != hs[y][1]:
+                continue
+            q1b, q1e, _t1b, t1e = _oriented(full, hs[x])
+            q2b, q2e, t2b, _t2e = _oriented(full, hs[y])
+            if q2b < q1e - tol or t2b < t1e - tol:
+                continue
+            d1, d2 = t1e - q1e, t2b - q2b
+            w = round_up(abs(d2 - d1) + 2 * slack, granule)
+            if w > cap:
+                continue
+            cands.append((k, x, y, q1b, q2e, min(d1, d2) - slack, w))
+            break
+    if not cands:
+        return False
+    names, seqs, specs, pieces = list(target_names), list(targets), [], []
+    for k, x, y, qb, qe, lo, w in cands:
+        job, rc = jobs[k], hits[k][x][1]
+        full = len(job.seq)
+        a, b = (full - qe, full - qb) if rc else (qb, qe)              # the piece in ORIGINAL read coordinates
+        names.append(f"{job.name}:{a}-{b}")
+        seqs.append(job.seq[a:b])
+        flo, fw = full_band(b - a, len(targets[job.target]), granule)
+        lo_p = lo + qb                                                  # diagonals relative to the piece
+        if w >= fw:
+            lo_p, w = flo, fw
+        specs.append((len(seqs) - 1, job.target, lo_p, w, PAIR_REVCOMP if rc else 0))
+        pieces.append((a, b))
+    res, cig = run_batch(engine, PairBatch.build(names, seqs, specs))
+    joined = False
+    for (k, x, y, *_rest), (a, b), row in zip(cands, pieces, res):
+        if int(row["status"]) & ~ST_CIGAR_OVF:
+            continue
+        hs = hits[k]
+        if int(row["q_beg"]) > tol or int(row["q_end"]) < (b - a) - tol or int(row["score"]) <= max(hs[x][0], hs[y][0]):
+            continue
+        merged = (int(row["score"]), hs[x][1], a, b, row.copy(), cig)
+        hits[k] = [h for i, h in enumerate(hs) if i not in (x, y)] + [merged]
+        joined = True
+    return joined
 
 
 def map_queries_to_best_target(engine, queries: dict[str, str], targets: dict[str, str], min_score: int = MIN_DP_SCORE,

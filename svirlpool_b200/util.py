@@ -85,42 +85,59 @@ def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", th
     the records on the sequence of its best primary alignment (primary + supplementary; what `--secondary=no` leaves of a
     multi-sequence reference, consensus.py:2089-2096). Of `aln_args` only `-Y` has a counterpart (supplementary records
     soft-clipped with the full read sequence instead of hard-clipped, consensus.py:851-857); `--sam-hit-only` and
-    `--secondary=no` are what the engine does anyway, seeding options (`-U`, `-H`, `-z`, `-r`) have none. `threads`,
-    `logfile` and `timeout` are accepted for signature compatibility (the call is bounded by the kernels, not by a child
-    process). Failures raise aligner.AlignerError, a subprocess.CalledProcessError,
-    which the reference's callers already catch. `engine`: an Aligner to reuse; default one per call.
+    `--secondary=no` are what the engine does anyway, seeding options (`-U`, `-H`, `-z`, `-r`) have none. `threads` and
+    `logfile` are accepted for signature compatibility.
+
+    `timeout` (seconds) is honoured the way the reference's callers rely on (util/util.py:205-226 kills the child and raises
+    TimeoutError; consensus.py:1387-1415 catches it and retries with half the reads): the work of the call is estimated from the
+    planner BEFORE anything is launched (aligner.estimate_seconds: spec cells at a conservative rate) and TimeoutError is raised
+    when it exceeds the budget — a pathological container (400x coverage, alignments_to_rafs.py:377) is refused, not run; a call
+    that nevertheless overruns raises TimeoutError afterwards and leaves no BAM. Other failures raise aligner.AlignerError, a
+    subprocess.CalledProcessError, which the reference's callers already catch. `engine`: an Aligner to use; default: the
+    process-wide handle of aligner.shared_aligner() (bounded arena, created once).
     Like the reference (`samtools index`, util.py:232-238) a `.bai` is written next to the BAM."""
+    import time
     from . import ava, sam
-    from .aligner import Aligner
+    from .aligner import estimate_seconds, shared_aligner
+    t_start = time.monotonic()
     paths = reads if isinstance(reads, list) else [reads]
     queries: dict[str, str] = {}
     for p in paths:
         queries.update(read_fasta(p))
     refs = read_fasta(reference)
-    own = engine is None
-    if own:
-        engine = Aligner(preset="ava-ont" if tech == "ava-ont" else "map-ont")
-    try:
+    if engine is None:
+        engine = shared_aligner("ava-ont" if tech == "ava-ont" else "map-ont")
+    if timeout is not None:
+        names = list(queries)
         if tech == "ava-ont":
-            records = ava.ava_align(engine, queries)
-            lengths = {n: len(s) for n, s in queries.items()}
+            first = ava.PairBatch.build_ava(names, [queries[n] for n in names], None, None, 300, 32, False)[0] if len(names) > 1 else None
         else:
-            records, _chosen = ava.map_queries_to_best_target(engine, queries, refs)
-            lengths = {n: len(s) for n, s in refs.items()}
-        soft_supplementary = "-Y" in aln_args.split()
-        for r in records:
-            seq = queries[r.query_name]
-            r.query_sequence = reverse_complement(seq) if r.is_reverse else seq
-            if r.is_supplementary and soft_supplementary:
-                r.cigartuples = [(4 if op == 5 else op, n) for op, n in r.cigartuples]
-            elif r.is_supplementary:                    # hard-clipped records carry only the aligned part
-                a = r.cigartuples[0][1] if r.cigartuples[0][0] == 5 else 0
-                r.query_sequence = r.query_sequence[a:a + r.query_alignment_length]
-        cmd = f"svirlpool_b200 -x {tech} {aln_args}".strip()
-        sam.write_bam(bamout, sam.sort_records(records, lengths), lengths, command=cmd, index=True)     # + <bamout>.bai
-    finally:
-        if own:
-            engine.close()
+            tn = list(refs)
+            specs = [(len(tn) + qi, ti, *ava.full_band(len(queries[q]), len(refs[t])), fl)
+                     for qi, q in enumerate(names) for ti, t in enumerate(tn) for fl in (0, ava.PAIR_REVCOMP)]
+            first = ava.PairBatch.build(tn + names, [refs[t] for t in tn] + [queries[q] for q in names], specs) if specs else None
+        need = estimate_seconds(engine.scoring, first) if first is not None else 0.0
+        if need > timeout:
+            raise TimeoutError(f"align_reads_with_minimap: estimated {need:.1f} s of alignment for {len(queries)} reads exceeds the timeout of {timeout} s")
+    if tech == "ava-ont":
+        records = ava.ava_align(engine, queries)
+        lengths = {n: len(s) for n, s in queries.items()}
+    else:
+        records, _chosen = ava.map_queries_to_best_target(engine, queries, refs)
+        lengths = {n: len(s) for n, s in refs.items()}
+    if timeout is not None and time.monotonic() - t_start > timeout:
+        raise TimeoutError(f"align_reads_with_minimap: exceeded the timeout of {timeout} s")
+    soft_supplementary = "-Y" in aln_args.split()
+    for r in records:
+        seq = queries[r.query_name]
+        r.query_sequence = reverse_complement(seq) if r.is_reverse else seq
+        if r.is_supplementary and soft_supplementary:
+            r.cigartuples = [(4 if op == 5 else op, n) for op, n in r.cigartuples]
+        elif r.is_supplementary:                    # hard-clipped records carry only the aligned part
+            a = r.cigartuples[0][1] if r.cigartuples[0][0] == 5 else 0
+            r.query_sequence = r.query_sequence[a:a + r.query_alignment_length]
+    cmd = f"svirlpool_b200 -x {tech} {aln_args}".strip()
+    sam.write_bam(bamout, sam.sort_records(records, lengths), lengths, command=cmd, index=True)     # + <bamout>.bai
 
 
 # ---------------------------------------------------------------------------------------------

@@ -241,3 +241,46 @@ def test_write_partitioned_alignments_reference_signature(oracle, tmp_path):
     assert sorted(l.split("\t")[:3] for l in paths2[0].read_text().splitlines()) == sorted(l.split("\t")[:3] for l in lines)
     with pytest.raises(ValueError):
         consensus_align.write_partitioned_alignments(recs, {0: tmp_path / "r0.tsv"}, {0: {"nobody"}}, "S")
+
+
+@pytest.mark.parametrize("kind,size", [("del", 6000), ("ins", 3000), ("del", 2500)])
+def test_sv_larger_than_half_the_band_is_one_record(oracle, kind, size):
+    """A consensus carrying a deletion / insertion larger than half the first round's band (band_w 4096): the unaligned flank is
+    found over the whole window and the two collinear hits are joined into ONE record whose CIGAR holds the event — what
+    minimap2's chained alignment reports — instead of a clipped primary (the 6 kb deletion used to come back as `7001M6999S`)."""
+    from svirlpool_b200 import ava
+    rng = np.random.default_rng(17)
+    chrom = "".join("ACGT"[k] for k in rng.integers(0, 4, 30000))
+    if kind == "del":
+        query = chrom[3000:10000] + chrom[10000 + size:17000 + size]
+    else:
+        query = chrom[3000:10000] + "".join("ACGT"[k] for k in rng.integers(0, 4, size)) + chrom[10000:17000]
+    window, w0 = chrom[1000:26000], 1000
+    job = ava.MapJob(name="c", seq=query, target=0, diag_fwd=3000 - w0, diag_rev=None, band_w=4096)
+    recs = ava.map_jobs(oracle, [job], ["w"], [window])
+    assert len(recs) == 1 and not recs[0].is_supplementary and not recs[0].is_reverse
+    ops = [(op, n) for op, n in recs[0].cigartuples if n >= 1000 and op in (1, 2)]
+    assert ops == [(2 if kind == "del" else 1, size)]
+    assert recs[0].reference_start == 3000 - w0 and recs[0].query_alignment_length == len(query)
+    # the consumer chain sees a DEL / INS signal, not breakends
+    from svirlpool_b200 import alignments_to_rafs
+    sig = alignments_to_rafs.parse_SVsignals_from_alignment(recs[0], recs[0].reference_start, recs[0].reference_end, 0, len(query), 12, 50)
+    assert [(s.sv_type, s.size) for s in sig] == [(1 if kind == "del" else 0, size)]
+
+
+def test_failure_bits_raise(oracle):
+    """A pair the kernels cannot run (band wider than a cluster covers) raises AlignerError from the host drivers instead of
+    turning into 'no hit' (aligner.py: never silently degrades)."""
+    from svirlpool_b200 import ava
+    from svirlpool_b200._abi import RESULT_DTYPE
+    from svirlpool_b200.aligner import AlignerError
+    res = np.zeros(3, dtype=RESULT_DTYPE)
+    res["status"] = [0, 8, 1]
+    with pytest.raises(AlignerError) as e:
+        ava.check_status(res, None, "test")
+    assert "BAD_PAIR 1" in str(e.value)
+    res["status"] = [0, 1, 2]
+    ava.check_status(res)                              # NOHIT / CIGAR_OVF are not failures
+    # 70 kb query vs 70 kb target over the "full matrix": the band is capped at what a cluster covers, the pair runs
+    lo, w = ava._job_band(70000, 70000, None, 0, 32, cap=ava.max_band_w(oracle))
+    assert w == 131008 and -(70000 - 1) <= lo and lo + w <= -(70000 - 1) + 140000

@@ -350,3 +350,38 @@ def test_file_seam_multi_reference_and_soft_supplementary(tmp_path, oracle):
     assert all(5 in (r.cigartuples[0][0], r.cigartuples[-1][0]) and len(r.query_sequence) == r.query_alignment_length for r in hard)
     assert all(4 in (r.cigartuples[0][0], r.cigartuples[-1][0]) and len(r.query_sequence) == len(inv) for r in soft)
     assert [(r.reference_start, r.reference_end, r.is_reverse) for r in hard] == [(r.reference_start, r.reference_end, r.is_reverse) for r in soft]
+
+
+def test_file_seam_timeout_contract(tmp_path, oracle):
+    """util.align_reads_with_minimap honours `timeout` like the reference (util/util.py:205-226: TimeoutError, which
+    consensus.py:1387-1415 catches to retry with half the reads): a container whose estimated work exceeds the budget is refused
+    before anything runs and leaves no BAM; a generous budget runs normally."""
+    rng = np.random.default_rng(61)
+    tmpl = "".join("ACGT"[k] for k in rng.integers(0, 4, 3000))
+    reads = {f"r{k:02d}": tmpl[int(rng.integers(0, 50)):len(tmpl) - int(rng.integers(0, 50))] for k in range(12)}
+    fa, bam = tmp_path / "reads.fa", tmp_path / "ava.bam"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in reads.items()))
+    with pytest.raises(TimeoutError):
+        util.align_reads_with_minimap(reference=fa, reads=fa, bamout=bam, tech="ava-ont", threads=1, timeout=1e-4, engine=oracle)
+    assert not bam.exists()
+    with pytest.raises(TimeoutError):
+        util.align_reads_with_minimap(reference=fa, reads=fa, bamout=bam, tech="map-ont", threads=1, timeout=1e-4, engine=oracle)
+    util.align_reads_with_minimap(reference=fa, reads=fa, bamout=bam, tech="ava-ont", threads=1, timeout=120.0, engine=oracle)
+    assert bam.exists() and len(list(sam.read_alignments(bam))) >= 60
+    # the estimate grows with the work: 4x the reads = ~16x the pairs
+    from svirlpool_b200 import aligner, ava
+    names = list(reads)
+    small = ava.PairBatch.build_ava(names[:3], [reads[n] for n in names[:3]], None, None, 300, 32, False)[0]
+    big = ava.PairBatch.build_ava(names, [reads[n] for n in names], None, None, 300, 32, False)[0]
+    sc = aligner.scoring_preset("map-ont")
+    assert aligner.estimate_seconds(sc, big, overhead=0) > 10 * aligner.estimate_seconds(sc, small, overhead=0)
+
+
+def test_ava_pairs_native_unknown_strand_entries():
+    """svp_ava_pairs emits both orientations of a pair when either strand is 0 (unknown): the binding sizes its buffer for that
+    (strands [1, 0, -1] used to fail with SVP_ERR_NOMEM)."""
+    from svirlpool_b200.aligner import ava_pairs_native
+    lens = np.array([900, 1000, 1100], dtype=np.uint32)
+    pairs, words = ava_pairs_native(lens, None, np.array([1, 0, -1], dtype=np.int8), None, 0, 3, 300, 32, False)
+    got = sorted((int(p["q"]), int(p["t"]), int(p["flags"]) & 1) for p in pairs)
+    assert got == [(0, 1, 0), (0, 1, 1), (0, 2, 1), (1, 2, 0), (1, 2, 1)] and words > 0
