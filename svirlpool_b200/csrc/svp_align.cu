@@ -232,6 +232,7 @@ enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3, FAM_FAST_RB = 4 
 
 // Every forward kernel has the same signature; the variant a group of pairs runs on is looked up here (svp_create sets the
 // attributes of every entry, run_plan launches through it). nullptr: no such variant.
+constexpr int SMEM_STATIC = 64;          // static shared memory of the forward kernels (the pair's arena slice note), rounded up
 using FwdKernel = void (*)(const Task*, const uint32_t*, const uint8_t*, const Arena, svp_result*, uint32_t*, const Consts);
 static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring, bool two) {
     if (fam == FAM_FAST || fam == FAM_FAST_RB) {        // s16x2 fast path: plain / rebased, whole images / sliding windows, one CTA / cluster
@@ -326,10 +327,13 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     for (int fam = 0; fam < 5; ++fam) for (int kp = 4; kp <= 8; ++kp) for (int m = 0; m < 2; ++m) for (int c = 0; c < 2; ++c)
         for (int r = 0; r < 2; ++r) for (int t = 0; t < 2; ++t)
             if (FwdKernel k = fwd_kernel(fam, kp, m != 0, c != 0, r != 0, t != 0)) {
-                cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-                cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                // (dynamic + the kernels' few bytes of static shared memory must stay within the per-block limit)
+                if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - SMEM_STATIC) != cudaSuccess ||
+                    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+                    cudaGetLastError();
+                    return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
+                }
             }
-    if (cudaGetLastError() != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
     // %nsmid: the range of the SM ids the per-SM arena pools are indexed with
     uint32_t* d_n = nullptr;
     if (cudaMalloc((void**)&d_n, sizeof(uint32_t)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
@@ -622,7 +626,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         Task& t = tasks[k];
         if (t.flags & (TASK_INVALID | TASK_RING)) continue;
         const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-        if (smem_need(t, cs, nw) + 64 > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;      // (+ the kernels' static shared memory)
+        if (smem_need(t, cs, nw) + SMEM_STATIC > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;      // (+ the kernels' static shared memory)
     }
     // ---- arena partition: which share goes to the global pool ----------------------------------------------------------
     {
@@ -699,7 +703,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
                 // ballast: CTAs per SM <= smem_per_sm / (smem + 1 KB the system reserves per CTA); keep 1.5 x their slices within the SM's region
                 const double per_cta = 1.5 * (double)g.max_slice / (double)h->sm_region * (double)h->smem_per_sm;
                 const size_t ballast = per_cta > 1024.0 ? (size_t)per_cta - 1024 + 16 : 0;
-                g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - 64);
+                g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - SMEM_STATIC);
             }
             std::copy(v.begin(), v.end(), order + pos);
             pos += v.size();

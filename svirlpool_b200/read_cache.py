@@ -13,6 +13,7 @@ defers to consensus.get_full_read_sequences_of_alignments, consensus.py:382-580)
 from __future__ import annotations
 
 import logging
+from dataclasses import dataclass, field
 from pathlib import Path
 
 import numpy as np
@@ -34,15 +35,21 @@ def _original_orientation(aln: AlignedRecord) -> str:
     return reverse_complement(aln.query_sequence) if aln.is_reverse else aln.query_sequence
 
 
+@dataclass
+class _CachedRead:
+    """Everything the cache knows about one read on the current chromosome."""
+
+    records: dict[tuple[int, int], AlignedRecord] = field(default_factory=dict)   # (flag, reference_start) -> the record kept for it
+    right_end: int = -1                 # rightmost reference end over its records: the read stays until a window starts beyond it
+    sequence: str | None = None         # full read, original orientation; None while unresolved
+
+
 class ReadSequenceCache:
     def __init__(self, path_alignments: Path):
         self.path_alignments = Path(path_alignments)
-        self._samfile = sam.BamFile(self.path_alignments)
-        self._seqs: dict[str, str] = {}                       # readname -> full sequence, original read orientation
-        self._alns: dict[str, list[AlignedRecord]] = {}
-        self._max_ref_end: dict[str, int] = {}
-        self._aln_keys: dict[str, set[tuple[int, int]]] = {}
-        self._current_chr: str | None = None
+        self._bam = sam.BamFile(self.path_alignments)
+        self._reads: dict[str, _CachedRead] = {}
+        self._chrom: str | None = None
         self.fetch_calls = 0
         self.cache_hits_reads = 0
         self.cache_misses_reads = 0
@@ -51,37 +58,31 @@ class ReadSequenceCache:
     def fetch_for_cr(self, cr) -> tuple[list[AlignedRecord], dict[str, str]]:
         """(alignments overlapping the candidate region, full sequences of their reads). `cr` needs .chr,
         .referenceStart, .referenceEnd."""
-        if self._current_chr != cr.chr:
-            self._flush()
-            self._current_chr = cr.chr
-        cr_alns: list[AlignedRecord] = []
-        new_readnames: set[str] = set()
-        new_alns: list[AlignedRecord] = []
+        if cr.chr != self._chrom:                  # the cache never spans chromosomes
+            self._reads = {}
+            self._chrom = cr.chr
         self.fetch_calls += 1
-        for aln in self._samfile.fetch(cr.chr, max(int(cr.referenceStart), 0), int(cr.referenceEnd)):
+        region_records: list[AlignedRecord] = []
+        unresolved: set[str] = set()               # reads without a sequence yet: first met in this fetch, or not resolvable so far
+        for aln in self._bam.fetch(cr.chr, max(int(cr.referenceStart), 0), int(cr.referenceEnd)):
             if aln.is_secondary:
                 continue
-            qname = aln.query_name
-            key = (int(aln.flag), int(aln.reference_start))
-            seen = self._aln_keys.setdefault(qname, set())
-            if key in seen:
-                cr_alns.append(_pick_existing_aln(self._alns[qname], key) or aln)
-                continue
-            seen.add(key)
-            self._alns.setdefault(qname, []).append(aln)
-            ref_end = aln.reference_end if aln.reference_end is not None else 0
-            if ref_end > self._max_ref_end.get(qname, -1):
-                self._max_ref_end[qname] = ref_end
-            cr_alns.append(aln)
-            if qname not in self._seqs:
-                new_readnames.add(qname)
-                new_alns.append(aln)
-        if new_readnames:
-            self.cache_misses_reads += len(new_readnames)
-            self._resolve_new_read_sequences(new_alns, new_readnames)
-        cr_readnames = {a.query_name for a in cr_alns}
-        self.cache_hits_reads += len(cr_readnames - new_readnames)
-        return cr_alns, {rn: self._seqs[rn] for rn in cr_readnames if rn in self._seqs}
+            read = self._reads.get(aln.query_name)
+            if read is None:
+                read = self._reads[aln.query_name] = _CachedRead()
+            if read.sequence is None:
+                unresolved.add(aln.query_name)
+            # an alignment met again through an overlapping region is answered with the record already held
+            kept = read.records.setdefault((int(aln.flag), int(aln.reference_start)), aln)
+            region_records.append(kept)
+            if kept is aln:
+                read.right_end = max(read.right_end, aln.reference_end or 0)
+        for name in unresolved:
+            self._reads[name].sequence = self._full_sequence(name, list(self._reads[name].records.values()))
+        names = {r.query_name for r in region_records}
+        self.cache_misses_reads += len(unresolved)
+        self.cache_hits_reads += len(names) - len(unresolved)
+        return region_records, {n: self._reads[n].sequence for n in names if self._reads[n].sequence is not None}
 
     def packed_for_cr(self, cr) -> tuple[list[str], np.ndarray, np.ndarray, np.ndarray, dict[str, str]]:
         """The region's reads ready for svp_align_batch(): (names, packed 2-bit bytes, seq_off, seq_len, strand per read).
@@ -97,21 +98,22 @@ class ReadSequenceCache:
         return names, packed, off, lens, strands
 
     def advance(self, window_start) -> None:
-        for rn in [rn for rn, end in self._max_ref_end.items() if end < window_start]:
-            self._seqs.pop(rn, None)
-            self._alns.pop(rn, None)
-            self._max_ref_end.pop(rn, None)
-            self._aln_keys.pop(rn, None)
+        """Drop every read none of whose alignments reaches window_start (the start of the next container on this chromosome)."""
+        self._reads = {name: read for name, read in self._reads.items() if read.right_end >= window_start}
+
+    def cached_readnames(self) -> set[str]:
+        """Names of the reads whose sequence is held right now."""
+        return {name for name, read in self._reads.items() if read.sequence is not None}
 
     def current_size_reads(self) -> int:
-        return len(self._seqs)
+        return sum(1 for read in self._reads.values() if read.sequence is not None)
 
     def current_size_bp(self) -> int:
-        return sum(len(s) for s in self._seqs.values())
+        return sum(len(read.sequence) for read in self._reads.values() if read.sequence is not None)
 
     def close(self) -> None:
-        self._samfile.close()
-        self._flush()
+        self._bam.close()
+        self._reads = {}
 
     def __enter__(self) -> "ReadSequenceCache":
         return self
@@ -120,48 +122,29 @@ class ReadSequenceCache:
         self.close()
 
     # ------------------------------------------------------------------ internals
-    def _flush(self) -> None:
-        self._seqs.clear()
-        self._alns.clear()
-        self._max_ref_end.clear()
-        self._aln_keys.clear()
-
-    def _resolve_new_read_sequences(self, new_alns: list[AlignedRecord], new_readnames: set[str]) -> None:
-        deferred = []
-        for aln in new_alns:
-            if aln.query_name in self._seqs:
-                continue
+    def _full_sequence(self, name: str, records: list[AlignedRecord]) -> str | None:
+        """The read's full sequence in original orientation: from a record of this fetch that carries it (no hard clip), else
+        from the record its SA tag points to."""
+        for aln in records:
             if aln.query_sequence and _full_read_length(aln) == len(aln.query_sequence):
-                self._seqs[aln.query_name] = _original_orientation(aln)
-            else:
-                deferred.append(aln)
-        for aln in deferred:                     # hard-clipped record: the full SEQ sits on another record of the read
-            if aln.query_name in self._seqs:
-                continue
+                return _original_orientation(aln)
+        for aln in records:                      # hard-clipped records only: the full SEQ sits on another record of the read
             full = self._find_full_record(aln)
             if full is not None:
-                self._seqs[aln.query_name] = _original_orientation(full)
-            else:
-                log.warning("ReadSequenceCache: no record with the full sequence of read %s", aln.query_name)
+                return _original_orientation(full)
+        log.warning("ReadSequenceCache: no record with the full sequence of read %s", name)
+        return None
 
     def _find_full_record(self, aln: AlignedRecord) -> AlignedRecord | None:
         """Follow the SA tag (rname,pos,strand,CIGAR,mapQ,NM;...) to the read's other records until one carries the
         full sequence (no hard clip)."""
         for entry in str(aln.tags.get("SA", "")).split(";"):
             parts = entry.split(",")
-            if len(parts) < 4 or parts[0] not in self._samfile.references:
+            if len(parts) < 4 or parts[0] not in self._bam.references:
                 continue
             pos = int(parts[1]) - 1
-            for cand in self._samfile.fetch(parts[0], pos, pos + 1):
+            for cand in self._bam.fetch(parts[0], pos, pos + 1):
                 clipped = any(op == CIGAR_H for op, _n in cand.cigartuples or ())
                 if cand.query_name == aln.query_name and cand.reference_start == pos and cand.query_sequence and not clipped:
                     return cand
         return None
-
-
-def _pick_existing_aln(alns: list[AlignedRecord], key: tuple[int, int]) -> AlignedRecord | None:
-    flag, ref_start = key
-    for a in alns:
-        if int(a.flag) == flag and int(a.reference_start) == ref_start:
-            return a
-    return None

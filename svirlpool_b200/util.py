@@ -55,24 +55,21 @@ def read_fasta(path) -> dict[str, str]:
 
 
 def read_fasta_records(path):
-    """(id, description, sequence) per FASTA record, with Bio.SeqIO's conventions: id = first word of the header,
-    description = the whole header line."""
-    rid, desc, chunks = None, None, []
+    """(id, description, sequence) per FASTA record with Bio.SeqIO's conventions (what svirltile._add_consensus_sequences_to_db
+    stores, localassembly/svirltile.py:78-110): the title is the header line without '>' and trailing white space, id = its first
+    word ("" for an empty title), description = the WHOLE title (it repeats the id); the sequence is the record's lines joined,
+    blanks and carriage returns removed."""
+    title, chunks = None, []
     with open(path) as f:
         for line in f:
-            line = line.rstrip("\n")
-            if not line:
-                continue
-            if line[0] == ">":
-                if rid is not None:
-                    yield rid, desc, "".join(chunks)
-                desc = line[1:].strip()
-                rid = desc.split()[0] if desc else ""
-                chunks = []
-            elif rid is not None:
-                chunks.append(line.strip())
-    if rid is not None:
-        yield rid, desc, "".join(chunks)
+            if line.startswith(">"):
+                if title is not None:
+                    yield (title.split(None, 1)[0] if title.strip() else ""), title, "".join(chunks).replace(" ", "").replace("\r", "")
+                title, chunks = line[1:].rstrip(), []
+            elif title is not None:
+                chunks.append(line.rstrip("\n"))
+    if title is not None:
+        yield (title.split(None, 1)[0] if title.strip() else ""), title, "".join(chunks).replace(" ", "").replace("\r", "")
 
 
 def align_reads_with_minimap(reference, reads, bamout, tech: str = "map-ont", threads: int = 3, aln_args: str = "",

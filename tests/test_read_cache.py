@@ -49,7 +49,7 @@ def test_cache_sliding_window_eviction(tmp_path):
         cache.fetch_for_cr(_CR(1, "chr1", 100, 300))
         assert cache.current_size_reads() == 2 and cache.current_size_bp() == 600
         cache.advance(window_start=400)
-        assert cache.current_size_reads() == 1 and "r2" in cache._seqs and "r1" not in cache._seqs
+        assert cache.current_size_reads() == 1 and "r2" in cache.cached_readnames() and "r1" not in cache.cached_readnames()
         cache.advance(window_start=600)
         assert cache.current_size_reads() == 0
 
@@ -61,7 +61,7 @@ def test_cache_flushes_on_chromosome_switch(tmp_path):
         cache.fetch_for_cr(_CR(1, "chr1", 100, 300))
         assert cache.current_size_reads() == 1
         cache.fetch_for_cr(_CR(2, "chr2", 100, 300))
-        assert "r1" not in cache._seqs and "r2" in cache._seqs and cache.current_size_reads() == 1
+        assert "r1" not in cache.cached_readnames() and "r2" in cache.cached_readnames() and cache.current_size_reads() == 1
 
 
 def test_cache_reverse_complement_preserves_original_orientation(tmp_path):

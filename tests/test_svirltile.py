@@ -45,3 +45,37 @@ def test_sample_database_roundtrip(tmp_path):
     # a missing copy-number database is skipped, an existing output is overwritten
     svirltile.create_sample_database(tmp_path / "svp.db", tmp_path / "cov.db", fasta, "S2", out, copynumber_db_path=tmp_path / "none.db")
     assert svirltile.get_metadata(out) == {"samplename": "S2"}
+
+
+def test_consensus_sequences_rows_byte_for_byte(tmp_path):
+    """The rows of consensus_sequences against what the reference's writer stores (localassembly/svirltile.py:78-110:
+    `SeqIO.parse(fasta, "fasta")`, then (record.id, pickle.dumps(str(record.seq)), record.description or "")), restated by hand
+    for a FASTA with Biopython-relevant details: a header with a description (record.description is the WHOLE title line, id
+    included), a header with trailing blanks, wrapped sequence lines, CRLF line ends and a blank line inside a record."""
+    fasta = tmp_path / "consensus.fasta"
+    fasta.write_bytes(b">12.1 crID=12 reads=7 \nacgtACGTNN\nACGTacgt\n>13.0\r\nGGGG\r\n\r\ncccc\r\n>14.0\tsample=HG002\nTTTT\n")
+    expected = [
+        ("12.1", pickle.dumps("acgtACGTNNACGTacgt"), "12.1 crID=12 reads=7"),
+        ("13.0", pickle.dumps("GGGGcccc"), "13.0"),
+        ("14.0", pickle.dumps("TTTT"), "14.0\tsample=HG002"),
+    ]
+    db = tmp_path / "t.db"
+    sqlite3.connect(db).close()
+    assert svirltile._add_consensus_sequences_to_db(db, fasta) == 3
+    with sqlite3.connect(db) as conn:
+        rows = conn.execute("SELECT consensusID, sequence, description FROM consensus_sequences ORDER BY consensusID").fetchall()
+        ddl = " ".join(conn.execute("SELECT sql FROM sqlite_master WHERE name='consensus_sequences'").fetchone()[0].split())
+        idx = conn.execute("SELECT name FROM sqlite_master WHERE type='index' AND tbl_name='consensus_sequences' AND name NOT LIKE 'sqlite_%'").fetchall()
+    assert [(a, bytes(b), c) for a, b, c in rows] == expected
+    assert ddl == "CREATE TABLE consensus_sequences ( consensusID VARCHAR(50) PRIMARY KEY, sequence BLOB NOT NULL, description TEXT )".replace("( ", "(").replace(" )", ")") \
+        or ddl == "CREATE TABLE consensus_sequences (consensusID VARCHAR(50) PRIMARY KEY, sequence BLOB NOT NULL, description TEXT)"
+    assert idx == [("idx_consensus_sequences_id",)]
+    # metadata table: the reference's layout and its single row
+    svirltile._add_metadata_to_db(db, "HG002")
+    with sqlite3.connect(db) as conn:
+        assert conn.execute("SELECT key, value FROM metadata").fetchall() == [("samplename", "HG002")]
+        mddl = " ".join(conn.execute("SELECT sql FROM sqlite_master WHERE name='metadata'").fetchone()[0].split())
+    assert mddl == "CREATE TABLE metadata (key VARCHAR(50) PRIMARY KEY, value TEXT NOT NULL)"
+    # and the reference's reader convention on those rows (svirltile.py:154-197: pickle.loads of the BLOB)
+    got = {cid: svirltile.decompress_sequence(d["sequence"]) for cid, d in svirltile.get_consensus_sequences(db)}
+    assert got == {"12.1": "acgtACGTNNACGTacgt", "13.0": "GGGGcccc", "14.0": "TTTT"}
