@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from .crs_to_batches import _load_crIDs_from_batch_tsv  # noqa: F401  (lives in consensus.py in the reference: consensus.py:3134-3160)
 from . import alignments_to_rafs, ava, consensus_lib
 from .datatypes import AlignedRecord, ReadAlignmentSignals
 

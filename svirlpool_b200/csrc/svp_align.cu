@@ -93,7 +93,7 @@ struct DevBuf {
 // Per-call state. Two sets alternate, so a submitted call (svp_submit_batch_device) can still be running while the next call
 // is planned and its kernels are enqueued behind / beside it.
 struct CallSet {
-    DevBuf d_tasks, d_order;
+    DevBuf d_tasks, d_order, d_queue;
     Task* h_tasks = nullptr; size_t h_tasks_cap = 0;            // pinned staging of the task / order arrays
     uint32_t* h_order = nullptr; size_t h_order_cap = 0;
     std::vector<cudaEvent_t> events;                            // pool, grown on demand (stream joins)
@@ -110,6 +110,10 @@ struct svp_handle {
     Consts cs{};
     cudaStream_t stream = nullptr;              // copies, joins, the first kernel group of a call
     cudaStream_t stream_aux[N_FWD_STREAMS - 1] = {};   // the other groups of a call run beside it
+    cudaStream_t stream_walk = nullptr;         // the call's walker kernel (highest priority: resident before the forward CTAs flood the SMs)
+    int sm_count = 0;
+    int walk_ctas_per_sm = 1;                   // walker CTAs (4 warps each) per SM and call (env SVP_WALK_CTAS_PER_SM)
+    bool fused_walk = false;                    // env SVP_FUSED_WALK: no queue, every CTA walks its own pair after its forward pass
     cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
     // arena: n_sm per-SM pools of sm_region bytes each, then one global pool (svp_kernels.cuh: ArenaPool)
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
@@ -225,6 +229,8 @@ static void read_env_knobs(svp_handle* h) {
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
+    if (const char* e = getenv("SVP_WALK_CTAS_PER_SM")) h->walk_ctas_per_sm = std::min(std::max(atoi(e), 1), 8);
+    if (const char* e = getenv("SVP_FUSED_WALK")) h->fused_walk = atoi(e) != 0;
 }
 
 // kernel family of a pair
@@ -271,6 +277,8 @@ static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring
 #undef SVP_W
     return nullptr;
 }
+
+__global__ void svp_queue_init_kernel(WalkQueue* q, uint32_t n) { q->head = 0; q->tail = 0; q->n = n; q->pad = 0; }
 
 __global__ void svp_nsmid_kernel(uint32_t* out) { uint32_t n; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n)); *out = n; }
 
@@ -319,7 +327,13 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     for (cudaStream_t& sx : h->stream_aux)
         if (cudaStreamCreateWithFlags(&sx, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+    }
     read_env_knobs(h);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&h->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     // every variant: the largest dynamic shared memory (sequence images, or the residency ballast of run_plan) and the whole
@@ -377,7 +391,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     if (h->d_clocks) cudaFree(h->d_clocks);
     for (DevBuf* b : { &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (CallSet& c : h->sets) {
-        for (DevBuf* b : { &c.d_tasks, &c.d_order }) b->release();
+        for (DevBuf* b : { &c.d_tasks, &c.d_order, &c.d_queue }) b->release();
         if (c.h_tasks) cudaFreeHost(c.h_tasks);
         if (c.h_order) cudaFreeHost(c.h_order);
         for (cudaEvent_t e : c.events) cudaEventDestroy(e);
@@ -386,6 +400,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
     delete h;
 }
 
@@ -723,6 +738,16 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     const Task* d_tasks = (const Task*)c.d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)c.d_order.p;
+    // the call's walk queue: one entry per valid pair, unpublished entries are all-ones
+    const size_t n_valid = inv_first;
+    WalkQueue* d_queue = nullptr;
+    if (!h->fused_walk && n_valid) {
+        const size_t qbytes = sizeof(WalkQueue) + n_valid * sizeof(WalkEntry);
+        CUDA_TRY(h, c.d_queue.reserve(qbytes));
+        d_queue = (WalkQueue*)c.d_queue.p;
+        CUDA_TRY(h, cudaMemsetAsync(d_queue, 0xFF, qbytes, st));
+        svp_queue_init_kernel<<<1, 1, 0, st>>>(d_queue, (uint32_t)n_valid);
+    }
 
     static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : N_FWD_STREAMS; return std::min(std::max(v, 1), N_FWD_STREAMS); }();
     cudaStream_t sF[N_FWD_STREAMS] = { st };
@@ -735,7 +760,18 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     const int rot = (int)(h->call_idx % (uint64_t)N_FWD_STREAMS);
     auto stream_of = [&](size_t gi) { return sF[(gi + (size_t)rot) % (size_t)n_streams]; };
     bool used[N_FWD_STREAMS] = {};
-    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks };
+    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, d_queue, d_tasks };
+    // The walkers first, on the highest-priority stream: a few warps per SM that stay for the whole call and walk the pairs the
+    // forward CTAs queue. (A forward CTA ends with its forward pass; its ~130 registers per thread go to the next pair instead of
+    // idling through a latency-bound walk — walking inside the forward CTA was measured at 37 % of the CTA's life, 482 instead of
+    // 571 regions/s on config 2.)
+    bool walker = false;
+    if (d_queue) {
+        const unsigned ctas = (unsigned)std::min<size_t>((size_t)h->sm_count * (size_t)h->walk_ctas_per_sm, (n_valid + 3) / 4);
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream_walk, ev_copied, 0));
+        svp_walk_kernel<<<ctas, 128, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs);
+        walker = true;
+    }
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         const Group& g = groups[gi];
         FwdKernel kern = fwd_kernel(g.fam, g.kp, g.nwarp > 1, g.cluster > 1, g.ring, cs.two_piece != 0);
@@ -754,6 +790,12 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         if (!used[a] || sF[a] == st) continue;
         CUDA_TRY(h, cudaEventRecord(c.events[a], sF[a]));
         CUDA_TRY(h, cudaStreamWaitEvent(st, c.events[a], 0));
+    }
+    if (walker) {
+        while (c.events.size() < (size_t)N_FWD_STREAMS + 2) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
+        CUDA_TRY(h, cudaEventRecord(c.events[N_FWD_STREAMS + 1], h->stream_walk));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, c.events[N_FWD_STREAMS + 1], 0));
+        c.stats.tb_launches = 1;
     }
     CUDA_TRY(h, cudaEventRecord(c.ev_t1, st));
     c.stats.waves = (uint32_t)groups.size();

@@ -252,47 +252,48 @@ struct ArenaPool {
     uint64_t off[POOL_MAX], len[POOL_MAX];   // live slices, ascending by offset (relative to base)
     unsigned long long waits;         // allocations that had to wait (statistics)
 };
+// Finished forward passes of a call, waiting for their walk. An entry is published by writing its task index last; entries are
+// popped in order (head), by the call's walker kernel and by any CTA that is waiting for arena space (it helps instead of idling).
+struct WalkEntry { uint64_t arena_off; uint32_t pool_id; uint32_t task; };
+constexpr uint32_t WALK_EMPTY = 0xFFFFFFFFu;
+struct WalkQueue {
+    uint32_t head, tail, n, pad;      // next entry to walk, entries handed out to writers, valid pairs of the call
+    WalkEntry e[1];                   // n entries, initialised to 0xFF
+};
 struct Arena {
     uint8_t* base;
     ArenaPool* pools;                 // pools[0 .. n_sm): per SM, pools[n_sm]: global
     uint32_t n_sm;
     uint32_t use_global;              // this launch's pairs allocate from the global pool
-    unsigned long long* clocks;       // [0] summed forward ns, [1] summed traceback ns, [2] pairs (statistics)
+    unsigned long long* clocks;       // [0] summed forward ns, [1] summed walk ns, [2] pairs walked, [3] walks done by waiting CTAs (statistics)
+    WalkQueue* queue;                 // the call's queue; nullptr: every CTA walks its own pair right after its forward pass
+    const Task* tasks;                // the call's task array (queue entries index it)
 };
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// one thread; returns the arena offset of a slice of `bytes` bytes (a multiple of 256) and the pool it came from
-__device__ __noinline__ uint64_t arena_alloc(const Arena& A, uint64_t bytes, uint32_t& pool_id) {
-    pool_id = A.use_global ? A.n_sm : min(smid(), A.n_sm - 1u);
-    ArenaPool* P = A.pools + pool_id;
+// one thread; one attempt to take a slice of `bytes` bytes (a multiple of 256) from pool P: arena offset, or ~0 when it does not fit now
+__device__ __noinline__ uint64_t arena_try_alloc(ArenaPool* P, uint64_t bytes) {
     volatile uint64_t* off = P->off; volatile uint64_t* len = P->len;
-    bool waited = false;
-    for (;;) {
-        while (atomicCAS(&P->lock, 0u, 1u) != 0u) __nanosleep(100);
-        __threadfence();
-        const uint32_t n = *(volatile uint32_t*)&P->n;
-        uint64_t prev_end = 0; int at = -1;
-        if (n < (uint32_t)POOL_MAX) {
-            for (uint32_t k = 0; k < n; ++k) {
-                if (off[k] - prev_end >= bytes) { at = (int)k; break; }
-                prev_end = off[k] + len[k];
-            }
-            if (at < 0 && P->bytes - prev_end >= bytes) at = (int)n;
+    while (atomicCAS(&P->lock, 0u, 1u) != 0u) __nanosleep(100);
+    __threadfence();
+    const uint32_t n = *(volatile uint32_t*)&P->n;
+    uint64_t prev_end = 0, got = ~(uint64_t)0; int at = -1;
+    if (n < (uint32_t)POOL_MAX) {
+        for (uint32_t k = 0; k < n; ++k) {
+            if (off[k] - prev_end >= bytes) { at = (int)k; break; }
+            prev_end = off[k] + len[k];
         }
-        if (at >= 0) {
-            for (int k = (int)n; k > at; --k) { off[k] = off[k - 1]; len[k] = len[k - 1]; }
-            off[at] = prev_end; len[at] = bytes;
-            *(volatile uint32_t*)&P->n = n + 1;
-            if (waited) P->waits += 1;
-            __threadfence();
-            atomicExch(&P->lock, 0u);
-            return P->base + prev_end;
-        }
-        __threadfence();
-        atomicExch(&P->lock, 0u);
-        waited = true;
-        __nanosleep(20000);
+        if (at < 0 && P->bytes - prev_end >= bytes) at = (int)n;
     }
+    if (at >= 0) {
+        for (int k = (int)n; k > at; --k) { off[k] = off[k - 1]; len[k] = len[k - 1]; }
+        off[at] = prev_end; len[at] = bytes;
+        *(volatile uint32_t*)&P->n = n + 1;
+        got = P->base + prev_end;
+    }
+    __threadfence();
+    atomicExch(&P->lock, 0u);
+    return got;
 }
 __device__ __noinline__ void arena_free(const Arena& A, uint32_t pool_id, uint64_t arena_off) {
     ArenaPool* P = A.pools + pool_id;
@@ -310,15 +311,61 @@ __device__ __noinline__ void arena_free(const Arena& A, uint32_t pool_id, uint64
     __threadfence();
     atomicExch(&P->lock, 0u);
 }
-// Start of a pair's CTA(s): thread 0 of the first CTA takes the slice and notes it in its shared memory (s_slice: uint64[3] =
-// arena offset, pool id, start time); after the caller's initial barrier every CTA of a cluster reads the offset from the first
-// CTA's shared memory (pair_rows; remote shared memory may only be touched once the cluster barrier has shown that CTA running).
-__device__ __forceinline__ void pair_begin(const Arena& A, const Task& tk, uint32_t crank, unsigned long long* s_slice) {
-    if (threadIdx.x == 0 && crank == 0) {
-        uint32_t pool_id;
-        s_slice[0] = arena_alloc(A, tk.slice_bytes, pool_id);
-        s_slice[1] = pool_id;
-        s_slice[2] = globaltimer_ns();
+// One walk by the calling warp (all 32 lanes): rows at arena offset `o` of pool `pool_id`; the slice is returned afterwards.
+__device__ __forceinline__ void walk_and_free(const Arena& A, const Task& tk, uint64_t o, uint32_t pool_id, const uint8_t* __restrict__ seqs,
+                                              svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, int helper) {
+    const unsigned long long t1 = globaltimer_ns();
+    svp_traceback_warp(tk, A.base + o, reinterpret_cast<const uint2*>(A.base + o + tk.tb_bytes), seqs, results, cigar, cs);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        arena_free(A, pool_id, o);
+        atomicAdd(A.clocks + 1, globaltimer_ns() - t1); atomicAdd(A.clocks + 2, 1ull);
+        if (helper) atomicAdd(A.clocks + 3, 1ull);
+    }
+}
+// Try to take the next queued pair and walk it (whole warp). Returns 0: walked one, 1: nothing ready, 2: the call's queue is drained.
+__device__ __noinline__ int walk_one_queued(const Arena& A, const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                            uint32_t* __restrict__ cigar, const Consts& cs, int helper) {
+    WalkQueue* Q = A.queue;
+    const int lane = threadIdx.x & 31;
+    uint32_t h = 0; int state = 1;
+    if (lane == 0) {
+        h = *(volatile uint32_t*)&Q->head;
+        if (h >= Q->n) state = 2;
+        else if (*(volatile uint32_t*)&Q->e[h].task != WALK_EMPTY && atomicCAS(&Q->head, h, h + 1u) == h) state = 0;
+    }
+    state = __shfl_sync(0xffffffffu, state, 0);
+    if (state != 0) return state;
+    h = __shfl_sync(0xffffffffu, h, 0);
+    __threadfence();
+    const uint32_t task = *(volatile uint32_t*)&Q->e[h].task, pool_id = *(volatile uint32_t*)&Q->e[h].pool_id;
+    const uint64_t o = *(volatile uint64_t*)&Q->e[h].arena_off;
+    const Task tk = A.tasks[task];
+    walk_and_free(A, tk, o, pool_id, seqs, results, cigar, cs, helper);
+    return 0;
+}
+// Start of a pair's CTA(s): warp 0 of the first CTA takes the pair's slice (lane 0 allocates) and notes it in shared memory
+// (s_slice: uint64[3] = arena offset, pool id, start time). When the pool is full the warp does not idle: it walks a queued pair
+// of the call (which frees a slice) and tries again — so the system makes progress even if the walker kernel is not resident.
+// After the caller's initial barrier every CTA of a cluster reads the offset from the first CTA's shared memory (pair_rows;
+// remote shared memory may only be touched once the cluster barrier has shown that CTA running).
+__device__ __forceinline__ void pair_begin(const Arena& A, const Task& tk, uint32_t crank, unsigned long long* s_slice,
+                                           const uint8_t* __restrict__ seqs, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs) {
+    if (threadIdx.x < 32 && crank == 0) {
+        const int lane = threadIdx.x;
+        const uint32_t pool_id = A.use_global ? A.n_sm : min(smid(), A.n_sm - 1u);
+        bool waited = false;
+        for (;;) {
+            unsigned long long o = ~0ull;
+            if (lane == 0) o = arena_try_alloc(A.pools + pool_id, tk.slice_bytes);
+            o = __shfl_sync(0xffffffffu, o, 0);
+            if (o != ~0ull) {
+                if (lane == 0) { s_slice[0] = o; s_slice[1] = pool_id; s_slice[2] = globaltimer_ns(); if (waited) atomicAdd(&A.pools[pool_id].waits, 1ull); }
+                break;
+            }
+            waited = true;
+            if (!A.queue || walk_one_queued(A, seqs, results, cigar, cs, 1) != 0) __nanosleep(20000);
+        }
     }
 }
 template <bool CL>
@@ -330,17 +377,31 @@ __device__ __forceinline__ uint8_t* pair_rows(const Arena& A, uint32_t crank, co
     } else o = s_slice[0];
     return A.base + o;
 }
-// End of a pair: called by warp 0 of the first CTA after the barrier that follows the forward pass.
-__device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
-                                         uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice) {
+// End of a pair: called by warp 0 of the first CTA after the barrier that follows the forward pass. The pair is queued for the
+// call's walkers (and the CTA ends, releasing its registers for the next forward pass), or — without a queue — walked right here.
+__device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, uint32_t task_index, const uint8_t* __restrict__ seqs,
+                                         svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice) {
     const uint64_t o = s_slice[0];
-    const unsigned long long t1 = globaltimer_ns();
-    svp_traceback_warp(tk, A.base + o, reinterpret_cast<const uint2*>(A.base + o + tk.tb_bytes), seqs, results, cigar, cs);
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        arena_free(A, (uint32_t)s_slice[1], o);
-        const unsigned long long t2 = globaltimer_ns();
-        atomicAdd(A.clocks + 0, t1 - s_slice[2]); atomicAdd(A.clocks + 1, t2 - t1); atomicAdd(A.clocks + 2, 1ull);
+    if ((threadIdx.x & 31) == 0) atomicAdd(A.clocks + 0, globaltimer_ns() - s_slice[2]);
+    if (A.queue) {
+        if ((threadIdx.x & 31) == 0) {
+            WalkQueue* Q = A.queue;
+            const uint32_t slot = atomicAdd(&Q->tail, 1u);
+            Q->e[slot].arena_off = o; Q->e[slot].pool_id = (uint32_t)s_slice[1];
+            __threadfence();                                  // rows, best records and the entry's payload before its publication
+            *(volatile uint32_t*)&Q->e[slot].task = task_index;
+        }
+        return;
+    }
+    walk_and_free(A, tk, o, (uint32_t)s_slice[1], seqs, results, cigar, cs, 0);
+}
+// The call's walkers: a few warps per SM, resident for the whole call; each takes queued pairs until the queue is drained.
+__global__ void __launch_bounds__(128)
+svp_walk_kernel(const uint8_t* __restrict__ seqs, const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+    for (;;) {
+        const int st = walk_one_queued(ar, seqs, results, cigar, cs, 0);
+        if (st == 2) return;
+        if (st == 1) __nanosleep(2000);
     }
 }
 
@@ -494,7 +555,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     extern __shared__ __align__(16) uint8_t smem8[];
     __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
-    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const uint32_t task_index = order[CL ? blockIdx.x / csize : blockIdx.x];
+    const Task tk = tasks[task_index];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
     const int g = (int)crank * (int)blockDim.x + gl;          // thread index across the cluster: owner of diagonals g*4KP ...
     const int ring = ring_bytes((int)blockDim.x, 2 * KP), rmask = ring - 1;
@@ -522,7 +584,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg);
     if (MULTI && RB && gl < nwarp + 2) sts_u32(s_wb + 4u * gl, 0u);
-    pair_begin(ar, tk, crank, s_slice);
+    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -736,7 +798,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     }
     // rows and best records of every warp (CTA of the cluster) are complete; no CTA leaves while a neighbour may still store into its mailbox
     step_barrier<CL>();
-    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
+    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -94,7 +94,8 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     extern __shared__ __align__(16) uint8_t smem8[];
     __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
-    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const uint32_t task_index = order[CL ? blockIdx.x / csize : blockIdx.x];
+    const Task tk = tasks[task_index];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
     const int g = (int)crank * (int)blockDim.x + gl;
     const int qbytes = seq_image_bytes(tk.m), tbytes = seq_image_bytes(tk.n);
@@ -117,7 +118,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     if (MULTI && gl <= nwarp) { sts_v4(s_mb + MB_A + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mb + MB_B + 16u * gl, 0u, 0u, c_neg, c_neg);
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, c_neg, c_neg);
-    pair_begin(ar, tk, crank, s_slice);
+    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -257,7 +258,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
         bests[2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
     }
     step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
-    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
+    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,7 +304,8 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     extern __shared__ __align__(16) uint8_t smem8[];
     __shared__ unsigned long long s_slice[3];
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
-    const Task tk = tasks[order[CL ? blockIdx.x / csize : blockIdx.x]];
+    const uint32_t task_index = order[CL ? blockIdx.x / csize : blockIdx.x];
+    const Task tk = tasks[task_index];
     const int gl = threadIdx.x, lane = gl & 31, warp = gl >> 5, nwarp = blockDim.x >> 5;
     const int g = (int)crank * (int)blockDim.x + gl;
     const int ring = ring_bytes((int)blockDim.x, K), rmask = ring - 1;
@@ -340,7 +342,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         step_link_init<CL>(s_mb, gl);
     }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-    pair_begin(ar, tk, crank, s_slice);
+    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -474,7 +476,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         bests[2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
     }
     step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
-    if (warp == 0 && crank == 0) pair_end(ar, tk, seqs, results, cigar, cs, s_slice);
+    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
 }
 
 }  // namespace svp

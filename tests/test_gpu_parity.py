@@ -536,12 +536,15 @@ def test_latency_plan_small_calls(oracle, monkeypatch):
         run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
 
 
-@pytest.mark.parametrize("arena_mb,streams", [(24, "1"), (24, "8"), (160, "8")])
-def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams):
+@pytest.mark.parametrize("arena_mb,streams,fused", [(24, "1", "0"), (24, "8", "0"), (160, "8", "0"), (24, "8", "1"), (12, "8", "0")])
+def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams, fused):
     """A small arena: the slices of short pairs come from the per-SM pools, the long pairs' from the global pool, and most CTAs
-    have to wait for a slice (arena_alloc) — results do not depend on who waited, nor on the number of launch streams."""
+    have to wait for a slice — while they wait they walk queued pairs themselves (pair_begin), so the call ends even where the
+    arena holds fewer pairs than the GPU has CTA slots. Results do not depend on who waited or walked, on the number of launch
+    streams, or on whether pairs are queued for the walker kernel or walked inside their own CTA (SVP_FUSED_WALK)."""
     from svirlpool_b200.aligner import Aligner
     monkeypatch.setenv("SVP_FWD_STREAMS", streams)
+    monkeypatch.setenv("SVP_FUSED_WALK", fused)
     rng = np.random.default_rng(92)
     names, seqs, specs = noisy_batch(rng, 48, 2200, 512)
     n2, s2, p2 = noisy_batch(rng, 3, 14000, 544)                      # long pairs: slices beyond a per-SM region

@@ -45,13 +45,13 @@ def main():
     batch = ava.PairBatch.build(names, seqs, specs)
     ok = True
     for label, env, kw in (("fast", {}, {"preset": "map-ont"}), ("general", {}, {"preset": "last"}),
-                           ("ring", {"SVP_FORCE_RING": "1"}, {"preset": "map-ont"}), ("small-arena", {}, {"preset": "map-ont", "tb_bytes": 48 << 20})):
+                           ("ring", {"SVP_FORCE_RING": "1"}, {"preset": "map-ont"}), ("small-arena", {}, {"preset": "map-ont", "tb_bytes": 600 << 20})):
         if label == "ring" and os.environ.get("SVP_FORCE_RING") != "1":
             continue                                            # the switch is read once per process: run this case in its own process
         if label != "ring" and os.environ.get("SVP_FORCE_RING") == "1":
             continue
         os.environ.update(env)
-        with Aligner(device=0, **{"tb_bytes": 1 << 30, **kw}) as g:
+        with Aligner(device=0, **{"tb_bytes": 4 << 30, **kw}) as g:
             gres, gcig = g.align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
         ores, ocig = OracleEngine(**{k: v for k, v in kw.items() if k != "tb_bytes"}).align_batch(batch.packed, batch.seq_off, batch.seq_len, batch.pairs, batch.cigar_words)
         same = all(np.array_equal(gres[f], ores[f]) for f in ("score", "status", "q_beg", "q_end", "t_beg", "t_end", "cigar_len"))
