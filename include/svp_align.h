@@ -117,8 +117,19 @@ const char* svp_last_error(const svp_handle* h);
 void*       svp_pinned_alloc(size_t bytes);
 void        svp_pinned_free(void* p);
 
+/* Letters outside A, C, G, T (N, IUPAC codes). The 2-bit alphabet has no fifth symbol; a sequence that contains such letters
+ * carries a 1-bit-per-base mask behind its 2-bit codes ("+1 bit/base mask only if N present"):
+ *     seq_off[s] | SVP_SEQ_NMASK      the sequence has a mask: ceil(len/8) bytes starting at byte offset
+ *                                     (seq_off[s] & ~15) + SVP_SEQ_CODE_BYTES(len); bit k%8 of its byte k/8 = base k is masked
+ * (seq_off entries are multiples of 16, so their low bits are free). A cell with a masked base on either side scores the LOWEST
+ * entry of the substitution matrix and counts as a mismatch — LAST's treatment of letters outside its matrix; with minimap2's
+ * scoring that is the mismatch score — so an N never matches anything. The 2-bit code stored for a masked
+ * base is ignored. svp_pack_2bit() writes the masks. */
+#define SVP_SEQ_NMASK 1ull
+#define SVP_SEQ_CODE_BYTES(len) ((((uint64_t)(len) + 3) / 4 + 15) & ~(uint64_t)15)
+
 /* Align n_pairs pairs. Sequences are 2-bit packed (A=0,C=1,G=2,T=3; base k of a sequence lives
- * in bits 2*(k%4).. of byte seq_off[s] + k/4); seq_off[] entries must be multiples of 16.
+ * in bits 2*(k%4).. of byte seq_off[s] + k/4); seq_off[] entries must be multiples of 16 (plus the flag above).
  * All buffers are HOST memory; results and CIGAR words are written to caller-allocated arrays.
  * On return the CIGARs are packed densely from cigar_buf[0] in pair order and result.cigar_off
  * points at each of them (the per-pair slots of svp_pair only size the device scratch; a pair whose
@@ -158,10 +169,11 @@ int svp_align_batch_device(svp_handle* h,
  * `minimap2 -x ava-ont -X` choose the read pairs (util/util.py:181-183) is two calls here; their outputs are the
  * arguments of svp_align_batch().
  *
- * svp_pack_bytes   bytes svp_pack_2bit() needs for these sequences (every sequence starts on a 16-byte boundary,
- *                  16 readable bytes follow the last one).
- * svp_pack_2bit    ASCII (ACGT, either case; anything else packs as A) -> 2 bits per base, base k of a sequence in bits
- *                  2*(k%4) of its byte k/4; fills seq_off[k] with the byte offset of sequence k.
+ * svp_pack_bytes   bytes svp_pack_2bit() needs for these sequences in the worst case (every sequence starts on a 16-byte boundary
+ *                  and may carry a mask, 16 readable bytes follow the last one).
+ * svp_pack_2bit    ASCII (ACGT, either case) -> 2 bits per base, base k of a sequence in bits 2*(k%4) of its byte k/4; a sequence
+ *                  with any other letter gets a mask behind its codes (SVP_SEQ_NMASK above; the letter's code is 0); fills
+ *                  seq_off[k] with the byte offset of sequence k (| SVP_SEQ_NMASK).
  * svp_ava_pairs    pair list of one container's all-vs-all alignment: reads seq_base .. seq_base+n_reads-1 of the sequence
  *                  table, every unordered pair once, query = the read that comes first in name_order (n_reads indices,
  *                  the reads sorted by name; NULL = table order). strand: +1 / -1 per read when the strands are known

@@ -68,6 +68,15 @@ int svpo_scoring_preset(const char* name, svp_scoring* s) {
 
 static inline int base_at(const uint8_t* p, uint32_t k) { return (p[k >> 2] >> ((k & 3) * 2)) & 3; }
 
+/* Letters outside A, C, G, T (N, IUPAC codes) are flagged by the optional 1-bit-per-base mask that follows a sequence's 2-bit
+ * codes (include/svp_align.h: SVP_SEQ_NMASK); unpacked, such a base has code 4. A cell with code 4 on either side scores the
+ * LOWEST entry of the substitution matrix and counts as a mismatch (LAST gives letters outside its matrix the minimum score;
+ * for minimap2's scoring the minimum is the mismatch score). DESIGN.md §3.1. */
+static inline int sub_score(const svp_scoring* sc, int n_score, int qi, int tj) {
+    return (qi > 3 || tj > 3) ? n_score : sc->matrix[qi * 4 + tj];
+}
+static inline int mask_at(const uint8_t* mask, uint32_t k) { return (mask[k >> 3] >> (k & 7)) & 1; }
+
 static inline int gap_cost(int open1, int ext1, int open2, int ext2, int k) {
     int c = open1 + k * ext1;
     if (open2 >= 0) { int c2 = open2 + k * ext2; if (c2 < c) c = c2; }
@@ -86,6 +95,8 @@ static void align_one(const svp_scoring* sc, const uint8_t* q, int m, const uint
     const int ioe1 = sc->ins_open1 + sc->ins_ext1, ie1 = sc->ins_ext1;
     const int doe2 = sc->del_open2 + sc->del_ext2, de2 = sc->del_ext2;
     const int ioe2 = sc->ins_open2 + sc->ins_ext2, ie2 = sc->ins_ext2;
+    int n_score = sc->matrix[0];
+    for (int k = 1; k < 16; ++k) if (sc->matrix[k] < n_score) n_score = sc->matrix[k];
 
     /* H stored for rows 0..m over the band; row i holds j = i+band_lo .. i+d_hi */
     size_t rows = (size_t)m + 1;
@@ -114,7 +125,7 @@ static void align_one(const svp_scoring* sc, const uint8_t* q, int m, const uint
             int Hd = (i - 1 >= 1 && j - 1 >= 1) ? HAT(i - 1, j - 1) : 0;
             int e1 = E1 - de1; { int o = Hleft - doe1; if (o > e1) e1 = o; }
             int f1 = F1up - ie1; { int o = Hup - ioe1; if (o > f1) f1 = o; }
-            int h = Hd + sc->matrix[qi * 4 + t[j - 1]];
+            int h = Hd + sub_score(sc, n_score, qi, t[j - 1]);
             if (e1 > h) h = e1;
             if (f1 > h) h = f1;
             int e2 = NEG, f2 = NEG;
@@ -162,9 +173,9 @@ static void align_one(const svp_scoring* sc, const uint8_t* q, int m, const uint
         }
         const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? HAT(i - 1, j - 1) : 0;
         const int qi = q[i - 1], tj = t[j - 1];
-        if (h == Hd + sc->matrix[qi * 4 + tj]) {
+        if (h == Hd + sub_score(sc, n_score, qi, tj)) {
             EMIT(SVP_CIGAR_M, 1);
-            if (qi == tj) res->n_match++; else res->n_mismatch++;
+            if (qi == tj && qi <= 3) res->n_match++; else res->n_mismatch++;
             --i; --j;
             continue;
         }
@@ -246,11 +257,20 @@ static void* batch_worker(void* arg) {
         const int m = (int)c->seq_len[pr->q], n = (int)c->seq_len[pr->t];
         uint8_t* q = (uint8_t*)malloc((size_t)m + 1);
         uint8_t* t = (uint8_t*)malloc((size_t)n + 1);
-        const uint8_t* pq = c->packed_seqs + c->seq_off[pr->q];
-        const uint8_t* pt = c->packed_seqs + c->seq_off[pr->t];
+        const uint64_t oq = c->seq_off[pr->q] & ~(uint64_t)15, ot = c->seq_off[pr->t] & ~(uint64_t)15;
+        const uint8_t* pq = c->packed_seqs + oq;
+        const uint8_t* pt = c->packed_seqs + ot;
         if (pr->flags & SVP_PAIR_REVCOMP) for (int k = 0; k < m; ++k) q[k] = (uint8_t)(3 - base_at(pq, (uint32_t)(m - 1 - k)));
         else for (int k = 0; k < m; ++k) q[k] = (uint8_t)base_at(pq, (uint32_t)k);
         for (int k = 0; k < n; ++k) t[k] = (uint8_t)base_at(pt, (uint32_t)k);
+        if (c->seq_off[pr->q] & SVP_SEQ_NMASK) {
+            const uint8_t* mq = pq + SVP_SEQ_CODE_BYTES(m);
+            for (int k = 0; k < m; ++k) if (mask_at(mq, (uint32_t)((pr->flags & SVP_PAIR_REVCOMP) ? m - 1 - k : k))) q[k] = 4;
+        }
+        if (c->seq_off[pr->t] & SVP_SEQ_NMASK) {
+            const uint8_t* mt = pt + SVP_SEQ_CODE_BYTES(n);
+            for (int k = 0; k < n; ++k) if (mask_at(mt, (uint32_t)k)) t[k] = 4;
+        }
         align_one(c->sc, q, m, t, n, pr->band_lo, (int)pr->band_w, r, c->cigar_buf + pr->cigar_off, pr->cigar_off, pr->cigar_cap);
         free(q); free(t);
     }
@@ -263,8 +283,11 @@ int svpo_align_batch(const svp_scoring* sc,
                      const svp_pair* pairs, uint32_t n_pairs,
                      svp_result* results, uint32_t* cigar_buf, size_t cigar_words) {
     if (!sc || !packed_seqs || !seq_off || !seq_len || (!pairs && n_pairs) || !results) return SVP_ERR_ARG;
-    for (uint32_t s = 0; s < n_seqs; ++s)
-        if (seq_off[s] + ((uint64_t)seq_len[s] + 3) / 4 > packed_bytes) return SVP_ERR_ARG;
+    for (uint32_t s = 0; s < n_seqs; ++s) {
+        const uint64_t o = seq_off[s] & ~(uint64_t)15;
+        const uint64_t need = (seq_off[s] & SVP_SEQ_NMASK) ? SVP_SEQ_CODE_BYTES(seq_len[s]) + ((uint64_t)seq_len[s] + 7) / 8 : ((uint64_t)seq_len[s] + 3) / 4;
+        if (o + need > packed_bytes) return SVP_ERR_ARG;
+    }
     batch_ctx c = { sc, packed_seqs, seq_off, seq_len, n_seqs, pairs, n_pairs, results, cigar_buf, cigar_words, 0 };
     int nt = g_threads;
     if (nt > (int)n_pairs) nt = (int)n_pairs;

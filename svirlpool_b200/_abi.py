@@ -48,48 +48,58 @@ def ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
 
+SEQ_NMASK = 1          # flag in seq_off: the sequence carries a 1-bit-per-base mask of its non-ACGT letters behind its 2-bit codes
+
+
+def _code_bytes(lens: np.ndarray) -> np.ndarray:
+    return ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
+
+
+def _layout(lens: np.ndarray, masked: np.ndarray) -> tuple[np.ndarray, int]:
+    """Byte offset of every sequence (16-byte aligned; a masked sequence is followed by ceil(len/8) mask bytes, padded to 16)
+    and the buffer size (16 readable bytes behind the last sequence)."""
+    nbytes = _code_bytes(lens) + np.where(masked, ((lens.astype(np.uint64) + 7) // 8 + 15) // 16 * 16, 0).astype(np.uint64)
+    off = np.zeros(len(lens), dtype=np.uint64)
+    if len(lens) > 1:
+        off[1:] = np.cumsum(nbytes[:-1])
+    return off, int(nbytes.sum()) + 16
+
+
+def _pack_into(packed: np.ndarray, start: int, codes: np.ndarray, mask: np.ndarray | None) -> None:
+    pad = (-len(codes)) % 4
+    c = np.concatenate((codes, np.zeros(pad, dtype=np.uint8))) if pad else codes
+    quad = (c & 3).reshape(-1, 4)
+    packed[start:start + len(quad)] = quad[:, 0] | (quad[:, 1] << 2) | (quad[:, 2] << 4) | (quad[:, 3] << 6)
+    if mask is not None:
+        bits = np.packbits(mask.astype(np.uint8), bitorder="little")
+        m0 = start + int(_code_bytes(np.array([len(codes)], dtype=np.uint32))[0])
+        packed[m0:m0 + len(bits)] = bits
+
+
+_LUT = np.full(256, 4, dtype=np.uint8)
+for _ch, _code in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("a", 0), ("c", 1), ("g", 2), ("t", 3)):
+    _LUT[ord(_ch)] = _code
+
+
 def pack_2bit(seqs: list[str | bytes]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """2-bit pack sequences (A=0 C=1 G=2 T=3, base k in bits 2*(k%4) of byte k//4), each sequence
     starting on a 16-byte boundary. Returns (packed uint8, seq_off uint64, seq_len uint32).
-    Letters outside ACGT (N, IUPAC) are packed as A: the 2-bit alphabet has no fifth symbol
-    (DESIGN.md §3.1)."""
-    lut = np.zeros(256, dtype=np.uint8)
-    for ch, code in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("a", 0), ("c", 1), ("g", 2), ("t", 3)):
-        lut[ord(ch)] = code
-    n = len(seqs)
-    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint32, count=n)
-    nbytes = ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
-    off = np.zeros(n, dtype=np.uint64)
-    if n > 1:
-        off[1:] = np.cumsum(nbytes[:-1])
-    total = int(nbytes.sum()) + 16
-    packed = np.zeros(total, dtype=np.uint8)
-    for k, s in enumerate(seqs):
-        raw = np.frombuffer(s.encode() if isinstance(s, str) else bytes(s), dtype=np.uint8)
-        codes = lut[raw]
-        pad = (-len(codes)) % 4
-        if pad:
-            codes = np.concatenate((codes, np.zeros(pad, dtype=np.uint8)))
-        quad = codes.reshape(-1, 4)
-        packed[int(off[k]):int(off[k]) + len(quad)] = quad[:, 0] | (quad[:, 1] << 2) | (quad[:, 2] << 4) | (quad[:, 3] << 6)
-    return packed, off, lens
+    A sequence with letters outside ACGT (N, IUPAC) carries a 1-bit-per-base mask of those positions behind its codes and has
+    SEQ_NMASK set in its seq_off entry (include/svp_align.h: SVP_SEQ_NMASK); such a base never matches anything."""
+    codes = [_LUT[np.frombuffer(s.encode() if isinstance(s, str) else bytes(s), dtype=np.uint8)] for s in seqs]
+    return pack_codes(codes)
 
 
 def pack_codes(seqs: list[np.ndarray]) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """pack_2bit() for sequences already given as base-code arrays (uint8, values 0..3)."""
+    """pack_2bit() for sequences already given as base-code arrays (uint8, values 0..3; 4 = a letter outside ACGT)."""
     n = len(seqs)
     lens = np.fromiter((len(s) for s in seqs), dtype=np.uint32, count=n)
-    nbytes = ((lens.astype(np.uint64) + 3) // 4 + 15) // 16 * 16
-    off = np.zeros(n, dtype=np.uint64)
-    if n > 1:
-        off[1:] = np.cumsum(nbytes[:-1])
-    packed = np.zeros(int(nbytes.sum()) + 16, dtype=np.uint8)
+    masked = np.fromiter((bool(len(s)) and bool((s > 3).any()) for s in seqs), dtype=bool, count=n)
+    off, total = _layout(lens, masked)
+    packed = np.zeros(total, dtype=np.uint8)
     for k, codes in enumerate(seqs):
-        pad = (-len(codes)) % 4
-        c = np.concatenate((codes, np.zeros(pad, dtype=np.uint8))) if pad else codes
-        quad = c.reshape(-1, 4)
-        packed[int(off[k]):int(off[k]) + len(quad)] = quad[:, 0] | (quad[:, 1] << 2) | (quad[:, 2] << 4) | (quad[:, 3] << 6)
-    return packed, off, lens
+        _pack_into(packed, int(off[k]), np.asarray(codes, dtype=np.uint8), (codes > 3) if masked[k] else None)
+    return packed, off | masked.astype(np.uint64) * np.uint64(SEQ_NMASK), lens
 
 
 def cigartuples(cigar_buf: np.ndarray, result) -> list[tuple[int, int]]:

@@ -109,7 +109,12 @@ def pack_2bit_native(seqs: list[str | bytes]) -> tuple[np.ndarray, np.ndarray, n
     rc = lib.svp_pack_2bit(ptrs, ptr(lens), n, ptr(packed), total, ptr(off))
     if rc != SVP_OK:
         raise AlignerError(rc, "svp_pack_2bit failed")
-    return packed, off, lens
+    # svp_pack_bytes is the worst case (a mask behind every sequence); trim to what was used + the 16 readable bytes
+    used = 16
+    if n:
+        last = int(lens[-1])
+        used += (int(off[-1]) & ~15) + ((last + 3) // 4 + 15) // 16 * 16 + (((last + 7) // 8 + 15) // 16 * 16 if int(off[-1]) & _abi.SEQ_NMASK else 0)
+    return packed[:used], off, lens
 
 
 def ava_pairs_native(seq_len: np.ndarray, name_order: np.ndarray | None, strand: np.ndarray | None, offsets: np.ndarray | None,

@@ -5,6 +5,8 @@
 // them — and time the call with CUDA events on the launching stream. No CPU fallback: without a CUDA
 // device every entry point that computes returns SVP_ERR_NODEVICE.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -215,6 +217,9 @@ static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
     c.i_ne1 = pk16(-c.i_ext1); c.i_noe1 = pk16(-(c.i_open1 + c.i_ext1)); c.i_ne2 = pk16(-c.i_ext2); c.i_noe2 = pk16(-(c.i_open2 + c.i_ext2));
     for (int q = 0; q < 4; ++q) for (int t = 0; t < 4; ++t) c.tab[q] |= (uint32_t)(s.matrix[q * 4 + t] & 0xFF) << (8 * t);
     c.a_max = a_max;
+    c.n_score = s.matrix[0];                     // a base outside ACGT scores the lowest entry of the matrix against everything
+    for (int k = 1; k < 16; ++k) c.n_score = std::min(c.n_score, s.matrix[k]);
+    c.n_pk = pk16(c.n_score);
     // rebased s16x2 kernel (scores beyond the s16 range on the fast path): the values of a warp, relative to its offset, must
     // stay inside +-RB_CLAMP between two rebases: (128*KP diagonals + RB_ITERS*2*KP steps) * Lip + 256 (svp_kernels.cuh)
     const int lip = a_max + std::max(g1d, g1i);
@@ -348,6 +353,13 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
                     return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
                 }
             }
+    // The walkers share their SMs with forward CTAs, and an SM's L1 / shared-memory split cannot change while a CTA is resident:
+    // a walker launched with the default split (all L1) would keep every forward CTA that needs shared memory off its SM —
+    // with a walker on all 148 SMs nothing would ever run (seen: walk queue head 0 tail 0). Same split for both.
+    if (cudaFuncSetAttribute(svp_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+        cudaGetLastError();
+        return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
+    }
     // %nsmid: the range of the SM ids the per-SM arena pools are indexed with
     uint32_t* d_n = nullptr;
     if (cudaMalloc((void**)&d_n, sizeof(uint32_t)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
@@ -418,7 +430,39 @@ extern "C" const char* svp_last_error(const svp_handle* h) { return h ? h->err.c
 static int collect_call(svp_handle* h, CallSet& c) {
     if (!c.pending) return SVP_OK;
     c.pending = false;
-    CUDA_TRY(h, cudaEventSynchronize(c.ev_t1));
+    // wait for the call with a deadline (env SVP_CALL_TIMEOUT_S, default 900): kernels that cannot finish — a bug, or an arena far
+    // too small for the batch — are reported with the state of the walk queue and the arena pools instead of blocking forever
+    {
+        static const double limit_s = [] { const char* e = getenv("SVP_CALL_TIMEOUT_S"); return e ? atof(e) : 900.0; }();
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(c.ev_t1);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return fail(h, SVP_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (waited > limit_s) {
+                std::string msg = "call did not finish within " + std::to_string((int)limit_s) + " s";
+                cudaStream_t dbg = nullptr;
+                if (cudaStreamCreateWithFlags(&dbg, cudaStreamNonBlocking) == cudaSuccess) {
+                    uint32_t qh[4] = { 0, 0, 0, 0 };
+                    if (c.d_queue.p && cudaMemcpyAsync(qh, c.d_queue.p, sizeof(qh), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess)
+                        msg += "; walk queue head " + std::to_string(qh[0]) + " tail " + std::to_string(qh[1]) + " of " + std::to_string(qh[2]);
+                    std::vector<ArenaPool> pools(h->n_sm + 1);
+                    if (cudaMemcpyAsync(pools.data(), h->d_pools, pools.size() * sizeof(ArenaPool), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess) {
+                        uint64_t live = 0, bytes = 0, waits = 0, locked = 0;
+                        for (const ArenaPool& p : pools) { live += p.n; waits += p.waits; locked += p.lock; for (uint32_t k = 0; k < p.n && k < (uint32_t)POOL_MAX; ++k) bytes += p.len[k]; }
+                        msg += "; arena: " + std::to_string(live) + " live slices, " + std::to_string(bytes >> 20) + " MB, " + std::to_string(waits) + " waits, " +
+                               std::to_string(locked) + " locks held, global pool " + std::to_string(pools[h->n_sm].n) + " slices of " + std::to_string(pools[h->n_sm].bytes >> 20) + " MB";
+                    }
+                    unsigned long long clk[4] = { 0, 0, 0, 0 };
+                    if (cudaMemcpyAsync(clk, h->d_clocks, sizeof(clk), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess)
+                        msg += "; pairs walked " + std::to_string(clk[2]) + " (" + std::to_string(clk[3]) + " by waiting CTAs)";
+                }
+                return fail(h, SVP_ERR_CUDA, msg);
+            }
+            if (waited > 0.002) std::this_thread::sleep_for(std::chrono::microseconds(waited > 0.05 ? 200 : 20));
+        }
+    }
     float tot = 0; cudaEventElapsedTime(&tot, c.ev_t0, c.ev_t1);
     c.stats.total_ms = tot;
     // forward pass and walk of a pair run inside one kernel: the kernel time of the call is split by the CTAs' own clocks
@@ -532,13 +576,17 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     bool ok = p.q < n_seqs && p.t < n_seqs && p.band_w > 0 && (p.band_w % 32u) == 0 && (size_t)p.cigar_off + p.cigar_cap <= cigar_words;
     if (ok) {
         for (uint32_t s : { p.q, p.t }) {
-            const uint64_t bytes = ((uint64_t)seq_len[s] + 3) / 4;
-            const uint64_t end = need_padding ? ((seq_off[s] + bytes + 15) & ~(uint64_t)15) : seq_off[s] + bytes;
-            if ((seq_off[s] & 15u) || end > packed_bytes || seq_len[s] == 0 || seq_len[s] > (1u << 28)) ok = false;
+            const uint64_t off = seq_off[s] & ~(uint64_t)15;
+            // codes, and — flagged in the low bits of seq_off — the mask of the letters outside ACGT behind them (SVP_SEQ_NMASK)
+            const uint64_t bytes = (seq_off[s] & SVP_SEQ_NMASK) ? SVP_SEQ_CODE_BYTES(seq_len[s]) + ((uint64_t)seq_len[s] + 7) / 8 : ((uint64_t)seq_len[s] + 3) / 4;
+            const uint64_t end = need_padding ? ((off + bytes + 15) & ~(uint64_t)15) : off + bytes;
+            if ((seq_off[s] & 14u) || end > packed_bytes || seq_len[s] == 0 || seq_len[s] > (1u << 28)) ok = false;
         }
     }
     if (!ok) { t.flags |= TASK_INVALID; return; }
-    t.q_off = seq_off[p.q]; t.t_off = seq_off[p.t];
+    t.q_off = seq_off[p.q] & ~(uint64_t)15; t.t_off = seq_off[p.t] & ~(uint64_t)15;
+    if (seq_off[p.q] & SVP_SEQ_NMASK) t.flags |= TASK_QN;
+    if (seq_off[p.t] & SVP_SEQ_NMASK) t.flags |= TASK_TN;
     t.m = (int32_t)seq_len[p.q]; t.n = (int32_t)seq_len[p.t];
     t.band_lo = p.band_lo; t.band_w = (int32_t)p.band_w;
     const Consts& cs = h->cs;
@@ -679,7 +727,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         }
     }
     // ---- groups ---------------------------------------------------------------------------------------------------------
-    struct Group { int fam, nwarp, kp, cluster; bool ring, huge; size_t first, count, smem; uint64_t work, max_slice; };
+    struct Group { int fam, nwarp, kp, cluster; bool ring, huge, inline_walk; size_t first, count, smem; uint64_t work, max_slice; };
     std::vector<Group> groups;
     uint32_t* order = c.h_order;
     size_t pos = 0;
@@ -706,7 +754,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
             std::vector<uint32_t>& v = kv.second;
             // longest pairs first inside a group: the tail of the launch is short pairs
             std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
-            Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, pos, v.size(), 0, 0, 0 };
+            Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, false, pos, v.size(), 0, 0, 0 };
             const int lane_cost = (g.fam == FAM_S32 || g.fam == FAM_S32_GEN) ? 2 : 1;
             for (uint32_t k : v) {
                 const Task& t = tasks[k];
@@ -720,6 +768,12 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
                 const size_t ballast = per_cta > 1024.0 ? (size_t)per_cta - 1024 + 16 : 0;
                 g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - SMEM_STATIC);
             }
+            // A CTA that needs (nearly) a whole SM — 14+ warps at up to 128 registers, or sequence images filling the shared memory —
+            // cannot become resident beside a walker CTA, and the walkers stay until every queued pair is walked: such groups must
+            // not depend on them. Their CTAs walk their own pair after the forward pass (long forward passes: the walk is a small
+            // share of the CTA's life there).
+            g.inline_walk = h->fused_walk || g.nwarp * 32 * 128 + h->walk_ctas_per_sm * 128 * 104 > 65536 ||
+                            g.smem + 1024 + (size_t)h->walk_ctas_per_sm * 2048 > (size_t)h->smem_per_sm;
             std::copy(v.begin(), v.end(), order + pos);
             pos += v.size();
             groups.push_back(g);
@@ -739,9 +793,10 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     const Task* d_tasks = (const Task*)c.d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)c.d_order.p;
     // the call's walk queue: one entry per valid pair, unpublished entries are all-ones
-    const size_t n_valid = inv_first;
+    size_t n_valid = 0;                               // pairs that will be queued
+    for (const Group& g : groups) if (!g.inline_walk) n_valid += g.count;
     WalkQueue* d_queue = nullptr;
-    if (!h->fused_walk && n_valid) {
+    if (n_valid) {
         const size_t qbytes = sizeof(WalkQueue) + n_valid * sizeof(WalkEntry);
         CUDA_TRY(h, c.d_queue.reserve(qbytes));
         d_queue = (WalkQueue*)c.d_queue.p;
@@ -760,7 +815,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     const int rot = (int)(h->call_idx % (uint64_t)N_FWD_STREAMS);
     auto stream_of = [&](size_t gi) { return sF[(gi + (size_t)rot) % (size_t)n_streams]; };
     bool used[N_FWD_STREAMS] = {};
-    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, d_queue, d_tasks };
+    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, d_queue, d_tasks, 0u };
     // The walkers first, on the highest-priority stream: a few warps per SM that stay for the whole call and walk the pairs the
     // forward CTAs queue. (A forward CTA ends with its forward pass; its ~130 registers per thread go to the next pair instead of
     // idling through a latency-bound walk — walking inside the forward CTA was measured at 37 % of the CTA's life, 482 instead of
@@ -780,6 +835,7 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         if (sF[si] != st && !used[si]) CUDA_TRY(h, cudaStreamWaitEvent(sF[si], ev_copied, 0));
         used[si] = true;
         ar.use_global = g.huge ? 1u : 0u;
+        ar.inline_walk = g.inline_walk ? 1u : 0u;
         CUDA_TRY(h, launch_group(kern, g.cluster, (unsigned)g.count, (unsigned)g.nwarp * 32u, g.smem, stream_of(gi), d_tasks, d_order + g.first, d_seqs, ar,
                                  d_results, d_cigar, cs));
         c.stats.fwd_launches++;

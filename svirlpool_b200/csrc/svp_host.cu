@@ -16,8 +16,8 @@ inline int64_t round_up64(int64_t x, int64_t g) { return (x + g - 1) / g * g; }
 struct CodeLut {
     uint8_t v[256];
     CodeLut() {
-        memset(v, 0, sizeof(v));                 // letters outside ACGT (N, IUPAC) pack as A: the alphabet has no fifth symbol
-        v[(int)'C'] = v[(int)'c'] = 1; v[(int)'G'] = v[(int)'g'] = 2; v[(int)'T'] = v[(int)'t'] = 3;
+        memset(v, 4, sizeof(v));                 // 4: a letter outside ACGT (N, IUPAC) — code 0 plus a bit in the sequence's mask (SVP_SEQ_NMASK)
+        v[(int)'A'] = v[(int)'a'] = 0; v[(int)'C'] = v[(int)'c'] = 1; v[(int)'G'] = v[(int)'g'] = 2; v[(int)'T'] = v[(int)'t'] = 3;
     }
 };
 const CodeLut g_lut;
@@ -27,7 +27,7 @@ const CodeLut g_lut;
 extern "C" size_t svp_pack_bytes(const uint32_t* seq_len, uint32_t n_seqs) {
     size_t total = 16;                           // readable slack behind the last sequence
     if (!seq_len) return total;
-    for (uint32_t k = 0; k < n_seqs; ++k) total += (((size_t)seq_len[k] + 3) / 4 + 15) / 16 * 16;
+    for (uint32_t k = 0; k < n_seqs; ++k) total += (size_t)SVP_SEQ_CODE_BYTES(seq_len[k]) + (((size_t)seq_len[k] + 7) / 8 + 15) / 16 * 16;   // codes + a mask
     return total;
 }
 
@@ -43,17 +43,28 @@ extern "C" int svp_pack_2bit(const char* const* seqs, const uint32_t* seq_len, u
         seq_off[k] = pos;
         uint8_t* out = packed + pos;
         const size_t whole = len / 4;
+        unsigned other = 0;                      // any letter outside ACGT
         for (size_t b = 0; b < whole; ++b) {
             const uint8_t* c = s + 4 * b;
-            out[b] = (uint8_t)(g_lut.v[c[0]] | (g_lut.v[c[1]] << 2) | (g_lut.v[c[2]] << 4) | (g_lut.v[c[3]] << 6));
+            const unsigned c0 = g_lut.v[c[0]], c1 = g_lut.v[c[1]], c2 = g_lut.v[c[2]], c3 = g_lut.v[c[3]];
+            other |= c0 | c1 | c2 | c3;
+            out[b] = (uint8_t)((c0 & 3) | ((c1 & 3) << 2) | ((c2 & 3) << 4) | ((c3 & 3) << 6));
         }
         if (len & 3) {
             uint8_t x = 0;
-            for (size_t r = 0; r < (len & 3); ++r) x |= (uint8_t)(g_lut.v[s[4 * whole + r]] << (2 * r));
+            for (size_t r = 0; r < (len & 3); ++r) { const unsigned cr = g_lut.v[s[4 * whole + r]]; other |= cr; x |= (uint8_t)((cr & 3) << (2 * r)); }
             out[whole] = x;
         }
         memset(out + bytes, 0, slot - bytes);
         pos += slot;
+        if (other & 4) {                         // the mask follows the codes: bit k % 8 of byte k / 8 = base k is not A, C, G or T
+            const size_t mbytes = (len + 7) / 8, mslot = (mbytes + 15) / 16 * 16;
+            uint8_t* mk = packed + pos;
+            memset(mk, 0, mslot);
+            for (size_t b = 0; b < len; ++b) if (g_lut.v[s[b]] & 4) mk[b >> 3] |= (uint8_t)(1u << (b & 7));
+            seq_off[k] |= SVP_SEQ_NMASK;
+            pos += mslot;
+        }
     }
     memset(packed + pos, 0, packed_bytes - pos);
     return SVP_OK;

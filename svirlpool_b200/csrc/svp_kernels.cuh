@@ -61,7 +61,11 @@ struct Consts {             // scoring in the forms the kernels use (svp_align.c
     int32_t  a_max;         // largest matrix entry (score-range test)
     int32_t  rebase_ok;     // the rebased s16x2 kernel is exact for this scoring (make_consts)
     int32_t  min_signal, zdrop, zdrop_ext;
+    int32_t  n_score;       // score of a cell with a base outside ACGT on either side: the lowest matrix entry
+    uint32_t n_pk;          // ... as s16x2
 };
+// byte offset of a sequence's mask behind its 2-bit codes (include/svp_align.h: SVP_SEQ_CODE_BYTES)
+__host__ __device__ __forceinline__ uint64_t seq_code_bytes(int len) { return (((uint64_t)len + 3) / 4 + 15) & ~(uint64_t)15; }
 
 constexpr uint32_t TASK_INVALID = 0x80000000u;   // Task.flags: descriptor rejected by the planner
 constexpr uint32_t TASK_TOO_LONG = 0x40000000u;  // ... because the two sequences do not fit the shared-memory images
@@ -71,6 +75,8 @@ constexpr uint32_t TASK_KP_SHIFT = 8;            // bits 8..12 of Task.flags: KP
 constexpr uint32_t TASK_KP_MASK = 0x1F00u;
 constexpr uint32_t TASK_CL_SHIFT = 16;           // bits 16..19: CTAs per cluster (0/1: no cluster)
 constexpr uint32_t TASK_CL_MASK = 0xF0000u;
+constexpr uint32_t TASK_QN = 0x04000000u;        // the query / the target carries a mask of letters outside ACGT behind its 2-bit codes
+constexpr uint32_t TASK_TN = 0x02000000u;
 constexpr uint32_t TASK_REBASE = 0x08000000u;    // pair runs on the s16x2 fast path with per-warp score offsets (scores beyond the s16 range)
 constexpr uint32_t NEGV = 0xC000C000u;   // s16x2 -16384: "minus infinity" for gap states
 constexpr uint32_t QNAN16 = 0x7E00u;     // fp16 NaN: sentinel base, never equal to anything
@@ -266,8 +272,9 @@ struct Arena {
     uint32_t n_sm;
     uint32_t use_global;              // this launch's pairs allocate from the global pool
     unsigned long long* clocks;       // [0] summed forward ns, [1] summed walk ns, [2] pairs walked, [3] walks done by waiting CTAs (statistics)
-    WalkQueue* queue;                 // the call's queue; nullptr: every CTA walks its own pair right after its forward pass
+    WalkQueue* queue;                 // the call's queue (nullptr: none); a CTA waiting for arena space walks entries of it
     const Task* tasks;                // the call's task array (queue entries index it)
+    uint32_t inline_walk;             // this launch's CTAs walk their own pair right after the forward pass instead of queueing it
 };
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -383,7 +390,7 @@ __device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, uint32_
                                          svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice) {
     const uint64_t o = s_slice[0];
     if ((threadIdx.x & 31) == 0) atomicAdd(A.clocks + 0, globaltimer_ns() - s_slice[2]);
-    if (A.queue) {
+    if (A.queue && !A.inline_walk) {
         if ((threadIdx.x & 31) == 0) {
             WalkQueue* Q = A.queue;
             const uint32_t slot = atomicAdd(&Q->tail, 1u);
@@ -421,6 +428,19 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
         o[k] = ((x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u) + 0x3C3C3C3Cu;
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// overwrite the image bytes of the masked positions of a sequence (include/svp_align.h: SVP_SEQ_NMASK) with `code`
+__device__ __forceinline__ void mask_to_image(const uint8_t* __restrict__ seq, int len, uint8_t* img, uint8_t code, bool rc) {
+    const uint32_t* mk = reinterpret_cast<const uint32_t*>(seq + seq_code_bytes(len));
+    for (int w = threadIdx.x; w < (len + 31) >> 5; w += blockDim.x) {
+        uint32_t bits = __ldg(mk + w);
+        while (bits) {
+            const int p = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (p < len) img[SEQ_PAD + (rc ? len - 1 - p : p)] = code;
+        }
+    }
 }
 
 // Stage both sequences of a pair as code bytes in shared memory (query reverse-complemented on the fly when
@@ -462,6 +482,9 @@ __device__ __forceinline__ void stage_sequences(const Task& tk, const uint8_t* _
         }
     }
     __syncthreads();
+    // letters outside ACGT (mask behind the codes): the pad code, which never equals anything -> the mismatch score
+    if (tk.flags & TASK_TN) mask_to_image(seqs + tk.t_off, tk.n, timg, 0x7D, false);
+    if (tk.flags & TASK_QN) mask_to_image(seqs + tk.q_off, tk.m, qimg, 0x7E, (tk.flags & SVP_PAIR_REVCOMP) != 0);
     // pads (after the bulk stores: the last 16-byte group may cover the trailing pad)
     for (int k = g; k < SEQ_PAD; k += blockDim.x) { qimg[k] = 0x7E; timg[k] = 0x7D; }
     for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) qimg[k] = 0x7E;
@@ -484,11 +507,16 @@ __host__ __device__ __forceinline__ int ring_bytes(int n_threads, int k) {
     return r;
 }
 // code (0..3) of oriented query position p / target position p (1-based), or -1 outside the sequence
-__device__ __forceinline__ int packed_code(const uint32_t* __restrict__ src, int len, int p, bool rc) {
+// (mask: the sequence's mask of letters outside ACGT, or nullptr — a masked position reads as "outside": the pad code)
+__device__ __forceinline__ int packed_code(const uint32_t* __restrict__ src, int len, int p, bool rc, const uint32_t* __restrict__ mask = nullptr) {
     if (p < 1 || p > len) return -1;
     const unsigned o = rc ? (unsigned)(len - p) : (unsigned)(p - 1);
+    if (mask && ((__ldg(mask + (o >> 5)) >> (o & 31u)) & 1u)) return -1;
     const int c = (int)((__ldg(src + (o >> 4)) >> ((o & 15u) * 2u)) & 3u);
     return rc ? 3 - c : c;
+}
+__device__ __forceinline__ const uint32_t* seq_mask(const uint8_t* __restrict__ seqs, uint64_t off, int len, bool has) {
+    return has ? reinterpret_cast<const uint32_t*>(seqs + off + seq_code_bytes(len)) : nullptr;
 }
 // fp16-coded windows of the fast path: `count` positions from q_first / t_first on
 __device__ __forceinline__ void ring_fill_fast(const Task& tk, const uint8_t* __restrict__ seqs, uint8_t* qring, uint8_t* tring,
@@ -496,8 +524,10 @@ __device__ __forceinline__ void ring_fill_fast(const Task& tk, const uint8_t* __
     const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
     const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
     const bool rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    const uint32_t* qm = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
+    const uint32_t* tm = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
     for (int x = threadIdx.x; x < count; x += blockDim.x) {
-        const int qc = packed_code(qsrc, tk.m, q_first + x, rc), tc = packed_code(tsrc, tk.n, t_first + x, false);
+        const int qc = packed_code(qsrc, tk.m, q_first + x, rc, qm), tc = packed_code(tsrc, tk.n, t_first + x, false, tm);
         qring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? 0x7E : 0x3C + qc);
         tring[(t_first + x) & mask] = (uint8_t)(tc < 0 ? 0x7D : 0x3C + tc);
     }
@@ -813,8 +843,21 @@ struct TbView {
     int band_lo, band_w, r_begin, pitch, m, n, kp, slot;
     uint32_t inv;             // ceil(2^32 / (4*kp)): x / (4*kp) = umulhi(x, inv), exact for x < 2^27
     uint64_t q_word, t_word;  // word offsets of the packed sequences
+    const uint32_t* q_mask;   // masks of letters outside ACGT (nullptr: none)
+    const uint32_t* t_mask;
     bool rc;
 
+    // is the base at 1-based position i of the ORIENTED query / j of the target a letter outside ACGT
+    __device__ __forceinline__ bool qn(int i) const {
+        if (!q_mask) return false;
+        const unsigned p = rc ? (unsigned)(m - i) : (unsigned)(i - 1);
+        return (__ldg(q_mask + (p >> 5)) >> (p & 31u)) & 1u;
+    }
+    __device__ __forceinline__ bool tn(int j) const {
+        if (!t_mask) return false;
+        const unsigned p = (unsigned)(j - 1);
+        return (__ldg(t_mask + (p >> 5)) >> (p & 31u)) & 1u;
+    }
     __device__ __forceinline__ void set_geometry(int band_w_, int kp_) {
         band_w = band_w_; kp = kp_; slot = tb_slot_bytes(kp_);
         pitch = (band_w_ / (4 * kp_)) * slot;
@@ -903,6 +946,8 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
     v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
     v.set_geometry(tk.band_w, KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    v.q_mask = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
+    v.t_mask = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
     const int d_hi = tk.band_lo + tk.band_w - 1;
 
     // ---- 1. end cell ---------------------------------------------------------------------------
@@ -992,8 +1037,9 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
             if (del_band) bl = v.lb(ci, cj - 1);          // left / up neighbours: a 1-base gap is resolved from this round's loads
             if (ins_band) bu = v.lb(ci - 1, cj);
             const int qc = v.qbase(ci), tc = v.tbase(cj);
-            same_l = qc == tc;
-            sub_l = (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
+            const bool other = v.qn(ci) || v.tn(cj);              // a letter outside ACGT: lowest score, never a match
+            same_l = !other && qc == tc;
+            sub_l = other ? cs.n_score : (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
         }
         if (ci - 33 >= 1 && cj - 33 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - 33, cj - 33)));   // next round's byte
         // ---- the run is resolved by all lanes at once: lane l assumes cells 0..l-1 were diagonal moves, so its H is the
@@ -1058,31 +1104,45 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
             }
         }
         // ---- gap: the smallest k with H == H(i, j-k) - del(k), else H == H(i-k, j) - ins(k) ----
+        // 32 candidates of the row and of the column per round, resolved by all lanes at once: lane l holds candidate k0 + l + 1,
+        // its H is the carried H plus the prefix sum of the byte differences along the row / column (5 SHFL.UP each), one ballot
+        // per gap kind finds the first lane whose H explains the gap (the sequential search cost ~15 instructions per candidate).
         const int d = j - i;
         int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
         bool found = false, dead = false;
         for (int k0 = 0; !found && !dead; k0 += 32) {
-            const int k = k0 + lane + 1;
-            const uint32_t bd = ((j - k >= 1) && (d - k >= tk.band_lo)) ? v.lb(i, j - k) : 0;
-            const uint32_t bi = ((i - k >= 1) && (d + k <= d_hi)) ? v.lb(i - k, j) : 0;
-            for (int l2 = 0; l2 < 32; ++l2) {
-                const int kk = k0 + l2 + 1;
-                const bool del_ok = (j - kk >= 1) && (d - kk >= tk.band_lo);
-                const bool ins_ok = (i - kk >= 1) && (d + kk <= d_hi);
-                if (!del_ok && !ins_ok) { dead = true; break; }
-                const uint32_t b1 = __shfl_sync(0xffffffffu, bd, l2), b2 = __shfl_sync(0xffffffffu, bi, l2);
-                if (del_ok) {
-                    Hrow += sext8(b1 - brow); brow = b1;
-                    if (H == Hrow - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, kk)) {
-                        SVP_EMITW(SVP_CIGAR_D, (uint32_t)kk); ++n_do; n_db += kk; j -= kk; H = Hrow; found = true; break;
-                    }
+            const int kk = k0 + lane + 1;
+            const bool del_ok = (j - kk >= 1) && (d - kk >= tk.band_lo);      // both are true for a prefix of the candidates only
+            const bool ins_ok = (i - kk >= 1) && (d + kk <= d_hi);
+            const uint32_t bd = del_ok ? v.lb(i, j - kk) : 0;
+            const uint32_t bi = ins_ok ? v.lb(i - kk, j) : 0;
+            uint32_t pd = __shfl_up_sync(0xffffffffu, bd, 1), pi = __shfl_up_sync(0xffffffffu, bi, 1);
+            if (lane == 0) { pd = brow; pi = bcol; }
+            int dr = del_ok ? sext8(bd - pd) : 0, dc = ins_ok ? sext8(bi - pi) : 0;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tr = __shfl_up_sync(0xffffffffu, dr, o), tc = __shfl_up_sync(0xffffffffu, dc, o);
+                if (lane >= o) { dr += tr; dc += tc; }
+            }
+            const int hr = Hrow + dr, hc = Hcol + dc;
+            const unsigned md = __ballot_sync(0xffffffffu, del_ok && H == hr - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, kk));
+            const unsigned mi = __ballot_sync(0xffffffffu, ins_ok && H == hc - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, kk));
+            const unsigned mx = __ballot_sync(0xffffffffu, !del_ok && !ins_ok);
+            const int fd = md ? __ffs(md) - 1 : 32, fi = mi ? __ffs(mi) - 1 : 32, fx = mx ? __ffs(mx) - 1 : 32;
+            if (min(fd, fi) < fx) {                       // at equal length the deletion comes first
+                found = true;
+                if (fd <= fi) {
+                    const int len = k0 + fd + 1;
+                    SVP_EMITW(SVP_CIGAR_D, (uint32_t)len); ++n_do; n_db += len; j -= len; H = __shfl_sync(0xffffffffu, hr, fd);
+                } else {
+                    const int len = k0 + fi + 1;
+                    SVP_EMITW(SVP_CIGAR_I, (uint32_t)len); ++n_io; n_ib += len; i -= len; H = __shfl_sync(0xffffffffu, hc, fi);
                 }
-                if (ins_ok) {
-                    Hcol += sext8(b2 - bcol); bcol = b2;
-                    if (H == Hcol - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, kk)) {
-                        SVP_EMITW(SVP_CIGAR_I, (uint32_t)kk); ++n_io; n_ib += kk; i -= kk; H = Hcol; found = true; break;
-                    }
-                }
+            } else if (fx < 32) {
+                dead = true;
+            } else {
+                Hrow = __shfl_sync(0xffffffffu, hr, 31); Hcol = __shfl_sync(0xffffffffu, hc, 31);
+                brow = __shfl_sync(0xffffffffu, bd, 31); bcol = __shfl_sync(0xffffffffu, bi, 31);
             }
         }
         if (!found) { bad = true; done = true; }

@@ -76,6 +76,12 @@ __device__ __forceinline__ void stage_sequences_gen(const Task& tk, const uint8_
         *reinterpret_cast<uint4*>(qsel2 + SEQ_PAD + 16 * w) = make_uint4(s2[0], s2[1], s2[2], s2[3]);
     }
     __syncthreads();
+    // letters outside ACGT: the pad codes (score(): a pad on either side scores the lowest matrix entry)
+    if (tk.flags & TASK_TN) mask_to_image(seqs + tk.t_off, tk.n, tsel, (uint8_t)GEN_PAD, false);
+    if (tk.flags & TASK_QN) {
+        mask_to_image(seqs + tk.q_off, tk.m, qsel, (uint8_t)GEN_PAD, (tk.flags & SVP_PAIR_REVCOMP) != 0);
+        mask_to_image(seqs + tk.q_off, tk.m, qsel2, (uint8_t)GEN_PAD2, (tk.flags & SVP_PAIR_REVCOMP) != 0);
+    }
     for (int k = g; k < SEQ_PAD; k += blockDim.x) { qsel[k] = GEN_PAD; qsel2[k] = GEN_PAD2; tsel[k] = GEN_PAD; }
     for (int k = SEQ_PAD + tk.m + g; k < qbytes; k += blockDim.x) { qsel[k] = GEN_PAD; qsel2[k] = GEN_PAD2; }
     for (int k = SEQ_PAD + tk.n + g; k < tbytes; k += blockDim.x) tsel[k] = GEN_PAD;
@@ -150,9 +156,14 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     // the last in-band thread reads the "outside the band" constants, whatever warp / CTA follows it
     const uint32_t s_upA = (g == n_thr_active - 1) ? s_mb + MB_CST : link.in_up(), s_loB = link.in_lo();
 
+    // a pad code (bit 3 of a selector byte: a position outside the sequence, or a letter outside ACGT) on either side -> the lowest
+    // matrix entry: the byte's bit 3 becomes a 16-bit lane mask (SHL + PRMT in sign mode) and one LOP3 blends the constant in
+    const uint32_t c_npk = pin(cs.n_pk);
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> uint32_t {
         const uint32_t sel = q | t;
-        return prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);
+        const uint32_t look = prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);
+        const uint32_t pad = prmt(sel << 4, 0u, 0x9988u);
+        return (look & ~pad) | (c_npk & pad);
     };
 
     #pragma unroll 1
@@ -277,8 +288,10 @@ __device__ __forceinline__ void ring_fill(const Task& tk, const uint8_t* __restr
     const uint32_t* qsrc = reinterpret_cast<const uint32_t*>(seqs + tk.q_off);
     const uint32_t* tsrc = reinterpret_cast<const uint32_t*>(seqs + tk.t_off);
     const bool rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    const uint32_t* qm = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
+    const uint32_t* tm = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
     for (int x = threadIdx.x; x < count; x += blockDim.x) {
-        const int qc = packed_code(qsrc, tk.m, q_first + x, rc), tc = packed_code(tsrc, tk.n, t_first + x, false);
+        const int qc = packed_code(qsrc, tk.m, q_first + x, rc, qm), tc = packed_code(tsrc, tk.n, t_first + x, false, tm);
         if (GEN) {
             qring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? GEN_PAD : (uint32_t)(qc & 1) << 2);
             q2ring[(q_first + x) & mask] = (uint8_t)(qc < 0 ? GEN_PAD2 : 0x80u | 0x44u * (uint32_t)(qc >> 1));
@@ -327,6 +340,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     const int i_ne2 = GEN ? (int)pin((uint32_t)-cs.i_ext2) : d_ne2, i_noe2 = GEN ? (int)pin((uint32_t)-(cs.i_open2 + cs.i_ext2)) : d_noe2;
     const int c_mat = (int)pin((uint32_t)cs.s_match), c_mis = (int)pin((uint32_t)cs.s_mismatch), c_neg = (int)pin((uint32_t)NEG);
     const uint32_t r0 = pin(cs.tab[0]), r1 = pin(cs.tab[1]), r2 = pin(cs.tab[2]), r3 = pin(cs.tab[3]);
+    const int c_nsc = (int)pin((uint32_t)cs.n_score);
 
     // lowest virtual positions the CTA touches at iteration 0 (thread gl = 0 has the largest I0 and the smallest J0)
     const int g_first = (int)crank * (int)blockDim.x;
@@ -386,7 +400,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
     auto score = [&](uint32_t q, uint32_t q2, uint32_t t) -> int {
         if (GEN) {
             const uint32_t sel = q | t;
-            return (int)prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);
+            return (sel & GEN_PAD) ? c_nsc : (int)prmt(prmt(r0, r1, sel), prmt(r2, r3, sel), q2);     // pad / letter outside ACGT: lowest entry
         }
         return (q == t) ? c_mat : c_mis;
     };

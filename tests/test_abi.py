@@ -56,9 +56,11 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_pack_2bit_layout():
-    packed, off, lens = _abi.pack_2bit(["ACGTAC", "TTTT", "n" * 5])
-    assert off.tolist() == [0, 16, 32] and lens.tolist() == [6, 4, 5]
-    assert packed[0] == 0b11100100 and packed[1] == 0b0100 and packed[16] == 0xFF and packed[32] == 0
+    packed, off, lens = _abi.pack_2bit(["ACGTAC", "TTTT", "n" * 5, "ACGNNRAC"])
+    # the third and fourth sequences hold letters outside ACGT: a 1-bit-per-base mask follows their codes, flagged in seq_off
+    assert off.tolist() == [0, 16, 32 | _abi.SEQ_NMASK, 64 | _abi.SEQ_NMASK] and lens.tolist() == [6, 4, 5, 8]
+    assert packed[0] == 0b11100100 and packed[1] == 0b0100 and packed[16] == 0xFF and packed[32] == 0 and packed[48] == 0b11111
+    assert packed[64] == 0b00100100 and packed[65] == 0b01000000 and packed[80] == 0b00111000 and len(packed) == 96 + 16
     codes = [np.array([0, 1, 2, 3, 0, 1], dtype=np.uint8), np.array([3, 3, 3, 3], dtype=np.uint8)]
     p2, o2, l2 = _abi.pack_codes(codes)
     assert p2[0] == packed[0] and p2[16] == 0xFF and o2.tolist() == [0, 16] and l2.tolist() == [6, 4]

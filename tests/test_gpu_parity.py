@@ -689,3 +689,57 @@ def test_band_widths_kp_5_6_7_long_reads_rebased(gpu, oracle, band_w):
     names, seqs, specs = fixed_band_batch(rng, 3, 18000, band_w, err=(0.02, 0.015, 0.015))
     gres, _ = run_both(gpu, oracle, names, seqs, specs)
     assert not gres["status"].any() and gres["score"].max() > 20000
+
+
+# ---------------------------------------------------------------------------------------------
+# letters outside ACGT (N runs, IUPAC codes): the 1-bit-per-base mask behind a sequence's codes
+# ---------------------------------------------------------------------------------------------
+
+def with_n_runs(rng, seq, n_runs=3, max_len=40):
+    s = list(seq)
+    for _ in range(n_runs):
+        pos = int(rng.integers(0, max(1, len(s) - max_len)))
+        for k in range(pos, min(len(s), pos + int(rng.integers(1, max_len)))):
+            s[k] = "NRYK"[int(rng.integers(4))]
+    return "".join(s)
+
+
+@pytest.mark.parametrize("variant", ["fast_images", "fast_windows", "rebased_long", "s32_long", "general", "general_long_s32"])
+def test_reads_with_letters_outside_acgt(oracle, monkeypatch, variant):
+    """N runs (and IUPAC letters) in queries and targets, forward and reverse-complemented, on every kernel family: an N never
+    matches — a poly-A query against an N run scores mismatches (it used to pack as A and match) — and the rows equal the
+    oracle's, which scores such a cell with the lowest matrix entry."""
+    from oracle_engine import OracleEngine
+    from svirlpool_b200.aligner import Aligner
+    rng = np.random.default_rng(["fast_images", "fast_windows", "rebased_long", "s32_long", "general", "general_long_s32"].index(variant) + 300)
+    long_reads = variant in ("rebased_long", "s32_long", "general_long_s32")
+    if variant == "fast_windows":
+        monkeypatch.setenv("SVP_RING_MIN", "0")
+    if variant == "fast_images":
+        monkeypatch.setenv("SVP_RING_MIN", "1000000000")
+    if variant == "s32_long":
+        monkeypatch.setenv("SVP_NO_REBASE", "1")
+    kw = {"scoring": SCORINGS["last_like_asym"]} if variant.startswith("general") else {"preset": "map-ont"}
+    length = 18000 if variant in ("rebased_long", "s32_long") else (9000 if variant == "general_long_s32" else 2600)
+    names, seqs, specs = [], [], []
+    for p, band in enumerate((544, 768, 1536, 2304) if not long_reads else (544, 1056)):
+        tmpl = randseq(rng, length)
+        a, b = mutate(rng, tmpl, 0.02, 0.015, 0.015), mutate(rng, tmpl, 0.02, 0.015, 0.015)
+        a, b = with_n_runs(rng, a), (with_n_runs(rng, b) if p % 2 == 0 else b)
+        rc = p % 2 == 1
+        seqs += [revcomp(a) if rc else a, b]
+        mid = (len(b) - len(a)) // 2
+        specs.append((2 * p, 2 * p + 1, mid - band // 2, band, PAIR_REVCOMP if rc else 0))
+    k = len(seqs)
+    seqs += ["A" * 300, "N" * 300, "ACGT" * 80, "ACGT" * 30 + "N" * 80 + "ACGT" * 30]       # poly-A vs an N run: no hit; a masked stretch inside a repeat
+    lo, w = ava.full_band(300, 300)
+    specs += [(k, k + 1, lo, w, 0), (k + 1, k + 1, lo, w, 0)]
+    lo, w = ava.full_band(320, 320)
+    specs += [(k + 2, k + 3, lo, w, 0), (k + 3, k + 2, lo, w, PAIR_REVCOMP)]
+    names = [f"s{i}" for i in range(len(seqs))]
+    with Aligner(device=0, tb_bytes=4 << 30, **kw) as g:
+        gres, _ = run_both(g, OracleEngine(**kw), names, seqs, specs)
+    n_pairs = len(specs) - 4
+    assert (gres["status"][:n_pairs] == 0).all() and gres["score"][:n_pairs].min() > 1000
+    assert gres["status"][n_pairs] == 1 and gres["status"][n_pairs + 1] == 1                # nothing aligns to an N run, not even itself
+    assert gres["n_mismatch"][n_pairs + 2] >= 80 or gres["n_ins_bp"][n_pairs + 2] + gres["n_del_bp"][n_pairs + 2] > 0
