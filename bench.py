@@ -421,7 +421,11 @@ def main() -> None:
     max_cig = max(b["cigar_words"] for b in batches)
     d_results = torch.empty(max_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_cigar = torch.empty(max_cig, dtype=torch.int32, device=dev)
-    al = Aligner(device=local, preset="map-ont")
+    # traceback arena of the bench: 85 % of the free HBM (wave scheduling: the larger the waves, the fewer wave boundaries; the library's
+    # own default is 60 %); SVP_ARENA_GB overrides
+    free_b, _total_b = torch.cuda.mem_get_info(local)
+    arena_bytes = 0 if os.environ.get("SVP_ARENA_GB") else int(free_b * 0.85) & ~255
+    al = Aligner(device=local, preset="map-ont", tb_bytes=arena_bytes)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -540,6 +544,7 @@ def main() -> None:
                        "region_seeds": {"config2": "10000+r", "config3": "20000+r", "config4": "30000+r"}[args.workload],
                        "band": f"|dlen|+2*{SLACK} rounded up to {GRANULE} diagonals" if args.workload != "config3" else "|dlen|+512", "sharding": "LPT by estimated cells, no collective",
                        "l2": "inputs+traceback rows per step >> 126 MB L2 (every pair writes 6-12 MB of rows)",
+                       "arena_gb": round((arena_bytes or 0) / 2**30, 1) or os.environ.get("SVP_ARENA_GB"),
                        "timing": "CUDA events on the library's launch stream (svp_timer_mark), max over ranks; wall clock reported beside it",
                        "pipeline": ("steps submitted back to back (svp_submit_batch_device), step k+1's kernels start as step k's CTAs retire; "
                                     "all K steps complete inside the timed region") if args.pipeline else "blocking calls"},
@@ -556,15 +561,17 @@ def main() -> None:
                          "traffic_note": (f"DRAM bytes per forward launch = algorithmic bytes per launch x {tr['ratio']:.4f} "
                                           f"(dram__bytes_read+write / algorithmic, ncu --set full, {tr['source']})") if tr else None,
                          "algorithmic_bytes_per_launch": algo_bytes / n_fwd,
-                         "kernel": "svp_fwd_kernel (one launch per kernel variant and call, forward pass + in-kernel walk; the launches of a call run concurrently)", "peak_source": pk["source"],
+                         "kernel": "svp_fwd_kernel (one launch per kernel variant and wave; the launches of a wave run concurrently)", "peak_source": pk["source"],
                          "launches": int(agg["fwd_launches"]), "avg_launch_ms": agg["fwd_ms"] / n_fwd,
                          "algorithmic_bytes_per_cell": 1.0,
                          "int_pipe": {"achieved_gcups": fwd_gcups, "peak_gcups": ip["gcups"], "frac": fwd_gcups / ip["gcups"],
                                       "peak_source": ip["source"],
                                       "alu_pipe_14op": {"peak_gcups": ap_["gcups"], "frac": fwd_gcups / ap_["gcups"], **{k: ap_[k] for k in ("ipc_per_smsp", "sm_mhz", "int_ops_per_cell", "source")}},
                                       "note": "the kernel is integer-ALU-bound, not HBM-bound (DESIGN.md §5); frac uses the stricter of the two denominators"}},
-            "kernel_ms": {"device_total": agg["total_ms"], "walk_share_ms": agg["tb_ms"], "launch_groups": agg["waves"],
-                          "note": "forward pass and walk of a pair run inside one kernel; walk_share_ms = kernel time x the CTAs' summed walk ns / (forward + walk ns)"},
+            "kernel_ms": {"device_total": agg["total_ms"], "fwd": agg["fwd_ms"], "walk": agg["tb_ms"], "waves_or_groups": agg["waves"],
+                          "scheduler": os.environ.get("SVP_MODE", "waves"),
+                          "note": "waves: fwd = union of the waves' forward intervals, walk = summed spans of the walk kernels (svp_tbg / svp_tbw / svp_tb); "
+                                  "arena / queue: fwd = the call's kernel time, walk = its share by the CTAs' own clocks"},
         }
         if scaling:
             line["strong_scaling"] = scaling

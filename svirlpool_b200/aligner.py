@@ -9,6 +9,7 @@ surface as a subprocess.CalledProcessError subclass, which the reference's calle
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -17,7 +18,7 @@ import numpy as np
 from . import _abi
 from ._abi import PAIR_DTYPE, RESULT_DTYPE, SCORING_DTYPE, STATS_DTYPE, SVP_OK, ptr
 
-LIB_PATH = Path(__file__).resolve().parent / "libsvp_align.so"
+LIB_PATH = Path(os.environ.get("SVP_LIB", Path(__file__).resolve().parent / "libsvp_align.so"))       # (SVP_LIB: A/B runs of two builds)
 
 
 class AlignerError(subprocess.CalledProcessError):

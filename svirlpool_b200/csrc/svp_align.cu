@@ -96,15 +96,19 @@ struct DevBuf {
 // is planned and its kernels are enqueued behind / beside it.
 struct CallSet {
     DevBuf d_tasks, d_order, d_queue;
+    uint32_t n_walkers = 0;                                     // queue scheduling: walker warps of this call
     Task* h_tasks = nullptr; size_t h_tasks_cap = 0;            // pinned staging of the task / order arrays
     uint32_t* h_order = nullptr; size_t h_order_cap = 0;
     std::vector<cudaEvent_t> events;                            // pool, grown on demand (stream joins)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;               // first enqueue on the main stream / last kernel done
     bool pending = false;                                       // enqueued, times not collected yet
+    size_t n_waves = 0;                                         // wave scheduling: waves of this call (their events: wave_events)
+    std::vector<cudaEvent_t> wave_events;                       // timing events, EV_PER_WAVE per wave
     svp_stats stats{};                                          // counts filled at submit, times at collection
 };
 
 constexpr int N_FWD_STREAMS = 8;
+constexpr size_t EV_PER_WAVE = 4 + (N_FWD_STREAMS - 1);         // [fwd start, fwd end, walks end, long walks end, stream joins ...]
 
 struct svp_handle {
     int device = 0;
@@ -112,10 +116,26 @@ struct svp_handle {
     Consts cs{};
     cudaStream_t stream = nullptr;              // copies, joins, the first kernel group of a call
     cudaStream_t stream_aux[N_FWD_STREAMS - 1] = {};   // the other groups of a call run beside it
-    cudaStream_t stream_walk = nullptr;         // the call's walker kernel (highest priority: resident before the forward CTAs flood the SMs)
+    // Scheduling (env SVP_MODE):
+    //   waves (default)  the host gives every pair of a wave its slice of the arena (halves alternate from wave to wave) and launches
+    //                    the wave's walks as bulk kernels under the next wave's forward pass: highest throughput, arena = two waves
+    //   arena            every CTA takes its slice from the device-side pools and walks its pair itself: no waves, a bounded arena
+    //                    (the pairs resident on the GPU), ~15 % slower on config 2
+    //   queue            arena scheduling, but a CTA ends with its forward pass and queues its pair for the call's resident walker
+    //                    kernel (one walk per lane)
+    bool waves = true;
+    bool queue = false;
+    cudaStream_t stream_walk = nullptr;         // queue: the call's walker kernel (highest priority: resident before the forward CTAs flood the SMs)
+    int walk_ctas_per_sm = 1;                   // queue: walker CTAs (one warp each) per SM and call (env SVP_WALK_CTAS_PER_SM)
+    long walk_wait_ns = 100000;                 // queue: how long a walker waits for a full batch of 32 (env SVP_WALK_WAIT_NS)
+    long queue_min_pairs = 2048;                // queue: calls of fewer pairs walk inside their CTAs (a warp per walk: a third of the latency)
+    cudaStream_t stream_tb = nullptr;           // waves: the walk kernels (high priority; they overlap the next wave's forward pass)
+    cudaStream_t stream_tb2 = nullptr;          // ... the warp-per-pair walks of a wave's long pairs, beside the bulk kernel
+    long tbw_long = 24000;                      // waves: pairs with m + n beyond this are walked by a warp each (env SVP_TBW_LONG)
+    int tbw_max = 2048;                         // waves of at most this many pairs use the warp-per-pair walk (env SVP_TBW_MAX)
+    uint64_t wave_idx = 0;                      // waves enqueued so far: wave w uses arena half (w & 1), across calls
+    cudaEvent_t half_free[2] = { nullptr, nullptr };   // walks-done event of the last wave that used each arena half
     int sm_count = 0;
-    int walk_ctas_per_sm = 1;                   // walker CTAs (4 warps each) per SM and call (env SVP_WALK_CTAS_PER_SM)
-    bool fused_walk = false;                    // env SVP_FUSED_WALK: no queue, every CTA walks its own pair after its forward pass
     cudaEvent_t marks[2] = { nullptr, nullptr };   // svp_timer_mark
     // arena: n_sm per-SM pools of sm_region bytes each, then one global pool (svp_kernels.cuh: ArenaPool)
     uint8_t* arena = nullptr; size_t arena_bytes = 0;
@@ -124,7 +144,7 @@ struct svp_handle {
     uint64_t sm_region = 0, global_region = 0;
     double global_frac = -1.0;                  // share of the arena given to the global pool (set_partition)
     unsigned long long* d_clocks = nullptr;     // summed forward ns / traceback ns / pairs over all CTAs
-    unsigned long long clocks_seen[3] = { 0, 0, 0 };
+    unsigned long long clocks_seen[6] = { 0, 0, 0, 0, 0, 0 };
     int smem_per_sm = 233472;
     CallSet sets[2];
     uint64_t call_idx = 0;                      // calls planned so far (set = call_idx & 1)
@@ -234,8 +254,12 @@ static void read_env_knobs(svp_handle* h) {
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
+    if (const char* e = getenv("SVP_MODE")) { const std::string m(e); h->waves = m == "waves"; h->queue = m == "queue"; }
     if (const char* e = getenv("SVP_WALK_CTAS_PER_SM")) h->walk_ctas_per_sm = std::min(std::max(atoi(e), 1), 8);
-    if (const char* e = getenv("SVP_FUSED_WALK")) h->fused_walk = atoi(e) != 0;
+    if (const char* e = getenv("SVP_WALK_WAIT_NS")) h->walk_wait_ns = std::max(atol(e), 0L);
+    if (const char* e = getenv("SVP_QUEUE_MIN_PAIRS")) h->queue_min_pairs = atol(e);
+    if (const char* e = getenv("SVP_TBW_LONG")) h->tbw_long = atol(e);
+    if (const char* e = getenv("SVP_TBW_MAX")) h->tbw_max = atoi(e);
 }
 
 // kernel family of a pair
@@ -245,18 +269,19 @@ enum { FAM_FAST = 0, FAM_GEN = 1, FAM_S32 = 2, FAM_S32_GEN = 3, FAM_FAST_RB = 4 
 // attributes of every entry, run_plan launches through it). nullptr: no such variant.
 constexpr int SMEM_STATIC = 64;          // static shared memory of the forward kernels (the pair's arena slice note), rounded up
 using FwdKernel = void (*)(const Task*, const uint32_t*, const uint8_t*, const Arena, svp_result*, uint32_t*, const Consts);
-static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring, bool two) {
+template <bool W>
+static FwdKernel fwd_kernel_w(int fam, int kp, bool multi, bool cluster, bool ring, bool two) {
     if (fam == FAM_FAST || fam == FAM_FAST_RB) {        // s16x2 fast path: plain / rebased, whole images / sliding windows, one CTA / cluster
         const bool rb = fam == FAM_FAST_RB;
         if (cluster) {
             if (kp != 8) return nullptr;
-#define SVP_FCL(T, R, G) if (two == T && rb == R && ring == G) return svp_fwd_kernel<8, true, T, true, R, G>;
+#define SVP_FCL(T, R, G) if (two == T && rb == R && ring == G) return svp_fwd_kernel<8, true, T, true, R, G, W>;
             SVP_FCL(true, false, false) SVP_FCL(true, false, true) SVP_FCL(true, true, false) SVP_FCL(true, true, true)
             SVP_FCL(false, false, false) SVP_FCL(false, false, true) SVP_FCL(false, true, false) SVP_FCL(false, true, true)
 #undef SVP_FCL
             return nullptr;
         }
-#define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) return svp_fwd_kernel<K, M, T, false, R, G>;
+#define SVP_F(K, M, T, R, G) if (kp == K && multi == M && two == T && rb == R && ring == G) return svp_fwd_kernel<K, M, T, false, R, G, W>;
 #define SVP_F4(K, M, T) SVP_F(K, M, T, false, false) SVP_F(K, M, T, false, true) SVP_F(K, M, T, true, false) SVP_F(K, M, T, true, true)
         SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
         SVP_F4(5, false, true) SVP_F4(5, true, true) SVP_F4(6, false, true) SVP_F4(6, true, true) SVP_F4(7, false, true) SVP_F4(7, true, true)
@@ -268,19 +293,23 @@ static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring
     if (kp != 4) return nullptr;                        // general scoring and 32-bit lanes: KP = 4 geometry
     if (fam == FAM_GEN) {                               // whole images only
         if (ring) return nullptr;
-#define SVP_G(M, T, C) if (multi == M && two == T && cluster == C) return svp_fwdg_kernel<M, T, C>;
+#define SVP_G(M, T, C) if (multi == M && two == T && cluster == C) return svp_fwdg_kernel<M, T, C, W>;
         SVP_G(false, true, false) SVP_G(true, true, false) SVP_G(false, false, false) SVP_G(true, false, false) SVP_G(true, true, true) SVP_G(true, false, true)
 #undef SVP_G
         return nullptr;
     }
     const bool gen = fam == FAM_S32_GEN;
-#define SVP_W(M, T, G, C, R) if (multi == M && two == T && gen == G && cluster == C && ring == R) return svp_fwd32_kernel<M, T, G, C, R>;
+#define SVP_W(M, T, G, C, R) if (multi == M && two == T && gen == G && cluster == C && ring == R) return svp_fwd32_kernel<M, T, G, C, R, W>;
 #define SVP_W2(M, C, R) SVP_W(M, true, false, C, R) SVP_W(M, false, false, C, R) SVP_W(M, true, true, C, R) SVP_W(M, false, true, C, R)
     SVP_W2(false, false, false) SVP_W2(true, false, false) SVP_W2(true, true, false)
     SVP_W2(false, false, true) SVP_W2(true, false, true) SVP_W2(true, true, true)
 #undef SVP_W2
 #undef SVP_W
     return nullptr;
+}
+// walk = false: the variants without the in-kernel walk (wave scheduling)
+static FwdKernel fwd_kernel(int fam, int kp, bool multi, bool cluster, bool ring, bool two, bool walk) {
+    return walk ? fwd_kernel_w<true>(fam, kp, multi, cluster, ring, two) : fwd_kernel_w<false>(fam, kp, multi, cluster, ring, two);
 }
 
 __global__ void svp_queue_init_kernel(WalkQueue* q, uint32_t n) { q->head = 0; q->tail = 0; q->n = n; q->pad = 0; }
@@ -335,7 +364,9 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+        if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->stream_tb2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     }
     read_env_knobs(h);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -344,8 +375,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     // every variant: the largest dynamic shared memory (sequence images, or the residency ballast of run_plan) and the whole
     // L1 / shared-memory array as shared memory (the kernels stream their stores and read the rows through L2)
     for (int fam = 0; fam < 5; ++fam) for (int kp = 4; kp <= 8; ++kp) for (int m = 0; m < 2; ++m) for (int c = 0; c < 2; ++c)
-        for (int r = 0; r < 2; ++r) for (int t = 0; t < 2; ++t)
-            if (FwdKernel k = fwd_kernel(fam, kp, m != 0, c != 0, r != 0, t != 0)) {
+        for (int r = 0; r < 2; ++r) for (int t = 0; t < 2; ++t) for (int w = 0; w < 2; ++w)
+            if (FwdKernel k = fwd_kernel(fam, kp, m != 0, c != 0, r != 0, t != 0, w != 0)) {
                 // (dynamic + the kernels' few bytes of static shared memory must stay within the per-block limit)
                 if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin - SMEM_STATIC) != cudaSuccess ||
                     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
@@ -355,8 +386,9 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
             }
     // The walkers share their SMs with forward CTAs, and an SM's L1 / shared-memory split cannot change while a CTA is resident:
     // a walker launched with the default split (all L1) would keep every forward CTA that needs shared memory off its SM —
-    // with a walker on all 148 SMs nothing would ever run (seen: walk queue head 0 tail 0). Same split for both.
-    if (cudaFuncSetAttribute(svp_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+    // with a walker on all 148 SMs nothing would ever run. Same split for both.
+    if (cudaFuncSetAttribute(svp_walkq_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaFuncSetAttribute(svp_walkq_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
         cudaGetLastError();
         return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
     }
@@ -372,10 +404,10 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     h->n_sm = nsm;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
-    // Default arena: 48 GB, at most 60 % of the free memory. The arena holds the traceback rows of the pairs RESIDENT on the GPU
-    // only (a slice lives from the start of a pair's CTA to the end of its walk), so it does not grow with the batch: config 2
-    // keeps ~2000 pairs x 6-12 MB in flight. Several handles / processes can share a device.
-    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>((size_t)48 << 30, free_b / 10 * 6);
+    // Default arena. Wave scheduling: 60 % of the free memory — a wave is what fits half the arena, and the larger the wave the
+    // smaller the share of its ramp and drain (r1: 32 / 64 / 128 / 160 GB -> 1377 / 1728 / 1912 / 2006 GCUPS on config 2). Arena
+    // scheduling: 48 GB — it holds the rows of the pairs RESIDENT on the GPU only (config 2: ~2000 pairs x 6-12 MB), whatever the batch.
+    size_t want = max_tb_bytes ? max_tb_bytes : (h->waves ? free_b / 10 * 6 : std::min<size_t>((size_t)(h->queue ? 64 : 48) << 30, free_b / 10 * 6));
     if (!max_tb_bytes) if (const char* e = getenv("SVP_ARENA_GB")) want = std::min<size_t>((size_t)std::max(atoi(e), 1) << 30, free_b / 20 * 19);   // tuning aid
     want = (want + 255) & ~(size_t)255;
     // the default size shrinks until the allocation succeeds (fragmentation, another process on the device); an explicit size does not
@@ -387,8 +419,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     }
     h->arena_bytes = want;
     if (cudaMalloc((void**)&h->d_pools, (h->n_sm + 1) * sizeof(ArenaPool)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
-    if (cudaMalloc((void**)&h->d_clocks, 4 * sizeof(unsigned long long)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
-    cudaMemset(h->d_clocks, 0, 4 * sizeof(unsigned long long));
+    if (cudaMalloc((void**)&h->d_clocks, 8 * sizeof(unsigned long long)) != cudaSuccess) return bail(SVP_ERR_NOMEM, "cudaMalloc failed");
+    cudaMemset(h->d_clocks, 0, 8 * sizeof(unsigned long long));
     if (set_partition(h, 0.25) != SVP_OK) return bail(SVP_ERR_CUDA, "cannot initialise the arena pools");
     *out = h;
     return SVP_OK;
@@ -404,6 +436,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     for (DevBuf* b : { &h->d_seqs, &h->d_results, &h->d_cigar, &h->d_dense, &h->d_dense_off }) b->release();
     for (CallSet& c : h->sets) {
         for (DevBuf* b : { &c.d_tasks, &c.d_order, &c.d_queue }) b->release();
+        for (cudaEvent_t e : c.wave_events) cudaEventDestroy(e);
         if (c.h_tasks) cudaFreeHost(c.h_tasks);
         if (c.h_order) cudaFreeHost(c.h_order);
         for (cudaEvent_t e : c.events) cudaEventDestroy(e);
@@ -412,7 +445,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
     if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream_walk) cudaStreamDestroy(h->stream_walk);
+    for (cudaStream_t sx : { h->stream_tb, h->stream_tb2, h->stream_walk }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
 
@@ -444,9 +477,6 @@ static int collect_call(svp_handle* h, CallSet& c) {
                 std::string msg = "call did not finish within " + std::to_string((int)limit_s) + " s";
                 cudaStream_t dbg = nullptr;
                 if (cudaStreamCreateWithFlags(&dbg, cudaStreamNonBlocking) == cudaSuccess) {
-                    uint32_t qh[4] = { 0, 0, 0, 0 };
-                    if (c.d_queue.p && cudaMemcpyAsync(qh, c.d_queue.p, sizeof(qh), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess)
-                        msg += "; walk queue head " + std::to_string(qh[0]) + " tail " + std::to_string(qh[1]) + " of " + std::to_string(qh[2]);
                     std::vector<ArenaPool> pools(h->n_sm + 1);
                     if (cudaMemcpyAsync(pools.data(), h->d_pools, pools.size() * sizeof(ArenaPool), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess) {
                         uint64_t live = 0, bytes = 0, waits = 0, locked = 0;
@@ -456,7 +486,7 @@ static int collect_call(svp_handle* h, CallSet& c) {
                     }
                     unsigned long long clk[4] = { 0, 0, 0, 0 };
                     if (cudaMemcpyAsync(clk, h->d_clocks, sizeof(clk), cudaMemcpyDeviceToHost, dbg) == cudaSuccess && cudaStreamSynchronize(dbg) == cudaSuccess)
-                        msg += "; pairs walked " + std::to_string(clk[2]) + " (" + std::to_string(clk[3]) + " by waiting CTAs)";
+                        msg += "; pairs walked " + std::to_string(clk[2]);
                 }
                 return fail(h, SVP_ERR_CUDA, msg);
             }
@@ -465,15 +495,38 @@ static int collect_call(svp_handle* h, CallSet& c) {
     }
     float tot = 0; cudaEventElapsedTime(&tot, c.ev_t0, c.ev_t1);
     c.stats.total_ms = tot;
-    // forward pass and walk of a pair run inside one kernel: the kernel time of the call is split by the CTAs' own clocks
+    if (c.n_waves) {
+        // wave scheduling: forward time = length of the union of the waves' forward intervals; walk time = sum of the walk kernels' spans
+        auto EV = [&](size_t wv, int which) { return c.wave_events[wv * EV_PER_WAVE + which]; };
+        float covered_to = 0;
+        for (size_t wv = 0; wv < c.n_waves; ++wv) {
+            float f0 = 0, f1 = 0, b = 0;
+            cudaEventElapsedTime(&f0, c.ev_t0, EV(wv, 0));
+            cudaEventElapsedTime(&f1, c.ev_t0, EV(wv, 1));
+            cudaEventElapsedTime(&b, EV(wv, 1), EV(wv, 2));
+            const float from = std::max(f0, covered_to);
+            if (f1 > from) { c.stats.fwd_ms += f1 - from; covered_to = f1; }
+            c.stats.tb_ms += b;
+        }
+        for (cudaEvent_t& hf : h->half_free)                     // this call's waves are done: the halves they used last are free
+            for (cudaEvent_t e : c.wave_events) if (hf == e) { hf = nullptr; break; }
+        h->stats = c.stats;
+        svp_stats& T = h->stats_total;
+        T.fwd_ms += c.stats.fwd_ms; T.tb_ms += c.stats.tb_ms; T.total_ms += c.stats.total_ms; T.cells += c.stats.cells; T.tb_bytes += c.stats.tb_bytes;
+        T.fwd_launches += c.stats.fwd_launches; T.tb_launches += c.stats.tb_launches; T.waves += c.stats.waves;
+        CUDA_TRY(h, cudaGetLastError());
+        return SVP_OK;
+    }
+    // arena scheduling: forward pass and walk of a pair run inside one kernel; the kernel time of the call is split by the CTAs' own clocks
     // (summed ns of the two phases since the last collection; a pipelined neighbour call's CTAs are in the same sums)
-    unsigned long long clk[3] = { 0, 0, 0 };
+    unsigned long long clk[6] = { 0, 0, 0, 0, 0, 0 };
     CUDA_TRY(h, cudaMemcpy(clk, h->d_clocks, sizeof(clk), cudaMemcpyDeviceToHost));
-    const double f_ns = (double)(clk[0] - h->clocks_seen[0]), t_ns = (double)(clk[1] - h->clocks_seen[1]);
-    for (int k = 0; k < 3; ++k) h->clocks_seen[k] = clk[k];
-    const double tb_share = (f_ns + t_ns) > 0 ? t_ns / (f_ns + t_ns) : 0.0;
+    const double f_ns = (double)(clk[0] - h->clocks_seen[0]), t_ns = (double)(clk[1] - h->clocks_seen[1]), w_ns = (double)(clk[4] - h->clocks_seen[4]);
+    for (int k = 0; k < 6; ++k) h->clocks_seen[k] = clk[k];
     c.stats.fwd_ms = tot;
-    c.stats.tb_ms = tot * tb_share;
+    // walks inside the CTAs: the call's time x the walks' share of the CTAs' summed phase times; walker kernel: the mean busy time of its warps
+    c.stats.tb_ms = (f_ns + t_ns) > 0 ? tot * t_ns / (f_ns + t_ns) : 0.0;
+    if (c.n_walkers) c.stats.tb_ms += w_ns / 1e6 / (double)c.n_walkers;
     h->stats = c.stats;
     svp_stats& T = h->stats_total;
     T.fwd_ms += c.stats.fwd_ms; T.tb_ms += c.stats.tb_ms; T.total_ms += c.stats.total_ms; T.cells += c.stats.cells; T.tb_bytes += c.stats.tb_bytes;
@@ -664,33 +717,276 @@ static int begin_call(svp_handle* h, size_t n, CallSet** out) {
     return SVP_OK;
 }
 
-// Enqueue the planned pairs of call set `c` (c.h_tasks[0..n)). wait = true: return when the results are complete and the
-// call's times are collected; false: return after the enqueue (svp_submit_batch_device) — the next call is planned while this
-// one runs, and its kernels start as CTA slots and arena slices free up.
-//
-// There are no waves. Every pair's CTA takes its traceback rows from the device-side arena when it starts and returns them when
-// its walk is done (svp_kernels.cuh: ArenaPool), so the arena bounds the pairs in flight, not the batch. What the host does:
+// ---- launch groups: the pairs of a call (or of one wave of it) that run on one kernel variant ------------------------------------
+struct Group { int fam, nwarp, kp, cluster; bool ring, huge, inline_walk; size_t first, count, smem; uint64_t work, max_slice; };
+
+static inline int warps_of(const Task& t) { const int cl = cluster_of(t); return cl > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t)); }
+static inline int family_of(const Task& t, const Consts& cs) {
+    return (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : (t.flags & TASK_REBASE) ? FAM_FAST_RB : FAM_FAST);
+}
+// Groups of the valid tasks among `idx` (task indices), appended to `groups`; their order lists go to order[pos...]. A group = one
+// kernel variant x CTA width x shared-memory class (<= 32 KB, then powers of two, so that a few long pairs do not cut the occupancy
+// of the short ones sharing their launch; sliding-window variants have a fixed size) [x slice-size class, arena scheduling].
+// Inside a group the longest pairs come first (the tail of the launch is short pairs); the groups with the longest-running CTAs
+// come first (+6 % over biggest-group-first: the many short single-warp CTAs fill the tail).
+static void make_groups(const svp_handle* h, const Task* tasks, const uint32_t* idx, size_t n_idx, bool slice_classes, uint32_t* order, size_t& pos,
+                        std::vector<Group>& groups) {
+    const Consts& cs = h->cs;
+    std::map<std::array<int64_t, 8>, std::vector<uint32_t>> by_key;
+    for (size_t a = 0; a < n_idx; ++a) {
+        const uint32_t k = idx ? idx[a] : (uint32_t)a;
+        const Task& t = tasks[k];
+        if (t.flags & TASK_INVALID) continue;
+        const int nw = warps_of(t);
+        const bool ring = (t.flags & TASK_RING) != 0;
+        int smem_cls = 0;
+        if (!ring) while (((size_t)32768 << smem_cls) < smem_need(t, cs, nw)) ++smem_cls;
+        const bool huge = slice_classes && t.slice_bytes * 3 > h->sm_region;
+        // slice-size classes (x1.5 steps) keep the ballast of a regular group close to what each of its pairs needs
+        int size_cls = 0;
+        if (slice_classes && !huge) for (uint64_t b = (uint64_t)1 << 20; b < t.slice_bytes; b += b / 2) ++size_cls;
+        by_key[{ family_of(t, cs), kp_of(t), nw, cluster_of(t), ring, smem_cls, huge, size_cls }].push_back(k);
+    }
+    const size_t g0 = groups.size();
+    for (auto& kv : by_key) {
+        std::vector<uint32_t>& v = kv.second;
+        std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
+        Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, false, pos, v.size(), 0, 0, 0 };
+        const int lane_cost = (g.fam == FAM_S32 || g.fam == FAM_S32_GEN) ? 2 : 1;
+        for (uint32_t k : v) {
+            const Task& t = tasks[k];
+            g.smem = std::max(g.smem, smem_need(t, cs, g.nwarp));
+            g.max_slice = std::max(g.max_slice, t.slice_bytes);
+            g.work += (uint64_t)t.n_iter * g.nwarp * g.kp * lane_cost * (steps_per_iter_of(t) / (2 * g.kp)) * g.cluster;
+        }
+        std::copy(v.begin(), v.end(), order + pos);
+        pos += v.size();
+        groups.push_back(g);
+    }
+    std::sort(groups.begin() + g0, groups.end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
+}
+
+static const bool g_corridor = [] { const char* e = getenv("SVP_CORRIDOR"); return e ? atoi(e) != 0 : true; }();  // A/B aid: 0 = the walks load every byte from global memory
+static const bool g_skip_walk = [] { const char* e = getenv("SVP_SKIP_WALK"); return e && atoi(e) != 0; }();      // measurement aid: forward passes only
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Wave scheduling. A call is cut into waves of consecutive pairs whose slices fit HALF the arena; the halves alternate from wave to
+// wave (across calls), the host assigns every pair its slice (Task.tb_off), and the walks of a wave run as kernels of their own
+// (svp_tb_kernel / svp_tbw_kernel) on a high-priority stream under the forward pass of the next wave.
+// ---------------------------------------------------------------------------------------------------------------------------------
+static int run_waves(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar, bool wait) {
+    const Consts& cs = h->cs;
+    cudaStream_t st = h->stream;
+    Task* tasks = c.h_tasks;
+    const uint64_t half = (h->arena_bytes / 2) & ~(uint64_t)255;
+    uint64_t cap = half;                        // bytes a wave may use
+    bool serial = false;
+    std::vector<std::pair<size_t, size_t>> waves;
+    {
+        uint64_t total_need = 0, total_len = 0, max_need = 0;
+        for (size_t k = 0; k < n; ++k)
+            if (!(tasks[k].flags & TASK_INVALID)) { total_need += tasks[k].slice_bytes; total_len += (uint64_t)tasks[k].m + tasks[k].n; max_need = std::max(max_need, tasks[k].slice_bytes); }
+        // Two ways to run the walks. CONCURRENT: waves of half the arena, the walks of a wave run under the forward pass of the next
+        // one. SERIAL: waves of the whole arena, the walks of a wave run alone on the warp-per-pair kernel (5-6 ms for 10 000 pairs)
+        // before the next forward pass starts. Concurrent walks slow the forward pass they share the SMs with by 12 % (config 2) to
+        // 18-50 % (config 4: many short pairs), more than they take alone, and whole-arena waves halve the number of wave
+        // boundaries; but waves of few, long pairs (config 3) have latency-bound walks that need the overlap, and on config 2 (8 kb
+        // reads) the two measure the same. Hence: serial when a half-arena wave would hold at least serial_min_pairs pairs of, on
+        // average, less than serial_max_len bases (m + n). Env SVP_TB_SERIAL = 0 / 1 forces the choice.
+        static const int serial_mode = [] { const char* e = getenv("SVP_TB_SERIAL"); return e ? atoi(e) : -1; }();
+        static const long serial_min_pairs = [] { const char* e = getenv("SVP_TB_SERIAL_PAIRS"); return e ? atol(e) : 4096L; }();
+        static const long serial_max_len = [] { const char* e = getenv("SVP_TB_SERIAL_LEN"); return e ? atol(e) : 20000L; }();
+        const uint64_t n_w_half = std::max<uint64_t>(1, (total_need + half - 1) / half);
+        serial = serial_mode >= 0 ? serial_mode != 0 : ((long)(n / n_w_half) >= serial_min_pairs && (long)(total_len / std::max<size_t>(n, 1)) < serial_max_len);
+        if (max_need > half) serial = true;      // a pair beyond half the arena: whole-arena waves, whatever the preference
+        if (serial) cap = h->arena_bytes & ~(uint64_t)255;
+        // a call that needs several waves gets waves of equal size (not full halves and a remainder: the short wave's forward pass
+        // would wait for the long wave's walks)
+        const uint64_t n_w = std::max<uint64_t>(1, (total_need + cap - 1) / cap);
+        const uint64_t target = std::min(cap, total_need / n_w + total_need / (n_w * 50) + 4096);
+        size_t first = 0; uint64_t used = 0;
+        for (size_t k = 0; k < n; ++k) {
+            Task& t = tasks[k];
+            uint64_t need = 0;
+            if (!(t.flags & TASK_INVALID)) {
+                need = t.slice_bytes;
+                if (need > cap) return fail(h, SVP_ERR_NOMEM, "one pair's traceback exceeds the arena; create the handle with a larger max_tb_bytes");
+            }
+            if (used + need > cap || (used >= target && need)) { waves.emplace_back(first, k); first = k; used = 0; }
+            t.tb_off = (serial ? 0 : ((h->wave_idx + waves.size()) & 1) * half) + used;
+            used += need;
+        }
+        waves.emplace_back(first, n);
+    }
+    // per wave: launch groups, then the walk lists — a wave that is not walked by the warp-per-pair kernel as a whole hands its
+    // long pairs (m + n beyond tbw_long: a 40-90 kb consensus against its reference window takes the thread-per-pair kernel 10 000
+    // dependent rounds) to warps, the rest to the bulk kernel
+    uint32_t* order = c.h_order;
+    std::vector<std::vector<Group>> wave_groups(waves.size());
+    struct TbList { size_t first_short, n_short, first_long, n_long; };
+    std::vector<TbList> tb_lists(waves.size());
+    size_t pos = 0;
+    std::vector<uint32_t> idx;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        idx.resize(waves[wv].second - waves[wv].first);
+        for (size_t a = 0; a < idx.size(); ++a) idx[a] = (uint32_t)(waves[wv].first + a);
+        make_groups(h, tasks, idx.data(), idx.size(), false, order, pos, wave_groups[wv]);
+    }
+    size_t n_invalid_total = 0;
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        TbList& L = tb_lists[wv];
+        L.first_short = pos;
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k) {
+            if (tasks[k].flags & TASK_INVALID) { ++n_invalid_total; continue; }
+            if ((long)tasks[k].m + tasks[k].n <= h->tbw_long) order[pos++] = (uint32_t)k;
+        }
+        L.n_short = pos - L.first_short;
+        L.first_long = pos;
+        for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
+            if (!(tasks[k].flags & TASK_INVALID) && (long)tasks[k].m + tasks[k].n > h->tbw_long) order[pos++] = (uint32_t)k;
+        L.n_long = pos - L.first_long;
+    }
+    const size_t inv_first = pos;
+    if (n_invalid_total) for (size_t k = 0; k < n; ++k) if (tasks[k].flags & TASK_INVALID) order[pos++] = (uint32_t)k;
+
+    CUDA_TRY(h, c.d_tasks.reserve(n * sizeof(Task)));
+    CUDA_TRY(h, c.d_order.reserve(std::max<size_t>(pos, 1) * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaEventRecord(c.ev_t0, st));
+    CUDA_TRY(h, cudaMemcpyAsync(c.d_tasks.p, tasks, n * sizeof(Task), cudaMemcpyHostToDevice, st));
+    if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    const Task* d_tasks = (const Task*)c.d_tasks.p;
+    const uint32_t* d_order = (const uint32_t*)c.d_order.p;
+    if (n_invalid_total)
+        svp_invalid_kernel<<<(unsigned)((n_invalid_total + 127) / 128), 128, 0, st>>>(d_tasks, d_order + inv_first, (int)n_invalid_total, d_results);
+
+    const size_t n_ev = waves.size() * EV_PER_WAVE;
+    while (c.wave_events.size() < n_ev) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreate(&e)); c.wave_events.push_back(e); }
+    auto EV = [&](size_t wv, int which) { return c.wave_events[wv * EV_PER_WAVE + which]; };
+    // Forward passes of consecutive waves stay in stream order. Letting them overlap was measured slower four times — on separate
+    // stream sets (1810 vs 1915 GCUPS) and on priority-tiered stream sets (1810-1909 vs 1923-1962): the union of the forward
+    // intervals gets longer, not shorter, and the walks are delayed. Inside a wave the groups run on up to four streams (2..6
+    // measure the same, one stream 10 % slower).
+    cudaStream_t sF[N_FWD_STREAMS] = { st };
+    for (int a = 1; a < N_FWD_STREAMS; ++a) sF[a] = h->stream_aux[a - 1];
+    static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), N_FWD_STREAMS); }();
+    cudaStream_t sT = h->stream_tb;
+    // Waves of few, long-running CTAs (long reads, wide bands: config 3) end in a tail of a few CTAs on an otherwise idle machine;
+    // there the forward pass of the next wave starts at once on the other half of the streams (it writes the other arena half
+    // anyway) instead of waiting in stream order. SVP_WAVE_OVERLAP = 0 / 1 forces the choice, default: waves averaging fewer than
+    // overlap_max_pairs pairs.
+    static const int overlap_mode = [] { const char* e = getenv("SVP_WAVE_OVERLAP"); return e ? atoi(e) : -1; }();
+    static const long overlap_max_pairs = [] { const char* e = getenv("SVP_WAVE_OVERLAP_PAIRS"); return e ? atol(e) : 4096L; }();
+    const bool overlap = !serial && waves.size() > 1 && (overlap_mode >= 0 ? overlap_mode != 0 : (long)(n / waves.size()) < overlap_max_pairs);
+    while (c.events.size() < 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
+    cudaEvent_t ev_copied = c.events[0];                 // the copies above precede every wave, whatever stream leads it
+    CUDA_TRY(h, cudaEventRecord(ev_copied, st));
+    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, 1u, 0u, nullptr, nullptr, 0u, 0u, 0u };
+    for (size_t wv = 0; wv < waves.size(); ++wv) {
+        const int half_id = (int)((h->wave_idx + wv) & 1);
+        cudaStream_t* sW = overlap ? sF + half_id * (N_FWD_STREAMS / 2) : sF;         // this wave's streams
+        const int avail = overlap ? N_FWD_STREAMS / 2 : max_streams;
+        const std::vector<Group>& groups = wave_groups[wv];
+        const int n_streams = (int)std::max<size_t>(1, std::min<size_t>((size_t)avail, groups.size()));
+        // join = true: the wave starts on all its streams at once, after the previous wave's forward pass has ended on all of them.
+        // join = false (env SVP_WAVE_JOIN=0): every stream goes on with this wave's groups as soon as its own groups of the previous
+        // wave are done and the arena half is free — no drain and ramp between waves
+        static const bool join = [] { const char* e = getenv("SVP_WAVE_JOIN"); return e ? atoi(e) != 0 : true; }();
+        for (int a = 0; a < (join ? 1 : n_streams); ++a) {
+            if (sW[a] != st) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], ev_copied, 0));
+            if (h->half_free[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], h->half_free[half_id], 0));      // this arena half is free again
+            if (serial && h->half_free[half_id ^ 1]) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], h->half_free[half_id ^ 1], 0));   // whole-arena wave
+        }
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 0), sW[0]));
+        if (join) for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(sW[a], EV(wv, 0), 0));
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const Group& g = groups[gi];
+            FwdKernel kern = fwd_kernel(g.fam, g.kp, g.nwarp > 1, g.cluster > 1, g.ring, cs.two_piece != 0, false);
+            if (!kern) return fail(h, SVP_ERR_UNSUPPORTED, "internal: no kernel variant for a planned group");
+            CUDA_TRY(h, launch_group(kern, g.cluster, (unsigned)g.count, (unsigned)g.nwarp * 32u, g.smem, sW[gi % (size_t)n_streams], d_tasks, d_order + g.first,
+                                     d_seqs, ar, d_results, d_cigar, cs));
+            c.stats.fwd_launches++;
+        }
+        if (join) {
+            for (int a = 1; a < n_streams; ++a) {
+                CUDA_TRY(h, cudaEventRecord(EV(wv, 3 + a), sW[a]));
+                CUDA_TRY(h, cudaStreamWaitEvent(sW[0], EV(wv, 3 + a), 0));
+            }
+            CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sW[0]));
+            CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
+        } else {                                 // only the walks wait for the whole wave
+            for (int a = 1; a < n_streams; ++a) {
+                CUDA_TRY(h, cudaEventRecord(EV(wv, 3 + a), sW[a]));
+                CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 3 + a), 0));
+            }
+            CUDA_TRY(h, cudaEventRecord(EV(wv, 1), sW[0]));
+            CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 1), 0));
+            if (h->stream_tb2) for (int a = 1; a < n_streams; ++a) CUDA_TRY(h, cudaStreamWaitEvent(h->stream_tb2, EV(wv, 3 + a), 0));
+        }
+        const TbList& L = tb_lists[wv];
+        const int nt = (int)(L.n_short + L.n_long);
+        if (nt > 0 && !g_skip_walk) {
+            // few pairs in the wave (one container per call; long tandem-repeat pairs): the warp-per-pair kernel walks 32 cells per
+            // memory round trip; in bulk the thread-per-pair kernel costs fewer issue slots under the next wave's forward pass.
+            // The last wave of a blocking call has no forward pass left to share the machine with: its walks are pure latency.
+            static const bool last_wave_warp = [] { const char* e = getenv("SVP_TBW_LAST"); return e ? atoi(e) != 0 : true; }();
+            if (nt <= h->tbw_max || serial || (last_wave_warp && wait && wv + 1 == waves.size())) {
+                // (the short and the long list of a wave are adjacent in the order array). Lanes per pair (env SVP_TB_LPP): 8 — four
+                // pairs share a warp's instruction stream; 32 — the whole warp, with its corridor in shared memory
+                static const int lpp = [] { const char* e = getenv("SVP_TB_LPP"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();
+                static const int tbg_min = [] { const char* e = getenv("SVP_TBG_MIN"); return e ? atoi(e) : -1; }();
+                const bool whole = lpp == 32 || nt < (tbg_min >= 0 ? tbg_min : 4 * h->sm_count);         // few pairs: latency counts, not issue slots
+                if (whole)
+                    svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, g_corridor ? 4 * COR_BYTES : 0, sT>>>(d_tasks, d_order + L.first_short, nt, d_seqs, h->arena, d_results, d_cigar, cs, g_corridor ? 1 : 0);
+                else {
+                    if (L.n_long) svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs, h->arena, d_results, d_cigar, cs, 0);
+                    if (L.n_short && lpp == 16) svp_tbg_kernel<16><<<((int)L.n_short * 16 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs);
+                    if (L.n_short && lpp == 8) svp_tbg_kernel<8><<<((int)L.n_short * 8 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs);
+                }
+                c.stats.tb_launches++;
+            } else {
+                if (L.n_long) {              // the long walks first, on their own stream beside the bulk kernel
+                    CUDA_TRY(h, cudaStreamWaitEvent(h->stream_tb2, EV(wv, 1), 0));
+                    svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, g_corridor ? 4 * COR_BYTES : 0, h->stream_tb2>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs,
+                                                                                                                       h->arena, d_results, d_cigar, cs, g_corridor ? 1 : 0);
+                    CUDA_TRY(h, cudaEventRecord(EV(wv, 3), h->stream_tb2));
+                    c.stats.tb_launches++;
+                }
+                if (L.n_short) {
+                    svp_tb_kernel<<<((int)L.n_short + 63) / 64, 64, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs);
+                    c.stats.tb_launches++;
+                }
+                if (L.n_long) CUDA_TRY(h, cudaStreamWaitEvent(sT, EV(wv, 3), 0));
+            }
+        }
+        CUDA_TRY(h, cudaEventRecord(EV(wv, 2), sT));
+        h->half_free[half_id] = EV(wv, 2);
+        if (serial) h->half_free[half_id ^ 1] = EV(wv, 2);
+        c.stats.waves++;
+    }
+    h->wave_idx += waves.size();
+    CUDA_TRY(h, cudaStreamWaitEvent(sT, ev_copied, 0));  // (a call of invalid pairs only: their rows are written on the main stream)
+    CUDA_TRY(h, cudaEventRecord(c.ev_t1, sT));           // walks run in wave order on one stream: the last one ends the call
+    c.n_waves = waves.size();
+    return SVP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Arena scheduling. There are no waves. Every pair's CTA takes its traceback rows from the device-side arena when it starts, walks
+// its pair itself after the forward pass and returns the slice (svp_kernels.cuh: ArenaPool), so the arena bounds the pairs in
+// flight, not the batch. What the host does:
 //   * classify the pairs: "regular" slices (at most a third of a per-SM region) come from the pool of the SM the CTA runs on,
 //     larger ones from the global pool; the split of the arena between the two follows the demand of the call;
 //   * group the pairs by kernel variant, CTA width, shared-memory class and slice-size class; one launch per group;
 //   * bound the residency: a regular group asks for at least 1.5 x slice / region of an SM's shared memory per CTA (ballast), so
 //     the block scheduler itself keeps the slices live on an SM within its region, with room for fragmentation — a CTA that still
-//     finds its pool full waits for a neighbour to finish (arena_alloc);
-//   * launch the groups with the longest-running CTAs first, round-robin over the streams, so that the many short single-warp
-//     CTAs fill the tail; consecutive calls rotate the streams and overlap freely.
-static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar, bool wait) {
+//     finds its pool full waits for a neighbour to finish (pair_begin);
+//   * launch the groups with the longest-running CTAs first, round-robin over the streams; consecutive calls rotate the streams
+//     and overlap freely.
+// ---------------------------------------------------------------------------------------------------------------------------------
+static int run_arena(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar) {
     const Consts& cs = h->cs;
     cudaStream_t st = h->stream;
     Task* tasks = c.h_tasks;
-    c.stats = svp_stats{};
-    if (n == 0) { h->stats = c.stats; return SVP_OK; }
-    // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
-    for (size_t k = 0; k < n; ++k) {
-        Task& t = tasks[k];
-        if (t.flags & (TASK_INVALID | TASK_RING)) continue;
-        const int nw = cluster_of(t) > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-        if (smem_need(t, cs, nw) + SMEM_STATIC > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;      // (+ the kernels' static shared memory)
-    }
     // ---- arena partition: which share goes to the global pool ----------------------------------------------------------
     {
         uint64_t max_slice = 0;
@@ -726,64 +1022,36 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
             }
         }
     }
-    // ---- groups ---------------------------------------------------------------------------------------------------------
-    struct Group { int fam, nwarp, kp, cluster; bool ring, huge, inline_walk; size_t first, count, smem; uint64_t work, max_slice; };
     std::vector<Group> groups;
     uint32_t* order = c.h_order;
     size_t pos = 0;
-    {
-        std::map<std::array<int64_t, 8>, std::vector<uint32_t>> by_key;
-        for (size_t k = 0; k < n; ++k) {
-            const Task& t = tasks[k];
-            if (t.flags & TASK_INVALID) continue;
-            const int cl = cluster_of(t);
-            const int nw = cl > 1 ? 16 : (t.band_w + 128 * kp_of(t) - 1) / (128 * kp_of(t));
-            const int fam = (t.flags & TASK_S32) ? (cs.general ? FAM_S32_GEN : FAM_S32) : (cs.general ? FAM_GEN : (t.flags & TASK_REBASE) ? FAM_FAST_RB : FAM_FAST);
-            const bool ring = (t.flags & TASK_RING) != 0;
-            // shared memory of the pair's CTA: sequence images + mailboxes, in classes (<= 32 KB, then powers of two) so that a few long
-            // pairs do not cut the occupancy of the short ones sharing their launch; sliding-window variants have a fixed size
-            int smem_cls = 0;
-            if (!ring) while (((size_t)32768 << smem_cls) < smem_need(t, cs, nw)) ++smem_cls;
-            const bool huge = t.slice_bytes * 3 > h->sm_region;
-            // slice-size classes (x1.5 steps) keep the ballast of a regular group close to what each of its pairs needs
-            int size_cls = 0;
-            if (!huge) for (uint64_t b = (uint64_t)1 << 20; b < t.slice_bytes; b += b / 2) ++size_cls;
-            by_key[{ fam, kp_of(t), nw, cl, ring, smem_cls, huge, size_cls }].push_back((uint32_t)k);
+    make_groups(h, tasks, nullptr, n, true, order, pos, groups);
+    for (Group& g : groups)
+        if (!g.huge) {
+            // ballast: CTAs per SM <= smem_per_sm / (smem + 1 KB the system reserves per CTA); keep 1.5 x their slices within the SM's region
+            static const double slack = [] { const char* e = getenv("SVP_BALLAST_SLACK"); return e ? atof(e) : 1.5; }();
+            const double per_cta = slack * (double)g.max_slice / (double)h->sm_region * (double)h->smem_per_sm;
+            const size_t ballast = per_cta > 1024.0 ? (size_t)per_cta - 1024 + 16 : 0;
+            g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - SMEM_STATIC);
         }
-        for (auto& kv : by_key) {
-            std::vector<uint32_t>& v = kv.second;
-            // longest pairs first inside a group: the tail of the launch is short pairs
-            std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
-            Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, false, pos, v.size(), 0, 0, 0 };
-            const int lane_cost = (g.fam == FAM_S32 || g.fam == FAM_S32_GEN) ? 2 : 1;
-            for (uint32_t k : v) {
-                const Task& t = tasks[k];
-                g.smem = std::max(g.smem, smem_need(t, cs, g.nwarp));
-                g.max_slice = std::max(g.max_slice, t.slice_bytes);
-                g.work += (uint64_t)t.n_iter * g.nwarp * g.kp * lane_cost * (steps_per_iter_of(t) / (2 * g.kp)) * g.cluster;
-            }
-            if (!g.huge) {
-                // ballast: CTAs per SM <= smem_per_sm / (smem + 1 KB the system reserves per CTA); keep 1.5 x their slices within the SM's region
-                const double per_cta = 1.5 * (double)g.max_slice / (double)h->sm_region * (double)h->smem_per_sm;
-                const size_t ballast = per_cta > 1024.0 ? (size_t)per_cta - 1024 + 16 : 0;
-                g.smem = std::min<size_t>(std::max(g.smem, ballast), (size_t)h->max_smem_optin - SMEM_STATIC);
-            }
-            // A CTA that needs (nearly) a whole SM — 14+ warps at up to 128 registers, or sequence images filling the shared memory —
-            // cannot become resident beside a walker CTA, and the walkers stay until every queued pair is walked: such groups must
-            // not depend on them. Their CTAs walk their own pair after the forward pass (long forward passes: the walk is a small
-            // share of the CTA's life there).
-            g.inline_walk = h->fused_walk || g.nwarp * 32 * 128 + h->walk_ctas_per_sm * 128 * 104 > 65536 ||
-                            g.smem + 1024 + (size_t)h->walk_ctas_per_sm * 2048 > (size_t)h->smem_per_sm;
-            std::copy(v.begin(), v.end(), order + pos);
-            pos += v.size();
-            groups.push_back(g);
-        }
-        // groups with the longest-running CTAs (most work per pair) first, the many short CTAs fill the tail
-        std::sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
-    }
+    if (g_corridor) for (Group& g : groups) g.smem = std::max<size_t>(g.smem, COR_BYTES);       // the walking warp's corridor (svp_kernels.cuh: TbView)
     const size_t inv_first = pos;
     for (size_t k = 0; k < n; ++k) if (tasks[k].flags & TASK_INVALID) order[pos++] = (uint32_t)k;
     const size_t n_invalid = pos - inv_first;
+    // ---- queue scheduling: which pairs are queued for the walker kernel ---------------------------------------------------------
+    // Not the pairs of a small call (a warp per walk inside the CTAs has a third of the latency), not long pairs (Arena.walk_long),
+    // and not the groups whose CTA needs (nearly) a whole SM — 14+ warps at up to 128 registers, or sequence images filling the
+    // shared memory: such a CTA cannot become resident beside a walker CTA, and the walkers stay until every queued pair is
+    // walked, so it must not depend on them.
+    constexpr int WALKER_REGS = 32 * 255;
+    size_t n_queued = 0;
+    const bool use_queue = h->queue && (long)(n - n_invalid) >= h->queue_min_pairs;
+    for (Group& g : groups) {
+        g.inline_walk = !use_queue || g.nwarp * 32 * 128 + h->walk_ctas_per_sm * WALKER_REGS > 65536 ||
+                        g.smem + 1024 + (size_t)h->walk_ctas_per_sm * 1024 > (size_t)h->smem_per_sm;
+        if (!g.inline_walk)
+            for (size_t a = 0; a < g.count; ++a) { const Task& t = tasks[order[g.first + a]]; if ((long)t.m + t.n <= h->tbw_long) ++n_queued; }
+    }
 
     CUDA_TRY(h, c.d_tasks.reserve(n * sizeof(Task)));
     CUDA_TRY(h, c.d_order.reserve(std::max<size_t>(pos, 1) * sizeof(uint32_t)));
@@ -792,51 +1060,50 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
     if (pos) CUDA_TRY(h, cudaMemcpyAsync(c.d_order.p, order, pos * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     const Task* d_tasks = (const Task*)c.d_tasks.p;
     const uint32_t* d_order = (const uint32_t*)c.d_order.p;
-    // the call's walk queue: one entry per valid pair, unpublished entries are all-ones
-    size_t n_valid = 0;                               // pairs that will be queued
-    for (const Group& g : groups) if (!g.inline_walk) n_valid += g.count;
     WalkQueue* d_queue = nullptr;
-    if (n_valid) {
-        const size_t qbytes = sizeof(WalkQueue) + n_valid * sizeof(WalkEntry);
+    if (n_queued) {                                     // one entry per queued pair, unpublished entries are all-ones
+        const size_t qbytes = sizeof(WalkQueue) + n_queued * sizeof(WalkEntry);
         CUDA_TRY(h, c.d_queue.reserve(qbytes));
         d_queue = (WalkQueue*)c.d_queue.p;
         CUDA_TRY(h, cudaMemsetAsync(d_queue, 0xFF, qbytes, st));
-        svp_queue_init_kernel<<<1, 1, 0, st>>>(d_queue, (uint32_t)n_valid);
+        svp_queue_init_kernel<<<1, 1, 0, st>>>(d_queue, (uint32_t)n_queued);
     }
 
     static const int max_streams = [] { const char* e = getenv("SVP_FWD_STREAMS"); int v = e ? atoi(e) : N_FWD_STREAMS; return std::min(std::max(v, 1), N_FWD_STREAMS); }();
     cudaStream_t sF[N_FWD_STREAMS] = { st };
     for (int a = 1; a < N_FWD_STREAMS; ++a) sF[a] = h->stream_aux[a - 1];
-    while (c.events.size() < (size_t)N_FWD_STREAMS + 1) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
+    while (c.events.size() < (size_t)N_FWD_STREAMS + 2) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
     const int n_streams = (int)std::min<size_t>((size_t)max_streams, std::max<size_t>(groups.size(), 1));
     cudaEvent_t ev_copied = c.events[N_FWD_STREAMS];
     CUDA_TRY(h, cudaEventRecord(ev_copied, st));
     // consecutive calls start on different streams: the heavy first group of call k+1 does not queue behind the one of call k
     const int rot = (int)(h->call_idx % (uint64_t)N_FWD_STREAMS);
-    auto stream_of = [&](size_t gi) { return sF[(gi + (size_t)rot) % (size_t)n_streams]; };
     bool used[N_FWD_STREAMS] = {};
-    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, d_queue, d_tasks, 0u };
-    // The walkers first, on the highest-priority stream: a few warps per SM that stay for the whole call and walk the pairs the
+    Arena ar{ h->arena, h->d_pools, h->n_sm, 0u, h->d_clocks, 0u, g_skip_walk ? 1u : 0u, d_queue, d_tasks, 0u, (uint32_t)std::min<long>(h->tbw_long, 0x7FFFFFFF), g_corridor ? 1u : 0u };
+    // The walkers first, on the highest-priority stream: one warp per SM that stays for the whole call and walks the pairs the
     // forward CTAs queue. (A forward CTA ends with its forward pass; its ~130 registers per thread go to the next pair instead of
-    // idling through a latency-bound walk — walking inside the forward CTA was measured at 37 % of the CTA's life, 482 instead of
-    // 571 regions/s on config 2.)
-    bool walker = false;
+    // idling through a latency-bound walk — walking inside the forward CTA was measured at 37 % of the CTA's life, 482 regions/s
+    // on config 2 where the forward passes alone run at 688.)
+    c.n_walkers = 0;
     if (d_queue) {
-        const unsigned ctas = (unsigned)std::min<size_t>((size_t)h->sm_count * (size_t)h->walk_ctas_per_sm, (n_valid + 3) / 4);
+        const unsigned ctas = (unsigned)std::min<size_t>((size_t)h->sm_count * (size_t)h->walk_ctas_per_sm, (n_queued + 31) / 32);
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream_walk, ev_copied, 0));
-        svp_walk_kernel<<<ctas, 128, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs);
-        walker = true;
+        static const bool lean = [] { const char* e = getenv("SVP_WALK_LEAN"); return e && atoi(e) != 0; }();
+        if (lean) svp_walkq_kernel<16><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
+        else svp_walkq_kernel<1><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
+        c.n_walkers = ctas;
+        c.stats.tb_launches = 1;
     }
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         const Group& g = groups[gi];
-        FwdKernel kern = fwd_kernel(g.fam, g.kp, g.nwarp > 1, g.cluster > 1, g.ring, cs.two_piece != 0);
+        FwdKernel kern = fwd_kernel(g.fam, g.kp, g.nwarp > 1, g.cluster > 1, g.ring, cs.two_piece != 0, true);
         if (!kern) return fail(h, SVP_ERR_UNSUPPORTED, "internal: no kernel variant for a planned group");
         const int si = (int)((gi + (size_t)rot) % (size_t)n_streams);
         if (sF[si] != st && !used[si]) CUDA_TRY(h, cudaStreamWaitEvent(sF[si], ev_copied, 0));
         used[si] = true;
         ar.use_global = g.huge ? 1u : 0u;
         ar.inline_walk = g.inline_walk ? 1u : 0u;
-        CUDA_TRY(h, launch_group(kern, g.cluster, (unsigned)g.count, (unsigned)g.nwarp * 32u, g.smem, stream_of(gi), d_tasks, d_order + g.first, d_seqs, ar,
+        CUDA_TRY(h, launch_group(kern, g.cluster, (unsigned)g.count, (unsigned)g.nwarp * 32u, g.smem, sF[si], d_tasks, d_order + g.first, d_seqs, ar,
                                  d_results, d_cigar, cs));
         c.stats.fwd_launches++;
     }
@@ -847,14 +1114,33 @@ static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, 
         CUDA_TRY(h, cudaEventRecord(c.events[a], sF[a]));
         CUDA_TRY(h, cudaStreamWaitEvent(st, c.events[a], 0));
     }
-    if (walker) {
-        while (c.events.size() < (size_t)N_FWD_STREAMS + 2) { cudaEvent_t e; CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.events.push_back(e); }
+    if (c.n_walkers) {
         CUDA_TRY(h, cudaEventRecord(c.events[N_FWD_STREAMS + 1], h->stream_walk));
         CUDA_TRY(h, cudaStreamWaitEvent(st, c.events[N_FWD_STREAMS + 1], 0));
-        c.stats.tb_launches = 1;
     }
     CUDA_TRY(h, cudaEventRecord(c.ev_t1, st));
     c.stats.waves = (uint32_t)groups.size();
+    c.n_waves = 0;
+    return SVP_OK;
+}
+
+// Enqueue the planned pairs of call set `c` (c.h_tasks[0..n)). wait = true: return when the results are complete and the
+// call's times are collected; false: return after the enqueue (svp_submit_batch_device) — the next call is planned while this
+// one runs, and its kernels start as CTA slots and arena space free up.
+static int run_plan(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs, svp_result* d_results, uint32_t* d_cigar, bool wait) {
+    const Consts& cs = h->cs;
+    Task* tasks = c.h_tasks;
+    c.stats = svp_stats{};
+    c.n_waves = 0;
+    if (n == 0) { h->stats = c.stats; return SVP_OK; }
+    // pairs whose sequence images do not fit the shared memory of a CTA are reported per pair (SVP_ST_TOO_LONG)
+    for (size_t k = 0; k < n; ++k) {
+        Task& t = tasks[k];
+        if (t.flags & (TASK_INVALID | TASK_RING)) continue;
+        if (smem_need(t, cs, warps_of(t)) + SMEM_STATIC > (size_t)h->max_smem_optin) t.flags |= TASK_INVALID | TASK_TOO_LONG;      // (+ the kernels' static shared memory)
+    }
+    const int rc = h->waves ? run_waves(h, c, n, d_seqs, d_results, d_cigar, wait) : run_arena(h, c, n, d_seqs, d_results, d_cigar);
+    if (rc != SVP_OK) return rc;
     for (size_t k = 0; k < n; ++k) if (!(tasks[k].flags & TASK_INVALID)) { c.stats.cells += tasks[k].cells; c.stats.tb_bytes += tasks[k].tb_bytes; }
     c.pending = true;
     h->call_idx++;

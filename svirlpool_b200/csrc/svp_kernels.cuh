@@ -40,6 +40,7 @@ struct Task {               // one pair, prepared on the host (svp_align.cu: pla
     uint32_t pair_index;    // index into the caller's pair / result arrays
     uint64_t tb_bytes;      // bytes of this pair's traceback rows; its per-thread best records (8 B each) follow them in the arena slice
     uint64_t slice_bytes;   // rows + best records, a multiple of 256: what the pair takes from the arena
+    uint64_t tb_off;        // wave scheduling: arena offset of the pair's slice, assigned by the host
     uint64_t cells;         // spec cells (band ∩ matrix), copied into the result
     uint32_t cigar_off, cigar_cap;
 };
@@ -238,9 +239,16 @@ template <bool CL> __device__ __forceinline__ void mailbox_store_B(const StepLin
     if (CL && L.rup) st_async_v4(L.rem_B, a, b, c, d, L.rem_bar_B);
     else if (L.up) { sts_v4(L.out_B(), a, b, c, d); mbar_arrive(L.sig_B()); }
 }
+// CG: the rows were written by the grid that reads them (arena scheduling: the walk runs inside the forward kernel, slices are
+// recycled under it) -> ld.global.cg, L1 must not serve them; false: written by an earlier kernel (wave scheduling) -> plain loads
+template <bool CG, int LPP = 32>
 __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
                                                 const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
-                                                uint32_t* __restrict__ cigar, const Consts& cs);
+                                                uint32_t* __restrict__ cigar, const Consts& cs, uint32_t s_cor);
+template <bool CG>
+__device__ __noinline__ void svp_traceback_thread(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
+                                                  const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                                  uint32_t* __restrict__ cigar, const Consts& cs);
 // ---------------------------------------------------------------------------------------------
 // Device-side arena. The traceback rows of a pair live from the start of its forward pass to the end of its walk, both inside
 // one CTA (cluster), so the arena only has to hold the pairs that are RESIDENT on the GPU: thread 0 of a pair's (first) CTA
@@ -251,19 +259,23 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
 // host bounds the residency per SM through the shared-memory request of every launch (svp_align.cu: ballast), so that the
 // slices live on an SM fit its region with room for fragmentation and the wait is the exception.
 // ---------------------------------------------------------------------------------------------
-constexpr int POOL_MAX = 48;
+#ifndef SVP_POOL_MAX
+#define SVP_POOL_MAX 48
+#endif
+constexpr int POOL_MAX = SVP_POOL_MAX;
 struct ArenaPool {
     uint32_t lock, n;                 // spin lock (0 free), live slices
     uint64_t base, bytes;             // the pool's region: arena offset and size
     uint64_t off[POOL_MAX], len[POOL_MAX];   // live slices, ascending by offset (relative to base)
     unsigned long long waits;         // allocations that had to wait (statistics)
 };
-// Finished forward passes of a call, waiting for their walk. An entry is published by writing its task index last; entries are
-// popped in order (head), by the call's walker kernel and by any CTA that is waiting for arena space (it helps instead of idling).
+// Queue scheduling: finished forward passes of a call, waiting for their walk. An entry is published by writing its task index
+// last; entries are popped in order (head) — in batches of up to 32 by the call's walker kernel (one walk per LANE), one at a
+// time by a CTA that is waiting for arena space (it helps instead of idling, one walk per WARP).
 struct WalkEntry { uint64_t arena_off; uint32_t pool_id; uint32_t task; };
 constexpr uint32_t WALK_EMPTY = 0xFFFFFFFFu;
 struct WalkQueue {
-    uint32_t head, tail, n, pad;      // next entry to walk, entries handed out to writers, valid pairs of the call
+    uint32_t head, tail, n, pad;      // next entry to walk, entries handed out to writers, queued pairs of the call
     WalkEntry e[1];                   // n entries, initialised to 0xFF
 };
 struct Arena {
@@ -271,10 +283,15 @@ struct Arena {
     ArenaPool* pools;                 // pools[0 .. n_sm): per SM, pools[n_sm]: global
     uint32_t n_sm;
     uint32_t use_global;              // this launch's pairs allocate from the global pool
-    unsigned long long* clocks;       // [0] summed forward ns, [1] summed walk ns, [2] pairs walked, [3] walks done by waiting CTAs (statistics)
-    WalkQueue* queue;                 // the call's queue (nullptr: none); a CTA waiting for arena space walks entries of it
-    const Task* tasks;                // the call's task array (queue entries index it)
-    uint32_t inline_walk;             // this launch's CTAs walk their own pair right after the forward pass instead of queueing it
+    unsigned long long* clocks;       // [0] summed forward ns, [1] summed inline-walk ns, [2] pairs walked, [3] walks by waiting CTAs,
+                                      // [4] summed busy ns of the walker warps, [5] batches they walked (statistics)
+    uint32_t static_slices;           // wave scheduling: the host assigned every pair its slice (Task.tb_off) and launches the walks itself
+    uint32_t skip_walk;               // measurement aid (env SVP_SKIP_WALK): no walk at all, results are not written — the forward-only rate
+    WalkQueue* queue;                 // queue scheduling: the call's queue (nullptr: none)
+    const Task* tasks;                // ... the call's task array (queue entries index it)
+    uint32_t inline_walk;             // ... this launch's CTAs walk their own pair after the forward pass instead of queueing it
+    uint32_t walk_long;               // ... and so does every pair with m + n beyond this (a long walk would hold a walker's 31 other lanes)
+    uint32_t cor_smem;                // the launch's dynamic shared memory holds at least COR_BYTES: walks inside the CTA keep their corridor there
 };
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -320,9 +337,9 @@ __device__ __noinline__ void arena_free(const Arena& A, uint32_t pool_id, uint64
 }
 // One walk by the calling warp (all 32 lanes): rows at arena offset `o` of pool `pool_id`; the slice is returned afterwards.
 __device__ __forceinline__ void walk_and_free(const Arena& A, const Task& tk, uint64_t o, uint32_t pool_id, const uint8_t* __restrict__ seqs,
-                                              svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, int helper) {
+                                              svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, int helper, uint32_t s_cor) {
     const unsigned long long t1 = globaltimer_ns();
-    svp_traceback_warp(tk, A.base + o, reinterpret_cast<const uint2*>(A.base + o + tk.tb_bytes), seqs, results, cigar, cs);
+    if (!A.skip_walk) svp_traceback_warp<true>(tk, A.base + o, reinterpret_cast<const uint2*>(A.base + o + tk.tb_bytes), seqs, results, cigar, cs, s_cor);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
         arena_free(A, pool_id, o);
@@ -348,16 +365,23 @@ __device__ __noinline__ int walk_one_queued(const Arena& A, const uint8_t* __res
     const uint32_t task = *(volatile uint32_t*)&Q->e[h].task, pool_id = *(volatile uint32_t*)&Q->e[h].pool_id;
     const uint64_t o = *(volatile uint64_t*)&Q->e[h].arena_off;
     const Task tk = A.tasks[task];
-    walk_and_free(A, tk, o, pool_id, seqs, results, cigar, cs, helper);
+    walk_and_free(A, tk, o, pool_id, seqs, results, cigar, cs, helper, 0u);     // (a helper's shared memory holds its own pair's sequences)
     return 0;
 }
-// Start of a pair's CTA(s): warp 0 of the first CTA takes the pair's slice (lane 0 allocates) and notes it in shared memory
-// (s_slice: uint64[3] = arena offset, pool id, start time). When the pool is full the warp does not idle: it walks a queued pair
-// of the call (which frees a slice) and tries again — so the system makes progress even if the walker kernel is not resident.
-// After the caller's initial barrier every CTA of a cluster reads the offset from the first CTA's shared memory (pair_rows;
-// remote shared memory may only be touched once the cluster barrier has shown that CTA running).
+// Start of a pair's CTA(s). Wave scheduling: the slice is where the host put it. Arena / queue scheduling: warp 0 of the first CTA
+// takes the pair's slice (lane 0 allocates) and notes it in shared memory (s_slice: uint64[3] = arena offset, pool id, start
+// time). When the pool is full the warp waits — the holders are running CTAs and queued walks that do not depend on the waiter;
+// with a queue it does not idle: it walks a queued pair of the call (which frees a slice) and tries again, so the call makes
+// progress even while its walker kernel is not resident. After the caller's initial barrier every CTA of a cluster reads the
+// offset from the first CTA's shared memory (pair_rows; remote shared memory may only be touched once the cluster barrier has
+// shown that CTA running).
+template <bool WALK>
 __device__ __forceinline__ void pair_begin(const Arena& A, const Task& tk, uint32_t crank, unsigned long long* s_slice,
                                            const uint8_t* __restrict__ seqs, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs) {
+    if (!WALK || A.static_slices) {
+        if (threadIdx.x == 0 && crank == 0) { s_slice[0] = tk.tb_off; s_slice[1] = 0; s_slice[2] = 0; }
+        return;
+    }
     if (threadIdx.x < 32 && crank == 0) {
         const int lane = threadIdx.x;
         const uint32_t pool_id = A.use_global ? A.n_sm : min(smid(), A.n_sm - 1u);
@@ -384,13 +408,16 @@ __device__ __forceinline__ uint8_t* pair_rows(const Arena& A, uint32_t crank, co
     } else o = s_slice[0];
     return A.base + o;
 }
-// End of a pair: called by warp 0 of the first CTA after the barrier that follows the forward pass. The pair is queued for the
-// call's walkers (and the CTA ends, releasing its registers for the next forward pass), or — without a queue — walked right here.
+// End of a pair: called by warp 0 of the first CTA after the barrier that follows the forward pass. Wave scheduling: nothing —
+// the host launches the wave's walks. Queue scheduling: the pair is queued for the call's walkers and the CTA ends, releasing its
+// registers for the next forward pass (long pairs excepted). Arena scheduling: the warp walks the pair right here.
 __device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, uint32_t task_index, const uint8_t* __restrict__ seqs,
-                                         svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice) {
+                                         svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts& cs, const unsigned long long* s_slice,
+                                         uint32_t s_cor) {
+    if (A.static_slices) return;
     const uint64_t o = s_slice[0];
     if ((threadIdx.x & 31) == 0) atomicAdd(A.clocks + 0, globaltimer_ns() - s_slice[2]);
-    if (A.queue && !A.inline_walk) {
+    if (A.queue && !A.inline_walk && (uint32_t)tk.m + (uint32_t)tk.n <= A.walk_long) {
         if ((threadIdx.x & 31) == 0) {
             WalkQueue* Q = A.queue;
             const uint32_t slot = atomicAdd(&Q->tail, 1u);
@@ -400,16 +427,7 @@ __device__ __forceinline__ void pair_end(const Arena& A, const Task& tk, uint32_
         }
         return;
     }
-    walk_and_free(A, tk, o, (uint32_t)s_slice[1], seqs, results, cigar, cs, 0);
-}
-// The call's walkers: a few warps per SM, resident for the whole call; each takes queued pairs until the queue is drained.
-__global__ void __launch_bounds__(128)
-svp_walk_kernel(const uint8_t* __restrict__ seqs, const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
-    for (;;) {
-        const int st = walk_one_queued(ar, seqs, results, cigar, cs, 0);
-        if (st == 2) return;
-        if (st == 1) __nanosleep(2000);
-    }
+    walk_and_free(A, tk, o, (uint32_t)s_slice[1], seqs, results, cigar, cs, 0, s_cor);
 }
 
 // Shared-memory image of a sequence: one byte per base = the HIGH byte of its fp16 code (0x3C..0x3F),
@@ -577,8 +595,19 @@ constexpr int RB_CLAMP = 16000;
 // (No minimum-CTAs bound on the single-warp variants: the sliding-window KP = 8 kernel compiles to 157 registers = 12 CTAs per
 // SM, profiles/ncu_fwd_r01_v5_small.json; capping it at 128 registers / 16 CTAs per SM was measured 2 % SLOWER on configs 2
 // and 4 — the kernel is bound by the ALU pipe, not by latency hiding.)
-template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false>
-__global__ void __launch_bounds__(fwd_max_threads(KP, MULTI))
+#ifndef SVP_SINGLE_MIN_CTAS
+#define SVP_SINGLE_MIN_CTAS 1
+#endif
+// The single-warp variants of wave scheduling (WALK = false) are held to 128 registers = 16 CTAs per SM: left alone ptxas takes 110-170
+// for scheduling slack; under the bound it finds 86-120 WITHOUT a spill, i.e. 17-19 CTAs per SM.
+#ifndef SVP_WAVE_MIN_CTAS
+#define SVP_WAVE_MIN_CTAS 16
+#endif
+// WALK = false: the variant wave scheduling launches — no call to the walk anywhere in the kernel, so its register count is the forward
+// pass's own (the walk needs ~130: with it KP = 4 goes from 72 to 124 registers, KP = 5 / 6 sliding windows from 127 to 136 / 142 = 14-15
+// instead of 16 CTAs per SM)
+template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false, bool WALK = true>
+__global__ void __launch_bounds__(fwd_max_threads(KP, MULTI), MULTI ? 1 : (!WALK ? SVP_WAVE_MIN_CTAS : SVP_SINGLE_MIN_CTAS))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
     static_assert(!CL || MULTI, "cluster variants are multi-warp");
@@ -614,7 +643,7 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_cst, c_noe1, c_noe2, c_neg, c_neg);
     if (MULTI && RB && gl < nwarp + 2) sts_u32(s_wb + 4u * gl, 0u);
-    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
+    pair_begin<WALK>(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -828,7 +857,8 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     }
     // rows and best records of every warp (CTA of the cluster) are complete; no CTA leaves while a neighbour may still store into its mailbox
     step_barrier<CL>();
-    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
+    // the walk's corridor takes over the CTA's dynamic shared memory (sequence images / windows and mailboxes are dead now)
+    if (WALK && warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice, ar.cor_smem ? (uint32_t)__cvta_generic_to_shared(smem8) : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -837,8 +867,13 @@ svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 // Byte layout of the traceback rows (store_pair): row = step pair (s >> 1), s = (i + j) - r_begin; pitch = threads * slot bytes;
 // inside a row thread g = x / (4*kp) owns one slot; the byte of its diagonal x' = x - g*4kp (x = (j - i) - band_lo, parity of x' =
 // parity of s) sits at 4*k + 2*half + (x' & 1) with c = x' >> 1, half = c >= kp, k = c - half*kp. kp is a runtime value (4..8).
+// loads of traceback rows / best records: through L2 only (CG) or cached (see svp_traceback_warp's declaration)
+template <bool CG> __device__ __forceinline__ uint32_t ldrow(const uint8_t* p) { return CG ? (uint32_t)__ldcg(p) : (uint32_t)*p; }
+template <bool CG> __device__ __forceinline__ uint2 ldbest(const uint2* p) { return CG ? __ldcg(p) : *p; }
+constexpr int COR_W = 96, COR_RING = 128, COR_MARGIN = 16, COR_BYTES = COR_W * COR_RING;       // 12 KB per walking warp
+template <bool CG>
 struct TbView {
-    const uint8_t* base;      // arena + tb_off
+    const uint8_t* base;      // the pair's slice of the arena
     const uint32_t* seqs32;   // packed sequences (global)
     int band_lo, band_w, r_begin, pitch, m, n, kp, slot;
     uint32_t inv;             // ceil(2^32 / (4*kp)): x / (4*kp) = umulhi(x, inv), exact for x < 2^27
@@ -875,10 +910,72 @@ struct TbView {
     __device__ __forceinline__ const uint8_t* addr_sx(int s, int x) const { return base + (ptrdiff_t)(s >> 1) * pitch + col(x); }
     // address of the stored byte of cell (i, j) (callers make sure the cell is real and inside the band)
     __device__ __forceinline__ const uint8_t* addr(int i, int j) const { return addr_sx((i + j) - r_begin, (j - i) - band_lo); }
+    // ---- corridor (svp_traceback_warp) ---------------------------------------------------------------------------------------
+    // A walk is a chain of dependent byte loads, ~1 us each from DRAM. But it only ever moves DOWN the rows (a predecessor lies on
+    // an earlier anti-diagonal) and drifts slowly across them (one diagonal per indel), so the bytes it will need lie in a narrow
+    // corridor below the current cell. The warp keeps that corridor in shared memory: a ring of COR_RING rows x COR_W bytes (a
+    // sector-aligned window of every row around the path's column), filled 32 rows at a time with cp.async (LDGSTS, through L2,
+    // no registers) two blocks AHEAD of the walk — so a round's loads are shared-memory loads (~30 cycles) and the DRAM latency
+    // of the refills hides behind the rounds in between. A cell outside the window (the far candidates of a long gap, a neighbour
+    // beyond the window's edge, a block still in flight) is loaded from global memory as before; when the path drifts to within
+    // COR_MARGIN bytes of the window's edge the window is re-centred (one synchronous refill).
+    uint32_t s_cor;           // shared address of the ring, 0: no corridor
+    int cor_wc, cor_w;        // first byte column of the window, its width (<= COR_W)
+    int cor_lo;               // lowest 32-row block issued so far (blocks are issued downwards); cor_lo + 3 is the highest still intact
+    int cor_ready;            // lowest block known complete
+    int cor_top;              // block of the row the corridor was (re)started at
+    int n_rows;               // rows of the pair
+    int cor_row_lo; unsigned cor_row_span;   // rows [cor_row_lo, cor_row_lo + cor_row_span] are complete in the ring
+    __device__ __forceinline__ void cor_issue(int blk, int lane) {      // one block = 32 rows, lane = row, one commit group
+        const int row = blk * 32 + lane;
+        if (row < n_rows) {
+            const uint8_t* src = base + (ptrdiff_t)row * pitch + cor_wc;
+            const uint32_t dst = s_cor + (uint32_t)(row & (COR_RING - 1)) * COR_W;
+            for (int b = 0; b < cor_w; b += 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + (uint32_t)b), "l"(src + b) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // before a round at cell (i, j): the blocks of the rows this round can touch (the current one and the one below) are complete,
+    // the two below them are on their way. Warp-uniform.
+    __device__ __forceinline__ void cor_advance(int i, int j, int lane) {
+        if (!s_cor) return;
+        const int s = (i + j) - r_begin;
+        if (s < 0) return;
+        const int row = s >> 1, blk = row >> 5;
+        const int off = col((j - i) - band_lo) - cor_wc;
+        const bool recentre = cor_top < 0 || (off < COR_MARGIN && cor_wc > 0) || (off >= cor_w - COR_MARGIN && cor_wc + cor_w < pitch);
+        if (!recentre && max(blk - 1, 0) >= cor_ready && cor_lo <= max(blk - 3, 0)) return;      // nothing to do (the common case)
+        if (recentre) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const int c = col((j - i) - band_lo);
+            cor_wc = min(max((c & ~31) - 32, 0), max(pitch - COR_W, 0));
+            cor_top = blk; cor_lo = blk + 1;
+        }
+        if (cor_lo > blk + 1) cor_lo = blk + 1;                        // the walk jumped over whole blocks (a long gap)
+        while (cor_lo > max(blk - 3, 0)) cor_issue(--cor_lo, lane);
+        // complete: everything but the blocks below blk - 1 (at most two groups)
+        const int in_flight = min(max(blk - 1 - cor_lo, 0), 2);
+        if (in_flight == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (in_flight == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+        cor_ready = cor_lo + in_flight;
+        cor_row_lo = cor_ready * 32;
+        cor_row_span = (unsigned)(min(cor_top, cor_lo + 3) * 32 + 31 - cor_row_lo);
+    }
+    // stored byte at (row, byte column): from the corridor when it holds it, else from global memory
+    __device__ __forceinline__ uint32_t ld(int row, int c) const {
+        const unsigned off = (unsigned)(c - cor_wc);
+        if (off < (unsigned)cor_w && (unsigned)(row - cor_row_lo) <= cor_row_span)
+            return lds_u8(s_cor + (uint32_t)(row & (COR_RING - 1)) * COR_W + off);
+        return ldrow<CG>(base + (ptrdiff_t)row * pitch + c);
+    }
     // stored byte of H(i, j); 0 for cells before the matrix or before the first stored row (callers check the band)
     __device__ __forceinline__ uint32_t lb(int i, int j) const {
         if (i < 1 || j < 1 || (i + j) < r_begin) return 0;
-        return __ldcg(addr(i, j));
+        return ld(((i + j) - r_begin) >> 1, col((j - i) - band_lo));
     }
     // single bases (codes 0..3) at 1-based positions of the ORIENTED query / the target
     __device__ __forceinline__ int qbase(int i) const {
@@ -922,6 +1019,217 @@ __device__ __forceinline__ int gap_cost2(int o1, int e1, int o2, int e2, int two
 
 __device__ __forceinline__ int sext8(uint32_t x) { return (int)(int8_t)(x & 0xFFu); }
 
+// One THREAD per pair, 32 independent walks per warp. A walk is a chain of dependent byte loads, so what
+// matters is the number of memory round trips and keeping the 32 lanes on ONE instruction stream:
+//   * a round = every lane issues all its loads (the diagonal/left/up predecessor bytes of the next S
+//     cells along its current diagonal, or — while it searches a gap longer than one — the next NSCAN
+//     cells of its row and column), then the loaded cells are processed by straight-line predicated
+//     code without data-dependent branches;
+//   * the Z-trim start (lowest H of the walk, §3.5) is only tracked as a position; the rare walk that is
+//     actually cut is replayed up to that position (same deterministic path) to rebuild CIGAR and counts.
+template <bool CG>
+__device__ __noinline__ void svp_traceback_thread(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
+                                                  const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                                  uint32_t* __restrict__ cigar, const Consts& cs) {
+    svp_result res;
+    res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
+    res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
+    res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
+    const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
+    TbView<CG> v;
+    v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
+    v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
+    v.set_geometry(tk.band_w, KP);
+    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    v.q_mask = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
+    v.t_mask = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
+    const bool any_mask = (tk.flags & (TASK_QN | TASK_TN)) != 0;
+    const int d_hi = tk.band_lo + tk.band_w - 1;
+
+    // ---- 1. end cell: maximum over the per-thread-half records, earliest iteration ------------
+    const int n_ent = (tk.band_w / (4 * KP)) * 2;
+    int M = 0; uint32_t blk = 0xFFFFFFFFu;
+    for (int e = 0; e < n_ent; ++e) {
+        const uint2 b = ldbest<CG>(bests + e);
+        const int val = (int)b.x;
+        if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
+    }
+    if (M <= 0) {
+        res.status = SVP_ST_NOHIT;
+        results[tk.pair_index] = res;
+        return;
+    }
+    if (!(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    // every (thread, half) block that reached M in iteration blk: rebuild its 2KP x 2KP cells from the low bytes
+    int end_s = 0x7FFFFFFF, end_x = -1;
+    for (int e = 0; e < n_ent; ++e) {
+        const uint2 b = ldbest<CG>(bests + e);
+        if ((int)b.x != M || b.y != blk) continue;
+        const int xbase = (e >> 1) * 4 * KP + (e & 1) * 2 * KP;      // first diagonal (band-relative) of the half
+        const int s0 = (int)blk * 2 * KP;
+        // cells id = 0 .. 2*KP*KP-1: step s0 + id/KP, diagonal xbase + 2*(id%KP) + (step odd); chained by neighbours
+        int rel = 0, rel_row0 = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
+        uint32_t bprev = 0, b_row0 = 0;
+        for (int id = 0; id < 2 * KP * KP; ++id) {
+            const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
+            const uint32_t bb = ldrow<CG>(v.addr_sx(s, x));
+            if (id == 0) rel = 0;
+            else if (id % KP == 0) rel = rel_row0 + sext8(bb - b_row0);
+            else rel = rel + sext8(bb - bprev);
+            if (id % KP == 0) { rel_row0 = rel; b_row0 = bb; }
+            bprev = bb;
+            if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
+            else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
+        }
+        if (cand_s < end_s || (cand_s == end_s && cand_x > end_x)) { end_s = cand_s; end_x = cand_x; }
+    }
+    const int best_i = ((tk.r_begin + end_s) - (tk.band_lo + end_x)) / 2;
+    const int best_j = ((tk.r_begin + end_s) + (tk.band_lo + end_x)) / 2;
+
+    // ---- 2. walk back --------------------------------------------------------------------------
+    constexpr int S = 8, NSCAN = 6;
+    uint32_t* slot = cigar + tk.cigar_off;
+    const ptrdiff_t two_rows = (ptrdiff_t)v.pitch;            // two steps = one row (step pair)
+    const int cost1d = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1);
+    const int cost1i = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1);
+    const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
+
+    int i, j, H, wpos, low, low_i, low_j, mrun, scan_k, Hrow, Hcol;
+    uint32_t brow, bcol, n_match, n_mis, n_io, n_ib, n_do, n_db;
+    bool ovf, bad = false;
+    int stop_i = -1, stop_j = -1;            // replay target (cut walk): stop when the walk reaches this cell
+    bool cut = false; int cut_low = 0;
+
+#define SVP_PUSH(op, len) do { if (wpos > 0) { --wpos; slot[wpos] = ((uint32_t)(len) << 4) | (op); } else ovf = true; } while (0)
+
+    for (int pass = 0; pass < 2; ++pass) {
+        i = best_i; j = best_j; H = M; wpos = (int)tk.cigar_cap; ovf = false;
+        low = M + 1; low_i = i; low_j = j; mrun = 0; scan_k = 0; Hrow = Hcol = 0; brow = bcol = 0;
+        n_match = n_mis = n_io = n_ib = n_do = n_db = 0;
+        bool done = false;
+        while (!done) {
+            const int d = j - i;
+            const bool in_scan = scan_k != 0;
+            // ---------------- loads of the round, all issued before any is used -----------------
+            const bool del_band = (d - 1 >= tk.band_lo), ins_band = (d + 1 <= d_hi);
+            const uint8_t* pd = v.addr(i - 1, j - 1);            // diagonal predecessor of cell 0 (stride: 2 rows per cell)
+            const uint8_t* pl = v.addr(i, j - 1);                // left neighbour of cell 0
+            const uint8_t* pu = v.addr(i - 1, j);                // up neighbour of cell 0
+            uint32_t bd[S], bl[S], bu[S];
+            #pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const bool in_q = (i - k - 1 >= 1), in_t = (j - k - 1 >= 1);
+                // (every load is issued — from a harmless address when its cell does not exist — and masked afterwards: a load under
+                // a condition becomes a branch around a ld.global.cg, and 24 of those in a row are 24 serial round trips)
+                const bool cd = !in_scan && in_q && in_t, cl = !in_scan && i - k >= 1 && in_t && del_band, cu = !in_scan && in_q && j - k >= 1 && ins_band;
+                const uint32_t xd = ldrow<CG>(cd ? pd - k * two_rows : v.base), xl = ldrow<CG>(cl ? pl - k * two_rows : v.base), xu = ldrow<CG>(cu ? pu - k * two_rows : v.base);
+                bd[k] = cd ? xd : 0u; bl[k] = cl ? xl : 0u; bu[k] = cu ? xu : 0u;
+            }
+            uint32_t br[NSCAN], bc[NSCAN]; bool okr[NSCAN], okc[NSCAN];
+            #pragma unroll
+            for (int t = 0; t < NSCAN; ++t) {
+                const int k = scan_k + t;
+                okr[t] = in_scan && (j - k >= 1) && (d - k >= tk.band_lo);
+                okc[t] = in_scan && (i - k >= 1) && (d + k <= d_hi);
+                const uint32_t xr = ldrow<CG>(okr[t] ? v.addr(i, j - k) : v.base), xc = ldrow<CG>(okc[t] ? v.addr(i - k, j) : v.base);
+                br[t] = okr[t] ? xr : 0u; bc[t] = okc[t] ? xc : 0u;
+            }
+            const uint32_t qwin = v.qwindow(i, S), twin = v.twindow(j, S);   // 2 bits per cell along the diagonal
+            if (!in_scan && i - S - 1 >= 1 && j - S - 1 >= 1) {              // L2 prefetch for the next round
+                #pragma unroll
+                for (int k = S; k < 2 * S; k += 2) {
+                    const uint8_t* pk = pd - k * two_rows;      // the sector holding a cell's diagonal, left and up predecessors
+                    if (pk - two_rows >= v.base) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(pk - two_rows));
+                    }
+                }
+            }
+            // ---------------- gap scan (lanes in the scan state) ------------------------------------
+            if (in_scan) {
+                bool found = false, dead = false;
+                #pragma unroll
+                for (int t = 0; t < NSCAN; ++t) {
+                    const int k = scan_k + t;
+                    const int costd = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, k);
+                    const int costi = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, k);
+                    if (!found && !dead) {
+                        if (!okr[t] && !okc[t]) dead = true;
+                        if (okr[t]) {
+                            Hrow += sext8(br[t] - brow); brow = br[t];
+                            if (H == Hrow - costd) { SVP_PUSH(SVP_CIGAR_D, k); ++n_do; n_db += k; j -= k; H = Hrow; found = true; }
+                        }
+                        if (!found && okc[t]) {
+                            Hcol += sext8(bc[t] - bcol); bcol = bc[t];
+                            if (H == Hcol - costi) { SVP_PUSH(SVP_CIGAR_I, k); ++n_io; n_ib += k; i -= k; H = Hcol; found = true; }
+                        }
+                    }
+                }
+                if (found) scan_k = 0;
+                else if (dead) { bad = true; done = true; }
+                else scan_k += NSCAN;
+                continue;
+            }
+            // ---------------- H state: up to S cells along the diagonal, predicated -----------------
+            bool alive = true, gap_here = false;
+            uint32_t gl = 0, gu = 0;
+            #pragma unroll
+            for (int k = 0; k < S; ++k) {
+                // stop conditions of the current cell
+                int dd = d - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+                const bool stop = alive && (H == 0 || i < 1 || j < 1 || (i == stop_i && j == stop_j) ||
+                                            (pass == 0 && H >= low && H - low > zdrop + cs.zdrop_ext * dd));
+                if (stop) { if (pass == 0 && H != 0 && i >= 1 && j >= 1) cut = true; done = true; alive = false; }
+                if (alive && H < low) { low = H; low_i = i; low_j = j; }
+                const uint32_t qc = (qwin >> (2 * k)) & 3u, tc = (twin >> (2 * k)) & 3u;
+                const bool other = any_mask && i >= 1 && j >= 1 && (v.qn(i) || v.tn(j));       // a letter outside ACGT: lowest score, never a match
+                const bool same = !other && qc == tc;
+                const int sub = other ? cs.n_score : (int)(int8_t)((cs.tab[qc] >> (8u * tc)) & 0xFFu);
+                const int Hd = (i - 1 >= 1 && j - 1 >= 1) ? H + sext8(bd[k] - (uint32_t)H) : 0;
+                const bool isdiag = alive && (H == Hd + sub);
+                if (alive && !isdiag) { gap_here = true; gl = bl[k]; gu = bu[k]; alive = false; }
+                if (isdiag) { ++mrun; n_match += same ? 1u : 0u; n_mis += same ? 0u : 1u; --i; --j; H = Hd; }
+            }
+            if (done) continue;
+            if (gap_here) {
+                // the M run since the previous gap, then a gap of length 1 (deletion first) or the scan state
+                if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
+                const bool del_ok = (j - 1 >= 1) && del_band, ins_ok = (i - 1 >= 1) && ins_band;
+                const int Hl = H + sext8(gl - (uint32_t)H), Hu = H + sext8(gu - (uint32_t)H);
+                if (!del_ok && !ins_ok) { bad = true; done = true; }
+                else if (del_ok && H == Hl - cost1d) { SVP_PUSH(SVP_CIGAR_D, 1); ++n_do; ++n_db; --j; H = Hl; }
+                else if (ins_ok && H == Hu - cost1i) { SVP_PUSH(SVP_CIGAR_I, 1); ++n_io; ++n_ib; --i; H = Hu; }
+                else { scan_k = 2; Hrow = Hl; brow = gl; Hcol = Hu; bcol = gu; }
+            }
+        }
+        if (mrun) { SVP_PUSH(SVP_CIGAR_M, mrun); mrun = 0; }
+        if (!cut || pass == 1) break;
+        stop_i = low_i; stop_j = low_j; cut_low = low;   // replay the (deterministic) walk up to the lowest point
+    }
+#undef SVP_PUSH
+    if (bad) res.status |= SVP_ST_SCORE_OVF;
+    res.score = M - (cut ? cut_low : 0);
+    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
+    res.n_match = n_match; res.n_mismatch = n_mis; res.n_ins_ops = n_io; res.n_ins_bp = n_ib; res.n_del_ops = n_do; res.n_del_bp = n_db;
+    if (ovf) {
+        res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
+    } else {
+        res.cigar_len = tk.cigar_cap - (uint32_t)wpos;
+        res.cigar_off = tk.cigar_off + (uint32_t)wpos;
+        double dist = 0.0;
+        for (uint32_t a = (uint32_t)wpos; a < tk.cigar_cap; ++a) {
+            const uint32_t w = slot[a];
+            const uint32_t op = w & 15u, len = w >> 4;
+            if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
+                const double sz = (double)len;
+                dist += (1.0 - exp(-pow(sz / 30.0, 1.5))) * sz;
+            }
+        }
+        res.sv_dist = dist;
+    }
+    results[tk.pair_index] = res;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Traceback, run by ONE WARP right after the forward pass of its pair, inside the same CTA (warp 0 of the pair's first CTA):
 // the rows it reads are the ones this CTA (cluster) just wrote, and the pair's slice of the arena is free again as soon as the
@@ -932,36 +1240,52 @@ __device__ __forceinline__ int sext8(uint32_t x) { return (int)(int8_t)(x & 0xFF
 // All loads of rows / best records are ld.global.cg: they were written by this grid (by other SMs when the band spans a cluster),
 // and an arena slice is reused by later CTAs, so L1 must not serve them.
 // ---------------------------------------------------------------------------------------------
+// s_cor: shared address of COR_BYTES bytes (16-byte aligned) this warp may use for its corridor, or 0.
+// LPP = lanes per pair: 32 = the whole warp walks one pair. A diagonal run between two indels is ~7 cells long on ONT-like reads
+// (13 % indel columns between two reads), so a round of a whole warp uses a quarter of its lanes, and the walk is bound by its
+// instruction count (~450 000 warp instructions per pair of 8 kb reads, profiles/ncu_tbw_r02.json), not by memory latency. With
+// LPP = 8 / 16 a warp walks 4 / 2 pairs at once, one per group of LPP lanes: every cross-lane operation stays inside the group
+// (shuffles with width LPP, ballots and reductions on the group's mask), so groups may diverge freely; `lane` below is the lane
+// inside the group. No corridor unless LPP = 32.
+template <bool CG, int LPP>
 __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* __restrict__ rows, const uint2* __restrict__ bests,
                                                 const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
-                                                uint32_t* __restrict__ cigar, const Consts& cs) {
-    const int lane = threadIdx.x & 31;
+                                                uint32_t* __restrict__ cigar, const Consts& cs, uint32_t s_cor) {
+    static_assert(LPP == 8 || LPP == 16 || LPP == 32, "lanes per pair");
+    const int lane = threadIdx.x & (LPP - 1);
+    const unsigned gsh = (unsigned)(threadIdx.x & 31 & ~(LPP - 1));
+    constexpr unsigned GM = LPP == 32 ? 0xffffffffu : ((1u << (LPP & 31)) - 1u);
+    const unsigned gmask = GM << gsh;
+    auto gballot = [&](bool p) -> unsigned { return (__ballot_sync(gmask, p) >> gsh) & GM; };
     svp_result res;
     res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
     res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
     res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
-    TbView v;
+    TbView<CG> v;
     v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
     v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
     v.set_geometry(tk.band_w, KP);
     v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
     v.q_mask = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
     v.t_mask = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
+    v.s_cor = s_cor; v.cor_wc = 0; v.cor_w = s_cor ? min(COR_W, v.pitch) : 0; v.cor_lo = 0; v.cor_ready = 0x7FFFFFF0; v.cor_top = -1;
+    v.cor_row_lo = 0; v.cor_row_span = 0;
+    v.n_rows = (int)(tk.tb_bytes / (uint64_t)v.pitch);
     const int d_hi = tk.band_lo + tk.band_w - 1;
 
     // ---- 1. end cell ---------------------------------------------------------------------------
     const int n_ent = (tk.band_w / (4 * KP)) * 2;
     int M = 0; uint32_t blk = 0xFFFFFFFFu;
-    for (int e = lane; e < n_ent; e += 32) {
-        const uint2 b = __ldcg(bests + e);
+    for (int e = lane; e < n_ent; e += LPP) {
+        const uint2 b = ldbest<CG>(bests + e);
         const int val = (int)b.x;
         if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
     }
     #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const int M2 = __shfl_xor_sync(0xffffffffu, M, o);
-        const uint32_t b2 = __shfl_xor_sync(0xffffffffu, blk, o);
+    for (int o = LPP / 2; o; o >>= 1) {
+        const int M2 = __shfl_xor_sync(gmask, M, o, LPP);
+        const uint32_t b2 = __shfl_xor_sync(gmask, blk, o, LPP);
         if (M2 > M || (M2 == M && b2 < blk)) { M = M2; blk = b2; }
     }
     if (M <= 0) {
@@ -972,27 +1296,27 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
     if (!(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
     int end_s = 0x7FFFFFFF, end_x = -1;
     const int NC = 2 * KP * KP;
-    for (int e0 = 0; e0 < n_ent; e0 += 32) {
+    for (int e0 = 0; e0 < n_ent; e0 += LPP) {
         const int e = e0 + lane;
         bool hit = false;
-        if (e < n_ent) { const uint2 b = __ldcg(bests + e); hit = ((int)b.x == M) && (b.y == blk); }
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (e < n_ent) { const uint2 b = ldbest<CG>(bests + e); hit = ((int)b.x == M) && (b.y == blk); }
+        unsigned mask = gballot(hit);
         while (mask) {
             const int ee = e0 + __ffs(mask) - 1; mask &= mask - 1;
             const int xbase = (ee >> 1) * 4 * KP + (ee & 1) * 2 * KP;     // first diagonal (band-relative) of the half
             const int s0 = (int)blk * 2 * KP;
             int rel_row0 = 0, rel = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
             uint32_t b_row0 = 0, bprev = 0;
-            for (int c0 = 0; c0 < NC; c0 += 32) {             // bytes fetched 32 at a time, chained by all lanes in lockstep
+            for (int c0 = 0; c0 < NC; c0 += LPP) {            // bytes fetched LPP at a time, chained by all lanes in lockstep
                 const int idx = c0 + lane;
                 uint32_t mine = 0;
                 if (idx < NC) {
                     const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
-                    mine = __ldcg(v.addr_sx(s, x));
+                    mine = ldrow<CG>(v.addr_sx(s, x));
                 }
-                const int lim = min(32, NC - c0);
+                const int lim = min(LPP, NC - c0);
                 for (int l = 0; l < lim; ++l) {
-                    const uint32_t b = __shfl_sync(0xffffffffu, mine, l);
+                    const uint32_t b = __shfl_sync(gmask, mine, l, LPP);
                     const int id = c0 + l;
                     if (id == 0) rel = 0;
                     else if (id % KP == 0) rel = rel_row0 + sext8(b - b_row0);
@@ -1025,23 +1349,41 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
 #define SVP_EMITW(op, len) do { if (cur_len && cur_op == (op)) cur_len += (len); else { SVP_PUSHW(); cur_op = (op); cur_len = (len); } } while (0)
 
 
+    // loop invariants in registers (tk and cs sit behind references: local / constant memory)
+    const int band_lo = tk.band_lo, r_begin = tk.r_begin;
+    const bool simple = cs.general == 0;                     // one match and one mismatch score (a letter outside ACGT scores the mismatch)
+    const int s_match = cs.s_match, s_mismatch = cs.s_mismatch, n_score = cs.n_score, zd_ext = cs.zdrop_ext;
+    const uint32_t tab0 = cs.tab[0], tab1 = cs.tab[1], tab2 = cs.tab[2], tab3 = cs.tab[3];
+    const int cost1d = gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1);
+    const int cost1i = gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1);
+    const unsigned lt_mask = (1u << lane) - 1u;
     bool done = false;
     while (!done) {
         // ---- diagonal run: lane l holds the diagonal predecessor byte and the bases of cell (i-l, j-l) ----
+        if (LPP == 32) v.cor_advance(i, j, lane);
         const int ci = i - lane, cj = j - lane;
         const int d0 = j - i;
-        const bool del_band = d0 - 1 >= tk.band_lo, ins_band = d0 + 1 <= d_hi;
-        uint32_t bp = 0, bl = 0, bu = 0; int sub_l = 0, same_l = 0;
-        if (ci >= 1 && cj >= 1) {
-            bp = v.lb(ci - 1, cj - 1);
-            if (del_band) bl = v.lb(ci, cj - 1);          // left / up neighbours: a 1-base gap is resolved from this round's loads
-            if (ins_band) bu = v.lb(ci - 1, cj);
+        const bool del_band = d0 - 1 >= band_lo, ins_band = d0 + 1 <= d_hi;
+        const bool inb = ci >= 1 && cj >= 1;
+        // The cells of a diagonal keep their byte column; their rows go down by one per cell. Columns once per round:
+        const int x0 = d0 - band_lo;
+        const int c0 = v.col(x0), cL = del_band ? v.col(x0 - 1) : 0, cU = ins_band ? v.col(x0 + 1) : 0;
+        const int sd = (i + j) - r_begin - 2 * lane - 2;     // step of the lane's diagonal predecessor; its left / up neighbours: sd + 1
+        uint32_t bp = 0, bl = 0, bu = 0; int sub_l = 0; bool same_l = false;
+        if (inb) {
+            if (ci >= 2 && cj >= 2 && sd >= 0) bp = v.ld(sd >> 1, c0);
+            if (del_band && cj >= 2 && sd + 1 >= 0) bl = v.ld((sd + 1) >> 1, cL);          // left / up neighbours: a 1-base gap is resolved from this round's loads
+            if (ins_band && ci >= 2 && sd + 1 >= 0) bu = v.ld((sd + 1) >> 1, cU);
             const int qc = v.qbase(ci), tc = v.tbase(cj);
             const bool other = v.qn(ci) || v.tn(cj);              // a letter outside ACGT: lowest score, never a match
             same_l = !other && qc == tc;
-            sub_l = other ? cs.n_score : (int)(int8_t)((cs.tab[qc] >> (8 * tc)) & 0xFFu);
+            if (simple) sub_l = same_l ? s_match : s_mismatch;
+            else {
+                const uint32_t trow = qc < 2 ? (qc == 0 ? tab0 : tab1) : (qc == 2 ? tab2 : tab3);
+                sub_l = other ? n_score : (int)(int8_t)((trow >> (8 * tc)) & 0xFFu);
+            }
         }
-        if (ci - 33 >= 1 && cj - 33 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - 33, cj - 33)));   // next round's byte
+        if (!s_cor && ci - LPP - 1 >= 1 && cj - LPP - 1 >= 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.addr(ci - LPP - 1, cj - LPP - 1)));   // next round's byte
         // ---- the run is resolved by all lanes at once: lane l assumes cells 0..l-1 were diagonal moves, so its H is the
         // incoming H minus the substitution scores before it (prefix sum); the first lane that stops (H = 0, matrix edge,
         // Z-drop) or does not continue diagonally ends the run. The lowest-H snapshot (strict minimum, first occurrence)
@@ -1049,28 +1391,41 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
         bool gap = false;
         int l_gap = 0;
         {
-            int incl = sub_l, cnt_same = 0;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const int Hl = H - (incl - sub_l);
-            int pmin = Hl;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pmin, o); if (lane >= o) pmin = min(pmin, v); }
-            const bool inb = ci >= 1 && cj >= 1;
+            const unsigned sameb = gballot(same_l);
+            int Hl, cnt_same = 0;
+            if (simple) {
+                // two score values: the prefix sum is a population count (lanes behind the first cell outside the matrix get a
+                // wrong value; the run ends at that cell or before it, and nothing behind the end of the run is used)
+                const int ns = __popc(sameb & lt_mask);
+                Hl = H - (ns * s_match + (lane - ns) * s_mismatch);
+            } else {
+                int incl = sub_l;
+                #pragma unroll
+                for (int o = 1; o < LPP; o <<= 1) { const int t = __shfl_up_sync(gmask, incl, o, LPP); if (lane >= o) incl += t; }
+                Hl = H - (incl - sub_l);
+            }
             const bool stop2 = (Hl == 0) || !inb;
-            int dd = d0 - (low_j - low_i); dd = dd < 0 ? -dd : dd;
-            if (pmin < low) dd = 0;                                   // the snapshot moved onto this diagonal at or before this cell
-            const bool stop3 = Hl - min(low, pmin) > zdrop + cs.zdrop_ext * dd;
-            const int Hd = (ci - 1 >= 1 && cj - 1 >= 1) ? Hl + sext8(bp - (uint32_t)Hl) : 0;
+            // Z-drop: Hl - min(low, prefix minimum) > zdrop + ... needs the prefix minimum only if some lane can exceed zdrop at all
+            bool stop3 = false, have_pmin = false;
+            int pmin = Hl;
+            if (__reduce_max_sync(gmask, Hl) - min(low, __reduce_min_sync(gmask, Hl)) > zdrop) {
+                #pragma unroll
+                for (int o = 1; o < LPP; o <<= 1) { const int t = __shfl_up_sync(gmask, pmin, o, LPP); if (lane >= o) pmin = min(pmin, t); }
+                int dd = d0 - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+                if (pmin < low) dd = 0;                                   // the snapshot moved onto this diagonal at or before this cell
+                stop3 = Hl - min(low, pmin) > zdrop + zd_ext * dd;
+                have_pmin = true;
+            }
+            const int Hd = (ci >= 2 && cj >= 2) ? Hl + sext8(bp - (uint32_t)Hl) : 0;
             const bool isdiag = inb && (Hl == Hd + sub_l);
-            const unsigned term = __ballot_sync(0xffffffffu, stop2 || stop3 || !isdiag);
-            const unsigned sameb = __ballot_sync(0xffffffffu, same_l != 0);
-            const int first = term ? __ffs(term) - 1 : 32;
-            const int K = first < 31 ? first : 31;
-            const int runmin = __shfl_sync(0xffffffffu, pmin, K);
+            const unsigned stopb = gballot(stop2 || stop3);
+            const unsigned term = stopb | gballot(!isdiag);
+            const int first = term ? __ffs(term) - 1 : LPP;
+            const int K = first < LPP - 1 ? first : LPP - 1;
+            const int runmin = have_pmin ? __shfl_sync(gmask, pmin, K, LPP) : __reduce_min_sync(gmask, lane <= K ? Hl : 0x7FFFFFFF);
             if (runmin < low) {                                       // snapshot at the first cell of the run that reaches the new minimum
                 const unsigned upto = K == 31 ? 0xffffffffu : ((2u << K) - 1u);
-                const int ks = __ffs(__ballot_sync(0xffffffffu, Hl == runmin) & upto) - 1;
+                const int ks = __ffs(gballot(Hl == runmin) & upto) - 1;
                 low = runmin; low_i = i - ks; low_j = j - ks;
                 low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf;
                 if (ks > 0) {                                         // CIGAR state after ks more M's
@@ -1081,25 +1436,25 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
                 l_match = n_match + (uint32_t)cnt_same; l_mis = n_mis + (uint32_t)(ks - cnt_same);
                 l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db;
             }
-            const int Hnext = first < 32 ? __shfl_sync(0xffffffffu, Hl, K) : __shfl_sync(0xffffffffu, Hl - sub_l, 31);
-            const bool fin = __shfl_sync(0xffffffffu, stop2 || stop3, K) && first < 32;
+            const int Hnext = __shfl_sync(gmask, first < LPP ? Hl : Hl - sub_l, K, LPP);
+            const bool fin = first < LPP && ((stopb >> K) & 1u);
             if (first > 0) {
                 SVP_EMITW(SVP_CIGAR_M, (uint32_t)first);
-                cnt_same = __popc(sameb & (first == 32 ? 0xffffffffu : ((1u << first) - 1u)));
+                cnt_same = __popc(sameb & (first >= 32 ? 0xffffffffu : ((1u << first) - 1u)));
                 n_match += (uint32_t)cnt_same; n_mis += (uint32_t)(first - cnt_same);
                 i -= first; j -= first; H = Hnext;
             }
             if (fin) done = true;
-            else if (first < 32) { gap = true; l_gap = first; }
+            else if (first < LPP) { gap = true; l_gap = first; }
         }
         if (done || !gap) continue;
         {   // 1-base gap at the cell the run stopped at (deletion first, as in the search below)
-            const uint32_t b1 = __shfl_sync(0xffffffffu, bl, l_gap), b2 = __shfl_sync(0xffffffffu, bu, l_gap);
+            const uint32_t b1 = __shfl_sync(gmask, bl, l_gap, LPP), b2 = __shfl_sync(gmask, bu, l_gap, LPP);
             const int Hl = H + sext8(b1 - (uint32_t)H), Hu = H + sext8(b2 - (uint32_t)H);
-            if (del_band && j - 1 >= 1 && H == Hl - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, 1)) {
+            if (del_band && j - 1 >= 1 && H == Hl - cost1d) {
                 SVP_EMITW(SVP_CIGAR_D, 1u); ++n_do; ++n_db; --j; H = Hl; continue;
             }
-            if (ins_band && i - 1 >= 1 && H == Hu - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, 1)) {
+            if (ins_band && i - 1 >= 1 && H == Hu - cost1i) {
                 SVP_EMITW(SVP_CIGAR_I, 1u); ++n_io; ++n_ib; --i; H = Hu; continue;
             }
         }
@@ -1107,46 +1462,48 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
         // 32 candidates of the row and of the column per round, resolved by all lanes at once: lane l holds candidate k0 + l + 1,
         // its H is the carried H plus the prefix sum of the byte differences along the row / column (5 SHFL.UP each), one ballot
         // per gap kind finds the first lane whose H explains the gap (the sequential search cost ~15 instructions per candidate).
+        if (LPP == 32) v.cor_advance(i, j, lane);
         const int d = j - i;
         int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
         bool found = false, dead = false;
-        for (int k0 = 0; !found && !dead; k0 += 32) {
+        for (int k0 = 0; !found && !dead; k0 += LPP) {
             const int kk = k0 + lane + 1;
             const bool del_ok = (j - kk >= 1) && (d - kk >= tk.band_lo);      // both are true for a prefix of the candidates only
             const bool ins_ok = (i - kk >= 1) && (d + kk <= d_hi);
             const uint32_t bd = del_ok ? v.lb(i, j - kk) : 0;
             const uint32_t bi = ins_ok ? v.lb(i - kk, j) : 0;
-            uint32_t pd = __shfl_up_sync(0xffffffffu, bd, 1), pi = __shfl_up_sync(0xffffffffu, bi, 1);
+            uint32_t pd = __shfl_up_sync(gmask, bd, 1, LPP), pi = __shfl_up_sync(gmask, bi, 1, LPP);
             if (lane == 0) { pd = brow; pi = bcol; }
             int dr = del_ok ? sext8(bd - pd) : 0, dc = ins_ok ? sext8(bi - pi) : 0;
             #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int tr = __shfl_up_sync(0xffffffffu, dr, o), tc = __shfl_up_sync(0xffffffffu, dc, o);
+            for (int o = 1; o < LPP; o <<= 1) {
+                const int tr = __shfl_up_sync(gmask, dr, o, LPP), tc = __shfl_up_sync(gmask, dc, o, LPP);
                 if (lane >= o) { dr += tr; dc += tc; }
             }
             const int hr = Hrow + dr, hc = Hcol + dc;
-            const unsigned md = __ballot_sync(0xffffffffu, del_ok && H == hr - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, kk));
-            const unsigned mi = __ballot_sync(0xffffffffu, ins_ok && H == hc - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, kk));
-            const unsigned mx = __ballot_sync(0xffffffffu, !del_ok && !ins_ok);
-            const int fd = md ? __ffs(md) - 1 : 32, fi = mi ? __ffs(mi) - 1 : 32, fx = mx ? __ffs(mx) - 1 : 32;
+            const unsigned md = gballot(del_ok && H == hr - gap_cost2(cs.d_open1, cs.d_ext1, cs.d_open2, cs.d_ext2, cs.two_piece, kk));
+            const unsigned mi = gballot(ins_ok && H == hc - gap_cost2(cs.i_open1, cs.i_ext1, cs.i_open2, cs.i_ext2, cs.two_piece, kk));
+            const unsigned mx = gballot(!del_ok && !ins_ok);
+            const int fd = md ? __ffs(md) - 1 : LPP, fi = mi ? __ffs(mi) - 1 : LPP, fx = mx ? __ffs(mx) - 1 : LPP;
             if (min(fd, fi) < fx) {                       // at equal length the deletion comes first
                 found = true;
                 if (fd <= fi) {
                     const int len = k0 + fd + 1;
-                    SVP_EMITW(SVP_CIGAR_D, (uint32_t)len); ++n_do; n_db += len; j -= len; H = __shfl_sync(0xffffffffu, hr, fd);
+                    SVP_EMITW(SVP_CIGAR_D, (uint32_t)len); ++n_do; n_db += len; j -= len; H = __shfl_sync(gmask, hr, fd, LPP);
                 } else {
                     const int len = k0 + fi + 1;
-                    SVP_EMITW(SVP_CIGAR_I, (uint32_t)len); ++n_io; n_ib += len; i -= len; H = __shfl_sync(0xffffffffu, hc, fi);
+                    SVP_EMITW(SVP_CIGAR_I, (uint32_t)len); ++n_io; n_ib += len; i -= len; H = __shfl_sync(gmask, hc, fi, LPP);
                 }
-            } else if (fx < 32) {
+            } else if (fx < LPP) {
                 dead = true;
             } else {
-                Hrow = __shfl_sync(0xffffffffu, hr, 31); Hcol = __shfl_sync(0xffffffffu, hc, 31);
-                brow = __shfl_sync(0xffffffffu, bd, 31); bcol = __shfl_sync(0xffffffffu, bi, 31);
+                Hrow = __shfl_sync(gmask, hr, LPP - 1, LPP); Hcol = __shfl_sync(gmask, hc, LPP - 1, LPP);
+                brow = __shfl_sync(gmask, bd, LPP - 1, LPP); bcol = __shfl_sync(gmask, bi, LPP - 1, LPP);
             }
         }
         if (!found) { bad = true; done = true; }
     }
+    if (s_cor) { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(gmask); }
     // the alignment starts at the lowest point of the walk
     const int cut_low = low;
     i = low_i; j = low_j; wpos = low_wpos; cur_op = low_op; cur_len = low_len; ovf = low_ovf;
@@ -1157,7 +1514,7 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
     res.score = M - cut_low;
     res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
     res.n_match = l_match; res.n_mismatch = l_mis; res.n_ins_ops = l_io; res.n_ins_bp = l_ib; res.n_del_ops = l_do; res.n_del_bp = l_db;
-    __syncwarp();
+    __syncwarp(gmask);
     if (lane == 0) {
         if (ovf) {
             res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0;
@@ -1177,6 +1534,101 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
         }
         results[tk.pair_index] = res;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wave scheduling: the walks of a wave as kernels of their own, launched by the host behind the wave's forward kernels. The rows
+// were written by earlier kernels, so plain (L1-cached) loads are legal here.
+//   svp_tb_kernel    one THREAD per pair: the bulk walker — 32 walks per warp on one instruction stream, ~1 % of the forward
+//                    pass's issue slots; latency ~10 ms per wave, hidden under the next wave's forward pass
+//   svp_tbw_kernel   one WARP per pair: a thirty-second of the throughput, a quarter of the latency — small waves, long pairs,
+//                    the last wave of a blocking call
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+svp_tb_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+              const uint8_t* __restrict__ arena, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_tasks) return;
+    const Task tk = tasks[order ? order[tid] : (uint32_t)tid];
+    svp_traceback_thread<false>(tk, arena + tk.tb_off, reinterpret_cast<const uint2*>(arena + tk.tb_off + tk.tb_bytes), seqs, results, cigar, cs);
+}
+__global__ void __launch_bounds__(128)
+svp_tbw_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+               const uint8_t* __restrict__ arena, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs, const int cor) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= n_tasks) return;
+    const Task tk = tasks[order ? order[wid] : (uint32_t)wid];
+    extern __shared__ __align__(16) uint8_t cor_smem[];           // COR_BYTES per warp (or none: cor = 0)
+    svp_traceback_warp<false>(tk, arena + tk.tb_off, reinterpret_cast<const uint2*>(arena + tk.tb_off + tk.tb_bytes), seqs, results, cigar, cs,
+                              cor ? (uint32_t)__cvta_generic_to_shared(cor_smem) + (threadIdx.x >> 5) * (uint32_t)COR_BYTES : 0u);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Queue scheduling: the call's walkers. One warp per CTA, a few CTAs per SM, resident for the whole call. A walker takes up to 32
+// consecutive published entries off the queue and walks them one per LANE (svp_traceback_thread: 32 walks on one instruction
+// stream). A walk is a chain of dependent loads — 2-4 ms for a pair of 8 kb reads whatever runs it — so what a walker costs the
+// forward passes it shares its SM with is its registers (one warp of ~5 k registers walks 8-10 pairs per millisecond; config 2
+// produces 2 pairs per millisecond and SM), not issue slots. The rows were written by concurrently running grids: loads
+// through L2 (CG). A partial batch waits up to `wait_ns` for more entries.
+// ---------------------------------------------------------------------------------------------
+template <int MIN_CTAS>                                  // 1: as many registers as the walk likes (168); 16: at most 128 (one forward CTA's worth)
+__global__ void __launch_bounds__(32, MIN_CTAS)
+svp_walkq_kernel(const uint8_t* __restrict__ seqs, const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs,
+                 const uint32_t wait_ns) {
+    WalkQueue* Q = ar.queue;
+    const int lane = threadIdx.x;
+    const uint32_t n = Q->n;
+    unsigned long long t_first = 0;
+    for (;;) {
+        uint32_t h = 0;
+        if (lane == 0) h = *(volatile uint32_t*)&Q->head;
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h >= n) return;
+        const bool ready = (h + (uint32_t)lane < n) && *(volatile uint32_t*)&Q->e[h + lane].task != WALK_EMPTY;
+        const unsigned m = __ballot_sync(0xffffffffu, ready);
+        const int cnt = m == 0xffffffffu ? 32 : __ffs(~m) - 1;                // published entries in a row from the head
+        const int want = (int)min(32u, n - h);
+        if (cnt == 0) { t_first = 0; __nanosleep(2000); continue; }
+        if (cnt < want) {
+            unsigned long long now = globaltimer_ns();
+            now = __shfl_sync(0xffffffffu, now, 0);
+            if (!t_first) t_first = now;
+            if (now - t_first < (unsigned long long)wait_ns) { __nanosleep(1000); continue; }
+        }
+        t_first = 0;
+        int ok = 0;
+        if (lane == 0) ok = atomicCAS(&Q->head, h, h + (uint32_t)cnt) == h;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        __threadfence();
+        const unsigned long long t0 = globaltimer_ns();
+        if (lane < cnt) {
+            const uint32_t task = *(volatile uint32_t*)&Q->e[h + lane].task, pool_id = *(volatile uint32_t*)&Q->e[h + lane].pool_id;
+            const uint64_t o = *(volatile uint64_t*)&Q->e[h + lane].arena_off;
+            const Task tk = ar.tasks[task];
+            if (!ar.skip_walk) svp_traceback_thread<true>(tk, ar.base + o, reinterpret_cast<const uint2*>(ar.base + o + tk.tb_bytes), seqs, results, cigar, cs);
+        }
+        __syncwarp();
+        for (int l = 0; l < cnt; ++l) {                        // slices back to their pools, one lane at a time (the pools' spin locks)
+            if (lane == l) arena_free(ar, *(volatile uint32_t*)&Q->e[h + l].pool_id, *(volatile uint64_t*)&Q->e[h + l].arena_off);
+            __syncwarp();
+        }
+        if (lane == 0) { atomicAdd(ar.clocks + 4, globaltimer_ns() - t0); atomicAdd(ar.clocks + 5, 1ull); atomicAdd(ar.clocks + 2, (unsigned long long)cnt); }
+    }
+}
+
+
+//   svp_tbg_kernel   LPP lanes per pair, 32 / LPP pairs per warp (svp_traceback_warp): the instruction count per pair of the warp
+//                    walk divided by the pairs that share a warp's instruction stream
+template <int LPP>
+__global__ void __launch_bounds__(128)
+svp_tbg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+               const uint8_t* __restrict__ arena, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+    const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPP);
+    if (gid >= n_tasks) return;                    // (every cross-lane operation of the walk names its own group only)
+    const Task tk = tasks[order ? order[gid] : (uint32_t)gid];
+    svp_traceback_warp<false, LPP>(tk, arena + tk.tb_off, reinterpret_cast<const uint2*>(arena + tk.tb_off + tk.tb_bytes), seqs, results, cigar, cs, 0u);
 }
 
 }  // namespace svp

@@ -91,7 +91,7 @@ __device__ __forceinline__ void stage_sequences_gen(const Task& tk, const uint8_
 // ---------------------------------------------------------------------------------------------
 // forward DP, s16x2 lanes, general scoring (KP = 4 geometry)
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool TWO, bool CL = false>
+template <bool MULTI, bool TWO, bool CL = false, bool WALK = true>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                 const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
@@ -124,7 +124,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
     if (MULTI && gl <= nwarp) { sts_v4(s_mb + MB_A + 16u * gl, 0u, 0u, c_neg, c_neg); sts_v4(s_mb + MB_B + 16u * gl, 0u, 0u, c_neg, c_neg);
                                 step_link_init<CL>(s_mb, gl); }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, c_neg, c_neg);
-    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
+    pair_begin<WALK>(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -269,7 +269,7 @@ svp_fwdg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ ord
         bests[2 * g + 1] = make_uint2((uint32_t)(int)(int16_t)(best >> 16), blk_hi);
     }
     step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
-    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
+    if (WALK && warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice, ar.cor_smem ? (uint32_t)__cvta_generic_to_shared(smem8) : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -308,7 +308,7 @@ __device__ __forceinline__ void ring_fill(const Task& tk, const uint8_t* __restr
 // 2K = 16 diagonals = the geometry of the s16 kernels with KP = 4, and the row bytes are written in their byte
 // order. One loop iteration is 2K = 16 steps = two end-cell blocks of 2*KP = 8 steps.
 // ---------------------------------------------------------------------------------------------
-template <bool MULTI, bool TWO, bool GEN, bool CL = false, bool RING = false>
+template <bool MULTI, bool TWO, bool GEN, bool CL = false, bool RING = false, bool WALK = true>
 __global__ void __launch_bounds__(MULTI ? 512 : 32)
 svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                  const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
@@ -356,7 +356,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         step_link_init<CL>(s_mb, gl);
     }
     if (MULTI && gl == 0) sts_v4(s_mb + MB_CST, 0u, 0u, (uint32_t)c_neg, (uint32_t)c_neg);
-    pair_begin(ar, tk, crank, s_slice, seqs, results, cigar, cs);
+    pair_begin<WALK>(ar, tk, crank, s_slice, seqs, results, cigar, cs);
     step_barrier<CL>();
     uint8_t* const rows = pair_rows<CL>(ar, crank, s_slice);
     uint2* const bests = reinterpret_cast<uint2*>(rows + tk.tb_bytes);
@@ -490,7 +490,7 @@ svp_fwd32_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ or
         bests[2 * g + 1] = make_uint2((uint32_t)best_hi, blk_hi);
     }
     step_barrier<CL>();                        // rows and best records complete; no CTA leaves while a neighbour may still store into its mailbox
-    if (warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice);
+    if (WALK && warp == 0 && crank == 0) pair_end(ar, tk, task_index, seqs, results, cigar, cs, s_slice, ar.cor_smem ? (uint32_t)__cvta_generic_to_shared(smem8) : 0u);
 }
 
 }  // namespace svp

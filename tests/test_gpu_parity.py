@@ -536,15 +536,18 @@ def test_latency_plan_small_calls(oracle, monkeypatch):
         run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
 
 
-@pytest.mark.parametrize("arena_mb,streams,fused", [(24, "1", "0"), (24, "8", "0"), (160, "8", "0"), (24, "8", "1"), (12, "8", "0")])
-def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams, fused):
-    """A small arena: the slices of short pairs come from the per-SM pools, the long pairs' from the global pool, and most CTAs
-    have to wait for a slice — while they wait they walk queued pairs themselves (pair_begin), so the call ends even where the
-    arena holds fewer pairs than the GPU has CTA slots. Results do not depend on who waited or walked, on the number of launch
-    streams, or on whether pairs are queued for the walker kernel or walked inside their own CTA (SVP_FUSED_WALK)."""
+@pytest.mark.parametrize("arena_mb,streams,mode", [(24, "1", "queue"), (24, "8", "queue"), (160, "8", "queue"), (24, "8", "arena"), (12, "8", "queue"),
+                                                   (24, "4", "waves"), (12, "4", "waves"), (160, "4", "waves")])
+def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams, mode):
+    """A small arena under the three schedulers (SVP_MODE). queue / arena: the slices of short pairs come from the
+    per-SM pools, the long pairs' from the global pool, and most CTAs have to wait for a slice — with a queue they walk queued pairs
+    themselves while they wait (pair_begin), so the call ends even where the arena holds fewer pairs than the GPU has CTA slots.
+    waves: many small waves, whole-arena waves where a pair exceeds half the arena. Results do not depend on who waited or walked
+    (a lane of the walker kernel, a waiting CTA's warp, the pair's own CTA, a bulk kernel) or on the number of launch streams."""
     from svirlpool_b200.aligner import Aligner
     monkeypatch.setenv("SVP_FWD_STREAMS", streams)
-    monkeypatch.setenv("SVP_FUSED_WALK", fused)
+    monkeypatch.setenv("SVP_MODE", mode)
+    monkeypatch.setenv("SVP_QUEUE_MIN_PAIRS", "0")                    # queue even this small call
     rng = np.random.default_rng(92)
     names, seqs, specs = noisy_batch(rng, 48, 2200, 512)
     n2, s2, p2 = noisy_batch(rng, 3, 14000, 544)                      # long pairs: slices beyond a per-SM region
@@ -554,7 +557,26 @@ def test_arena_pressure_and_stream_counts(oracle, monkeypatch, arena_mb, streams
     with Aligner(device=0, preset="map-ont", tb_bytes=arena_mb << 20) as g:
         for _ in range(2):
             run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
-        assert g.stats()["waves"] >= 2                                 # launch groups
+        assert g.stats()["waves"] >= 1                                 # launch groups / waves
+
+
+@pytest.mark.parametrize("mode", ["queue", "arena", "waves"])
+def test_schedulers_on_a_mixed_batch(oracle, monkeypatch, mode):
+    """The three schedulers on one batch that mixes many short pairs (queued: one walk per lane of the walker kernel), multi-warp
+    bands and a few long pairs (walked inside their own CTA), with the default arena."""
+    from svirlpool_b200.aligner import Aligner
+    monkeypatch.setenv("SVP_MODE", mode)
+    monkeypatch.setenv("SVP_QUEUE_MIN_PAIRS", "64")
+    rng = np.random.default_rng(93)
+    names, seqs, specs = noisy_batch(rng, 150, 1500, 384)
+    for n_pairs, length, band in ((40, 2500, 640), (12, 3000, 1536), (3, 13000, 768)):
+        _n, s2, p2 = noisy_batch(rng, n_pairs, length, band)
+        off = len(seqs)
+        seqs += s2
+        specs += [(q + off, t + off, lo, w, fl) for q, t, lo, w, fl in p2]
+    with Aligner(device=0, preset="map-ont") as g:
+        run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
+        run_both(g, oracle, [f"r{k}" for k in range(len(seqs))], seqs, specs)
 
 
 def test_pair_beyond_the_arena_is_an_error():
@@ -742,4 +764,4 @@ def test_reads_with_letters_outside_acgt(oracle, monkeypatch, variant):
     n_pairs = len(specs) - 4
     assert (gres["status"][:n_pairs] == 0).all() and gres["score"][:n_pairs].min() > 1000
     assert gres["status"][n_pairs] == 1 and gres["status"][n_pairs + 1] == 1                # nothing aligns to an N run, not even itself
-    assert gres["n_mismatch"][n_pairs + 2] >= 80 or gres["n_ins_bp"][n_pairs + 2] + gres["n_del_bp"][n_pairs + 2] > 0
+    assert gres["n_match"][n_pairs + 2] <= 240 and gres["n_match"][n_pairs + 3] <= 240       # the 80 masked bases never count as matches
