@@ -31,18 +31,26 @@ constexpr int S16_SCORE_LIMIT = 32000;
 static inline int max_warps_of(int kp) { return kp <= 8 ? 16 : 8; }
 // warp-instructions per step of the inner loop (SASS counts), used only to rank variants
 static inline int step_cost(int kp, int nwarp) { return 22 + kp * 25 / 2 + (nwarp > 1 ? 10 : 0); }
-static int g_kp_mask = -1;          // tuning aid: env SVP_KP_MASK, bit (KP - 4) allows that KP (default: all)
 // latency = true (a call of few pairs, e.g. one container: the GPU is not full): the variant with the shortest step, i.e. more,
-// narrower warps per pair, instead of the one with the fewest issue slots
-static inline int choose_kp(uint32_t band_w, bool latency, bool two_piece) {
-    if (g_kp_mask < 0) { const char* e = getenv("SVP_KP_MASK"); g_kp_mask = e ? atoi(e) : 31; if (!(g_kp_mask & 31)) g_kp_mask = 31; }
+// narrower warps per pair, instead of the one with the fewest issue slots.
+// kp_mask (env SVP_KP_MASK, tuning / test aid): bit (KP - 4) allows that KP; kp_multi (env SVP_KP_MULTI): KP = 5 / 6 / 7 on multi-warp CTAs too
+static inline int choose_kp(uint32_t band_w, bool latency, bool two_piece, bool plain_s16, bool wide_ok, int kp_mask, bool kp_multi) {
     int best_kp = 0; long best_cost = 0;
-    for (int kp : { 4, 5, 6, 7, 8 }) {      // KP 12 / 16 single-warp variants were measured slower on B200 (150-250 registers per thread)
-        if (!(g_kp_mask & (1 << (kp - 4)))) continue;
+    for (int kp : { 4, 5, 6, 7, 8, 12 }) {
+        if (!(kp_mask & (1 << (kp - 4)))) continue;
+        // KP = 12: single-warp CTAs of wave scheduling, plain s16 range, two-piece scoring (the only instantiations)
+        if (kp == 12 && !(wide_ok && plain_s16 && two_piece && band_w <= 1536)) continue;
         if ((kp & 3) && !two_piece) continue;          // one-piece simple scoring: KP = 4 / 8 only (fewer instantiations)
         if (band_w % (uint32_t)(4 * kp)) continue;
         const int nw = (int)((band_w + 128 * kp - 1) / (128 * kp));
         if (nw > max_warps_of(kp)) continue;
+        // KP = 5 / 6 / 7 for single-warp CTAs only: they exist to fit a band of 640 / 768 / 896 diagonals into one warp without padding it
+        // to 1024. On multi-warp CTAs they only multiply the launch groups of a wave (config 3: 218 instead of 104 launches per 6 steps,
+        // 977 instead of 1162 GCUPS; config 4: 653 instead of 696 loci/s)
+        // ... and for pairs inside the s16 score range only: on the long reads of config 3 the rebased KP = 5 / 6 / 7 variants cost more
+        // than they save (1058 against 1162 GCUPS with KP = 4 / 8 alone)
+        if ((kp & 3) && (nw > 1 || !plain_s16) && !kp_multi) continue;
+        if (kp == 12 && nw > 1) continue;
         const long cost = latency ? (long)step_cost(kp, nw) : (long)nw * step_cost(kp, nw);
         if (!best_kp || cost < best_cost) { best_kp = kp; best_cost = cost; }
     }
@@ -156,6 +164,8 @@ struct svp_handle {
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
     long latency_pairs = 0;                     // calls of at most this many pairs are planned for short steps (more, narrower warps) instead of fewest
                                                 // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call
+    int kp_mask = 31; bool kp_multi = false;      // kernel widths the planner may use (env SVP_KP_MASK, SVP_KP_MULTI: choose_kp); KP = 12 is off by default
+                                                  // (bit 8): one 220-register warp for a band of 1025..1536 diagonals measured SLOWER than three KP = 4 warps (config 2: 538 against 565 regions/s)
     bool force_ring = false;                    // test aid (env SVP_FORCE_RING): every pair on a sliding-window variant
 };
 
@@ -254,6 +264,8 @@ static void read_env_knobs(svp_handle* h) {
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
+    if (const char* e = getenv("SVP_KP_MASK")) { h->kp_mask = atoi(e); if (!(h->kp_mask & 0x11F)) h->kp_mask = 31; }
+    if (const char* e = getenv("SVP_KP_MULTI")) h->kp_multi = atoi(e) != 0;
     if (const char* e = getenv("SVP_MODE")) { const std::string m(e); h->waves = m == "waves"; h->queue = m == "queue"; }
     if (const char* e = getenv("SVP_WALK_CTAS_PER_SM")) h->walk_ctas_per_sm = std::min(std::max(atoi(e), 1), 8);
     if (const char* e = getenv("SVP_WALK_WAIT_NS")) h->walk_wait_ns = std::max(atol(e), 0L);
@@ -286,6 +298,7 @@ static FwdKernel fwd_kernel_w(int fam, int kp, bool multi, bool cluster, bool ri
         SVP_F4(4, false, true) SVP_F4(4, true, true) SVP_F4(8, false, true) SVP_F4(8, true, true)
         SVP_F4(5, false, true) SVP_F4(5, true, true) SVP_F4(6, false, true) SVP_F4(6, true, true) SVP_F4(7, false, true) SVP_F4(7, true, true)
         SVP_F4(4, false, false) SVP_F4(4, true, false) SVP_F4(8, false, false) SVP_F4(8, true, false)
+        if constexpr (!W) { SVP_F(12, false, true, false, false) SVP_F(12, false, true, false, true) }
 #undef SVP_F4
 #undef SVP_F
         return nullptr;
@@ -374,7 +387,7 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     cudaDeviceGetAttribute(&h->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     // every variant: the largest dynamic shared memory (sequence images, or the residency ballast of run_plan) and the whole
     // L1 / shared-memory array as shared memory (the kernels stream their stores and read the rows through L2)
-    for (int fam = 0; fam < 5; ++fam) for (int kp = 4; kp <= 8; ++kp) for (int m = 0; m < 2; ++m) for (int c = 0; c < 2; ++c)
+    for (int fam = 0; fam < 5; ++fam) for (int kp = 4; kp <= 12; ++kp) for (int m = 0; m < 2; ++m) for (int c = 0; c < 2; ++c)
         for (int r = 0; r < 2; ++r) for (int t = 0; t < 2; ++t) for (int w = 0; w < 2; ++w)
             if (FwdKernel k = fwd_kernel(fam, kp, m != 0, c != 0, r != 0, t != 0, w != 0)) {
                 // (dynamic + the kernels' few bytes of static shared memory must stay within the per-block limit)
@@ -662,7 +675,7 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     int kp, cl = 1;
     if (wide32 || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
     else {
-        kp = choose_kp(p.band_w, latency, cs.two_piece != 0);
+        kp = choose_kp(p.band_w, latency, cs.two_piece != 0, !beyond_s16, h->waves, h->kp_mask, h->kp_multi);
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
         if (!ring && cl) {
             const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));

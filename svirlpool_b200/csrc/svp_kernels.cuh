@@ -558,7 +558,7 @@ __device__ __forceinline__ void ring_fill_fast(const Task& tk, const uint8_t* __
 // row — or, for a B cell, left / up in the cell's own sector — so a walk touches one new sector per cell instead of three
 // (the former one-row-per-step layout cost the traceback 270 DRAM bytes per path cell, profiles/ncu_tbw_r01_v3.json).
 // Slots are padded to a multiple of 8 bytes (KP = 5: 24, KP = 7: 32) so that the stores stay 8- or 16-byte vectors.
-__host__ __device__ constexpr int tb_slot_bytes(int kp) { return kp <= 4 ? 16 : (kp <= 6 ? 24 : 32); }
+__host__ __device__ constexpr int tb_slot_bytes(int kp) { return kp <= 4 ? 16 : (kp <= 6 ? 24 : (kp <= 8 ? 32 : 48)); }
 // low bytes of the 2*KP A values and 2*KP B values of one step pair -> this thread's slot of the row
 template <int KP>
 __device__ __forceinline__ void store_pair(uint8_t* p, const uint32_t (&HA)[KP], const uint32_t (&HB)[KP]) {
@@ -603,11 +603,16 @@ constexpr int RB_CLAMP = 16000;
 #ifndef SVP_WAVE_MIN_CTAS
 #define SVP_WAVE_MIN_CTAS 16
 #endif
+// KP = 12: one warp covers 1536 diagonals (the bands of 1025..1536 diagonals that otherwise take three KP = 4 warps with mailboxes:
+// 24 % more instructions per diagonal at 73 % instead of 86 % of the ALU pipe, profiles/ncu_fwd_r02_v2.json). 120 state registers.
+#ifndef SVP_WIDE_MIN_CTAS
+#define SVP_WIDE_MIN_CTAS 1
+#endif
 // WALK = false: the variant wave scheduling launches — no call to the walk anywhere in the kernel, so its register count is the forward
 // pass's own (the walk needs ~130: with it KP = 4 goes from 72 to 124 registers, KP = 5 / 6 sliding windows from 127 to 136 / 142 = 14-15
 // instead of 16 CTAs per SM)
 template <int KP, bool MULTI, bool TWO, bool CL = false, bool RB = false, bool RING = false, bool WALK = true>
-__global__ void __launch_bounds__(fwd_max_threads(KP, MULTI), MULTI ? 1 : (!WALK ? SVP_WAVE_MIN_CTAS : SVP_SINGLE_MIN_CTAS))
+__global__ void __launch_bounds__(fwd_max_threads(KP, MULTI), MULTI ? 1 : (KP > 8 ? SVP_WIDE_MIN_CTAS : (!WALK ? SVP_WAVE_MIN_CTAS : SVP_SINGLE_MIN_CTAS)))
 svp_fwd_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, const uint8_t* __restrict__ seqs,
                const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
     static_assert(!CL || MULTI, "cluster variants are multi-warp");

@@ -171,7 +171,7 @@ def test_planner_kernel_families(monkeypatch):
     specs = [(0, 1, -462, 1024),        # 8 kb reads, band 1024: one KP = 8 warp, windows (16 KB of images for one warp)
              (2, 3, -206, 512),         # 1 kb reads, band 512: one KP = 4 warp, whole images
              (0, 1, -1000, 2048),       # two KP = 8 warps
-             (0, 1, -700, 1536),        # two KP = 6 warps beat three KP = 4 warps and two KP = 8 warps
+             (0, 1, -700, 1536),        # three KP = 4 warps beat two KP = 8 warps (KP = 5 / 6 / 7 serve single-warp CTAs only; KP = 12 is off by default)
              (4, 5, -500, 2048),        # 20 kb reads: scores leave the s16 range -> rebased 16-bit lanes
              (0, 1, -7999, 20000),      # band beyond one CTA (16 384 diagonals): a cluster of 2 CTAs
              (6, 7, -768, 1536),        # 130 kb x 120 kb: whole images cannot fit -> windows, rebased
@@ -187,10 +187,10 @@ def test_planner_kernel_families(monkeypatch):
     assert fam[0] == (PLAN_WINDOWS, 8, 1, 1)
     assert fam[1] == (0, 4, 1, 1)
     assert fam[2] == (PLAN_WINDOWS, 8, 2, 1)
-    assert fam[3] == (PLAN_WINDOWS, 6, 2, 1)
+    assert fam[3] == (PLAN_WINDOWS, 4, 3, 1)
     assert fam[4] == (PLAN_REBASE | PLAN_WINDOWS, 8, 2, 1)
     assert fam[5][1:] == (8, 16, 2) and not fam[5][0] & (PLAN_S32 | PLAN_REBASE)
-    assert fam[6] == (PLAN_REBASE | PLAN_WINDOWS, 6, 2, 1) and plan[6]["smem_bytes"] < 16384
+    assert fam[6] == (PLAN_REBASE | PLAN_WINDOWS, 4, 3, 1) and plan[6]["smem_bytes"] < 16384
     assert [f[0] for f in fam[7:10]] == [PLAN_INVALID] * 3
     assert [f[1:] for f in fam[10:]] == [(5, 1, 1), (6, 1, 1), (7, 1, 1), (6, 1, 1)]
     for k in (0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13):                  # cells = the closed form the scheduler uses; 1 traceback byte per cell (+ virtual cells)

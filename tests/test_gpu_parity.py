@@ -688,12 +688,20 @@ def fixed_band_batch(rng, n_pairs, length, band_w, err=(0.035, 0.03, 0.035)):
 
 @pytest.mark.parametrize("ring_min", ["0", "1000000000"])
 @pytest.mark.parametrize("band_w,kp,warps", [(640, 5, 1), (768, 6, 1), (896, 7, 1), (672, 6, 1), (1280, 5, 2), (1536, 6, 2), (1792, 7, 2),
-                                              (2304, 6, 3), (3200, 5, 5), (5376, 7, 6), (10752, 7, 12), (13440, 7, 15)])
+                                              (2304, 6, 3), (3200, 5, 5), (5376, 7, 6), (10752, 7, 12), (13440, 7, 15),
+                                              (1152, 12, 1), (1536, 12, 1), (1056, 12, 1)])
 def test_band_widths_kp_5_6_7(oracle, monkeypatch, band_w, kp, warps, ring_min):
     """Every KP = 5 / 6 / 7 geometry (single warp, CTAs of 2..16 warps whose warps are linked by mbarriers instead of a CTA
-    barrier; whole images and sliding windows) against the oracle, and the planner picks the geometry the test names."""
+    barrier; whole images and sliding windows) and the single-warp KP = 12 geometry (bands of up to 1536 diagonals) against the
+    oracle, and the planner picks the geometry the test names. (By default KP = 5 / 6 / 7 serve single-warp CTAs only: the
+    multi-warp cases switch them on, SVP_KP_MULTI, and KP = 12 off.)"""
     from svirlpool_b200 import aligner as al
     monkeypatch.setenv("SVP_RING_MIN", ring_min)
+    monkeypatch.setenv("SVP_MODE", "waves")
+    if warps > 1:
+        monkeypatch.setenv("SVP_KP_MULTI", "1")
+    if kp == 12:
+        monkeypatch.setenv("SVP_KP_MASK", str(0x11F))                 # off by default (measured slower than three KP = 4 warps)
     rng = np.random.default_rng(band_w)
     names, seqs, specs = fixed_band_batch(rng, 6, 2600 if band_w < 4000 else 4200, band_w)
     batch = ava.PairBatch.build(names, seqs, specs)
