@@ -216,7 +216,7 @@ SCALING_SETS = {
     "config5": {"sets": [(40_000, True), (50_000, True), (60_000, True)],
                 "what": "trio: three sets (seeds 40000/50000/60000+r) with a Pareto(1.3) core-length tail, one joint pool"},
 }
-SCALING_CHUNK = 128          # loci per engine call
+SCALING_CHUNK = 384          # loci per engine call
 
 
 def scaling_items(name: str, pool: int) -> list[tuple[int, int, bool]]:
@@ -421,10 +421,11 @@ def main() -> None:
     max_cig = max(b["cigar_words"] for b in batches)
     d_results = torch.empty(max_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_cigar = torch.empty(max_cig, dtype=torch.int32, device=dev)
-    # traceback arena of the bench: 85 % of the free HBM (wave scheduling: the larger the waves, the fewer wave boundaries; the library's
-    # own default is 60 %); SVP_ARENA_GB overrides
+    # traceback arena of the bench: 92 % of the free HBM (wave scheduling: the larger the waves, the fewer wave boundaries — 96 regions
+    # per step are 2 whole-arena waves at 165 GB, 3 at 150 GB: 577 against 565 regions/s; the library's own default is 60 %,
+    # DESIGN.md §4.8); SVP_ARENA_GB overrides
     free_b, _total_b = torch.cuda.mem_get_info(local)
-    arena_bytes = 0 if os.environ.get("SVP_ARENA_GB") else int(free_b * 0.85) & ~255
+    arena_bytes = 0 if os.environ.get("SVP_ARENA_GB") else int(free_b * 0.92) & ~255
     al = Aligner(device=local, preset="map-ont", tb_bytes=arena_bytes)
 
     def sync_all():

@@ -194,7 +194,12 @@ def shared_aligner(preset: str = "map-ont", device: int | None = None) -> "Align
     key = (device, preset)
     eng = _SHARED.get(key)
     if eng is None or eng._h is None:
-        eng = Aligner(device=-1 if device is None else device, preset=preset)
+        # one container per call: a few GB of traceback rows at most (435 pairs x 8.5 MB); 16 GB leave the device to the other jobs
+        gb = int(os.environ.get("SVP_SHARED_ARENA_GB", "16"))
+        try:
+            eng = Aligner(device=-1 if device is None else device, preset=preset, tb_bytes=gb << 30)
+        except AlignerError:                       # less than that is free: the library's default shrinks until it fits
+            eng = Aligner(device=-1 if device is None else device, preset=preset)
         if not _SHARED:
             atexit.register(close_shared_aligners)
         _SHARED[key] = eng

@@ -417,10 +417,12 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     h->n_sm = nsm;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaMemGetInfo failed");
-    // Default arena. Wave scheduling: 60 % of the free memory — a wave is what fits half the arena, and the larger the wave the
-    // smaller the share of its ramp and drain (r1: 32 / 64 / 128 / 160 GB -> 1377 / 1728 / 1912 / 2006 GCUPS on config 2). Arena
-    // scheduling: 48 GB — it holds the rows of the pairs RESIDENT on the GPU only (config 2: ~2000 pairs x 6-12 MB), whatever the batch.
-    size_t want = max_tb_bytes ? max_tb_bytes : (h->waves ? free_b / 10 * 6 : std::min<size_t>((size_t)(h->queue ? 64 : 48) << 30, free_b / 10 * 6));
+    // Default arena: 64 GB, at most 60 % of the free memory — bounded, so that several handles / processes share a device (the
+    // reference runs several consensus jobs per node, main.smk:649-707). Wave scheduling runs faster with more: a wave is what fits
+    // the arena (serial walks) or half of it, and every wave boundary drains the machine (config 2, 96 regions per call: 64 / 107 /
+    // 150 / 165 GB -> 6 / 4 / 3 / 2 waves -> ~520 / 545 / 565 / 577 regions/s); a caller that owns the GPU passes max_tb_bytes
+    // (bench.py: 92 % of the free memory). Arena / queue scheduling hold the rows of the pairs RESIDENT on the GPU only.
+    size_t want = max_tb_bytes ? max_tb_bytes : std::min<size_t>((size_t)64 << 30, free_b / 10 * 6);
     if (!max_tb_bytes) if (const char* e = getenv("SVP_ARENA_GB")) want = std::min<size_t>((size_t)std::max(atoi(e), 1) << 30, free_b / 20 * 19);   // tuning aid
     want = (want + 255) & ~(size_t)255;
     // the default size shrinks until the allocation succeeds (fragmentation, another process on the device); an explicit size does not

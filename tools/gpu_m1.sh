@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+export SVP_CALL_TIMEOUT_S=120
+run() { name=$1; w=$2; shift; shift; env "$@" timeout 300 python bench.py --workload $w --no-cpu-baseline --scaling-pool 0 > $O/m1_$name.json 2>$O/m1_$name.err; python -c "
+import json,sys
+try:
+    d=json.load(open('gpurun_out/m1_$name.json')); print('$name: regions/s', round(d['regions_per_s'],1), 'GCUPS', round(d['value']), 'e2e r/s', round(d['e2e']['regions_per_s'],1), {k:(round(v,1) if isinstance(v,float) else v) for k,v in d['kernel_ms'].items() if k!='note'}, 'launches', d['roofline']['launches'])
+except Exception as e: print('$name failed', e); print(open('gpurun_out/m1_$name.err').read()[-600:])"; }
+run s2 config2 SVP_FWD_STREAMS=2
+run s6 config2 SVP_FWD_STREAMS=6
+run s8 config2 SVP_FWD_STREAMS=8
+run a165 config2 SVP_ARENA_GB=165
+run a165_s8 config2 SVP_ARENA_GB=165 SVP_FWD_STREAMS=8
