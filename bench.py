@@ -216,7 +216,7 @@ SCALING_SETS = {
     "config5": {"sets": [(40_000, True), (50_000, True), (60_000, True)],
                 "what": "trio: three sets (seeds 40000/50000/60000+r) with a Pareto(1.3) core-length tail, one joint pool"},
 }
-SCALING_CHUNK = 384          # loci per engine call
+SCALING_CHUNK = 256          # loci per engine call
 
 
 def scaling_items(name: str, pool: int) -> list[tuple[int, int, bool]]:
@@ -357,7 +357,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the one the metric is quoted on)")
-    ap.add_argument("--regions", type=int, default=None, help="regions per GPU per step (default 96; 8 for config3, 48 for config4)")
+    ap.add_argument("--regions", type=int, default=None, help="regions per GPU per step (default 80; 8 for config3, 48 for config4)")
     ap.add_argument("--distinct-batches", type=int, default=3, help="distinct synthetic batches cycled over the steps")
     ap.add_argument("--ref-regions", type=int, default=2, help="regions per step of the CPU arm (bounded sample)")
     ap.add_argument("--cpu-sample-regions", type=int, default=2)
@@ -369,7 +369,7 @@ def main() -> None:
                     help="HBM-resident steps as blocking calls instead of pipelined submits (svp_submit_batch_device)")
     args = ap.parse_args()
     if args.regions is None:
-        args.regions = {"config2": 96, "config3": 8, "config4": 48}[args.workload]
+        args.regions = {"config2": 80, "config3": 8, "config4": 48}[args.workload]
     if args.impl == "reference":
         run_reference(args)
         return
@@ -421,11 +421,14 @@ def main() -> None:
     max_cig = max(b["cigar_words"] for b in batches)
     d_results = torch.empty(max_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     d_cigar = torch.empty(max_cig, dtype=torch.int32, device=dev)
-    # traceback arena of the bench: 92 % of the free HBM (wave scheduling: the larger the waves, the fewer wave boundaries — 96 regions
-    # per step are 2 whole-arena waves at 165 GB, 3 at 150 GB: 577 against 565 regions/s; the library's own default is 60 %,
-    # DESIGN.md §4.8); SVP_ARENA_GB overrides
+    # traceback arena of the bench: the free HBM minus 26 GB for the batch buffers (CIGAR slots of the largest strong-scaling chunk).
+    # Wave scheduling: the larger the waves, the fewer wave boundaries — a step of 80 regions is 2 whole-arena waves from 148 GB on
+    # (the library's own default is a bounded 64 GB); SVP_ARENA_GB overrides
     free_b, _total_b = torch.cuda.mem_get_info(local)
-    arena_bytes = 0 if os.environ.get("SVP_ARENA_GB") else int(free_b * 0.92) & ~255
+    arena_bytes = 0 if os.environ.get("SVP_ARENA_GB") else max(int(free_b * 0.5), int(free_b) - (26 << 30)) & ~255
+    # every call of this handle is planned like a large call (all kernel widths), so that the parity check below — 870 pairs, a small
+    # call by itself — runs on the same kernel variants as the timed steps
+    os.environ.setdefault("SVP_SMALL_CALL_PAIRS", "0")
     al = Aligner(device=local, preset="map-ont", tb_bytes=arena_bytes)
 
     def sync_all():

@@ -162,6 +162,7 @@ struct svp_handle {
     std::string err;
     int max_smem_optin = 0;
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
+    long small_call_pairs = 1024;               // calls of at most this many pairs use the KP = 4 / 8 widths only (env SVP_SMALL_CALL_PAIRS; plan_pair)
     long latency_pairs = 0;                     // calls of at most this many pairs are planned for short steps (more, narrower warps) instead of fewest
                                                 // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call
     int kp_mask = 31; bool kp_multi = false;      // kernel widths the planner may use (env SVP_KP_MASK, SVP_KP_MULTI: choose_kp); KP = 12 is off by default
@@ -264,6 +265,7 @@ static void read_env_knobs(svp_handle* h) {
     if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
+    if (const char* e = getenv("SVP_SMALL_CALL_PAIRS")) h->small_call_pairs = atol(e);
     if (const char* e = getenv("SVP_KP_MASK")) { h->kp_mask = atoi(e); if (!(h->kp_mask & 0x11F)) h->kp_mask = 31; }
     if (const char* e = getenv("SVP_KP_MULTI")) h->kp_multi = atoi(e) != 0;
     if (const char* e = getenv("SVP_MODE")) { const std::string m(e); h->waves = m == "waves"; h->queue = m == "queue"; }
@@ -637,7 +639,7 @@ struct Plan {
     std::vector<std::pair<size_t, size_t>> waves;   // [first, last) task ranges
 };
 
-static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
+static void plan_pair(const svp_handle* h, int call_kind, const svp_pair& p, uint32_t index, const uint64_t* seq_off, const uint32_t* seq_len, uint32_t n_seqs,
                       size_t packed_bytes, size_t cigar_words, bool need_padding, Task& t) {
     memset(&t, 0, sizeof(t));
     t.pair_index = index; t.cigar_off = p.cigar_off; t.cigar_cap = p.cigar_cap; t.flags = p.flags & SVP_PAIR_REVCOMP;
@@ -677,7 +679,11 @@ static void plan_pair(const svp_handle* h, bool latency, const svp_pair& p, uint
     int kp, cl = 1;
     if (wide32 || cs.general) { kp = 4; cl = cluster_for(p.band_w, 128 * 4); }
     else {
-        kp = choose_kp(p.band_w, latency, cs.two_piece != 0, !beyond_s16, h->waves, h->kp_mask, h->kp_multi);
+        // a small call (one or two containers: fewer warps than the GPU has schedulers) runs on KP = 4 / 8 only: a container of 435 pairs
+        // x 8 kb takes 3.6 ms on them against 5.6 ms on its four single-warp widths (measured; a lone KP = 5 / 6 / 7 warp per scheduler
+        // is latency-bound, and four half-empty launches replace two)
+        const int kp_mask = (call_kind & 2) && (h->kp_mask & 0x11) ? (h->kp_mask & 0x11) : h->kp_mask;
+        kp = choose_kp(p.band_w, (call_kind & 1) != 0, cs.two_piece != 0, !beyond_s16, h->waves, kp_mask, h->kp_multi);
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
         if (!ring && cl) {
             const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));
@@ -1170,7 +1176,7 @@ static int plan_and_run(svp_handle* h, const uint8_t* d_seqs, size_t packed_byte
     int rc = begin_call(h, n_pairs, &c);
     if (rc != SVP_OK) return rc;
     // few pairs: optionally favour short steps (see latency_pairs)
-    const bool latency = (long)n_pairs <= h->latency_pairs;
+    const int latency = ((long)n_pairs <= h->latency_pairs ? 1 : 0) | ((long)n_pairs <= h->small_call_pairs ? 2 : 0);
     for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
     return run_plan(h, *c, n_pairs, d_seqs, d_results, d_cigar, wait);
 }
@@ -1185,7 +1191,7 @@ extern "C" int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, c
     if (rc != SVP_OK) return fail(nullptr, rc, why);
     pseudo.max_smem_optin = 232448;                      // 227 KB: cudaDevAttrMaxSharedMemoryPerBlockOptin of sm_100
     read_env_knobs(&pseudo);
-    const bool latency = (long)n_pairs <= pseudo.latency_pairs;
+    const int latency = ((long)n_pairs <= pseudo.latency_pairs ? 1 : 0) | ((long)n_pairs <= pseudo.small_call_pairs ? 2 : 0);
     for (uint32_t k = 0; k < n_pairs; ++k) {
         Task t;
         plan_pair(&pseudo, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, false, t);

@@ -167,6 +167,7 @@ def test_planner_kernel_families(monkeypatch):
     from svirlpool_b200._abi import PLAN_GENERAL, PLAN_INVALID, PLAN_REBASE, PLAN_S32, PLAN_WINDOWS
     for var in ("SVP_NO_REBASE", "SVP_RING_MIN", "SVP_FORCE_RING", "SVP_FORCE_GENERAL", "SVP_LATENCY_PAIRS", "SVP_KP_MASK"):
         monkeypatch.delenv(var, raising=False)
+    monkeypatch.setenv("SVP_SMALL_CALL_PAIRS", "0")          # plan these few pairs as part of a large call
     lens = [8000, 8100, 1000, 1100, 20000, 21000, 130000, 120000]
     specs = [(0, 1, -462, 1024),        # 8 kb reads, band 1024: one KP = 8 warp, windows (16 KB of images for one warp)
              (2, 3, -206, 512),         # 1 kb reads, band 512: one KP = 4 warp, whole images
@@ -203,6 +204,10 @@ def test_planner_kernel_families(monkeypatch):
     monkeypatch.setenv("SVP_NO_REBASE", "1")
     p2, _, _ = _plan(lens, [specs[4], specs[6]])
     assert [int(x["flags"]) for x in p2] == [PLAN_S32, PLAN_S32 | PLAN_WINDOWS] and [int(x["kp"]) for x in p2] == [4, 4]
+    # a small call (one or two containers) keeps to the KP = 4 / 8 widths: fewer, fuller launches and shorter steps per pair
+    monkeypatch.setenv("SVP_SMALL_CALL_PAIRS", "1024")
+    p3, _, _ = _plan(lens, specs[10:13])
+    assert [(int(x["kp"]), int(x["warps"])) for x in p3] == [(8, 1), (8, 1), (8, 1)]
     monkeypatch.delenv("SVP_NO_REBASE")
     p3, _, _ = _plan(lens, [specs[1], specs[0]], preset="last")          # largest matrix entry 6: 8 kb reads already leave the s16 range
     assert [int(x["flags"]) for x in p3] == [PLAN_GENERAL, PLAN_GENERAL | PLAN_S32] and [int(x["warps"]) for x in p3] == [1, 2]

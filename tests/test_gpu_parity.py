@@ -698,6 +698,7 @@ def test_band_widths_kp_5_6_7(oracle, monkeypatch, band_w, kp, warps, ring_min):
     from svirlpool_b200 import aligner as al
     monkeypatch.setenv("SVP_RING_MIN", ring_min)
     monkeypatch.setenv("SVP_MODE", "waves")
+    monkeypatch.setenv("SVP_SMALL_CALL_PAIRS", "0")                   # (small calls keep to KP = 4 / 8)
     if warps > 1:
         monkeypatch.setenv("SVP_KP_MULTI", "1")
     if kp == 12:

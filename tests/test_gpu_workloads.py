@@ -16,8 +16,19 @@ INT_FIELDS = ("score", "status", "q_beg", "q_end", "t_beg", "t_end", "n_match", 
 
 @pytest.fixture(scope="module")
 def gpu():
+    """The engine of this module plans every call as part of a LARGE call (all kernel widths, as in bench.py's steps): by default a
+    call of up to 1024 pairs keeps to the KP = 4 / 8 widths (test_config2_one_container_default_planning)."""
+    import os
     from svirlpool_b200.aligner import Aligner
-    a = Aligner(device=0, preset="map-ont", tb_bytes=24 << 30)
+    old = os.environ.get("SVP_SMALL_CALL_PAIRS")
+    os.environ["SVP_SMALL_CALL_PAIRS"] = "0"
+    try:
+        a = Aligner(device=0, preset="map-ont", tb_bytes=24 << 30)
+    finally:
+        if old is None:
+            del os.environ["SVP_SMALL_CALL_PAIRS"]
+        else:
+            os.environ["SVP_SMALL_CALL_PAIRS"] = old
     yield a
     a.close()
 
@@ -60,6 +71,15 @@ def test_config2_full_size_parity(gpu, oracle_mt):
     gres, gcig = assert_parity(b, gpu, oracle_mt)
     assert (gres["status"] == 0).all() and int(gres["cells"].sum()) > 5e9
     assert len({int(w) for w in b["pairs"]["band_w"]}) > 4             # several kernel geometries in one batch
+
+
+def test_config2_one_container_default_planning(oracle_mt):
+    """One container per call, the way the reference's seam is driven, on a handle with the default planning (small calls keep to the
+    KP = 4 / 8 widths): region 2 of config 2, every pair bit-exact against the oracle."""
+    from svirlpool_b200.aligner import Aligner
+    b = workloads.batch_config2([2])
+    with Aligner(device=0, preset="map-ont", tb_bytes=8 << 30) as a:
+        assert_parity(b, a, oracle_mt)
 
 
 def test_config5_reduced_parity(gpu, oracle_mt):
