@@ -953,15 +953,21 @@ static int run_waves(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
             if (nt <= h->tbw_max || serial || (last_wave_warp && wait && wv + 1 == waves.size())) {
                 // (the short and the long list of a wave are adjacent in the order array). Lanes per pair (env SVP_TB_LPP): 8 — four
                 // pairs share a warp's instruction stream; 32 — the whole warp, with its corridor in shared memory
-                static const int lpp = [] { const char* e = getenv("SVP_TB_LPP"); const int v = e ? atoi(e) : 8; return v == 16 || v == 32 ? v : 8; }();
+                static const int lpp = [] { const char* e = getenv("SVP_TB_LPP"); const int v = e ? atoi(e) : 8; return v == 4 || v == 16 || v == 32 ? v : 8; }();
                 static const int tbg_min = [] { const char* e = getenv("SVP_TBG_MIN"); return e ? atoi(e) : -1; }();
                 const bool whole = lpp == 32 || nt < (tbg_min >= 0 ? tbg_min : 4 * h->sm_count);         // few pairs: latency counts, not issue slots
                 if (whole)
                     svp_tbw_kernel<<<(nt * 32 + 127) / 128, 128, g_corridor ? 4 * COR_BYTES : 0, sT>>>(d_tasks, d_order + L.first_short, nt, d_seqs, h->arena, d_results, d_cigar, cs, g_corridor ? 1 : 0);
                 else {
                     if (L.n_long) svp_tbw_kernel<<<((int)L.n_long * 32 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_long, (int)L.n_long, d_seqs, h->arena, d_results, d_cigar, cs, 0);
-                    if (L.n_short && lpp == 16) svp_tbg_kernel<16><<<((int)L.n_short * 16 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs);
-                    if (L.n_short && lpp == 8) svp_tbg_kernel<8><<<((int)L.n_short * 8 + 127) / 128, 128, 0, sT>>>(d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs);
+                    // SVP_TBG_UNIFORM=0: the groups of a warp walk independently (group masks, divergent) instead of on one instruction stream
+                    static const int uni = [] { const char* e = getenv("SVP_TBG_UNIFORM"); return e ? atoi(e) : 1; }();
+#define SVP_TBG_ARGS d_tasks, d_order + L.first_short, (int)L.n_short, d_seqs, h->arena, d_results, d_cigar, cs
+                    const unsigned grid = (unsigned)(((size_t)L.n_short * (size_t)lpp + 127) / 128);
+                    if (L.n_short && lpp == 16) { if (uni) svp_tbu_kernel<16><<<grid, 128, 0, sT>>>(SVP_TBG_ARGS); else svp_tbg_kernel<16><<<grid, 128, 0, sT>>>(SVP_TBG_ARGS); }
+                    if (L.n_short && lpp == 8) { if (uni) svp_tbu_kernel<8><<<grid, 128, 0, sT>>>(SVP_TBG_ARGS); else svp_tbg_kernel<8><<<grid, 128, 0, sT>>>(SVP_TBG_ARGS); }
+                    if (L.n_short && lpp == 4) svp_tbu_kernel<4><<<grid, 128, 0, sT>>>(SVP_TBG_ARGS);
+#undef SVP_TBG_ARGS
                 }
                 c.stats.tb_launches++;
             } else {

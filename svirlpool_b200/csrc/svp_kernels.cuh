@@ -1542,6 +1542,325 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// The group walk with WARP-UNIFORM control flow: 32 / LPP pairs per warp, one per group of LPP lanes, all of them on one
+// instruction stream. Same walk, same results as svp_traceback_warp; what differs is how the groups share the warp:
+//   * every cross-lane operation is issued by all 32 lanes with the full mask at a point all groups reach together (ballots are
+//     shifted and masked to the group, shuffles use width LPP, minima are butterflies inside the group) — a ballot or reduction on
+//     a per-group mask makes the compiler loop over the distinct masks (MATCH.ANY), one pass per group;
+//   * nothing a group decides changes the program counter of another: the diagonal-run round, the 1-base gap and the first LPP
+//     candidates of a longer gap are straight-line code in every iteration, applied under per-group predicates; loops run while
+//     ANY group needs them (further gap candidates, the Z-drop prefix minimum, ties of the end-cell search are the rare cases);
+//   * a finished group idles until the last group of its warp is done (the pairs of a warp are neighbours in the wave's order).
+// profiles/ncu_tbg_r02_v1.json (group masks, divergent groups): 524 k warp instructions per warp of four pairs, 771 per round,
+// every VOTE / REDUX executed four times.
+// ---------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, const uint8_t* __restrict__ arena,
+                                                  const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
+                                                  uint32_t* __restrict__ cigar, const Consts& cs) {
+    static_assert(LPP == 4 || LPP == 8 || LPP == 16, "lanes per pair");
+    constexpr unsigned FULL = 0xffffffffu, GM = (1u << LPP) - 1u;
+    const int lane = threadIdx.x & (LPP - 1);
+    const unsigned gsh = (unsigned)(threadIdx.x & 31 & ~(LPP - 1));
+    auto gballot = [&](bool p) -> unsigned { return (__ballot_sync(FULL, p) >> gsh) & GM; };
+    auto gmin = [&](int x) -> int {
+        #pragma unroll
+        for (int o = LPP / 2; o; o >>= 1) x = min(x, __shfl_xor_sync(FULL, x, o, LPP));
+        return x;
+    };
+    const bool have = tkp != nullptr;
+    // the group's pair (an idle group gets a harmless geometry; everything it does is predicated off)
+    Task tk;
+    if (have) tk = *tkp;
+    else { memset(&tk, 0, sizeof(tk)); tk.flags = 4u << TASK_KP_SHIFT; tk.band_w = 16; tk.m = 1; tk.n = 1; tk.tb_bytes = 16; tk.r_begin = 2; }
+    const uint8_t* rows = arena + tk.tb_off;
+    const uint2* bests = reinterpret_cast<const uint2*>(rows + tk.tb_bytes);
+    svp_result res;
+    res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
+    res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
+    res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
+    const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
+    TbView<false> v;
+    v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
+    v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
+    v.set_geometry(tk.band_w, KP);
+    v.q_word = tk.q_off >> 2; v.t_word = tk.t_off >> 2; v.rc = (tk.flags & SVP_PAIR_REVCOMP) != 0;
+    v.q_mask = seq_mask(seqs, tk.q_off, tk.m, (tk.flags & TASK_QN) != 0);
+    v.t_mask = seq_mask(seqs, tk.t_off, tk.n, (tk.flags & TASK_TN) != 0);
+    v.s_cor = 0; v.cor_wc = 0; v.cor_w = 0; v.cor_lo = 0; v.cor_ready = 0x7FFFFFF0; v.cor_top = -1; v.cor_row_lo = 0; v.cor_row_span = 0;
+    v.n_rows = (int)(tk.tb_bytes / (uint64_t)v.pitch);
+    const int band_lo = tk.band_lo, r_begin = tk.r_begin;
+    const int d_hi = band_lo + tk.band_w - 1;
+
+    // ---- 1. end cell: maximum over the per-(thread, half) records, earliest block; then the exact cell inside the winning blocks ----
+    const int n_ent = have ? (tk.band_w / (4 * KP)) * 2 : 0;
+    const int n_ent_max = __reduce_max_sync(FULL, n_ent);
+    int M = 0; uint32_t blk = 0xFFFFFFFFu;
+    for (int e = lane; e < n_ent_max; e += LPP) {
+        if (e < n_ent) {
+            const uint2 b = bests[e];
+            const int val = (int)b.x;
+            if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
+        }
+    }
+    #pragma unroll
+    for (int o = LPP / 2; o; o >>= 1) {
+        const int M2 = __shfl_xor_sync(FULL, M, o, LPP);
+        const uint32_t b2 = __shfl_xor_sync(FULL, blk, o, LPP);
+        if (M2 > M || (M2 == M && b2 < blk)) { M = M2; blk = b2; }
+    }
+    const bool act = have && M > 0;                              // the group has a walk to do
+    if (have && !act) { res.status = SVP_ST_NOHIT; if (lane == 0) results[tk.pair_index] = res; }
+    if (act && !(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    int end_s = 0x7FFFFFFF, end_x = -1;
+    const int NC = 2 * KP * KP;
+    const int NC_max = __reduce_max_sync(FULL, NC);
+    for (int e0 = 0; e0 < n_ent_max; e0 += LPP) {
+        const int e = e0 + lane;
+        bool hit = false;
+        if (act && e < n_ent) { const uint2 b = bests[e]; hit = ((int)b.x == M) && (b.y == blk); }
+        unsigned mask = gballot(hit);
+        while (__any_sync(FULL, mask != 0u)) {
+            const bool on = mask != 0u;
+            const int ee = e0 + (on ? __ffs(mask) - 1 : 0);
+            mask &= mask - 1u;                                   // (0 stays 0)
+            const int xbase = (ee >> 1) * 4 * KP + (ee & 1) * 2 * KP;     // first diagonal (band-relative) of the half
+            const int s0 = (int)blk * 2 * KP;
+            int rel_row0 = 0, rel = 0, relmax = -(1 << 30), cand_s = 0x7FFFFFFF, cand_x = -1;
+            uint32_t b_row0 = 0, bprev = 0;
+            for (int c0 = 0; c0 < NC_max; c0 += LPP) {           // bytes fetched LPP at a time, chained by all lanes in lockstep
+                const int idx = c0 + lane;
+                uint32_t mine = 0;
+                if (on && idx < NC) {
+                    const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
+                    mine = (uint32_t)*v.addr_sx(s, x);
+                }
+                #pragma unroll
+                for (int l = 0; l < LPP; ++l) {
+                    const uint32_t b = __shfl_sync(FULL, mine, l, LPP);
+                    const int id = c0 + l;
+                    if (on && id < NC) {
+                        if (id == 0) rel = 0;
+                        else if (id % KP == 0) rel = rel_row0 + sext8(b - b_row0);
+                        else rel = rel + sext8(b - bprev);
+                        if (id % KP == 0) { rel_row0 = rel; b_row0 = b; }
+                        bprev = b;
+                        const int s = s0 + id / KP, x = xbase + 2 * (id % KP) + (s & 1);
+                        if (rel > relmax) { relmax = rel; cand_s = s; cand_x = x; }
+                        else if (rel == relmax && (s < cand_s || (s == cand_s && x > cand_x))) { cand_s = s; cand_x = x; }
+                    }
+                }
+            }
+            if (on && (cand_s < end_s || (cand_s == end_s && cand_x > end_x))) { end_s = cand_s; end_x = cand_x; }
+        }
+    }
+    int i = 1, j = 1;
+    if (act) { i = ((r_begin + end_s) - (band_lo + end_x)) / 2; j = ((r_begin + end_s) + (band_lo + end_x)) / 2; }
+    const int best_i = i, best_j = j;
+
+    // ---- 2. walk back --------------------------------------------------------------------------
+    int H = M;
+    uint32_t* slot = cigar + tk.cigar_off;
+    int wpos = (int)tk.cigar_cap;                    // runs are written right-aligned, backwards
+    uint32_t cur_op = 0, cur_len = 0; bool ovf = false, bad = false;
+    uint32_t n_match = 0, n_mis = 0, n_io = 0, n_ib = 0, n_do = 0, n_db = 0;
+    // snapshot at the lowest H of the walk: where the alignment starts if the walk is cut (Z-trim, §3.5) or ends at H = 0
+    int low = M + 1, low_i = i, low_j = j, low_wpos = wpos; uint32_t low_op = 0, low_len = 0; bool low_ovf = false;
+    uint32_t l_match = 0, l_mis = 0, l_io = 0, l_ib = 0, l_do = 0, l_db = 0;
+    const int zdrop = cs.zdrop > 0 ? cs.zdrop : 0x3FFFFFFF;
+    const bool simple = cs.general == 0;
+    const int s_match = cs.s_match, s_mismatch = cs.s_mismatch, n_score = cs.n_score, zd_ext = cs.zdrop_ext, a_max = cs.a_max;
+    const uint32_t tab0 = cs.tab[0], tab1 = cs.tab[1], tab2 = cs.tab[2], tab3 = cs.tab[3];
+    const int d_o1 = cs.d_open1, d_e1 = cs.d_ext1, d_o2 = cs.d_open2, d_e2 = cs.d_ext2, i_o1 = cs.i_open1, i_e1 = cs.i_ext1, i_o2 = cs.i_open2, i_e2 = cs.i_ext2;
+    const int two = cs.two_piece;
+    const int cost1d = gap_cost2(d_o1, d_e1, d_o2, d_e2, two, 1), cost1i = gap_cost2(i_o1, i_e1, i_o2, i_e2, two, 1);
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+#define SVP_PUSHG() do { if (cur_len) { if (wpos > 0) { --wpos; if (lane == 0) slot[wpos] = (cur_len << 4) | cur_op; } else ovf = true; } } while (0)
+#define SVP_EMITG(op, len) do { if (cur_len && cur_op == (op)) cur_len += (len); else { SVP_PUSHG(); cur_op = (op); cur_len = (len); } } while (0)
+
+    // byte columns of the current diagonal and its two neighbours, kept across rounds (a 1-base gap shifts them by one)
+    int xc = (j - i) - band_lo;
+    int c0 = v.col(xc), cL = v.col(xc - 1), cU = v.col(xc + 1);
+    bool done = !act;
+    while (__any_sync(FULL, !done)) {
+        const bool run = !done;
+        // ---- diagonal run: lane l holds the diagonal predecessor byte and the bases of cell (i-l, j-l) ----
+        const int ci = i - lane, cj = j - lane;
+        const int d0 = j - i;
+        const bool del_band = d0 - 1 >= band_lo, ins_band = d0 + 1 <= d_hi;
+        const bool inb = ci >= 1 && cj >= 1;
+        const int x0 = d0 - band_lo;
+        {   // columns: one new one per round in the common case (the diagonal moved by one), all three after a longer gap
+            const int shift = x0 - xc;
+            if (__any_sync(FULL, run && (shift > 1 || shift < -1))) {
+                if (shift > 1 || shift < -1) { c0 = v.col(x0); cL = v.col(x0 - 1); cU = v.col(x0 + 1); }
+                else if (shift) { const int cn = v.col(shift < 0 ? x0 - 1 : x0 + 1); if (shift < 0) { cU = c0; c0 = cL; cL = cn; } else { cL = c0; c0 = cU; cU = cn; } }
+            } else if (__any_sync(FULL, shift != 0)) {
+                const int cn = v.col(shift < 0 ? x0 - 1 : x0 + 1);
+                if (shift < 0) { cU = c0; c0 = cL; cL = cn; } else if (shift > 0) { cL = c0; c0 = cU; cU = cn; }
+            }
+            xc = x0;
+        }
+        const int sd = (i + j) - r_begin - 2 * lane - 2;     // step of the lane's diagonal predecessor; its left / up neighbours: sd + 1
+        uint32_t bp = 0, bl = 0, bu = 0; int sub_l = 0; bool same_l = false;
+        if (run && inb) {
+            if (ci >= 2 && cj >= 2 && sd >= 0) bp = v.ld(sd >> 1, c0);
+            if (del_band && cj >= 2 && sd + 1 >= 0) bl = v.ld((sd + 1) >> 1, cL);
+            if (ins_band && ci >= 2 && sd + 1 >= 0) bu = v.ld((sd + 1) >> 1, cU);
+            const int qc = v.qbase(ci), tc = v.tbase(cj);
+            const bool other = v.qn(ci) || v.tn(cj);              // a letter outside ACGT: lowest score, never a match
+            same_l = !other && qc == tc;
+            if (simple) sub_l = same_l ? s_match : s_mismatch;
+            else {
+                const uint32_t trow = qc < 2 ? (qc == 0 ? tab0 : tab1) : (qc == 2 ? tab2 : tab3);
+                sub_l = other ? n_score : (int)(int8_t)((trow >> (8 * tc)) & 0xFFu);
+            }
+        }
+        if (run && ci - LPP - 1 >= 1 && cj - LPP - 1 >= 1 && sd - 2 * LPP >= 0)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(v.base + (ptrdiff_t)((sd - 2 * LPP) >> 1) * v.pitch + c0));     // next round's byte
+        const unsigned sameb = gballot(same_l);
+        int Hl;
+        if (simple) {
+            const int ns = __popc(sameb & lt_mask);
+            Hl = H - (ns * s_match + (lane - ns) * s_mismatch);
+        } else {
+            int incl = sub_l;
+            #pragma unroll
+            for (int o = 1; o < LPP; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o, LPP); if (lane >= o) incl += t; }
+            Hl = H - (incl - sub_l);
+        }
+        const bool stop2 = (Hl == 0) || !inb;
+        // Z-drop: Hl - min(low, prefix minimum) > zdrop + ... ; the prefix minimum is at least H - lane * a_max, so the scan is only
+        // needed when some lane of some group passes the test with that bound
+        bool stop3 = false;
+        int pmin = Hl;
+        const bool scan = __any_sync(FULL, run && (Hl - min(low, H - lane * a_max) > zdrop));
+        if (scan) {
+            #pragma unroll
+            for (int o = 1; o < LPP; o <<= 1) { const int t = __shfl_up_sync(FULL, pmin, o, LPP); if (lane >= o) pmin = min(pmin, t); }
+            int dd = d0 - (low_j - low_i); dd = dd < 0 ? -dd : dd;
+            if (pmin < low) dd = 0;                                   // the snapshot moved onto this diagonal at or before this cell
+            stop3 = Hl - min(low, pmin) > zdrop + zd_ext * dd;
+        }
+        const int Hd = (ci >= 2 && cj >= 2) ? Hl + sext8(bp - (uint32_t)Hl) : 0;
+        const bool isdiag = inb && (Hl == Hd + sub_l);
+        const unsigned stopb = gballot(stop2 || stop3);
+        const unsigned term = stopb | gballot(!isdiag);
+        const int first = term ? __ffs(term) - 1 : LPP;
+        const int K = first < LPP - 1 ? first : LPP - 1;
+        const int runmin = scan ? __shfl_sync(FULL, pmin, K, LPP) : gmin(lane <= K ? Hl : 0x7FFFFFFF);
+        const unsigned eqb = gballot(Hl == runmin);
+        const int Hnext = __shfl_sync(FULL, first < LPP ? Hl : Hl - sub_l, K, LPP);
+        const uint32_t b1 = __shfl_sync(FULL, bl, K, LPP), b2 = __shfl_sync(FULL, bu, K, LPP);      // neighbours of the cell the run stops at
+        bool search = false;
+        if (run) {
+            if (runmin < low) {                                       // snapshot at the first cell of the run that reaches the new minimum
+                const unsigned upto = (2u << K) - 1u;
+                const int ks = __ffs(eqb & upto) - 1;
+                low = runmin; low_i = i - ks; low_j = j - ks;
+                low_wpos = wpos; low_op = cur_op; low_len = cur_len; low_ovf = ovf;
+                if (ks > 0) {                                         // CIGAR state after ks more M's
+                    if (low_len && low_op == SVP_CIGAR_M) low_len += (uint32_t)ks;
+                    else { if (low_len) { if (low_wpos > 0) --low_wpos; else low_ovf = true; } low_op = SVP_CIGAR_M; low_len = (uint32_t)ks; }
+                }
+                const int cs_ = __popc(sameb & ((1u << ks) - 1u));
+                l_match = n_match + (uint32_t)cs_; l_mis = n_mis + (uint32_t)(ks - cs_);
+                l_io = n_io; l_ib = n_ib; l_do = n_do; l_db = n_db;
+            }
+            const bool fin = first < LPP && ((stopb >> K) & 1u);
+            if (first > 0) {
+                SVP_EMITG(SVP_CIGAR_M, (uint32_t)first);
+                const int cs_ = __popc(sameb & ((1u << first) - 1u));
+                n_match += (uint32_t)cs_; n_mis += (uint32_t)(first - cs_);
+                i -= first; j -= first; H = Hnext;
+            }
+            if (fin) done = true;
+            else if (first < LPP) {
+                // 1-base gap at the cell the run stopped at (deletion first, as in the search below)
+                const int Hl1 = H + sext8(b1 - (uint32_t)H), Hu1 = H + sext8(b2 - (uint32_t)H);
+                if (del_band && j - 1 >= 1 && H == Hl1 - cost1d) { SVP_EMITG(SVP_CIGAR_D, 1u); ++n_do; ++n_db; --j; H = Hl1; }
+                else if (ins_band && i - 1 >= 1 && H == Hu1 - cost1i) { SVP_EMITG(SVP_CIGAR_I, 1u); ++n_io; ++n_ib; --i; H = Hu1; }
+                else search = true;
+            }
+        }
+        // ---- longer gap: the smallest k with H == H(i, j-k) - del(k), else H == H(i-k, j) - ins(k); LPP candidates of the row and of the
+        // column per pass, for every group that needs them (all groups go through a pass together: no group waits for another's branch)
+        {
+            const int d = j - i;
+            int Hrow = H, Hcol = H; uint32_t brow = (uint32_t)H & 0xFFu, bcol = (uint32_t)H & 0xFFu;
+            int k0 = 0;
+            while (__any_sync(FULL, search)) {
+                const int kk = k0 + lane + 1;
+                const bool del_ok = search && (j - kk >= 1) && (d - kk >= band_lo);      // both are true for a prefix of the candidates only
+                const bool ins_ok = search && (i - kk >= 1) && (d + kk <= d_hi);
+                const uint32_t bd = del_ok ? v.lb(i, j - kk) : 0;
+                const uint32_t bi = ins_ok ? v.lb(i - kk, j) : 0;
+                uint32_t pd = __shfl_up_sync(FULL, bd, 1, LPP), pi = __shfl_up_sync(FULL, bi, 1, LPP);
+                if (lane == 0) { pd = brow; pi = bcol; }
+                int dr = del_ok ? sext8(bd - pd) : 0, dc = ins_ok ? sext8(bi - pi) : 0;
+                #pragma unroll
+                for (int o = 1; o < LPP; o <<= 1) {
+                    const int tr = __shfl_up_sync(FULL, dr, o, LPP), tc = __shfl_up_sync(FULL, dc, o, LPP);
+                    if (lane >= o) { dr += tr; dc += tc; }
+                }
+                const int hr = Hrow + dr, hc = Hcol + dc;
+                const unsigned md = gballot(del_ok && H == hr - gap_cost2(d_o1, d_e1, d_o2, d_e2, two, kk));
+                const unsigned mi = gballot(ins_ok && H == hc - gap_cost2(i_o1, i_e1, i_o2, i_e2, two, kk));
+                const unsigned mx = gballot(!del_ok && !ins_ok);
+                const int fd = md ? __ffs(md) - 1 : LPP, fi = mi ? __ffs(mi) - 1 : LPP, fx = mx ? __ffs(mx) - 1 : LPP;
+                const int src = min(min(fd, fi), LPP - 1);
+                const int Hfd = __shfl_sync(FULL, hr, src, LPP), Hfi = __shfl_sync(FULL, hc, src, LPP);
+                const int hr_l = __shfl_sync(FULL, hr, LPP - 1, LPP), hc_l = __shfl_sync(FULL, hc, LPP - 1, LPP);
+                const uint32_t bd_l = __shfl_sync(FULL, bd, LPP - 1, LPP), bi_l = __shfl_sync(FULL, bi, LPP - 1, LPP);
+                if (search) {
+                    if (min(fd, fi) < fx) {                       // at equal length the deletion comes first
+                        search = false;
+                        if (fd <= fi) { const int len = k0 + fd + 1; SVP_EMITG(SVP_CIGAR_D, (uint32_t)len); ++n_do; n_db += len; j -= len; H = Hfd; }
+                        else { const int len = k0 + fi + 1; SVP_EMITG(SVP_CIGAR_I, (uint32_t)len); ++n_io; n_ib += len; i -= len; H = Hfi; }
+                    } else if (fx < LPP) {
+                        search = false; bad = true; done = true;      // no predecessor explains H
+                    } else { Hrow = hr_l; Hcol = hc_l; brow = bd_l; bcol = bi_l; }
+                }
+                k0 += LPP;
+            }
+        }
+    }
+    // ---- 3. the alignment starts at the lowest point of the walk ------------------------------------------------------------
+    const int cut_low = low;
+    i = low_i; j = low_j; wpos = low_wpos; cur_op = low_op; cur_len = low_len; ovf = low_ovf;
+    if (act) SVP_PUSHG();
+#undef SVP_PUSHG
+#undef SVP_EMITG
+    if (bad) res.status |= SVP_ST_SCORE_OVF;
+    res.score = M - cut_low;
+    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
+    res.n_match = l_match; res.n_mismatch = l_mis; res.n_ins_ops = l_io; res.n_ins_bp = l_ib; res.n_del_ops = l_do; res.n_del_bp = l_db;
+    __syncwarp();
+    // directed distance over the CIGAR the group just wrote: the lanes of the group share the runs
+    const int n_runs = (act && !ovf) ? (int)tk.cigar_cap - wpos : 0;
+    const int n_runs_max = __reduce_max_sync(FULL, n_runs);
+    double dist = 0.0;
+    for (int a = lane; a < n_runs_max; a += LPP) {
+        if (a < n_runs) {
+            const uint32_t w = slot[wpos + a];
+            const uint32_t op = w & 15u, len = w >> 4;
+            if (op != SVP_CIGAR_M && (int)len >= cs.min_signal) {
+                const double sz = (double)len;
+                dist += (1.0 - exp(-pow(sz / 30.0, 1.5))) * sz;
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = LPP / 2; o; o >>= 1) dist += __shfl_xor_sync(FULL, dist, o, LPP);
+    if (act && lane == 0) {
+        if (ovf) { res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0; }
+        else { res.cigar_len = tk.cigar_cap - (uint32_t)wpos; res.cigar_off = tk.cigar_off + (uint32_t)wpos; res.sv_dist = dist; }
+        results[tk.pair_index] = res;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Wave scheduling: the walks of a wave as kernels of their own, launched by the host behind the wave's forward kernels. The rows
 // were written by earlier kernels, so plain (L1-cached) loads are legal here.
 //   svp_tb_kernel    one THREAD per pair: the bulk walker — 32 walks per warp on one instruction stream, ~1 % of the forward
@@ -1634,6 +1953,20 @@ svp_tbg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     if (gid >= n_tasks) return;                    // (every cross-lane operation of the walk names its own group only)
     const Task tk = tasks[order ? order[gid] : (uint32_t)gid];
     svp_traceback_warp<false, LPP>(tk, arena + tk.tb_off, reinterpret_cast<const uint2*>(arena + tk.tb_off + tk.tb_bytes), seqs, results, cigar, cs, 0u);
+}
+
+//   svp_tbu_kernel   the same on ONE instruction stream per warp (svp_traceback_groups): the bulk walker of serial waves
+#ifndef SVP_TBU_MIN_CTAS
+#define SVP_TBU_MIN_CTAS 5
+#endif
+template <int LPP>
+__global__ void __launch_bounds__(128, SVP_TBU_MIN_CTAS)
+svp_tbu_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ order, int n_tasks, const uint8_t* __restrict__ seqs,
+               const uint8_t* __restrict__ arena, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs) {
+    const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPP);
+    if ((int)((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / LPP) >= n_tasks) return;       // the whole warp is beyond the list
+    // all 32 lanes stay together; a group without a pair idles
+    svp_traceback_groups<LPP>(gid < n_tasks ? tasks + (order ? order[gid] : (uint32_t)gid) : nullptr, arena, seqs, results, cigar, cs);
 }
 
 }  // namespace svp
