@@ -862,6 +862,11 @@ static int run_waves(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
             if ((long)tasks[k].m + tasks[k].n <= h->tbw_long) order[pos++] = (uint32_t)k;
         }
         L.n_short = pos - L.first_short;
+        // the groups of a warp walk in lockstep until the longest of them is done (svp_traceback_groups): neighbours in the list
+        // should be equally long; longest first, so that the kernel's tail is short walks
+        std::sort(order + L.first_short, order + pos, [&](uint32_t a, uint32_t b) {
+            const long la = (long)tasks[a].m + tasks[a].n, lb = (long)tasks[b].m + tasks[b].n;
+            return la != lb ? la > lb : a < b; });
         L.first_long = pos;
         for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
             if (!(tasks[k].flags & TASK_INVALID) && (long)tasks[k].m + tasks[k].n > h->tbw_long) order[pos++] = (uint32_t)k;

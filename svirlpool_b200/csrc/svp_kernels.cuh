@@ -1555,7 +1555,7 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
 // every VOTE / REDUX executed four times.
 // ---------------------------------------------------------------------------------------------
 template <int LPP>
-__device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, const uint8_t* __restrict__ arena,
+__device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tkp, const uint8_t* __restrict__ arena,
                                                   const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
                                                   uint32_t* __restrict__ cigar, const Consts& cs) {
     static_assert(LPP == 4 || LPP == 8 || LPP == 16, "lanes per pair");
@@ -1569,16 +1569,23 @@ __device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, 
         return x;
     };
     const bool have = tkp != nullptr;
-    // the group's pair (an idle group gets a harmless geometry; everything it does is predicated off)
-    Task tk;
-    if (have) tk = *tkp;
-    else { memset(&tk, 0, sizeof(tk)); tk.flags = 4u << TASK_KP_SHIFT; tk.band_w = 16; tk.m = 1; tk.n = 1; tk.tb_bytes = 16; tk.r_begin = 2; }
+    // the group's pair, field by field into registers (an idle group gets a harmless geometry; everything it does is predicated off)
+    struct { uint64_t q_off, t_off, tb_bytes, tb_off, cells; int32_t m, n, band_lo, band_w, r_begin; uint32_t flags, pair_index, cigar_off, cigar_cap; } tk;
+    tk.q_off = have ? tkp->q_off : 0; tk.t_off = have ? tkp->t_off : 0; tk.tb_bytes = have ? tkp->tb_bytes : 16; tk.tb_off = have ? tkp->tb_off : 0;
+    tk.cells = have ? tkp->cells : 0; tk.m = have ? tkp->m : 1; tk.n = have ? tkp->n : 1; tk.band_lo = have ? tkp->band_lo : 0;
+    tk.band_w = have ? tkp->band_w : 16; tk.r_begin = have ? tkp->r_begin : 2; tk.flags = have ? tkp->flags : (4u << TASK_KP_SHIFT);
+    tk.pair_index = have ? tkp->pair_index : 0; tk.cigar_off = have ? tkp->cigar_off : 0; tk.cigar_cap = have ? tkp->cigar_cap : 0;
     const uint8_t* rows = arena + tk.tb_off;
     const uint2* bests = reinterpret_cast<const uint2*>(rows + tk.tb_bytes);
-    svp_result res;
-    res.score = 0; res.status = 0; res.q_beg = res.q_end = res.t_beg = res.t_end = 0;
-    res.n_match = res.n_mismatch = res.n_ins_ops = res.n_ins_bp = res.n_del_ops = res.n_del_bp = 0;
-    res.cigar_off = tk.cigar_off; res.cigar_len = 0; res.sv_dist = 0.0; res.cells = tk.cells;
+    auto write_result = [&](uint32_t status, int score, int q_beg, int q_end, int t_beg, int t_end, uint32_t nm, uint32_t nx, uint32_t io, uint32_t ib,
+                            uint32_t dop, uint32_t db, uint32_t c_off, uint32_t c_len, double dist) {
+        svp_result r;
+        r.score = score; r.status = status; r.q_beg = q_beg; r.q_end = q_end; r.t_beg = t_beg; r.t_end = t_end;
+        r.n_match = nm; r.n_mismatch = nx; r.n_ins_ops = io; r.n_ins_bp = ib; r.n_del_ops = dop; r.n_del_bp = db;
+        r.cigar_off = c_off; r.cigar_len = c_len; r.sv_dist = dist; r.cells = tk.cells;
+        results[tk.pair_index] = r;
+    };
+    uint32_t status = 0;
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
     TbView<false> v;
     v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
@@ -1610,8 +1617,8 @@ __device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, 
         if (M2 > M || (M2 == M && b2 < blk)) { M = M2; blk = b2; }
     }
     const bool act = have && M > 0;                              // the group has a walk to do
-    if (have && !act) { res.status = SVP_ST_NOHIT; if (lane == 0) results[tk.pair_index] = res; }
-    if (act && !(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) res.status |= SVP_ST_SCORE_OVF;
+    if (have && !act && lane == 0) write_result(SVP_ST_NOHIT, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, tk.cigar_off, 0, 0.0);
+    if (act && !(tk.flags & (TASK_S32 | TASK_REBASE)) && M >= 32767 - cs.a_max) status |= SVP_ST_SCORE_OVF;
     int end_s = 0x7FFFFFFF, end_x = -1;
     const int NC = 2 * KP * KP;
     const int NC_max = __reduce_max_sync(FULL, NC);
@@ -1832,10 +1839,7 @@ __device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, 
     if (act) SVP_PUSHG();
 #undef SVP_PUSHG
 #undef SVP_EMITG
-    if (bad) res.status |= SVP_ST_SCORE_OVF;
-    res.score = M - cut_low;
-    res.q_beg = i; res.q_end = best_i; res.t_beg = j; res.t_end = best_j;
-    res.n_match = l_match; res.n_mismatch = l_mis; res.n_ins_ops = l_io; res.n_ins_bp = l_ib; res.n_del_ops = l_do; res.n_del_bp = l_db;
+    if (bad) status |= SVP_ST_SCORE_OVF;
     __syncwarp();
     // directed distance over the CIGAR the group just wrote: the lanes of the group share the runs
     const int n_runs = (act && !ovf) ? (int)tk.cigar_cap - wpos : 0;
@@ -1854,9 +1858,8 @@ __device__ __noinline__ void svp_traceback_groups(const Task* __restrict__ tkp, 
     #pragma unroll
     for (int o = LPP / 2; o; o >>= 1) dist += __shfl_xor_sync(FULL, dist, o, LPP);
     if (act && lane == 0) {
-        if (ovf) { res.status |= SVP_ST_CIGAR_OVF; res.cigar_len = 0; }
-        else { res.cigar_len = tk.cigar_cap - (uint32_t)wpos; res.cigar_off = tk.cigar_off + (uint32_t)wpos; res.sv_dist = dist; }
-        results[tk.pair_index] = res;
+        if (ovf) write_result(status | SVP_ST_CIGAR_OVF, M - cut_low, i, best_i, j, best_j, l_match, l_mis, l_io, l_ib, l_do, l_db, tk.cigar_off, 0, 0.0);
+        else write_result(status, M - cut_low, i, best_i, j, best_j, l_match, l_mis, l_io, l_ib, l_do, l_db, tk.cigar_off + (uint32_t)wpos, tk.cigar_cap - (uint32_t)wpos, dist);
     }
 }
 
