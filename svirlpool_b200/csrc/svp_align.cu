@@ -134,7 +134,7 @@ struct svp_handle {
     bool waves = true;
     bool queue = false;
     cudaStream_t stream_walk = nullptr;         // queue: the call's walker kernel (highest priority: resident before the forward CTAs flood the SMs)
-    int walk_ctas_per_sm = 1;                   // queue: walker CTAs (one warp each) per SM and call (env SVP_WALK_CTAS_PER_SM)
+    int walk_ctas_per_sm = 4;                   // queue: walker CTAs (one warp each) per SM and call (env SVP_WALK_CTAS_PER_SM)
     long walk_wait_ns = 100000;                 // queue: how long a walker waits for a full batch of 32 (env SVP_WALK_WAIT_NS)
     long queue_min_pairs = 2048;                // queue: calls of fewer pairs walk inside their CTAs (a warp per walk: a third of the latency)
     cudaStream_t stream_tb = nullptr;           // waves: the walk kernels (high priority; they overlap the next wave's forward pass)
@@ -403,7 +403,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
     // a walker launched with the default split (all L1) would keep every forward CTA that needs shared memory off its SM —
     // with a walker on all 148 SMs nothing would ever run. Same split for both.
     if (cudaFuncSetAttribute(svp_walkq_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
-        cudaFuncSetAttribute(svp_walkq_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+        cudaFuncSetAttribute(svp_walkq_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaFuncSetAttribute(svp_walkqg_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
         cudaGetLastError();
         return bail(SVP_ERR_CUDA, "cudaFuncSetAttribute failed");
     }
@@ -1075,7 +1076,7 @@ static int run_arena(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
     // and not the groups whose CTA needs (nearly) a whole SM — 14+ warps at up to 128 registers, or sequence images filling the
     // shared memory: such a CTA cannot become resident beside a walker CTA, and the walkers stay until every queued pair is
     // walked, so it must not depend on them.
-    constexpr int WALKER_REGS = 32 * 255;
+    constexpr int WALKER_REGS = 32 * 128;
     size_t n_queued = 0;
     const bool use_queue = h->queue && (long)(n - n_invalid) >= h->queue_min_pairs;
     for (Group& g : groups) {
@@ -1118,10 +1119,13 @@ static int run_arena(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
     // on config 2 where the forward passes alone run at 688.)
     c.n_walkers = 0;
     if (d_queue) {
-        const unsigned ctas = (unsigned)std::min<size_t>((size_t)h->sm_count * (size_t)h->walk_ctas_per_sm, (n_queued + 31) / 32);
+        const unsigned ctas = (unsigned)std::min<size_t>((size_t)h->sm_count * (size_t)h->walk_ctas_per_sm, (n_queued + 3) / 4);
         CUDA_TRY(h, cudaStreamWaitEvent(h->stream_walk, ev_copied, 0));
+        // walkers (env SVP_WALKER): groups (default) — 4 pairs per warp on one instruction stream, 8 lanes each; lanes — one pair per lane
+        static const bool lane_walkers = [] { const char* e = getenv("SVP_WALKER"); return e && std::string(e) == "lanes"; }();
         static const bool lean = [] { const char* e = getenv("SVP_WALK_LEAN"); return e && atoi(e) != 0; }();
-        if (lean) svp_walkq_kernel<16><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
+        if (!lane_walkers) svp_walkqg_kernel<8><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
+        else if (lean) svp_walkq_kernel<16><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
         else svp_walkq_kernel<1><<<ctas, 32, 0, h->stream_walk>>>(d_seqs, ar, d_results, d_cigar, cs, (uint32_t)h->walk_wait_ns);
         c.n_walkers = ctas;
         c.stats.tb_launches = 1;

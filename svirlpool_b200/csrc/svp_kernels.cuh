@@ -1554,8 +1554,9 @@ __device__ __noinline__ void svp_traceback_warp(const Task& tk, const uint8_t* _
 // profiles/ncu_tbg_r02_v1.json (group masks, divergent groups): 524 k warp instructions per warp of four pairs, 771 per round,
 // every VOTE / REDUX executed four times.
 // ---------------------------------------------------------------------------------------------
-template <int LPP>
-__device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tkp, const uint8_t* __restrict__ arena,
+// rows: the group's slice (rows, then best records); CG: loads of the slice through L2 (written by a concurrently running grid)
+template <int LPP, bool CG>
+__device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tkp, const uint8_t* __restrict__ rows,
                                                   const uint8_t* __restrict__ seqs, svp_result* __restrict__ results,
                                                   uint32_t* __restrict__ cigar, const Consts& cs) {
     static_assert(LPP == 4 || LPP == 8 || LPP == 16, "lanes per pair");
@@ -1570,12 +1571,11 @@ __device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tk
     };
     const bool have = tkp != nullptr;
     // the group's pair, field by field into registers (an idle group gets a harmless geometry; everything it does is predicated off)
-    struct { uint64_t q_off, t_off, tb_bytes, tb_off, cells; int32_t m, n, band_lo, band_w, r_begin; uint32_t flags, pair_index, cigar_off, cigar_cap; } tk;
-    tk.q_off = have ? tkp->q_off : 0; tk.t_off = have ? tkp->t_off : 0; tk.tb_bytes = have ? tkp->tb_bytes : 16; tk.tb_off = have ? tkp->tb_off : 0;
+    struct { uint64_t q_off, t_off, tb_bytes, cells; int32_t m, n, band_lo, band_w, r_begin; uint32_t flags, pair_index, cigar_off, cigar_cap; } tk;
+    tk.q_off = have ? tkp->q_off : 0; tk.t_off = have ? tkp->t_off : 0; tk.tb_bytes = have ? tkp->tb_bytes : 16;
     tk.cells = have ? tkp->cells : 0; tk.m = have ? tkp->m : 1; tk.n = have ? tkp->n : 1; tk.band_lo = have ? tkp->band_lo : 0;
     tk.band_w = have ? tkp->band_w : 16; tk.r_begin = have ? tkp->r_begin : 2; tk.flags = have ? tkp->flags : (4u << TASK_KP_SHIFT);
     tk.pair_index = have ? tkp->pair_index : 0; tk.cigar_off = have ? tkp->cigar_off : 0; tk.cigar_cap = have ? tkp->cigar_cap : 0;
-    const uint8_t* rows = arena + tk.tb_off;
     const uint2* bests = reinterpret_cast<const uint2*>(rows + tk.tb_bytes);
     auto write_result = [&](uint32_t status, int score, int q_beg, int q_end, int t_beg, int t_end, uint32_t nm, uint32_t nx, uint32_t io, uint32_t ib,
                             uint32_t dop, uint32_t db, uint32_t c_off, uint32_t c_len, double dist) {
@@ -1587,7 +1587,7 @@ __device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tk
     };
     uint32_t status = 0;
     const int KP = (int)((tk.flags & TASK_KP_MASK) >> TASK_KP_SHIFT);
-    TbView<false> v;
+    TbView<CG> v;
     v.base = rows; v.seqs32 = reinterpret_cast<const uint32_t*>(seqs);
     v.band_lo = tk.band_lo; v.r_begin = tk.r_begin; v.m = tk.m; v.n = tk.n;
     v.set_geometry(tk.band_w, KP);
@@ -1605,7 +1605,7 @@ __device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tk
     int M = 0; uint32_t blk = 0xFFFFFFFFu;
     for (int e = lane; e < n_ent_max; e += LPP) {
         if (e < n_ent) {
-            const uint2 b = bests[e];
+            const uint2 b = ldbest<CG>(bests + e);
             const int val = (int)b.x;
             if (val > M || (val == M && b.y < blk)) { M = val; blk = b.y; }
         }
@@ -1625,7 +1625,7 @@ __device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tk
     for (int e0 = 0; e0 < n_ent_max; e0 += LPP) {
         const int e = e0 + lane;
         bool hit = false;
-        if (act && e < n_ent) { const uint2 b = bests[e]; hit = ((int)b.x == M) && (b.y == blk); }
+        if (act && e < n_ent) { const uint2 b = ldbest<CG>(bests + e); hit = ((int)b.x == M) && (b.y == blk); }
         unsigned mask = gballot(hit);
         while (__any_sync(FULL, mask != 0u)) {
             const bool on = mask != 0u;
@@ -1640,7 +1640,7 @@ __device__ __forceinline__ void svp_traceback_groups(const Task* __restrict__ tk
                 uint32_t mine = 0;
                 if (on && idx < NC) {
                     const int s = s0 + idx / KP, x = xbase + 2 * (idx % KP) + (s & 1);
-                    mine = (uint32_t)*v.addr_sx(s, x);
+                    mine = ldrow<CG>(v.addr_sx(s, x));
                 }
                 #pragma unroll
                 for (int l = 0; l < LPP; ++l) {
@@ -1969,7 +1969,60 @@ svp_tbu_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
     const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) / LPP);
     if ((int)((blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) / LPP) >= n_tasks) return;       // the whole warp is beyond the list
     // all 32 lanes stay together; a group without a pair idles
-    svp_traceback_groups<LPP>(gid < n_tasks ? tasks + (order ? order[gid] : (uint32_t)gid) : nullptr, arena, seqs, results, cigar, cs);
+    const Task* tp = gid < n_tasks ? tasks + (order ? order[gid] : (uint32_t)gid) : nullptr;
+    svp_traceback_groups<LPP, false>(tp, arena + (tp ? tp->tb_off : 0), seqs, results, cigar, cs);
+}
+
+
+// Queue scheduling, group walkers: one warp per CTA, resident for the whole call; a walker takes up to 32 / LPP consecutive published
+// entries off the queue and walks them on one instruction stream (svp_traceback_groups), one pair per group of LPP lanes. A partial
+// batch waits up to `wait_ns` for more entries. Loads of the rows through L2 (written by concurrently running grids, slices recycled).
+template <int LPP>
+__global__ void __launch_bounds__(32, 16)
+svp_walkqg_kernel(const uint8_t* __restrict__ seqs, const Arena ar, svp_result* __restrict__ results, uint32_t* __restrict__ cigar, const Consts cs,
+                  const uint32_t wait_ns) {
+    constexpr int NG = 32 / LPP;
+    WalkQueue* Q = ar.queue;
+    const int lane = threadIdx.x, grp = lane / LPP;
+    const uint32_t n = Q->n;
+    unsigned long long t_first = 0;
+    for (;;) {
+        uint32_t h = 0;
+        if (lane == 0) h = *(volatile uint32_t*)&Q->head;
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h >= n) return;
+        const bool ready = (h + (uint32_t)grp < n) && *(volatile uint32_t*)&Q->e[h + grp].task != WALK_EMPTY;
+        const unsigned m = __ballot_sync(0xffffffffu, ready);
+        int cnt = 0;                                             // published entries in a row from the head (one bit per group's first lane)
+        #pragma unroll
+        for (int g = 0; g < NG; ++g) if (cnt == g && ((m >> (g * LPP)) & 1u)) cnt = g + 1;
+        const int want = (int)min((uint32_t)NG, n - h);
+        if (cnt == 0) { t_first = 0; __nanosleep(2000); continue; }
+        if (cnt < want) {
+            unsigned long long now = globaltimer_ns();
+            now = __shfl_sync(0xffffffffu, now, 0);
+            if (!t_first) t_first = now;
+            if (now - t_first < (unsigned long long)wait_ns) { __nanosleep(1000); continue; }
+        }
+        t_first = 0;
+        int ok = 0;
+        if (lane == 0) ok = atomicCAS(&Q->head, h, h + (uint32_t)cnt) == h;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        __threadfence();
+        const unsigned long long t0 = globaltimer_ns();
+        const bool mine = grp < cnt;
+        const uint32_t task = mine ? *(volatile uint32_t*)&Q->e[h + grp].task : 0u;
+        const uint32_t pool_id = mine ? *(volatile uint32_t*)&Q->e[h + grp].pool_id : 0u;
+        const uint64_t o = mine ? *(volatile uint64_t*)&Q->e[h + grp].arena_off : 0ull;
+        if (!ar.skip_walk) svp_traceback_groups<LPP, true>(mine ? ar.tasks + task : nullptr, ar.base + o, seqs, results, cigar, cs);
+        __syncwarp();
+        for (int g = 0; g < cnt; ++g) {                          // slices back to their pools, one group at a time (the pools' spin locks)
+            if (grp == g && (lane % LPP) == 0) arena_free(ar, pool_id, o);
+            __syncwarp();
+        }
+        if (lane == 0) { atomicAdd(ar.clocks + 4, globaltimer_ns() - t0); atomicAdd(ar.clocks + 5, 1ull); atomicAdd(ar.clocks + 2, (unsigned long long)cnt); }
+    }
 }
 
 }  // namespace svp
