@@ -162,6 +162,8 @@ struct svp_handle {
     std::string err;
     int max_smem_optin = 0;
     long ring_min = 4096;                       // fast path: sliding windows when whole images exceed this many bytes per warp of the CTA (env SVP_RING_MIN)
+    long ring_min_single = 4096;                // ... of a single-warp CTA (env SVP_RING_MIN_SINGLE). Whole images for 8 kb pairs (20000) were measured
+                                                // within +-2 % on config 2 and 6 % slower on config 4 (more launch groups): windows stay
     long small_call_pairs = 1024;               // calls of at most this many pairs use the KP = 4 / 8 widths only (env SVP_SMALL_CALL_PAIRS; plan_pair)
     long latency_pairs = 0;                     // calls of at most this many pairs are planned for short steps (more, narrower warps) instead of fewest
                                                 // issue slots (env SVP_LATENCY_PAIRS). Off by default: measured SLOWER for one container per call
@@ -262,7 +264,8 @@ static int make_consts(const svp_scoring& s, Consts& c, std::string& why) {
 
 // tuning / test knobs read from the environment when a handle (or a planning-only pseudo handle) is set up
 static void read_env_knobs(svp_handle* h) {
-    if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = atol(e);
+    if (const char* e = getenv("SVP_RING_MIN")) h->ring_min = h->ring_min_single = atol(e);
+    if (const char* e = getenv("SVP_RING_MIN_SINGLE")) h->ring_min_single = atol(e);
     if (const char* e = getenv("SVP_FORCE_RING")) h->force_ring = atoi(e) != 0;
     if (const char* e = getenv("SVP_LATENCY_PAIRS")) h->latency_pairs = atol(e);
     if (const char* e = getenv("SVP_SMALL_CALL_PAIRS")) h->small_call_pairs = atol(e);
@@ -688,7 +691,7 @@ static void plan_pair(const svp_handle* h, int call_kind, const svp_pair& p, uin
         if (kp == 0) { kp = 8; cl = cluster_for(p.band_w, 128 * 8); }
         if (!ring && cl) {
             const int nw = cl > 1 ? 16 : (int)((p.band_w + 128 * kp - 1) / (128 * kp));
-            ring = ((long)seq_image_bytes(t.m) + (long)seq_image_bytes(t.n)) / nw > ring_min;
+            ring = ((long)seq_image_bytes(t.m) + (long)seq_image_bytes(t.n)) / nw > (nw == 1 ? h->ring_min_single : ring_min);
         }
     }
     if (cl == 0) { t.flags |= TASK_INVALID; return; }                         // band too wide for every variant
