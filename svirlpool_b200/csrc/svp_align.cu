@@ -757,7 +757,12 @@ static inline int family_of(const Task& t, const Consts& cs) {
 static void make_groups(const svp_handle* h, const Task* tasks, const uint32_t* idx, size_t n_idx, bool slice_classes, uint32_t* order, size_t& pos,
                         std::vector<Group>& groups) {
     const Consts& cs = h->cs;
-    std::map<std::array<int64_t, 8>, std::vector<uint32_t>> by_key;
+    // one 64-bit sort key per pair: [group key: 31 bits][0xFFFFFFFF - n_iter: 32 bits] + the task index beside it; a single sort puts the
+    // pairs of a group next to each other, longest first (a map of vectors and a sort per group cost ~4 ms per 35 000 pairs — GPU idle
+    // time of a blocking call)
+    struct Item { uint64_t key; uint32_t task; };
+    std::vector<Item> items;
+    items.reserve(n_idx);
     for (size_t a = 0; a < n_idx; ++a) {
         const uint32_t k = idx ? idx[a] : (uint32_t)a;
         const Task& t = tasks[k];
@@ -770,23 +775,28 @@ static void make_groups(const svp_handle* h, const Task* tasks, const uint32_t* 
         // slice-size classes (x1.5 steps) keep the ballast of a regular group close to what each of its pairs needs
         int size_cls = 0;
         if (slice_classes && !huge) for (uint64_t b = (uint64_t)1 << 20; b < t.slice_bytes; b += b / 2) ++size_cls;
-        by_key[{ family_of(t, cs), kp_of(t), nw, cluster_of(t), ring, smem_cls, huge, size_cls }].push_back(k);
+        const uint64_t gkey = ((uint64_t)family_of(t, cs) << 28) | ((uint64_t)kp_of(t) << 23) | ((uint64_t)nw << 18) | ((uint64_t)cluster_of(t) << 14) |
+                              ((uint64_t)ring << 13) | ((uint64_t)smem_cls << 8) | ((uint64_t)huge << 7) | (uint64_t)std::min(size_cls, 127);
+        items.push_back({ (gkey << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)t.n_iter), k });
     }
+    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.key != b.key ? a.key < b.key : a.task < b.task; });
     const size_t g0 = groups.size();
-    for (auto& kv : by_key) {
-        std::vector<uint32_t>& v = kv.second;
-        std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tasks[a].n_iter > tasks[b].n_iter; });
-        Group g{ (int)kv.first[0], (int)kv.first[2], (int)kv.first[1], (int)kv.first[3], kv.first[4] != 0, kv.first[6] != 0, false, pos, v.size(), 0, 0, 0 };
+    for (size_t a = 0; a < items.size();) {
+        const uint64_t gkey = items[a].key >> 32;
+        size_t e = a;
+        while (e < items.size() && (items[e].key >> 32) == gkey) ++e;
+        Group g{ (int)((gkey >> 28) & 7), (int)((gkey >> 18) & 31), (int)((gkey >> 23) & 31), (int)((gkey >> 14) & 15), ((gkey >> 13) & 1) != 0, ((gkey >> 7) & 1) != 0,
+                 false, pos, e - a, 0, 0, 0 };
         const int lane_cost = (g.fam == FAM_S32 || g.fam == FAM_S32_GEN) ? 2 : 1;
-        for (uint32_t k : v) {
-            const Task& t = tasks[k];
+        for (size_t x = a; x < e; ++x) {
+            const Task& t = tasks[items[x].task];
             g.smem = std::max(g.smem, smem_need(t, cs, g.nwarp));
             g.max_slice = std::max(g.max_slice, t.slice_bytes);
             g.work += (uint64_t)t.n_iter * g.nwarp * g.kp * lane_cost * (steps_per_iter_of(t) / (2 * g.kp)) * g.cluster;
+            order[pos++] = items[x].task;
         }
-        std::copy(v.begin(), v.end(), order + pos);
-        pos += v.size();
         groups.push_back(g);
+        a = e;
     }
     std::sort(groups.begin() + g0, groups.end(), [](const Group& a, const Group& b) { return a.work * b.count > b.work * a.count; });
 }
@@ -868,9 +878,15 @@ static int run_waves(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
         L.n_short = pos - L.first_short;
         // the groups of a warp walk in lockstep until the longest of them is done (svp_traceback_groups): neighbours in the list
         // should be equally long; longest first, so that the kernel's tail is short walks
-        std::sort(order + L.first_short, order + pos, [&](uint32_t a, uint32_t b) {
-            const long la = (long)tasks[a].m + tasks[a].n, lb = (long)tasks[b].m + tasks[b].n;
-            return la != lb ? la > lb : a < b; });
+        {
+            std::vector<uint64_t> keyed(pos - L.first_short);
+            for (size_t a = 0; a < keyed.size(); ++a) {
+                const uint32_t k = order[L.first_short + a];
+                keyed[a] = ((uint64_t)(0xFFFFFFFFu - (uint32_t)(tasks[k].m + tasks[k].n)) << 32) | k;
+            }
+            std::sort(keyed.begin(), keyed.end());
+            for (size_t a = 0; a < keyed.size(); ++a) order[L.first_short + a] = (uint32_t)keyed[a];
+        }
         L.first_long = pos;
         for (size_t k = waves[wv].first; k < waves[wv].second; ++k)
             if (!(tasks[k].flags & TASK_INVALID) && (long)tasks[k].m + tasks[k].n > h->tbw_long) order[pos++] = (uint32_t)k;
@@ -1195,7 +1211,20 @@ static int plan_and_run(svp_handle* h, const uint8_t* d_seqs, size_t packed_byte
     if (rc != SVP_OK) return rc;
     // few pairs: optionally favour short steps (see latency_pairs)
     const int latency = ((long)n_pairs <= h->latency_pairs ? 1 : 0) | ((long)n_pairs <= h->small_call_pairs ? 2 : 0);
-    for (uint32_t k = 0; k < n_pairs; ++k) plan_pair(h, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
+    // planning is the GPU's idle time in a blocking call: large batches are planned by several host threads (every pair is independent)
+    static const int plan_threads = [] { const char* e = getenv("SVP_PLAN_THREADS"); int v = e ? atoi(e) : 4; return std::min(std::max(v, 1), 16); }();
+    const int nt = n_pairs >= 8192 ? std::min<int>(plan_threads, (int)std::max(1u, std::thread::hardware_concurrency())) : 1;
+    auto plan_range = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t k = lo; k < hi; ++k) plan_pair(h, latency, pairs[k], k, seq_off, seq_len, n_seqs, packed_bytes, cigar_words, need_padding, c->h_tasks[k]);
+    };
+    if (nt <= 1) plan_range(0, n_pairs);
+    else {
+        std::vector<std::thread> workers;
+        const uint32_t per = (n_pairs + (uint32_t)nt - 1) / (uint32_t)nt;
+        for (int w = 1; w < nt; ++w) workers.emplace_back(plan_range, std::min(n_pairs, (uint32_t)w * per), std::min(n_pairs, (uint32_t)(w + 1) * per));
+        plan_range(0, std::min(n_pairs, per));
+        for (std::thread& w : workers) w.join();
+    }
     return run_plan(h, *c, n_pairs, d_seqs, d_results, d_cigar, wait);
 }
 

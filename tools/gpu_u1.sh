@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+export SVP_CALL_TIMEOUT_S=60
+run() { name=$1; w=$2; shift; shift; env "$@" timeout 300 python bench.py --workload $w --no-cpu-baseline --scaling-pool 0 > $O/u1_$name.json 2>$O/u1_$name.err; python -c "
+import json,sys
+try:
+    d=json.load(open('gpurun_out/u1_$name.json')); print('$name: regions/s', round(d['regions_per_s'],1), 'GCUPS', round(d['value']), 'e2e r/s', round(d['e2e']['regions_per_s'],1), {k:(round(v,1) if isinstance(v,float) else v) for k,v in d['kernel_ms'].items() if k!='note'}, 'launches', d['roofline']['launches'])
+except Exception as e: print('$name failed', e); print(open('gpurun_out/u1_$name.err').read()[-600:])"; }
+run base config2 A=1
+run nokp4 config2 SVP_KP_MASK=30
+run multi2 config2 SVP_KP_MULTI=1
