@@ -111,6 +111,7 @@ struct CallSet {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;               // first enqueue on the main stream / last kernel done
     bool pending = false;                                       // enqueued, times not collected yet
     size_t n_waves = 0;                                         // wave scheduling: waves of this call (their events: wave_events)
+    std::vector<std::pair<size_t, size_t>> wave_ranges;        // ... their [first, last) task ranges (input order)
     std::vector<cudaEvent_t> wave_events;                       // timing events, EV_PER_WAVE per wave
     svp_stats stats{};                                          // counts filled at submit, times at collection
 };
@@ -133,6 +134,7 @@ struct svp_handle {
     //                    kernel (one walk per lane)
     bool waves = true;
     bool queue = false;
+    cudaStream_t stream_copy = nullptr;         // host-buffer calls: results and CIGARs of a finished wave go home under the next wave
     cudaStream_t stream_walk = nullptr;         // queue: the call's walker kernel (highest priority: resident before the forward CTAs flood the SMs)
     int walk_ctas_per_sm = 4;                   // queue: walker CTAs (one warp each) per SM and call (env SVP_WALK_CTAS_PER_SM)
     long walk_wait_ns = 100000;                 // queue: how long a walker waits for a full batch of 32 (env SVP_WALK_WAIT_NS)
@@ -384,7 +386,8 @@ extern "C" int svp_create(int device, const svp_scoring* scoring, size_t max_tb_
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if (cudaStreamCreateWithPriority(&h->stream_tb, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaStreamCreateWithPriority(&h->stream_tb2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
+            cudaStreamCreateWithPriority(&h->stream_walk, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) != cudaSuccess) return bail(SVP_ERR_CUDA, "cudaStreamCreate failed");
     }
     read_env_knobs(h);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -466,7 +469,7 @@ extern "C" void svp_destroy(svp_handle* h) {
     for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t sx : h->stream_aux) if (sx) cudaStreamDestroy(sx);
     if (h->stream) cudaStreamDestroy(h->stream);
-    for (cudaStream_t sx : { h->stream_tb, h->stream_tb2, h->stream_walk }) if (sx) cudaStreamDestroy(sx);
+    for (cudaStream_t sx : { h->stream_tb, h->stream_tb2, h->stream_walk, h->stream_copy }) if (sx) cudaStreamDestroy(sx);
     delete h;
 }
 
@@ -1019,6 +1022,7 @@ static int run_waves(svp_handle* h, CallSet& c, size_t n, const uint8_t* d_seqs,
     CUDA_TRY(h, cudaStreamWaitEvent(sT, ev_copied, 0));  // (a call of invalid pairs only: their rows are written on the main stream)
     CUDA_TRY(h, cudaEventRecord(c.ev_t1, sT));           // walks run in wave order on one stream: the last one ends the call
     c.n_waves = waves.size();
+    c.wave_ranges = waves;
     return SVP_OK;
 }
 
@@ -1292,9 +1296,60 @@ static int align_host(svp_handle* h, const uint8_t* packed_seqs, size_t packed_b
     CUDA_TRY(h, cudaMemcpyAsync(h->d_seqs.p, packed_seqs, packed_bytes, cudaMemcpyHostToDevice, h->stream));
     // a submitted device-resident call may still read the handle's sequence / result buffers only if it came through this
     // function, which always waits: nothing of ours is in flight on them here
-    int rc = plan_and_run(h, (const uint8_t*)h->d_seqs.p, padded, seq_off, seq_len, n_seqs, pairs, n_pairs, (svp_result*)h->d_results.p,
-                          (uint32_t*)h->d_cigar.p, cigar_words, false, true);
-    if (rc != SVP_OK) return rc;
+    static const bool stream_back = [] { const char* e = getenv("SVP_STREAM_BACK"); return e ? atoi(e) != 0 : true; }();
+    if (want_cigars && h->waves && stream_back && n_pairs) {
+        // Wave scheduling, several waves: the rows and CIGARs of a finished wave are copied back while the next wave computes (a wave is
+        // a range of consecutive pairs, so its part of the dense CIGAR layout follows the previous wave's). The dense staging buffer is
+        // sized before the kernels start: growing it later would wait for the device.
+        CUDA_TRY(h, h->d_dense.reserve(std::max<size_t>(cigar_words / 2, 1) * sizeof(uint32_t)));
+        CUDA_TRY(h, h->d_dense_off.reserve(n_pairs * sizeof(uint32_t)));
+        int rc = plan_and_run(h, (const uint8_t*)h->d_seqs.p, padded, seq_off, seq_len, n_seqs, pairs, n_pairs, (svp_result*)h->d_results.p,
+                              (uint32_t*)h->d_cigar.p, cigar_words, false, false);
+        if (rc != SVP_OK) return rc;
+        CallSet& c = h->sets[(h->call_idx - 1) & 1];
+        if (c.n_waves >= 2 && c.pending) {
+            cudaStream_t sc = h->stream_copy;
+            std::vector<uint32_t> dense_off(n_pairs), rel(n_pairs);
+            uint64_t total = 0;
+            bool too_small = false;
+            for (size_t wv = 0; wv < c.n_waves && !too_small; ++wv) {
+                const size_t first = c.wave_ranges[wv].first, last = c.wave_ranges[wv].second, cnt = last - first;
+                if (!cnt) continue;
+                CUDA_TRY(h, cudaStreamWaitEvent(sc, c.wave_events[wv * EV_PER_WAVE + 2], 0));            // this wave's walks are done
+                CUDA_TRY(h, cudaMemcpyAsync(results + first, (const svp_result*)h->d_results.p + first, cnt * sizeof(svp_result), cudaMemcpyDeviceToHost, sc));
+                CUDA_TRY(h, cudaStreamSynchronize(sc));
+                uint64_t wave_total = 0;
+                for (size_t k = first; k < last; ++k) { rel[k] = (uint32_t)wave_total; dense_off[k] = (uint32_t)(total + wave_total); wave_total += results[k].cigar_len; }
+                if (total + wave_total > cigar_words) { too_small = true; break; }
+                if (wave_total) {
+                    if (wave_total * sizeof(uint32_t) > h->d_dense.cap) {          // (rare: more than half of the slots used) — wait, then grow
+                        CUDA_TRY(h, cudaDeviceSynchronize());
+                        CUDA_TRY(h, h->d_dense.reserve(wave_total * sizeof(uint32_t)));
+                    }
+                    CUDA_TRY(h, cudaMemcpyAsync((uint32_t*)h->d_dense_off.p + first, rel.data() + first, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, sc));
+                    const int wpb = 8;
+                    svp_cigar_gather<<<(unsigned)((cnt + wpb - 1) / wpb), wpb * 32, 0, sc>>>((const svp_result*)h->d_results.p + first, (const uint32_t*)h->d_dense_off.p + first,
+                                                                                              (const uint32_t*)h->d_cigar.p, (uint32_t*)h->d_dense.p, (int)cnt);
+                    CUDA_TRY(h, cudaMemcpyAsync(cigar_buf + total, h->d_dense.p, wave_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc));
+                }
+                total += wave_total;
+            }
+            CUDA_TRY(h, cudaStreamSynchronize(sc));
+            rc = collect_call(h, c);
+            if (rc != SVP_OK) return rc;
+            if (too_small) return fail(h, SVP_ERR_ARG, "cigar_buf smaller than the CIGARs produced");
+            for (uint32_t k = 0; k < n_pairs; ++k) results[k].cigar_off = dense_off[k];
+            h->stats.reserved = 1;
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            return SVP_OK;
+        }
+        rc = collect_call(h, c);             // one wave: nothing to overlap with — the plain copy-back below
+        if (rc != SVP_OK) return rc;
+    } else {
+        int rc = plan_and_run(h, (const uint8_t*)h->d_seqs.p, padded, seq_off, seq_len, n_seqs, pairs, n_pairs, (svp_result*)h->d_results.p,
+                              (uint32_t*)h->d_cigar.p, cigar_words, false, true);
+        if (rc != SVP_OK) return rc;
+    }
     if (n_pairs) {
         CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, n_pairs * sizeof(svp_result), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
