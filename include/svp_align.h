@@ -104,10 +104,11 @@ typedef struct svp_handle svp_handle;
 int         svp_abi_version(void);
 int         svp_device_count(void);
 int         svp_scoring_preset(const char* name, svp_scoring* out);
-/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default: 48 GB, at most 60 % of the free
- * device memory). The arena holds the traceback rows of the pairs RESIDENT on the GPU (a pair's CTA takes a slice when it starts
- * and returns it when its walk is done), not of the batch; a pair whose rows exceed the arena makes the call fail with
- * SVP_ERR_NOMEM. Several handles / processes can share a device. */
+/* device < 0: current device. max_tb_bytes: size of the device traceback arena (0 = default: 64 GB, at most 60 % of the free
+ * device memory, so that several handles / processes share a device). With the default wave scheduler a call is cut into waves of
+ * pairs whose traceback rows fit the arena (or half of it), so a caller that owns the GPU and submits large batches should pass more
+ * (INTEGRATION.md "Memory and scheduling"); with SVP_MODE=arena / queue the arena only holds the rows of the pairs resident on the
+ * GPU. A pair whose rows exceed the arena makes the call fail with SVP_ERR_NOMEM. */
 int         svp_create(int device, const svp_scoring* scoring, size_t max_tb_bytes, svp_handle** out);
 void        svp_destroy(svp_handle* h);
 const char* svp_last_error(const svp_handle* h);
@@ -222,14 +223,15 @@ int svp_plan_pairs(const svp_scoring* scoring, size_t packed_bytes, const uint64
                    uint32_t n_seqs, const svp_pair* pairs, uint32_t n_pairs, size_t cigar_words, svp_pair_plan* out);
 
 typedef struct svp_stats {
-    double   fwd_ms;        /* device time of the call's kernels (forward pass and walk of a pair run inside one kernel) */
-    double   tb_ms;         /* fwd_ms x the walks' share of the CTAs' summed phase times (informational) */
+    double   fwd_ms;        /* wave scheduling: length of the union of the waves' forward intervals; arena / queue: the call's kernel time */
+    double   tb_ms;         /* wave scheduling: summed spans of the walk kernels; arena: fwd_ms x the walks' share of the CTAs' phase times;
+                             * queue: mean busy time of the walker warps (informational) */
     double   total_ms;      /* first enqueue -> last kernel end */
     uint64_t cells;         /* spec cells aligned */
     uint64_t tb_bytes;      /* traceback bytes written to HBM */
     uint32_t fwd_launches;  /* kernels launched */
-    uint32_t tb_launches;   /* 0 (no separate traceback kernel) */
-    uint32_t waves;         /* launch groups (kernel variant x CTA width x size class) */
+    uint32_t tb_launches;   /* walk kernels launched (0 when every CTA walks its own pair) */
+    uint32_t waves;         /* wave scheduling: waves; arena / queue: launch groups (kernel variant x CTA width x size class) */
     uint32_t reserved;
 } svp_stats;
 int svp_get_stats(const svp_handle* h, svp_stats* out);

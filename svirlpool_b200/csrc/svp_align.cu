@@ -1,9 +1,8 @@
 // svp_align.cu — C-ABI of the alignment hot path (include/svp_align.h) on top of the sm_100a
-// kernels in svp_kernels.cuh. Host side: validate, plan every pair (kernel geometry, arena slice), group the
-// pairs of a call by kernel variant, launch ONE kernel per group — forward pass and traceback of a pair
-// run back to back inside its CTA, which takes its traceback rows from the device-side arena and returns
-// them — and time the call with CUDA events on the launching stream. No CPU fallback: without a CUDA
-// device every entry point that computes returns SVP_ERR_NODEVICE.
+// kernels in svp_kernels.cuh. Host side: validate, plan every pair (kernel geometry, slice of traceback rows), group the
+// pairs by kernel variant, schedule them (SVP_MODE: waves — the host assigns the slices, forward kernels and walk kernels
+// alternate; arena / queue — device-side slice allocator, in-kernel or resident walkers), and time the call with CUDA events
+// on the launching stream. No CPU fallback: without a CUDA device every entry point that computes returns SVP_ERR_NODEVICE.
 #include <algorithm>
 #include <chrono>
 #include <thread>

@@ -10,16 +10,18 @@
 //   VIADDMNMX.S16x2 / VIMNMX3.S16x2(.RELU) / VIADD.16x2; match/mismatch comes from one HSET2.EQ
 //   on fp16-coded bases. Neighbour diagonals that belong to the adjacent thread travel by
 //   __shfl_up/__shfl_down (one register per state array per step), to the adjacent warp through
-//   a 16-byte shared-memory mailbox and one CTA barrier per step (st.async + mbarrier links into the
-//   neighbouring CTA's shared memory when the band spans the CTAs of a cluster). The 2-bit packed sequences are read with coalesced 128-bit
-//   loads and staged in shared memory as one code byte per base. Per step each thread streams the
-//   low byte of its 2*KP H values to the traceback arena in HBM (one 8/16-byte st.global.cs).
+//   a 16-byte shared-memory mailbox with its own mbarrier (no CTA barrier in the loop; st.async + mbarrier links into the
+//   neighbouring CTA's shared memory when the band spans the CTAs of a cluster). The 2-bit packed sequences are read with
+//   coalesced 128-bit loads and staged in shared memory as one code byte per base (whole images or sliding windows). Per step
+//   pair each thread streams the low bytes of its 4*KP H values to its slot of the pair's traceback rows in HBM (st.global.cs).
+//   Every variant exists with (arena / queue scheduling) and without (WALK = false: wave scheduling) the in-kernel walk.
 //
-// Traceback    svp_traceback_warp, called by warp 0 of the pair's CTA right after its forward pass
-//   Rebuilds exact H values along the path from the stored low bytes (neighbouring H differ by less than
-//   128); latency-bound, hidden behind the forward passes of the other CTAs on the SM.
-// Arena        every pair takes its traceback rows from a device-side allocator when its CTA starts and
-//   gives them back when its walk is done (ArenaPool): memory in use = the pairs resident on the GPU.
+// Walk (traceback)   rebuilds exact H values along the path from the stored low bytes (neighbouring H differ by less than
+//   128). svp_traceback_warp<CG, LPP>: a group of LPP lanes per pair, a diagonal run per round (the whole
+//   warp keeps a corridor of the rows in shared memory); svp_traceback_groups<LPP, CG>: 32 / LPP pairs per warp on ONE
+//   instruction stream (the bulk walker of serial waves, svp_tbu_kernel); svp_traceback_thread: one pair per lane.
+// Scheduling   waves (the host assigns the slices, walks are kernels of their own), arena (device-side slice allocator
+//   ArenaPool, the CTA walks its own pair), queue (resident walker kernels): svp_align.cu, DESIGN.md §4.8.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
