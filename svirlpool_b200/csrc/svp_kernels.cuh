@@ -1962,7 +1962,7 @@ svp_tbg_kernel(const Task* __restrict__ tasks, const uint32_t* __restrict__ orde
 
 //   svp_tbu_kernel   the same on ONE instruction stream per warp (svp_traceback_groups): the bulk walker of serial waves
 #ifndef SVP_TBU_MIN_CTAS
-#define SVP_TBU_MIN_CTAS 5
+#define SVP_TBU_MIN_CTAS 8
 #endif
 template <int LPP>
 __global__ void __launch_bounds__(128, SVP_TBU_MIN_CTAS)
