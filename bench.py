@@ -429,7 +429,15 @@ def main() -> None:
     # every call of this handle is planned like a large call (all kernel widths), so that the parity check below — 870 pairs, a small
     # call by itself — runs on the same kernel variants as the timed steps
     os.environ.setdefault("SVP_SMALL_CALL_PAIRS", "0")
-    al = Aligner(device=local, preset="map-ont", tb_bytes=arena_bytes)
+    al = None
+    for attempt in range(4):                               # an explicit arena size does not shrink by itself: step down if the allocation fails
+        try:
+            al = Aligner(device=local, preset="map-ont", tb_bytes=arena_bytes)
+            break
+        except Exception:
+            if not arena_bytes or attempt == 3:
+                raise
+            arena_bytes = int(arena_bytes * 0.85) & ~255
 
     def sync_all():
         torch.cuda.synchronize()
